@@ -1,0 +1,419 @@
+"""Minimal pure-Python reader for the NetCDF-4/HDF5 ``composite.nc`` files FHMCAnalysis writes.
+
+Why this exists: the reference loads ``composite.nc`` through ``netCDF4.Dataset``
+(reference moments/histogram/one_dim/ntot/gc_hist.pyx:143-182; the file is produced by
+``window.to_nc``, moments/win_patch/fhmc_patch.pyx:551-634).  Neither netCDF4, h5py nor libhdf5
+exist in the build container or on the GPU box, so the loader falls back to this reader when
+``netCDF4`` cannot be imported.
+
+Supported subset (everything the shipped fixtures and example composites use):
+superblock v0 and v2, version-2 object headers (``OHDR`` + ``OCHK`` continuation chunks), root
+group links in dense storage (LinkInfo -> fractal heap ``FRHP`` -> ``FHIB``/``FHDB``) or compact
+Link messages, contiguous or compact dataset layout, little/big-endian fixed-point and IEEE float
+element types, fixed-length string / numeric scalar attributes.  Chunked or filtered datasets raise
+``NotImplementedError`` (the reference never writes them for the variables the hot path reads).
+"""
+
+import struct
+
+import numpy as np
+
+_SIG = b"\x89HDF\r\n\x1a\n"
+_UNDEF = 0xFFFFFFFFFFFFFFFF
+
+
+class HDF5FormatError(Exception):
+    pass
+
+
+class _Reader(object):
+    def __init__(self, buf):
+        self.b = buf
+        self.O = 8  # size of offsets
+        self.L = 8  # size of lengths
+
+    def u(self, pos, n):
+        return int.from_bytes(self.b[pos:pos + n], "little")
+
+
+def _parse_datatype(b, pos):
+    """Return (numpy dtype or ('S', n) / None, total element size)."""
+    cls_ver = b[pos]
+    cls = cls_ver & 0x0F
+    bits0 = b[pos + 1]
+    size = int.from_bytes(b[pos + 4:pos + 8], "little")
+    order = ">" if (bits0 & 1) else "<"
+    if cls == 0:  # fixed point
+        signed = bool(bits0 & 0x08)
+        return np.dtype("%s%s%d" % (order, "i" if signed else "u", size)), size
+    if cls == 1:  # floating point
+        return np.dtype("%sf%d" % (order, size)), size
+    if cls == 3:  # fixed-length string
+        return np.dtype("S%d" % size), size
+    return None, size  # references, vlen, compound ...: not needed on the hot path
+
+
+def _parse_dataspace(r, pos):
+    b = r.b
+    ver = b[pos]
+    rank = b[pos + 1]
+    flags = b[pos + 2]
+    if ver == 1:
+        p = pos + 8
+    elif ver == 2:
+        if b[pos + 3] == 2:  # null dataspace
+            return None
+        p = pos + 4
+    else:
+        raise HDF5FormatError("dataspace version %d" % ver)
+    dims = tuple(r.u(p + i * r.L, r.L) for i in range(rank))
+    return dims
+
+
+class _Object(object):
+    """Parsed object header: the messages we care about."""
+
+    def __init__(self):
+        self.shape = None
+        self.dtype = None
+        self.layout = None  # ('contiguous', addr, size) | ('compact', bytes)
+        self.attrs = {}
+        self.links = {}  # compact link messages
+        self.linkinfo_heap = None
+
+
+def _parse_link(r, pos):
+    """Parse one Link message body at ``pos``; return (name, address or None, next_pos)."""
+    b = r.b
+    ver = b[pos]
+    if ver != 1:
+        return None, None, pos
+    flags = b[pos + 1]
+    p = pos + 2
+    ltype = 0
+    if flags & 0x08:
+        ltype = b[p]
+        p += 1
+    if flags & 0x04:
+        p += 8
+    if flags & 0x10:
+        p += 1
+    nlen_size = 1 << (flags & 3)
+    nlen = r.u(p, nlen_size)
+    p += nlen_size
+    name = bytes(b[p:p + nlen]).decode("utf-8", "replace")
+    p += nlen
+    addr = None
+    if ltype == 0:
+        addr = r.u(p, r.O)
+        p += r.O
+    elif ltype == 1:  # soft link
+        n = r.u(p, 2)
+        p += 2 + n
+    else:  # external / user defined
+        n = r.u(p, 2)
+        p += 2 + n
+    return name, addr, p
+
+
+def _parse_attribute(r, pos, obj):
+    b = r.b
+    ver = b[pos]
+    name_size = r.u(pos + 2, 2)
+    dt_size = r.u(pos + 4, 2)
+    ds_size = r.u(pos + 6, 2)
+    if ver == 1:
+        p = pos + 8
+
+        def pad(n):
+            return (n + 7) & ~7
+    elif ver == 2:
+        p = pos + 8
+
+        def pad(n):
+            return n
+    elif ver == 3:
+        p = pos + 9
+
+        def pad(n):
+            return n
+    else:
+        return
+    name = bytes(b[p:p + name_size]).split(b"\x00")[0].decode("utf-8", "replace")
+    p += pad(name_size)
+    dtype, esize = _parse_datatype(b, p)
+    p += pad(dt_size)
+    dims = _parse_dataspace(r, p)
+    p += pad(ds_size)
+    if dtype is None or dims is None:
+        return
+    count = 1
+    for d in dims:
+        count *= d
+    raw = bytes(b[p:p + count * esize])
+    if dtype.kind == "S":
+        val = raw.split(b"\x00")[0].decode("utf-8", "replace")
+    else:
+        arr = np.frombuffer(raw, dtype=dtype, count=count)
+        val = arr[0].item() if count == 1 else arr.astype(dtype.newbyteorder("=")).reshape(dims)
+    obj.attrs[name] = val
+
+
+def _parse_messages(r, pos, end, hdr_flags, obj, todo):
+    b = r.b
+    extra = 2 if (hdr_flags & 0x04) else 0
+    while pos + 4 + extra <= end:
+        mtype = b[pos]
+        msize = r.u(pos + 1, 2)
+        body = pos + 4 + extra
+        if body + msize > end:
+            break
+        if mtype == 0x01:
+            obj.shape = _parse_dataspace(r, body)
+        elif mtype == 0x03:
+            obj.dtype, _ = _parse_datatype(b, body)
+        elif mtype == 0x08:
+            lver = b[body]
+            lclass = b[body + 1]
+            if lver not in (3, 4):
+                raise HDF5FormatError("layout version %d unsupported" % lver)
+            if lclass == 1:
+                obj.layout = ("contiguous", r.u(body + 2, r.O), r.u(body + 2 + r.O, r.L))
+            elif lclass == 0:
+                n = r.u(body + 2, 2)
+                obj.layout = ("compact", bytes(b[body + 4:body + 4 + n]))
+            else:
+                obj.layout = ("chunked",)
+        elif mtype == 0x0C:
+            _parse_attribute(r, body, obj)
+        elif mtype == 0x06:
+            name, addr, _ = _parse_link(r, body)
+            if name is not None and addr is not None:
+                obj.links[name] = addr
+        elif mtype == 0x02:
+            lflags = b[body + 1]
+            p = body + 2 + (8 if (lflags & 1) else 0)
+            heap = r.u(p, r.O)
+            if heap != _UNDEF:
+                obj.linkinfo_heap = heap
+        elif mtype == 0x10:
+            todo.append((r.u(body, r.O), r.u(body + r.O, r.L)))
+        pos = body + msize
+
+
+def _parse_object_header(r, addr):
+    b = r.b
+    if bytes(b[addr:addr + 4]) != b"OHDR":
+        raise HDF5FormatError("only version-2 object headers are supported (no OHDR at %d)" % addr)
+    if b[addr + 4] != 2:
+        raise HDF5FormatError("object header version %d" % b[addr + 4])
+    flags = b[addr + 5]
+    p = addr + 6
+    if flags & 0x20:
+        p += 16
+    if flags & 0x10:
+        p += 4
+    csize_bytes = 1 << (flags & 3)
+    csize = r.u(p, csize_bytes)
+    p += csize_bytes
+    obj = _Object()
+    todo = []
+    _parse_messages(r, p, p + csize, flags, obj, todo)
+    while todo:
+        caddr, clen = todo.pop(0)
+        if bytes(b[caddr:caddr + 4]) != b"OCHK":
+            raise HDF5FormatError("bad continuation chunk at %d" % caddr)
+        _parse_messages(r, caddr + 4, caddr + clen - 4, flags, obj, todo)
+    return obj
+
+
+def _fractal_heap_links(r, heap_addr):
+    """Walk a fractal heap holding dense link storage; return {name: object header address}."""
+    b = r.b
+    if bytes(b[heap_addr:heap_addr + 4]) != b"FRHP":
+        raise HDF5FormatError("no fractal heap at %d" % heap_addr)
+    O, L = r.O, r.L
+    p = heap_addr + 5
+    p += 2  # heap id length
+    filt_len = r.u(p, 2)
+    p += 2
+    hflags = b[p]
+    p += 1
+    p += 4  # max size of managed objects
+    p += L + O + L + O  # next huge id, huge btree, free space, free-space manager
+    p += 4 * L  # managed space, allocated, iterator offset, n managed objects
+    p += 4 * L  # huge size, n huge, tiny size, n tiny
+    width = r.u(p, 2)
+    p += 2
+    start_size = r.u(p, L)
+    p += L
+    max_direct = r.u(p, L)
+    p += L
+    max_heap_bits = r.u(p, 2)
+    p += 2
+    p += 2  # starting rows in root indirect block
+    root = r.u(p, O)
+    p += O
+    cur_rows = r.u(p, 2)
+    if filt_len:
+        raise NotImplementedError("filtered fractal heaps are not supported")
+    off_bytes = (max_heap_bits + 7) // 8
+    has_cksum = bool(hflags & 0x02)
+    links = {}
+
+    def row_size(row):
+        return start_size if row < 2 else start_size << (row - 1)
+
+    def direct(addr, size):
+        if bytes(b[addr:addr + 4]) != b"FHDB":
+            raise HDF5FormatError("no direct block at %d" % addr)
+        q = addr + 5 + O + off_bytes + (4 if has_cksum else 0)
+        end = addr + size
+        while q < end and b[q] == 1:
+            name, a, nq = _parse_link(r, q)
+            if name is None or nq <= q or nq > end:
+                break
+            if a is not None:
+                links[name] = a
+            q = nq
+
+    def indirect(addr, nrows):
+        if bytes(b[addr:addr + 4]) != b"FHIB":
+            raise HDF5FormatError("no indirect block at %d" % addr)
+        q = addr + 5 + O + off_bytes
+        max_direct_rows = 2
+        s = start_size
+        while s < max_direct:
+            s <<= 1
+            max_direct_rows += 1
+        for row in range(nrows):
+            for _ in range(width):
+                child = r.u(q, O)
+                q += O
+                if child == _UNDEF:
+                    continue
+                if row < max_direct_rows:
+                    direct(child, row_size(row))
+                else:
+                    sub_rows = 1
+                    t = row_size(row) // (start_size * width)
+                    while t > 1:
+                        t >>= 1
+                        sub_rows += 1
+                    indirect(child, sub_rows + 1)
+
+    if root != _UNDEF:
+        if cur_rows == 0:
+            direct(root, start_size)
+        else:
+            indirect(root, cur_rows)
+    return links
+
+
+class Variable(object):
+    """Lazy dataset handle; ``var[:]`` (or any numpy index) returns a native-endian ndarray."""
+
+    def __init__(self, f, name, obj):
+        self._f = f
+        self.name = name
+        self.shape = obj.shape if obj.shape is not None else ()
+        self.dtype = obj.dtype
+        self._layout = obj.layout
+        self.attrs = obj.attrs
+
+    def read(self):
+        if self.dtype is None:
+            raise NotImplementedError("dataset %r has an unsupported element type" % self.name)
+        count = 1
+        for d in self.shape:
+            count *= d
+        if self._layout is None:
+            raise HDF5FormatError("dataset %r has no layout message" % self.name)
+        kind = self._layout[0]
+        if kind == "contiguous":
+            addr = self._layout[1]
+            if addr == _UNDEF:
+                arr = np.zeros(count, dtype=self.dtype)
+            else:
+                addr += self._f._base
+                arr = np.frombuffer(self._f._buf, dtype=self.dtype, count=count, offset=addr)
+        elif kind == "compact":
+            arr = np.frombuffer(self._layout[1], dtype=self.dtype, count=count)
+        else:
+            raise NotImplementedError("dataset %r uses chunked storage; only contiguous/compact "
+                                      "layouts are supported by the built-in reader" % self.name)
+        return np.array(arr.reshape(self.shape), dtype=self.dtype.newbyteorder("="))
+
+    def __getitem__(self, idx):
+        return self.read()[idx]
+
+    def __len__(self):
+        return self.shape[0]
+
+
+class File(object):
+    """Read-only view of the root group of an HDF5 file: ``.attrs`` and ``.variables``."""
+
+    def __init__(self, fname):
+        with open(fname, "rb") as fh:
+            self._buf = fh.read()
+        b = memoryview(self._buf)
+        if bytes(b[:8]) != _SIG:
+            raise HDF5FormatError("%s is not an HDF5 file" % fname)
+        r = _Reader(b)
+        ver = b[8]
+        if ver in (0, 1):
+            r.O = b[13]
+            r.L = b[14]
+            p = 24 + (4 if ver == 1 else 0)
+            self._base = r.u(p, r.O)
+            ste = p + 4 * r.O
+            root_addr = r.u(ste + r.O, r.O)
+        elif ver in (2, 3):
+            r.O = b[9]
+            r.L = b[10]
+            self._base = r.u(12, r.O)
+            root_addr = r.u(12 + 3 * r.O, r.O)
+        else:
+            raise HDF5FormatError("superblock version %d" % ver)
+        if r.O != 8 or r.L != 8:
+            raise HDF5FormatError("only 8-byte offsets/lengths are supported")
+        root = _parse_object_header(r, root_addr + self._base)
+        self.attrs = root.attrs
+        links = dict(root.links)
+        if root.linkinfo_heap is not None:
+            links.update(_fractal_heap_links(r, root.linkinfo_heap + self._base))
+        self.variables = {}
+        for name, addr in links.items():
+            try:
+                obj = _parse_object_header(r, addr + self._base)
+            except HDF5FormatError:
+                continue
+            if obj.layout is not None:
+                self.variables[name] = Variable(self, name, obj)
+
+    def close(self):
+        self._buf = None
+
+
+class Dataset(object):
+    """Just enough of ``netCDF4.Dataset`` for ``histogram.reload`` (reference gc_hist.pyx:143-182):
+    ``.variables[name][:]``, global attributes as Python attributes, ``.close()``."""
+
+    def __init__(self, fname, mode="r", format="NETCDF4"):
+        if mode != "r":
+            raise NotImplementedError("built-in reader is read-only; use write_composite() to write")
+        self._f = File(fname)
+        self.variables = self._f.variables
+
+    def __getattr__(self, name):
+        f = self.__dict__.get("_f")
+        if f is not None and name in f.attrs:
+            return f.attrs[name]
+        raise AttributeError(name)
+
+    def ncattrs(self):
+        return list(self._f.attrs.keys())
+
+    def close(self):
+        self._f.close()
