@@ -1,0 +1,120 @@
+"""ctypes binding of libfhmc_b200.so (C ABI declared in include/fhmc_b200.h).
+
+The library is built in-tree by ``fhmcanalysis_b200.build`` (nvcc, sm_100a).  There is NO CPU
+fallback: if the library is missing or no CUDA device is present every compute entry point raises.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfhmc_b200.so")
+
+MAX_TERMS = 8
+MAX_SEL = 4
+
+# enum fhmc_monomial
+M_DB, M_DD, M_DB2, M_DBDD, M_DD2, M_DB3, M_DB_MU1, M_ONE = range(8)
+
+ST_CODE_MASK = 0xFF
+ST_SAFE = 0x100
+ST_GAP_FILL = 0x200
+ST_SLOW_PATH = 0x400
+ST_RESCUED = 0x800
+E_CAPACITY = 8
+E_NO_COEX = 100
+
+STATUS_TEXT = {
+    0: "ok",
+    1: "ln(PI) not long enough to analyze for relative extrema",
+    2: "Bad relative extrema calculation",
+    3: "Bad relative extrema calculation",
+    4: "local maxima and local minima cannot be alternating, try adjusting the value of smooth",
+    5: "Local maxima and minima not sorted correctly, try adjusting the value of smooth",
+    6: "index out of bounds while assigning phase bounds",
+    7: "tied extrema between neighbouring maxima/minima",
+    8: "more extrema than pmax",
+    100: "no pair of sufficiently wide phases / no bracket for coexistence",
+}
+
+
+class HistDesc(ctypes.Structure):
+    _fields_ = [
+        ("n", ctypes.c_int), ("n_pad", ctypes.c_int), ("n_rows", ctypes.c_int), ("n_coef", ctypes.c_int),
+        ("coef_row", ctypes.c_int * MAX_TERMS), ("coef_kind", ctypes.c_int * MAX_TERMS),
+        ("n_sel", ctypes.c_int), ("n_term", ctypes.c_int),
+        ("sel_row", ctypes.c_int * MAX_SEL), ("sel_kind", ctypes.c_int * MAX_TERMS),
+        ("smooth", ctypes.c_int), ("pmax", ctypes.c_int), ("complete", ctypes.c_int), ("compare_raw", ctypes.c_int),
+        ("cutoff", ctypes.c_double), ("beta_ref", ctypes.c_double), ("mu1_ref", ctypes.c_double),
+        ("dmu_ref", ctypes.c_double),
+    ]
+
+
+class States(ctypes.Structure):
+    _fields_ = [
+        ("n_states", ctypes.c_longlong),
+        ("mu1", ctypes.c_void_p), ("n_mu1", ctypes.c_longlong), ("mu1_div", ctypes.c_longlong),
+        ("beta", ctypes.c_void_p), ("n_beta", ctypes.c_longlong), ("beta_div", ctypes.c_longlong),
+        ("dmu", ctypes.c_void_p), ("n_dmu", ctypes.c_longlong), ("dmu_div", ctypes.c_longlong),
+    ]
+
+
+class SweepOut(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in
+                ("status", "nphase", "nmin", "lnnorm", "fe", "avg", "bounds", "max_idx", "min_idx")]
+
+
+EXPORTS = [
+    "fhmc_version", "fhmc_last_error", "fhmc_device_info", "fhmc_sweep_1d", "fhmc_lnpi_1d",
+    "fhmc_phase_moments", "fhmc_axpy_rows", "fhmc_find_phase_eq_1d", "fhmc_reweight_2d",
+    "fhmc_reweight_2d_workspace",
+    "fhmc_bench_dfma", "fhmc_bench_exp",
+]
+
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def load():
+    """Load libfhmc_b200.so; raises LibraryMissing (no fallback) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            "%s not found: build it with `python -m fhmcanalysis_b200.build` (nvcc, sm_100a). "
+            "fhmcanalysis_b200 has no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, cd, cll = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_longlong
+    L.fhmc_version.restype = ci
+    L.fhmc_last_error.restype = ctypes.c_char_p
+    L.fhmc_device_info.restype = ci
+    L.fhmc_device_info.argtypes = [ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    L.fhmc_sweep_1d.restype = ci
+    L.fhmc_sweep_1d.argtypes = [ctypes.POINTER(HistDesc), vp, ctypes.POINTER(States), ctypes.POINTER(SweepOut), ci, vp]
+    L.fhmc_lnpi_1d.restype = ci
+    L.fhmc_lnpi_1d.argtypes = [ctypes.POINTER(HistDesc), vp, ctypes.POINTER(States), vp, vp, vp]
+    L.fhmc_phase_moments.restype = ci
+    L.fhmc_phase_moments.argtypes = [vp, ci, vp, ci, vp, ci, vp, vp, vp]
+    L.fhmc_axpy_rows.restype = ci
+    L.fhmc_axpy_rows.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(cd), ci, cll, vp, vp]
+    L.fhmc_find_phase_eq_1d.restype = ci
+    L.fhmc_find_phase_eq_1d.argtypes = [ctypes.POINTER(HistDesc), vp, ctypes.POINTER(States), cd, cd, ci,
+                                        vp, vp, vp, ctypes.POINTER(SweepOut), vp]
+    L.fhmc_reweight_2d.restype = ci
+    L.fhmc_reweight_2d_workspace.restype = ctypes.c_size_t
+    L.fhmc_reweight_2d_workspace.argtypes = [ci, ci, ci, cll]
+    L.fhmc_reweight_2d.argtypes = [vp, vp, ci, ci, vp, vp, vp, ci, vp, vp, cll, vp, vp, ctypes.c_size_t, vp]
+    L.fhmc_bench_dfma.restype = cll
+    L.fhmc_bench_dfma.argtypes = [ci, vp, vp]
+    L.fhmc_bench_exp.restype = cll
+    L.fhmc_bench_exp.argtypes = [ci, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed: %s" % (what, load().fhmc_last_error().decode("utf-8", "replace")))

@@ -1,0 +1,46 @@
+"""In-tree build of libfhmc_b200.so: nvcc, sm_100a only (`python -m fhmcanalysis_b200.build`)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SOURCES = ["fhmc_b200.cu", "fhmc_solver.cu", "fhmc_2d.cu"]
+HEADERS = ["fhmc_common.cuh", "fhmc_point.cuh"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "csrc")]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source to an object (in parallel) and link the shared library."""
+    nvcc = os.environ.get("NVCC", "nvcc")
+    csrc = os.path.join(HERE, "csrc")
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    common = [os.path.join(csrc, h) for h in HEADERS] + [os.path.join(ROOT, "include", "fhmc_b200.h"),
+                                                         os.path.abspath(__file__)]
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _newer(obj, [os.path.join(csrc, src)] + common):
+            cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(csrc, src), "-o", obj]
+            procs.append((src, subprocess.Popen(cmd)))
+    for src, p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("nvcc failed on %s" % src)
+    lib = os.path.join(HERE, "libfhmc_b200.so")
+    if procs or not os.path.exists(lib):
+        subprocess.check_call([nvcc, "-shared", "-cudart", "static", "-o", lib] + objs)
+    return lib
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,377 @@
+// fhmc_b200.cu -- kernels + C ABI of libfhmc_b200.so (sm_100a only).
+//
+//   K1+K3+K2  k_sweep_1d        fused reweight / normalise / phase split / thermo / is_safe sweep
+//   K1        k_lnpi_1d         normalised reweighted ln(PI) rows (what reweight() leaves behind)
+//   K2        k_phase_moments   per-phase averages of every moment array (drop-in thermo(props=True))
+//             k_axpy_rows       pointwise Taylor / mixing update of array stacks
+//   roofline  k_bench_dfma / k_bench_exp
+// K4 (solver) and K5 (2-D) live in fhmc_solver.cu / fhmc_2d.cu.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "fhmc_point.cuh"
+
+namespace fhmc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return 0;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// state point s -> (mu1, beta, dmu)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_state(const SweepArgs &a, long long sp, double &mu1, double &beta, double &dmu)
+{
+    const fhmc_states &st = a.st;
+    mu1 = st.mu1[(sp / st.mu1_div) % st.n_mu1];
+    beta = st.beta ? st.beta[(sp / st.beta_div) % st.n_beta] : a.d.beta_ref;
+    dmu = st.dmu ? st.dmu[(sp / st.dmu_div) % st.n_dmu] : a.d.dmu_ref;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1+K3+K2: persistent CTAs; the histogram blob is staged ONCE per CTA by a TMA bulk copy, then the
+// CTA walks tiles of FHMC_CTA/G state points.
+// ---------------------------------------------------------------------------------------------
+template <int G, bool TAYLOR>
+__global__ void __launch_bounds__(FHMC_CTA) k_sweep_1d(const __grid_constant__ SweepArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sm = reinterpret_cast<double *>(smem_raw);
+    const uint32_t blob_bytes = (uint32_t)a.d.n_rows * (uint32_t)a.d.n_pad * 8u;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + blob_bytes);
+    stage_blob(sm, a.blob, blob_bytes, bar);
+
+    constexpr int GPC = FHMC_CTA / G;  // state points per CTA tile
+    const int grp = threadIdx.x / G;
+    const long long S = a.st.n_states;
+    const long long ntiles = (S + GPC - 1) / GPC;
+    PointEval<G, TAYLOR> pe(a, sm, threadIdx.x & 31);
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long sp = tile * GPC + grp;
+        if (sp >= S) continue;  // whole groups drop out together; collectives use the group mask
+        double mu1, beta, dmu;
+        load_state(a, sp, mu1, beta, dmu);
+        pe.setup(mu1, beta, dmu);
+        pe.run(sp);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 output: lnpi_out[s][i] = fl(u_s(i) - lnnorm[s]).  One CTA per (state point, chunk of bins):
+// coalesced 8-byte stores, HBM-write bound.
+// ---------------------------------------------------------------------------------------------
+template <bool TAYLOR>
+__global__ void __launch_bounds__(FHMC_CTA) k_lnpi_1d(const __grid_constant__ SweepArgs a, const double *__restrict__ lnnorm,
+                                                      double *__restrict__ lnpi_out)
+{
+    const int n = a.d.n, npad = a.d.n_pad;
+    const long long S = a.st.n_states;
+    for (long long sp = blockIdx.y; sp < S; sp += gridDim.y) {
+        double mu1, beta, dmu;
+        load_state(a, sp, mu1, beta, dmu);
+        const double s = __dmul_rn(__dsub_rn(mu1, a.d.mu1_ref), a.d.beta_ref);
+        double xi[FHMC_MAX_TERMS];
+        if (TAYLOR) {
+            const double dB = beta - a.d.beta_ref, dD = dmu - a.d.dmu_ref;
+#pragma unroll
+            for (int t = 0; t < FHMC_MAX_TERMS; ++t) xi[t] = (t < a.d.n_coef) ? monomial(a.d.coef_kind[t], dB, dD, mu1) : 0.0;
+        }
+        const double c = lnnorm[sp];
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            double u = __dadd_rn(a.blob[i], __dmul_rn(s, a.blob[npad + i]));
+            if (TAYLOR) {
+#pragma unroll
+                for (int t = 0; t < FHMC_MAX_TERMS; ++t)
+                    if (t < a.d.n_coef) u = fma(xi[t], a.blob[(size_t)a.d.coef_row[t] * npad + i], u);
+            }
+            lnpi_out[sp * n + i] = __dsub_rn(u, c);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 (drop-in): avg[p][arr] = sum_{j in phase p} exp(lnpi_j) mom[arr][j] / sum_{j in phase p} exp(lnpi_j)
+// One warp per (phase, array); rows are read once from HBM with coalesced 8-byte loads.
+// exp(lnpi_j) of a normalised distribution is <= 1; the sums are shifted by the phase maximum so
+// that phases of negligible total weight keep full relative precision.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_phase_moments(const double *__restrict__ lnpi, int n, const double *__restrict__ mom,
+                                                       int n_arrays, const int *__restrict__ bounds, int n_phase,
+                                                       double *__restrict__ avg, double *__restrict__ lnsum)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int per_phase = n_arrays + 1;  // job `n_arrays` of each phase is the ln-sum itself
+    for (int job = warp; job < n_phase * per_phase; job += nwarps) {
+        const int p = job / per_phase, arr = job % per_phase;
+        const int left = bounds[2 * p], right = bounds[2 * p + 1];
+        double mx = -CUDART_INF;
+        for (int j = left + lane; j < right; j += 32) mx = fmax(mx, lnpi[j]);
+        mx = group_max<32>(mx, 0xffffffffu);
+        double S = 0.0, A = 0.0;
+        if (arr == n_arrays) {
+            for (int j = left + lane; j < right; j += 32) S += exp_nonpos(lnpi[j] - mx);
+            S = group_sum<32>(S, 0xffffffffu);
+            if (lane == 0 && lnsum) lnsum[p] = (right > left) ? mx + log(S) : -1.7976931348623157e308;
+            continue;
+        }
+        const double *row = mom + (size_t)arr * n;
+        for (int j = left + lane; j < right; j += 32) {
+            const double e = exp_nonpos(lnpi[j] - mx);
+            S += e;
+            A = fma(e, row[j], A);
+        }
+        S = group_sum<32>(S, 0xffffffffu);
+        A = group_sum<32>(A, 0xffffffffu);
+        if (lane == 0) avg[(size_t)p * n_arrays + arr] = A / S;
+    }
+}
+
+// out[i] = sum_t w[t] * src[t][i]
+struct AxpyArgs {
+    const double *src[FHMC_MAX_TERMS];
+    double w[FHMC_MAX_TERMS];
+    int n_src;
+};
+__global__ void __launch_bounds__(256) k_axpy_rows(const __grid_constant__ AxpyArgs a, long long count, double *__restrict__ out)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        double v = a.w[0] * a.src[0][i];
+#pragma unroll
+        for (int t = 1; t < FHMC_MAX_TERMS; ++t)
+            if (t < a.n_src) v = fma(a.w[t], a.src[t][i], v);
+        out[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// roofline micro-benchmarks: register-resident fp64 FMA chains / exp_nonpos chains
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bench_dfma(int iters, double *sink)
+{
+    double x0 = 1.0 + threadIdx.x * 1e-9, x1 = 0.5, x2 = 0.25, x3 = 0.125, x4 = 1.5, x5 = 1.25, x6 = 1.125, x7 = 0.75;
+    const double a = 0.999999, b = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (r == 123.456) sink[0] = r;
+}
+
+__global__ void __launch_bounds__(256) k_bench_exp(int iters, double *sink)
+{
+    double t0 = -1e-3 * (threadIdx.x + 1), t1 = t0 - 0.3, t2 = t0 - 1.7, t3 = t0 - 11.0;
+    double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+    for (int i = 0; i < iters; ++i) {
+        acc0 += exp_nonpos(t0); acc1 += exp_nonpos(t1); acc2 += exp_nonpos(t2); acc3 += exp_nonpos(t3);
+        t0 -= 1e-6; t1 -= 1e-6; t2 -= 1e-6; t3 -= 1e-6;
+    }
+    const double r = acc0 + acc1 + acc2 + acc3;
+    if (r == 123.456) sink[0] = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct DevInfo {
+    int sm_count = 0, smem_optin = 0, ok = 0;
+};
+static DevInfo g_dev[64];
+
+static const DevInfo *dev_info()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    DevInfo &d = g_dev[dev];
+    if (!d.ok) {
+        if (cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return nullptr;
+        if (cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return nullptr;
+        d.ok = 1;
+    }
+    return &d;
+}
+
+static int validate_desc(const fhmc_hist_desc *d)
+{
+    if (!d) { set_error("null descriptor"); return 1; }
+    if (d->n < 1 || d->n_pad < d->n || (d->n_pad & 1)) { set_error("bad n/n_pad (%d/%d): n_pad must be even and >= n", d->n, d->n_pad); return 1; }
+    if (d->n_rows < 2) { set_error("blob needs at least the ln(PI) and N rows"); return 1; }
+    if (d->n_coef < 0 || d->n_coef > FHMC_MAX_TERMS || d->n_term < 0 || d->n_term > FHMC_MAX_TERMS) { set_error("too many Taylor terms"); return 1; }
+    if (d->n_sel < 0 || d->n_sel > FHMC_MAX_SEL) { set_error("n_sel must be in [0,%d]", FHMC_MAX_SEL); return 1; }
+    if (d->n_sel > 0 && d->n_term < 1) { set_error("n_term must be >= 1 when n_sel > 0"); return 1; }
+    for (int c = 0; c < d->n_coef; ++c)
+        if (d->coef_row[c] < 0 || d->coef_row[c] >= d->n_rows) { set_error("coef_row[%d] out of range", c); return 1; }
+    for (int q = 0; q < d->n_sel; ++q)
+        if (d->sel_row[q] < 0 || d->sel_row[q] + d->n_term > d->n_rows) { set_error("sel_row[%d] out of range", q); return 1; }
+    if (!d->complete && d->smooth < 1) { set_error("smooth must be >= 1 (scipy argrelextrema order)"); return 1; }
+    if (d->pmax < 1) { set_error("pmax must be >= 1"); return 1; }
+    return 0;
+}
+
+static int validate_states(const fhmc_states *st)
+{
+    if (!st || st->n_states < 0 || !st->mu1 || st->n_mu1 < 1 || st->mu1_div < 1) { set_error("bad state-point description"); return 1; }
+    if (st->beta && (st->n_beta < 1 || st->beta_div < 1)) { set_error("bad beta array description"); return 1; }
+    if (st->dmu && (st->n_dmu < 1 || st->dmu_div < 1)) { set_error("bad dmu array description"); return 1; }
+    return 0;
+}
+
+template <int G, bool TAYLOR>
+static int launch_sweep(const SweepArgs &args, size_t smem, const DevInfo *di, cudaStream_t stream)
+{
+    auto kern = k_sweep_1d<G, TAYLOR>;
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return 1;
+    int occ = 0;
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FHMC_CTA, smem), "occupancy query")) return 1;
+    if (occ < 1) { set_error("sweep kernel does not fit on an SM (smem %zu bytes)", smem); return 1; }
+    const long long gpc = FHMC_CTA / G;
+    const long long ntiles = (args.st.n_states + gpc - 1) / gpc;
+    long long grid = (long long)di->sm_count * occ;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, FHMC_CTA, smem, stream>>>(args);
+    return check_cuda(cudaGetLastError(), "k_sweep_1d launch");
+}
+
+template <int G>
+static int launch_sweep_t(bool taylor, const SweepArgs &args, size_t smem, const DevInfo *di, cudaStream_t stream)
+{
+    return taylor ? launch_sweep<G, true>(args, smem, di, stream) : launch_sweep<G, false>(args, smem, di, stream);
+}
+
+int choose_lanes(long long n_states, const DevInfo *di)
+{
+    // enough groups to give every SM >= 1024 busy threads, otherwise widen the groups
+    const long long target = (long long)di->sm_count * 1024;
+    if (n_states >= target) return 1;
+    if (n_states * 4 >= target) return 4;
+    return 32;
+}
+
+}  // namespace fhmc
+
+using namespace fhmc;
+
+extern "C" {
+
+int fhmc_version(void) { return FHMC_ABI_VERSION; }
+
+const char *fhmc_last_error(void) { return g_err; }
+
+int fhmc_device_info(int *sm_count, int *max_smem_optin)
+{
+    const DevInfo *di = dev_info();
+    if (!di) { set_error("no CUDA device"); return 1; }
+    if (sm_count) *sm_count = di->sm_count;
+    if (max_smem_optin) *max_smem_optin = di->smem_optin;
+    return 0;
+}
+
+int fhmc_sweep_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states, const fhmc_sweep_out *out,
+                  int lanes_per_point, void *stream)
+{
+    if (validate_desc(desc) || validate_states(states)) return 1;
+    if (!blob || ((uintptr_t)blob & 15)) { set_error("blob must be a 16-byte aligned device pointer"); return 1; }
+    if (!out || !out->status || !out->nphase || !out->nmin || !out->lnnorm || !out->fe || !out->bounds || !out->max_idx ||
+        !out->min_idx || (desc->n_sel > 0 && !out->avg)) { set_error("missing output buffer"); return 1; }
+    if (states->n_states == 0) return 0;
+    const DevInfo *di = dev_info();
+    if (!di) { set_error("no CUDA device"); return 1; }
+    const size_t smem = (size_t)desc->n_rows * desc->n_pad * 8 + 16;
+    if (smem > (size_t)di->smem_optin) { set_error("histogram blob (%zu bytes) exceeds shared memory (%d bytes)", smem, di->smem_optin); return 1; }
+    SweepArgs args;
+    args.d = *desc;
+    args.blob = blob;
+    args.st = *states;
+    args.out = *out;
+    const bool taylor = desc->n_coef > 0 || desc->n_term > 1;
+    int G = lanes_per_point > 0 ? lanes_per_point : choose_lanes(states->n_states, di);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (G) {
+    case 1: return launch_sweep_t<1>(taylor, args, smem, di, s);
+    case 4: return launch_sweep_t<4>(taylor, args, smem, di, s);
+    case 32: return launch_sweep_t<32>(taylor, args, smem, di, s);
+    default: set_error("lanes_per_point must be 0, 1, 4 or 32"); return 1;
+    }
+}
+
+int fhmc_lnpi_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states, const double *lnnorm,
+                 double *lnpi_out, void *stream)
+{
+    if (validate_desc(desc) || validate_states(states)) return 1;
+    if (!blob || !lnnorm || !lnpi_out) { set_error("null pointer"); return 1; }
+    if (states->n_states == 0) return 0;
+    SweepArgs args;
+    memset(&args, 0, sizeof(args));
+    args.d = *desc;
+    args.blob = blob;
+    args.st = *states;
+    dim3 grid((desc->n + FHMC_CTA - 1) / FHMC_CTA, (unsigned)(states->n_states < 65535 ? states->n_states : 65535));
+    if (desc->n_coef > 0) k_lnpi_1d<true><<<grid, FHMC_CTA, 0, (cudaStream_t)stream>>>(args, lnnorm, lnpi_out);
+    else k_lnpi_1d<false><<<grid, FHMC_CTA, 0, (cudaStream_t)stream>>>(args, lnnorm, lnpi_out);
+    return check_cuda(cudaGetLastError(), "k_lnpi_1d launch");
+}
+
+int fhmc_phase_moments(const double *lnpi, int n, const double *mom, int n_arrays, const int *bounds, int n_phase,
+                       double *avg, double *lnsum, void *stream)
+{
+    if (!lnpi || !bounds || n < 1 || n_arrays < 0 || n_phase < 0 || (n_arrays > 0 && (!mom || !avg))) { set_error("bad arguments"); return 1; }
+    if (n_phase == 0) return 0;
+    const long long jobs = (long long)n_phase * (n_arrays + 1);
+    long long blocks = (jobs + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_phase_moments<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(lnpi, n, mom, n_arrays, bounds, n_phase, avg, lnsum);
+    return check_cuda(cudaGetLastError(), "k_phase_moments launch");
+}
+
+int fhmc_axpy_rows(const double *const *src, const double *w_host, int n_src, long long count, double *out, void *stream)
+{
+    if (!src || !w_host || !out || n_src < 1 || n_src > FHMC_MAX_TERMS || count < 0) { set_error("bad arguments"); return 1; }
+    if (count == 0) return 0;
+    AxpyArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_src = n_src;
+    for (int t = 0; t < n_src; ++t) { a.src[t] = src[t]; a.w[t] = w_host[t]; }
+    long long blocks = (count + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_axpy_rows<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, count, out);
+    return check_cuda(cudaGetLastError(), "k_axpy_rows launch");
+}
+
+long long fhmc_bench_dfma(int iters, double *sink, void *stream)
+{
+    const DevInfo *di = dev_info();
+    if (!di) return -1;
+    const int blocks = di->sm_count * 8;
+    k_bench_dfma<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return (long long)blocks * 256 * 8 * iters;
+}
+
+long long fhmc_bench_exp(int iters, double *sink, void *stream)
+{
+    const DevInfo *di = dev_info();
+    if (!di) return -1;
+    const int blocks = di->sm_count * 8;
+    k_bench_exp<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return (long long)blocks * 256 * 4 * iters;
+}
+
+}  // extern "C"

@@ -1,0 +1,188 @@
+// fhmc_solver.cu -- K4: batched find_phase_eq.
+//
+// Reference: histogram.find_phase_eq (gc_hist.pyx:598-668) minimises, per temperature and one at a
+// time, phase_eq_error(mu) = min over pairs of phases at least 2*smooth bins wide of
+// (F.E._i - F.E._j)^2 (gc_hist.pyx:2570-2630) with scipy's Nelder-Mead.  Here every solve is an
+// independent group of G lanes that finds the ROOT of the signed difference d(mu) = F.E._i - F.E._j of
+// the pair that objective selects.  d is smooth and monotone while the pair exists:
+//     d'(mu) = beta * (<N>_j - <N>_i)          (averages of the N row, free from K2)
+// so a bracketed Newton iteration converges in a handful of evaluations; each evaluation is the
+// full fused state-point pass of fhmc_point.cuh (reweight + Taylor + phase split + thermo).
+#include "fhmc_point.cuh"
+
+namespace fhmc {
+
+struct SolveArgs {
+    SweepArgs sw;
+    double lnz_tol, mu_step;
+    int max_iter;
+    double *mu_coex, *dfe;
+    int *iters;
+};
+
+template <int G, bool TAYLOR>
+__global__ void __launch_bounds__(FHMC_CTA) k_find_phase_eq(const __grid_constant__ SolveArgs sa)
+{
+    const SweepArgs &a = sa.sw;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sm = reinterpret_cast<double *>(smem_raw);
+    const uint32_t blob_bytes = (uint32_t)a.d.n_rows * (uint32_t)a.d.n_pad * 8u;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + blob_bytes);
+    stage_blob(sm, a.blob, blob_bytes, bar);
+
+    constexpr int GPC = FHMC_CTA / G;
+    const int grp = threadIdx.x / G;
+    const long long T = a.st.n_states;
+    const long long ntiles = (T + GPC - 1) / GPC;
+    const int pmax = a.d.pmax, nsel = a.d.n_sel;
+    const int min_width = 2 * a.d.smooth;  // gc_hist.pyx:652
+    PointEval<G, TAYLOR> pe(a, sm, threadIdx.x & 31);
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long rec = tile * GPC + grp;
+        if (rec >= T) continue;
+        double mu, beta, dmu;
+        const fhmc_states &st = a.st;
+        mu = st.mu1[(rec / st.mu1_div) % st.n_mu1];
+        beta = st.beta ? st.beta[(rec / st.beta_div) % st.n_beta] : a.d.beta_ref;
+        dmu = st.dmu ? st.dmu[(rec / st.dmu_div) % st.n_dmu] : a.d.dmu_ref;
+
+        bool have_lo = false, have_hi = false, converged = false;
+        double lo = 0.0, hi = 0.0, mu_good = mu, d = 0.0;
+        unsigned status = 0;
+        int code = FHMC_E_NO_COEX, it = 0, nevals = 0;
+        for (it = 0; it < sa.max_iter; ++it) {
+            pe.setup(mu, beta, dmu);
+            status = pe.run(rec);
+            ++nevals;
+            if (G > 1) __syncwarp(pe.member);
+            // pair selection of gc_hist.pyx:2614-2630 (every lane, uniform)
+            bool ok = false;
+            double slope = 0.0;
+            if ((status & FHMC_ST_CODE_MASK) == FHMC_OK) {
+                const double *fe = a.out.fe + rec * pmax;
+                const int *bl = a.out.bounds + rec * pmax * 2;
+                double best = 1.7976931348623157e308;
+                int bi = -1, bj = -1;
+                for (int i = 0; i < pe.P; ++i) {
+                    if (bl[2 * i + 1] - bl[2 * i] < min_width) continue;
+                    for (int j = i + 1; j < pe.P; ++j) {
+                        if (bl[2 * j + 1] - bl[2 * j] < min_width) continue;
+                        const double dd = fe[i] - fe[j];
+                        if (dd * dd < best) { best = dd * dd; bi = i; bj = j; d = dd; }
+                    }
+                }
+                if (bi >= 0) {
+                    ok = true;
+                    const double *av = a.out.avg + rec * pmax * nsel;
+                    slope = beta * (av[bj * nsel] - av[bi * nsel]);
+                }
+            }
+            if (!ok) {
+                if (it == 0) { code = ((status & FHMC_ST_CODE_MASK) != FHMC_OK) ? (int)(status & FHMC_ST_CODE_MASK) : FHMC_E_NO_COEX; break; }
+                mu = 0.5 * (mu + mu_good);  // stepped out of the two-phase window: come back half way
+                continue;
+            }
+            mu_good = mu;
+            if (fabs(d) <= sa.lnz_tol) { converged = true; code = FHMC_OK; break; }
+            const bool below = (slope >= 0.0) ? (d < 0.0) : (d > 0.0);
+            if (below) { lo = mu; have_lo = true; } else { hi = mu; have_hi = true; }
+            double mu_n = mu;
+            if (slope != 0.0) {
+                double dm = -d / slope;
+                if (dm > sa.mu_step) dm = sa.mu_step;
+                if (dm < -sa.mu_step) dm = -sa.mu_step;
+                mu_n = mu + dm;
+            } else {
+                mu_n = mu + (below ? sa.mu_step : -sa.mu_step);
+            }
+            if (have_lo && have_hi) {
+                const double l = fmin(lo, hi), h = fmax(lo, hi);
+                if (!(mu_n > l && mu_n < h)) mu_n = 0.5 * (lo + hi);
+                if (mu_n == mu || h - l <= 4.0 * 2.220446049250313e-16 * fmax(fabs(l), fabs(h))) {
+                    converged = true;  // bracket exhausted at fp64 resolution
+                    code = FHMC_OK;
+                    break;
+                }
+            }
+            mu = mu_n;
+        }
+        if (!converged && code == FHMC_E_NO_COEX && it >= sa.max_iter) code = FHMC_E_NO_COEX + 1;  // iteration cap
+        if (pe.g == 0) {
+            sa.mu_coex[rec] = mu_good;
+            sa.dfe[rec] = d;
+            sa.iters[rec] = nevals;
+            if (code != FHMC_OK) a.out.status[rec] = (a.out.status[rec] & ~FHMC_ST_CODE_MASK) | (unsigned)code;
+        }
+    }
+}
+
+struct DevCaps {
+    int sm_count, smem_optin;
+};
+static int get_caps(DevCaps &c)
+{
+    int dev = 0;
+    if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
+    if (check_cuda(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev), "device attribute")) return 1;
+    if (check_cuda(cudaDeviceGetAttribute(&c.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev), "device attribute")) return 1;
+    return 0;
+}
+
+template <int G, bool TAYLOR>
+static int launch_solver(const SolveArgs &sa, size_t smem, const DevCaps &caps, cudaStream_t stream)
+{
+    auto kern = k_find_phase_eq<G, TAYLOR>;
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return 1;
+    int occ = 0;
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FHMC_CTA, smem), "occupancy query")) return 1;
+    if (occ < 1) { set_error("solver kernel does not fit on an SM"); return 1; }
+    const long long gpc = FHMC_CTA / G;
+    const long long ntiles = (sa.sw.st.n_states + gpc - 1) / gpc;
+    long long grid = (long long)caps.sm_count * occ;
+    if (grid > ntiles) grid = ntiles;
+    kern<<<(unsigned)grid, FHMC_CTA, smem, stream>>>(sa);
+    return check_cuda(cudaGetLastError(), "k_find_phase_eq launch");
+}
+
+}  // namespace fhmc
+
+using namespace fhmc;
+
+extern "C" int fhmc_find_phase_eq_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states,
+                                     double lnz_tol, double mu_step, int max_iter, double *mu_coex, double *dfe,
+                                     int *iters, const fhmc_sweep_out *out, void *stream)
+{
+    if (!desc || !blob || !states || !out || !mu_coex || !dfe || !iters) { set_error("null pointer"); return 1; }
+    if (desc->n_sel < 1 || desc->sel_row[0] != 1) { set_error("solver needs quantity 0 to be the N row (sel_row[0] == 1)"); return 1; }
+    if (desc->complete || desc->smooth < 1 || desc->pmax < 2) { set_error("solver needs complete=0, smooth>=1, pmax>=2"); return 1; }
+    if (!out->status || !out->nphase || !out->nmin || !out->lnnorm || !out->fe || !out->avg || !out->bounds ||
+        !out->max_idx || !out->min_idx) { set_error("missing output buffer"); return 1; }
+    if (!(lnz_tol >= 0.0) || !(mu_step > 0.0) || max_iter < 1) { set_error("bad solver controls"); return 1; }
+    if (states->n_states == 0) return 0;
+    if (((uintptr_t)blob & 15) || (desc->n_pad & 1)) { set_error("blob must be 16-byte aligned with even n_pad"); return 1; }
+    DevCaps caps;
+    if (get_caps(caps)) return 1;
+    const size_t smem = (size_t)desc->n_rows * desc->n_pad * 8 + 16;
+    if (smem > (size_t)caps.smem_optin) { set_error("histogram blob exceeds shared memory"); return 1; }
+    SolveArgs sa;
+    sa.sw.d = *desc;
+    sa.sw.blob = blob;
+    sa.sw.st = *states;
+    sa.sw.out = *out;
+    sa.lnz_tol = lnz_tol;
+    sa.mu_step = mu_step;
+    sa.max_iter = max_iter;
+    sa.mu_coex = mu_coex;
+    sa.dfe = dfe;
+    sa.iters = iters;
+    const bool taylor = desc->n_coef > 0 || desc->n_term > 1;
+    const long long T = states->n_states;
+    cudaStream_t s = (cudaStream_t)stream;
+    // a solve is ~10 dependent state-point passes: prefer wide groups unless there are very many solves
+    if (T * 32 <= (long long)caps.sm_count * 2048 * 4)
+        return taylor ? launch_solver<32, true>(sa, smem, caps, s) : launch_solver<32, false>(sa, smem, caps, s);
+    if (T * 4 <= (long long)caps.sm_count * 2048 * 4)
+        return taylor ? launch_solver<4, true>(sa, smem, caps, s) : launch_solver<4, false>(sa, smem, caps, s);
+    return taylor ? launch_solver<1, true>(sa, smem, caps, s) : launch_solver<1, false>(sa, smem, caps, s);
+}

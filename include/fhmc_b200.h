@@ -1,0 +1,196 @@
+/*
+ * fhmc_b200.h -- C ABI of libfhmc_b200.so: B200 (sm_100a) kernels for the histogram-reweighting
+ * hot path of FHMCAnalysis.
+ *
+ * The reference (jeetain/FHMCAnalysis) has no FFI of its own: its native layer is a handful of
+ * Cython cdef functions bound onto the Python class `histogram`
+ * (moments/histogram/one_dim/ntot/gc_hist.pyx, "GH").  Each entry point below names the
+ * reference routine(s) it replaces; INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add to call it.
+ *
+ * Conventions
+ *   - every pointer inside the fhmc_* structs is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns all buffers; no call allocates device memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return value: 0 = ok, non-zero = error (text via fhmc_last_error());
+ *   - all floating point is IEEE fp64; indices are 32-bit signed.
+ */
+#ifndef FHMC_B200_H
+#define FHMC_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FHMC_ABI_VERSION 1
+#define FHMC_MAX_TERMS 8   /* Taylor terms per array                      */
+#define FHMC_MAX_SEL 4     /* quantities averaged inside the fused sweep   */
+
+/* Monomials in (dB = beta - beta_ref, dD = dmu2 - dmu2_ref, mu1) multiplying a coefficient row.
+ * They are the terms of the second/third-order Taylor expansion the reference builds in
+ * GH:968-1239 (_temp_dmu_extrap_{1,2}[_multi]) and GH:2208 (_dB3).                            */
+enum fhmc_monomial {
+    FHMC_M_DB = 0,        /* dB            */
+    FHMC_M_DD = 1,        /* dD            */
+    FHMC_M_DB2 = 2,       /* dB^2 / 2      */
+    FHMC_M_DBDD = 3,      /* dB * dD       */
+    FHMC_M_DD2 = 4,       /* dD^2 / 2      */
+    FHMC_M_DB3 = 5,       /* dB^3 / 6      */
+    FHMC_M_DB_MU1 = 6,    /* dB * mu1      (the mu1*N part of d lnPI / d beta, GH:1660-1722)    */
+    FHMC_M_ONE = 7        /* 1             */
+};
+
+/* per-state-point status word (fhmc_sweep_out.status) */
+#define FHMC_ST_CODE_MASK   0xFFu   /* 0 ok, else "the reference would raise": codes below        */
+#define FHMC_ST_SAFE        0x100u  /* is_safe(cutoff) == True (GH:556-596, fresh extrema)        */
+#define FHMC_ST_GAP_FILL    0x200u  /* GH:355-363 / 370-378 branch taken (unique gap extremum)    */
+#define FHMC_ST_SLOW_PATH   0x400u  /* extrema had to be re-evaluated on the normalised array     */
+#define FHMC_ST_RESCUED     0x800u  /* a phase with negligible weight was re-summed about its own max */
+enum fhmc_status_code {
+    FHMC_OK = 0,
+    FHMC_E_TOO_SHORT = 1,       /* GH:326-327                                                    */
+    FHMC_E_BAD_FRONT = 2,       /* GH:341-342                                                    */
+    FHMC_E_BAD_BACK = 3,        /* GH:350-351                                                    */
+    FHMC_E_COUNT_MISMATCH = 4,  /* GH:403-404 (and the NumPy slice-assignment errors of 408-412) */
+    FHMC_E_NOT_SORTED = 5,      /* GH:414-415                                                    */
+    FHMC_E_INDEX = 6,           /* IndexError in GH:504 / 511                                    */
+    FHMC_E_RAGGED_GAP = 7,      /* GH:355-363 / 370-378 with tied gap extrema                    */
+    FHMC_E_CAPACITY = 8         /* more extrema than pmax: call again with a larger pmax         */
+};
+
+/*
+ * One histogram, packed by the host as a dense "blob" of fp64 rows of stride n_pad (n_pad even,
+ * n_pad >= n; the blob base must be 16-byte aligned so one TMA bulk copy can stage it in shared
+ * memory):
+ *   row 0                    ln(PI)(N)                       (GH:148)
+ *   row 1                    N_tot as fp64                   (GH:154)
+ *   rows 2 .. n_rows-1       Taylor coefficient rows / rows of quantities to average.
+ * lnPI'(N) = row0 + fl(s*row1) + sum_c mono(coef_kind[c]) * row[coef_row[c]],   s = fl(fl(mu1-mu1_ref)*beta_ref)
+ * (the un-fused s*N product and add reproduce GH:77 bit-for-bit).
+ * Quantity q (q < n_sel):   X_q(N) = sum_t mono(sel_kind[t]) * row[sel_row[q] + t],  t < n_term
+ * (sel_kind[0] must be FHMC_M_ONE).
+ */
+typedef struct fhmc_hist_desc {
+    int n;                          /* bins                                                      */
+    int n_pad;                      /* row stride (doubles), even                                */
+    int n_rows;                     /* rows in the blob                                          */
+    int n_coef;                     /* Taylor terms added to lnPI, <= FHMC_MAX_TERMS             */
+    int coef_row[FHMC_MAX_TERMS];
+    int coef_kind[FHMC_MAX_TERMS];
+    int n_sel;                      /* <= FHMC_MAX_SEL                                           */
+    int n_term;                     /* rows per quantity, <= FHMC_MAX_TERMS                      */
+    int sel_row[FHMC_MAX_SEL];
+    int sel_kind[FHMC_MAX_TERMS];
+    int smooth;                     /* extrema window, metadata['smooth'] (GH:329-330), >= 1     */
+    int pmax;                       /* capacity of the per-state-point phase arrays              */
+    int complete;                   /* thermo(complete=True): one phase [0,n), no extrema        */
+    int compare_raw;                /* relextrema() on the array as given (GH:329): compare u, not fl(u-c) */
+    double cutoff;                  /* is_safe cutoff (GH:556)                                   */
+    double beta_ref;                /* data['curr_beta'] of the stored histogram                 */
+    double mu1_ref;                 /* data['curr_mu'][0]                                        */
+    double dmu_ref;                 /* data['curr_mu'][1]-data['curr_mu'][0] (0 for 1 species)   */
+} fhmc_hist_desc;
+
+/*
+ * State points.  State point s (0 <= s < n_states) uses
+ *   mu1  = mu1 [(s / mu1_div ) % n_mu1 ],  beta = beta[(s / beta_div) % n_beta] (NULL: beta_ref),
+ *   dmu2 = dmu [(s / dmu_div ) % n_dmu ]   (NULL: dmu_ref).
+ * Flat list: all div = 1 and n_* = n_states (or 1 to broadcast).  (beta x dmu) grid like
+ * temp_dmu_extrap_multi (GH:813-887): beta_div = n_dmu, dmu_div = 1, n_states = n_beta*n_dmu.
+ */
+typedef struct fhmc_states {
+    long long n_states;
+    const double *mu1;  long long n_mu1;  long long mu1_div;
+    const double *beta; long long n_beta; long long beta_div;
+    const double *dmu;  long long n_dmu;  long long dmu_div;
+} fhmc_states;
+
+/* Results, one record per state point.  status, nphase, lnnorm, fe, bounds, max_idx, min_idx, nmin
+ * are required (max_idx/min_idx/bounds double as kernel work space); avg may be NULL iff n_sel==0. */
+typedef struct fhmc_sweep_out {
+    unsigned *status;   /* [S]               see FHMC_ST_*                                       */
+    int *nphase;        /* [S]               len(data['ln(PI)_maxima_idx'])                      */
+    int *nmin;          /* [S]               len(data['ln(PI)_minima_idx'])                      */
+    double *lnnorm;     /* [S]               c:  normalised lnPI = lnPI' - c          (GH:57-67) */
+    double *fe;         /* [S][pmax]         thermo[p]['F.E./kT']                    (GH:523-526) */
+    double *avg;        /* [S][pmax][n_sel]  phase averages                          (GH:530-541) */
+    int *bounds;        /* [S][pmax][2]      thermo[p]['bound_idx']                  (GH:498-520) */
+    int *max_idx;       /* [S][pmax]                                                             */
+    int *min_idx;       /* [S][pmax+1]                                                           */
+} fhmc_sweep_out;
+
+int fhmc_version(void);
+const char *fhmc_last_error(void);
+
+/* Device/SM query used by the host layer to size grids. */
+int fhmc_device_info(int *sm_count, int *max_smem_optin);
+
+/*
+ * K1+K3+K2 fused: for every state point  reweight (GH:268-289, 71-78) [+ Taylor extrapolation,
+ * GH:813-1239] + normalise (GH:57-67) + relextrema (GH:317-415) + phase bounds / free energies /
+ * selected averages (thermo, GH:451-554) + is_safe (GH:556-596).
+ * lanes_per_point in {1,4,32}: threads cooperating on one state point (0 = choose).
+ */
+int fhmc_sweep_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states,
+                  const fhmc_sweep_out *out, int lanes_per_point, void *stream);
+
+/* Normalised, reweighted ln(PI) rows: lnpi_out[s][i] = fl(lnPI'_s(i) - lnnorm[s]); what
+ * histogram.reweight()/normalize() leave in data['ln(PI)'] (GH:67, 77). */
+int fhmc_lnpi_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states,
+                 const double *lnnorm, double *lnpi_out, void *stream);
+
+/*
+ * K2 for the drop-in thermo(props=True): phase averages of EVERY moment array (GH:530-541).
+ *   lnpi  [n]            normalised ln(PI)
+ *   mom   [n_arrays][n]  moment tensor flattened over (i,j,k,m,p)
+ *   bounds[n_phase][2]
+ *   avg   [n_phase][n_arrays]   out (may be NULL when n_arrays == 0)
+ *   lnsum [n_phase]             out: ln sum_{j in phase} exp(lnpi_j)  (F.E./kT = -(lnsum - lnpi[0]), GH:523-526)
+ */
+int fhmc_phase_moments(const double *lnpi, int n, const double *mom, int n_arrays, const int *bounds,
+                       int n_phase, double *avg, double *lnsum, void *stream);
+
+/*
+ * Pointwise Taylor update of a stack of arrays (moment extrapolation, GH:1027-1034 / 1162-1171,
+ * and histogram.mix, GH:244-252):  out[a][i] = sum_t w[t] * src[t][a][i],  t < n_src.
+ */
+int fhmc_axpy_rows(const double *const *src, const double *w_host, int n_src, long long count,
+                   double *out, void *stream);
+
+/*
+ * K4: batched find_phase_eq (GH:598-668 with the objective of GH:2570-2630).  One solve per
+ * entry of `states` (mu1 there is the initial guess).  Root of the signed dF.E./kT between the
+ * two phases the reference objective would select, by bracketing + bisection/secant, to
+ * |dF.E.| <= lnz_tol.  Outputs: mu_coex[T], dfe[T] (signed residual), iters[T], status as above
+ * (code FHMC_E_* or 100 = no two wide phases / no bracket).  The thermo at mu_coex is written
+ * through `out` (same layout as fhmc_sweep_1d).
+ */
+#define FHMC_E_NO_COEX 100
+int fhmc_find_phase_eq_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states,
+                          double lnz_tol, double mu_step, int max_iter,
+                          double *mu_coex, double *dfe, int *iters,
+                          const fhmc_sweep_out *out, void *stream);
+
+/*
+ * K5: 2-D joint histogram lnPI(op1,op2) (container: two_dim/joint_hist.pyx:201-247) reweighted to
+ * S state points:  v = lnPI[i][j] + a1[s]*op1[i] + a2[s]*op2[j]  over the support
+ * [bounds[i][0], bounds[i][1]) of each row (-inf padding ignored);
+ * out[s][0] = ln sum exp v, out[s][1] = <op1>, out[s][2] = <op2>, out[s][3+q] = <prop_q>  (n_prop <= 2).
+ * `workspace` (device, fhmc_reweight_2d_workspace() bytes) holds the per-row-chunk partial sums.
+ */
+size_t fhmc_reweight_2d_workspace(int n1, int n2, int n_prop, long long n_states);
+int fhmc_reweight_2d(const double *lnpi, const int *bounds, int n1, int n2, const double *op1,
+                     const double *op2, const double *props, int n_prop, const double *a1,
+                     const double *a2, long long n_states, double *out, double *workspace,
+                     size_t workspace_bytes, void *stream);
+
+/* Roofline micro-benchmarks (register-resident): return ops executed; time with CUDA events. */
+long long fhmc_bench_dfma(int iters, double *sink, void *stream);
+long long fhmc_bench_exp(int iters, double *sink, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FHMC_B200_H */
