@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the histogram-reweighting hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload config2|config3]
+
+Workload (config.workload): BASELINE config 2 -- synthetic 1-component N_tot ln(PI), N_max = 1000 (1001 bins),
+smooth = 10; a "step" is one pass of the fused sweep (reweight + normalise + phase split + per-phase lnZ +
+<N>, <N^2>) over 10^6 state points mu in [-0.03, 0.03] PER GPU (weak scaling: state points are independent,
+each rank owns a contiguous slice of the N*10^6-point sweep; no collective on the data path, one NCCL
+all_gather of the packed results after the timed region, timed separately).
+
+Timed numbers
+  value      state points/s, inputs resident in HBM, CUDA events around each step on the launch stream,
+             L2 flushed (256 MiB write) before every step, max over ranks.
+  e2e        the same metric through the public batched API with HOST buffers: pinned-host mu -> device,
+             kernel, packed results -> pinned host, every step.
+  roofline   fp64-exp issue roofline: algorithmic exps = 1001 per state point, peak = the
+             register-resident exp micro-benchmark run in this same process (DFMA peak beside it).
+  cpu_baseline / --impl reference
+             the compiled reference (oracle/_ref; else the C port) driven like its notebooks
+             (fresh copy -> reweight -> thermo -> is_safe) on a bounded sample over all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_BINS = 1001
+SMOOTH = 10
+S_PER_GPU = 1000000
+MU_LO, MU_HI = -0.03, 0.03
+PMAX = 4
+METRIC = "reweighted state points/sec (lnPI+thermo) at N_max=1000"
+UNIT = "state points/s"
+
+
+def workload_arrays():
+    from fhmcanalysis_b200 import synth
+    lnpi = synth.two_peak_lnpi(N_BINS)
+    mom = synth.one_comp_moments(N_BINS)
+    return lnpi, mom
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation on host cores (bounded sample)
+# ------------------------------------------------------------------------------------------------
+def _cpu_chunk(args):
+    kind, mus = args
+    lnpi, mom = workload_arrays()
+    t0 = time.perf_counter()
+    if kind == "reference":
+        from oracle import ref
+        import copy
+        base = ref.make_histogram(lnpi, mom, 1.0, [0.0], SMOOTH)
+        acc = 0.0
+        for mu in mus:
+            h = copy.deepcopy(base)
+            h.reweight(float(mu))
+            h.thermo()
+            acc += h.is_safe() + h.data["thermo"][0]["F.E./kT"]
+    else:
+        from oracle import fhmc_oracle as fo
+        i = np.arange(N_BINS, dtype=float)
+        sel = np.stack([i, i * i])
+        acc = 0.0
+        for mu in mus:
+            r = fo.state_point(lnpi, np.arange(N_BINS), 1.0, 0.0, float(mu), SMOOTH, sel=sel, pmax=PMAX)
+            acc += r["fe"][0]
+    return len(mus), time.perf_counter() - t0, acc
+
+
+def cpu_arm(sample_per_core, cores=None):
+    """Time the CPU reference on `cores` processes; returns dict(value, cores, kind, sample)."""
+    import multiprocessing as mp
+    from oracle import ref
+    kind = "reference" if ref.available() else "port"
+    if kind == "port":
+        from oracle import fhmc_oracle
+        fhmc_oracle.build()
+    cores = cores or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
+    total = sample_per_core * cores
+    mus = np.linspace(MU_LO, MU_HI, total)
+    chunks = [(kind, mus[c::cores]) for c in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_chunk, [(kind, mus[:2])] * cores)  # warm-up: imports, page-in
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_chunk, chunks)
+        wall = time.perf_counter() - t0
+    n = sum(r[0] for r in res)
+    return {"value": n / wall, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d of the 10^6 state points of the workload (every %d-th), %s driven as deepcopy->reweight->thermo->is_safe, "
+                      "%d processes, %.1f s wall" % (n, max(S_PER_GPU // n, 1), "compiled reference (oracle/_ref)" if kind == "reference" else "C port (oracle/fhmc_oracle.c)", cores, wall),
+            "wall_s": wall}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return 0
+    per_core = 6000
+    steps, warm = max(args.steps, 1), args.warmup
+    vals = []
+    last = None
+    for k in range(steps + min(warm, 1)):
+        last = cpu_arm(per_core)
+        if k >= min(warm, 1):
+            vals.append(last["value"])
+    v = float(np.mean(vals))
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": 1e3 * per_core * last["cores"] / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "gpu_launches": 0,
+            "config": {"workload": "config2: synthetic 1-comp N_tot lnPI, N_max=1000, smooth=10, mu sweep in [-0.03,0.03]; bounded sample",
+                       "state_points_per_step": per_core * last["cores"]},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc, self.idx = None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from fhmcanalysis_b200 import engine
+    from fhmcanalysis_b200.moments.histogram.one_dim.ntot.gc_hist import histogram
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # CPU baseline first, on rank 0 at N=1 only (bounded sample), before the GPU is busy
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-worker"], capture_output=True, text=True,
+                                 timeout=600)
+            cpu = json.loads(out.stdout.strip().splitlines()[-1])
+        except Exception as e:  # keep the GPU measurement even if the CPU leg breaks
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": "cpu baseline failed: %r" % (e,)}
+
+    lnpi, mom = workload_arrays()
+    hist = histogram.from_arrays(lnpi, mom, 1.0, [0.0], SMOOTH)
+    moments = ("N", "N2")
+    dh = hist.device_histogram(moments=moments, device=dev)
+    S = args.points
+    # this rank's slice of the global sweep
+    mu_all_lo = MU_LO + (MU_HI - MU_LO) * rank / world
+    mu_all_hi = MU_LO + (MU_HI - MU_LO) * (rank + 1) / world
+    mu_host = torch.from_numpy(np.linspace(mu_all_lo, mu_all_hi, S, endpoint=(rank == world - 1))).pin_memory()
+    mu_dev = mu_host.to(dev)
+    states = dh.make_states(mu_dev)
+    out = engine.SweepResult(S, PMAX, dh.n_sel, dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    peaks = engine.measure_peaks(dev)
+
+    def step():
+        dh.sweep(None, states=states, out=out, pmax=PMAX, lanes=args.lanes)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()            # samples cover warm-up + timed region + e2e loop (same kernel under load throughout)
+    t_w = time.perf_counter()
+    n_warm = 0
+    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_w < 1.0:   # >= 1 s of load before timing
+        flush.zero_()
+        step()
+        n_warm += 1
+        if n_warm % 8 == 0:
+            torch.cuda.synchronize(dev)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()          # L2 flush: inputs (8 MB of mu + 32 KB blob) are far smaller than the 126 MB L2
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    kern_ms = [a.elapsed_time(b) for a, b in ev]
+    t_ms = torch.tensor([float(np.sum(kern_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(t_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = world * S / (ms_per_step * 1e-3)
+
+    # ---- e2e through the public batched API with host buffers ------------------------------------
+    host_out = {k: torch.empty_like(getattr(out, k), device="cpu").pin_memory() for k in out.FIELDS if getattr(out, k) is not None}
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+    h2d = mu_host.numel() * 8 + dh.h2d_bytes
+
+    def e2e_step():
+        mu_d = mu_host.to(dev, non_blocking=True)
+        blob_d = torch.from_numpy(dh.blob_host).to(dev, non_blocking=True)
+        dh.blob = blob_d
+        st = dh.make_states(mu_d)
+        r = dh.sweep(None, states=st, out=out, pmax=PMAX, lanes=args.lanes)
+        for k, v in host_out.items():
+            v.copy_(getattr(r, k), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * S / (float(e2e_ms.item()) * 1e-3)
+    clocks = sampler.stop()
+
+    # ---- the one collective of the path: final gather of packed results (not in `value`) ----------
+    gather_ms = None
+    if world > 1:
+        packed = torch.cat([out.lnnorm.view(-1), out.fe.view(-1), out.avg.view(-1)])
+        gathered = torch.empty(world * packed.numel(), dtype=packed.dtype, device=dev)
+        dist.all_gather_into_tensor(gathered, packed)
+        torch.cuda.synchronize(dev)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.all_gather_into_tensor(gathered, packed)
+        g1.record()
+        g1.synchronize()
+        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        gather_ms = float(gt.item())
+
+    # sanity: the timed kernel really produced results
+    h_status = out.status.cpu().numpy().view(np.uint32)
+    ok_frac = float(np.mean((h_status & 0xFF) == 0))
+
+    if rank == 0:
+        exps = S * N_BINS / (np.mean(kern_ms) * 1e-3)   # this rank's kernel
+        mp_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak = None
+        if os.path.exists(mp_path):
+            try:
+                hbm_peak = json.load(open(mp_path)).get("hbm_gbs")
+            except Exception:
+                hbm_peak = None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_sweep_dram_bytes.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        algo_bytes = S * (8 + out.nbytes() / S)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "gpu_launches": args.steps,
+            "config": {"workload": "config2: synthetic 1-comp N_tot lnPI, N_max=1000 (1001 bins), smooth=10, 10^6-point mu sweep per GPU with thermo "
+                                   "(<N>, <N^2>, per-phase lnZ, phase split, is_safe)",
+                       "state_points_per_gpu": S, "bins": N_BINS, "smooth": SMOOTH, "pmax": PMAX, "moments": list(moments),
+                       "lanes_per_point": args.lanes or "auto", "l2": "flushed (256 MiB memset) before every timed step",
+                       "parallelism": "dp%d over state points, no data-path collective" % world,
+                       "final_gather_ms": gather_ms, "ok_fraction": ok_frac, "wall_s_timed_region": wall},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "roofline": {"bound": "fp64_exp", "achieved": exps / 1e9, "peak": peaks["exp_per_s"] / 1e9, "unit": "Gexp/s",
+                         "frac": exps / peaks["exp_per_s"], "traffic": traffic,
+                         "peak_source": "exp_nonpos micro-benchmark measured in this process (no fp64-exp figure in MEASURED_PEAKS.json)",
+                         "dfma_peak_gops": peaks["dfma_per_s"] / 1e9,
+                         "algorithmic_exp_per_state_point": N_BINS,
+                         "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (np.mean(kern_ms) * 1e-3) / 1e9,
+                                 "peak_gbs": hbm_peak, "frac": (algo_bytes / (np.mean(kern_ms) * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
+                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else "absent"}},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=S_PER_GPU, help="state points per GPU per step")
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per state point (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.cpu_baseline_worker:
+        print(json.dumps(cpu_arm(12000)))
+        return 0
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+    return run_gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
