@@ -154,7 +154,7 @@ extern "C" int fhmc_find_phase_eq_1d(const fhmc_hist_desc *desc, const double *b
                                      int *iters, const fhmc_sweep_out *out, void *stream)
 {
     if (!desc || !blob || !states || !out || !mu_coex || !dfe || !iters) { set_error("null pointer"); return 1; }
-    if (desc->n_sel < 1 || desc->sel_row[0] != 1) { set_error("solver needs quantity 0 to be the N row (sel_row[0] == 1)"); return 1; }
+    if (desc->n_sel < 1) { set_error("solver needs quantity 0 to be N_tot (its phase averages give the Newton slope)"); return 1; }
     if (desc->complete || desc->smooth < 1 || desc->pmax < 2) { set_error("solver needs complete=0, smooth>=1, pmax>=2"); return 1; }
     if (!out->status || !out->nphase || !out->nmin || !out->lnnorm || !out->fe || !out->avg || !out->bounds ||
         !out->max_idx || !out->min_idx) { set_error("missing output buffer"); return 1; }

@@ -252,8 +252,8 @@ class DeviceHistogram(object):
         (SweepResult at coexistence with extra['mu_coex','dfe','iters'])."""
         L = _lib.load()
         t = torch()
-        if self.n_sel < 1 or self.desc.sel_row[0] != 1 or self.n_term != 1 and False:
-            raise ValueError("the solver needs quantity 0 to be 'N' (construct DeviceHistogram with sel=['N', ...])")
+        if self.n_sel < 1:
+            raise ValueError("the solver needs quantity 0 to be N_tot (construct DeviceHistogram with sel=['N', ...])")
         st = self.make_states(mu_guess, beta, dmu, grid=False)
         d = self._desc(max(pmax, 2), False, False, cutoff, smooth)
         out = SweepResult(st.n_states, d.pmax, self.n_sel, self.device)
