@@ -46,6 +46,7 @@ class HistDesc(ctypes.Structure):
         ("smooth", ctypes.c_int), ("pmax", ctypes.c_int), ("complete", ctypes.c_int), ("compare_raw", ctypes.c_int),
         ("cutoff", ctypes.c_double), ("beta_ref", ctypes.c_double), ("mu1_ref", ctypes.c_double),
         ("dmu_ref", ctypes.c_double),
+        ("hull_row", ctypes.c_int), ("hull_len", ctypes.c_int),
     ]
 
 

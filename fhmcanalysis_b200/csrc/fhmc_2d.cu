@@ -31,6 +31,9 @@ template <int NPROP>
 __global__ void __launch_bounds__(FHMC_2D_CTA) k_rw2d_partial(const __grid_constant__ Rw2dArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double s_tab[64];
+    stage_exp_table(s_tab);
+    const uint32_t tab = smem_u32(s_tab);
     const int n2 = a.n2;
     const int r0 = blockIdx.x * a.rows;
     const int nr = min(a.rows, a.n1 - r0);
@@ -97,8 +100,8 @@ __global__ void __launch_bounds__(FHMC_2D_CTA) k_rw2d_partial(const __grid_const
             double Sa = 0.0, Sb = 0.0, S2a = 0.0, S2b = 0.0;
             int j = lo;
             for (; j + 1 < hi; j += 2) {
-                const double ea = exp_nonpos(fma(a2, s_op2[j], row[j] + ri));
-                const double eb = exp_nonpos(fma(a2, s_op2[j + 1], row[j + 1] + ri));
+                const double ea = exp_nonpos(fma(a2, s_op2[j], row[j] + ri), tab);
+                const double eb = exp_nonpos(fma(a2, s_op2[j + 1], row[j + 1] + ri), tab);
                 Sa += ea;
                 Sb += eb;
                 S2a = fma(ea, s_op2[j], S2a);
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(FHMC_2D_CTA) k_rw2d_partial(const __grid_const
                 }
             }
             if (j < hi) {
-                const double ea = exp_nonpos(fma(a2, s_op2[j], row[j] + ri));
+                const double ea = exp_nonpos(fma(a2, s_op2[j], row[j] + ri), tab);
                 Sa += ea;
                 S2a = fma(ea, s_op2[j], S2a);
 #pragma unroll

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include "fhmc_point.cuh"
+#include "fhmc_fast.cuh"
 
 namespace fhmc {
 
@@ -53,13 +54,15 @@ __global__ void __launch_bounds__(FHMC_CTA) k_sweep_1d(const __grid_constant__ S
     double *sm = reinterpret_cast<double *>(smem_raw);
     const uint32_t blob_bytes = (uint32_t)a.d.n_rows * (uint32_t)a.d.n_pad * 8u;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + blob_bytes);
-    stage_blob(sm, a.blob, blob_bytes, bar);
+    double *s_tab = reinterpret_cast<double *>(smem_raw + blob_bytes + 16);
+    stage_exp_table(s_tab);
+    stage_blob(sm, a.blob, blob_bytes, bar);  // contains a __syncthreads after the table stores
 
     constexpr int GPC = FHMC_CTA / G;  // state points per CTA tile
     const int grp = threadIdx.x / G;
     const long long S = a.st.n_states;
     const long long ntiles = (S + GPC - 1) / GPC;
-    PointEval<G, TAYLOR> pe(a, sm, threadIdx.x & 31);
+    PointEval<G, TAYLOR> pe(a, sm, threadIdx.x & 31, s_tab);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long sp = tile * GPC + grp;
         if (sp >= S) continue;  // whole groups drop out together; collectives use the group mask
@@ -113,6 +116,10 @@ __global__ void __launch_bounds__(256) k_phase_moments(const double *__restrict_
                                                        int n_arrays, const int *__restrict__ bounds, int n_phase,
                                                        double *__restrict__ avg, double *__restrict__ lnsum)
 {
+    __shared__ double s_tab[64];
+    stage_exp_table(s_tab);
+    __syncthreads();
+    const uint32_t tab = smem_u32(s_tab);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -125,14 +132,14 @@ __global__ void __launch_bounds__(256) k_phase_moments(const double *__restrict_
         mx = group_max<32>(mx, 0xffffffffu);
         double S = 0.0, A = 0.0;
         if (arr == n_arrays) {
-            for (int j = left + lane; j < right; j += 32) S += exp_nonpos(lnpi[j] - mx);
+            for (int j = left + lane; j < right; j += 32) S += exp_nonpos(lnpi[j] - mx, tab);
             S = group_sum<32>(S, 0xffffffffu);
             if (lane == 0 && lnsum) lnsum[p] = (right > left) ? mx + log(S) : -1.7976931348623157e308;
             continue;
         }
         const double *row = mom + (size_t)arr * n;
         for (int j = left + lane; j < right; j += 32) {
-            const double e = exp_nonpos(lnpi[j] - mx);
+            const double e = exp_nonpos(lnpi[j] - mx, tab);
             S += e;
             A = fma(e, row[j], A);
         }
@@ -176,10 +183,14 @@ __global__ void __launch_bounds__(256) k_bench_dfma(int iters, double *sink)
 
 __global__ void __launch_bounds__(256) k_bench_exp(int iters, double *sink)
 {
+    __shared__ double s_tab[64];
+    stage_exp_table(s_tab);
+    __syncthreads();
+    const uint32_t tab = smem_u32(s_tab);
     double t0 = -1e-3 * (threadIdx.x + 1), t1 = t0 - 0.3, t2 = t0 - 1.7, t3 = t0 - 11.0;
     double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
     for (int i = 0; i < iters; ++i) {
-        acc0 += exp_nonpos(t0); acc1 += exp_nonpos(t1); acc2 += exp_nonpos(t2); acc3 += exp_nonpos(t3);
+        acc0 += exp_nonpos(t0, tab); acc1 += exp_nonpos(t1, tab); acc2 += exp_nonpos(t2, tab); acc3 += exp_nonpos(t3, tab);
         t0 -= 1e-6; t1 -= 1e-6; t2 -= 1e-6; t3 -= 1e-6;
     }
     const double r = acc0 + acc1 + acc2 + acc3;
@@ -255,6 +266,34 @@ static int launch_sweep_t(bool taylor, const SweepArgs &args, size_t smem, const
     return taylor ? launch_sweep<G, true>(args, smem, di, stream) : launch_sweep<G, false>(args, smem, di, stream);
 }
 
+// one-pass mu-sweep kernel (fhmc_fast.cuh): one thread per state point
+template <int NSEL, bool SEL0N>
+static int launch_fast(const SweepArgs &args, size_t smem, const DevInfo *di, cudaStream_t stream)
+{
+    auto kern = k_sweep_mu_fast<NSEL, SEL0N>;
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return 1;
+    int occ = 0;
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FHMC_CTA, smem), "occupancy query")) return 1;
+    if (occ < 1) { set_error("fast sweep kernel does not fit on an SM (smem %zu bytes)", smem); return 1; }
+    const long long ntiles = (args.st.n_states + FHMC_CTA - 1) / FHMC_CTA;
+    long long grid = (long long)di->sm_count * occ;
+    if (grid > ntiles) grid = ntiles;
+    kern<<<(unsigned)grid, FHMC_CTA, smem, stream>>>(args);
+    return check_cuda(cudaGetLastError(), "k_sweep_mu_fast launch");
+}
+
+static int launch_fast_dispatch(const SweepArgs &args, size_t smem, const DevInfo *di, cudaStream_t stream)
+{
+    const bool s0n = args.d.n_sel > 0 && args.d.sel_row[0] == 1;
+    switch (args.d.n_sel) {
+    case 0: return launch_fast<0, false>(args, smem, di, stream);
+    case 1: return s0n ? launch_fast<1, true>(args, smem, di, stream) : launch_fast<1, false>(args, smem, di, stream);
+    case 2: return s0n ? launch_fast<2, true>(args, smem, di, stream) : launch_fast<2, false>(args, smem, di, stream);
+    case 3: return s0n ? launch_fast<3, true>(args, smem, di, stream) : launch_fast<3, false>(args, smem, di, stream);
+    default: return s0n ? launch_fast<4, true>(args, smem, di, stream) : launch_fast<4, false>(args, smem, di, stream);
+    }
+}
+
 int choose_lanes(long long n_states, const DevInfo *di)
 {
     // enough groups to give every SM >= 1024 busy threads, otherwise widen the groups
@@ -293,7 +332,7 @@ int fhmc_sweep_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_sta
     if (states->n_states == 0) return 0;
     const DevInfo *di = dev_info();
     if (!di) { set_error("no CUDA device"); return 1; }
-    const size_t smem = (size_t)desc->n_rows * desc->n_pad * 8 + 16;
+    const size_t smem = (size_t)desc->n_rows * desc->n_pad * 8 + 16 + 512;
     if (smem > (size_t)di->smem_optin) { set_error("histogram blob (%zu bytes) exceeds shared memory (%d bytes)", smem, di->smem_optin); return 1; }
     SweepArgs args;
     args.d = *desc;
@@ -303,6 +342,12 @@ int fhmc_sweep_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_sta
     const bool taylor = desc->n_coef > 0 || desc->n_term > 1;
     int G = lanes_per_point > 0 ? lanes_per_point : choose_lanes(states->n_states, di);
     cudaStream_t s = (cudaStream_t)stream;
+    // pure mu sweep with a precomputed hull, one lane per point: the one-pass kernel.  lanes_per_point = -1 forces
+    // the generic one-lane kernel (tests compare the two).
+    if (lanes_per_point == -1) G = 1;
+    else if (G == 1 && !taylor && !desc->complete && desc->hull_len >= 2 && desc->n >= 3 && desc->hull_row > 1 &&
+             desc->hull_row + 2 <= desc->n_rows)
+        return launch_fast_dispatch(args, smem, di, s);
     switch (G) {
     case 1: return launch_sweep_t<1>(taylor, args, smem, di, s);
     case 4: return launch_sweep_t<4>(taylor, args, smem, di, s);

@@ -17,38 +17,89 @@ void set_error(const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);
 
 // ---------------------------------------------------------------------------------------------
-// fp64 exp for arguments t <= 0 (the only kind the max-shifted sums produce).
-//   k = rint(t*log2 e) by the 1.5*2^52 trick, r = t - k ln2 (two-constant Cody-Waite),
-//   exp(r) by a degree-13 Taylor polynomial (|r| <= 0.3466 -> remainder 4e-18), 2^k by integer add to
-//   the exponent field (no fp64 op).  Inputs below -707 return 0: the reference sums them as
-//   (sub)normal numbers < 1e-307 next to a leading term of 1 (np.seterr(under='ignore'), GH:29).
-//   17 fp64-pipe instructions, no special-case branch, max error < 1 ulp.
+// fp64 exp for the max-shifted sums:   exp_scaled(u, Mq) = exp(u - Mq*ln2),  u - Mq*ln2 <~ 0.
+//   k = rint(u * 64/ln2) (1.5*2^52 trick), r = u - k*ln2/64 (two-constant Cody-Waite, |r| <= ln2/128),
+//   exp(r) by a degree-5 Taylor polynomial (remainder 3.5e-17), 2^(j/64) (j = k & 63) from a 64-entry
+//   shared-memory table, 2^((k>>6) - Mq) by an integer add to the exponent field (no fp64 op).
+//   10 fp64-pipe instructions (the register-resident roofline micro-benchmark times exactly this
+//   function), no special-case branch, max error ~2 ulp.  Results below 2^-1021 return 0: the reference
+//   sums them as (sub)normal numbers < 1e-307 next to a leading term of ~1 (np.seterr(under='ignore'), GH:29).
+// The polynomial/reduction constants live in __constant__ memory so that DFMA takes them as
+// constant-bank operands (no per-use UMOV/IMAD.MOV materialisation).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double exp_nonpos(double t)
+struct ExpConst {
+    double inv, hi, lo, c5, c4, c3, c2, ln2_hi, ln2_lo, inv_ln2;
+    double tab[64];
+};
+__constant__ ExpConst c_exp = {
+    92.33248261689366,        // 64/ln2
+    0.01083042469326756,      // ln2/64, upper 32 bits (k*hi exact for |k| < 2^20)
+    2.9815858269852933e-12,   // ln2/64 - hi
+    8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5,
+    0.6931471803691238, 1.9082149292705877e-10, 1.4426950408889634074,
+    {1, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.1023825833078409, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.2021567314527031, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.2553807570246911, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.3396675240533029,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.5590044002378369, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.6457554781539649, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.7186192981224779, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.9784560263879509}};
+
+#define FHMC_EXP_MAGIC 6755399441055744.0
+
+// stage the 2^(j/64) table into shared memory (call from all threads, then __syncthreads)
+__device__ __forceinline__ void stage_exp_table(double *s_tab)
 {
-    const double magic = 6755399441055744.0;
-    const double kd0 = fma(t, 1.4426950408889634074, magic);
+    for (int j = threadIdx.x; j < 64; j += blockDim.x) s_tab[j] = c_exp.tab[j];
+}
+
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ double exp_scaled(double u, int Mq, uint32_t tab_addr)
+{
+    const double kd0 = fma(u, c_exp.inv, FHMC_EXP_MAGIC);
     const int k = __double2loint(kd0);
-    const double kd = kd0 - magic;
-    double r = fma(kd, -6.93147180369123816490e-01, t);
-    r = fma(kd, -1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;
-    p = fma(p, r, 2.08767569878681e-09);
-    p = fma(p, r, 2.505210838544172e-08);
-    p = fma(p, r, 2.755731922398589e-07);
-    p = fma(p, r, 2.7557319223985893e-06);
-    p = fma(p, r, 2.48015873015873e-05);
-    p = fma(p, r, 1.984126984126984e-04);
-    p = fma(p, r, 1.388888888888889e-03);
-    p = fma(p, r, 8.333333333333333e-03);
-    p = fma(p, r, 4.1666666666666664e-02);
-    p = fma(p, r, 1.6666666666666666e-01);
-    p = fma(p, r, 0.5);
+    const double kd = kd0 - FHMC_EXP_MAGIC;
+    double r = fma(kd, -c_exp.hi, u);
+    r = fma(kd, -c_exp.lo, r);
+    double p = fma(r, c_exp.c5, c_exp.c4);
+    p = fma(p, r, c_exp.c3);
+    p = fma(p, r, c_exp.c2);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    const int hi = __double2hiint(p) + (k << 20);
-    const double res = __hiloint2double(hi, __double2loint(p));
-    return (t < -707.0) ? 0.0 : res;
+    const double T = lds_f64(tab_addr + ((k & 63) << 3));
+    const double v = T * p;
+    const int q = (k >> 6) - Mq;
+    const int hi = __double2hiint(v) + (q << 20);
+    const double res = __hiloint2double(hi, __double2loint(v));
+    return (q < -1021) ? 0.0 : res;
+}
+
+// exp(t) for t <= ~0 (generic paths): same algorithm, no exponent offset
+__device__ __forceinline__ double exp_nonpos(double t, uint32_t tab_addr) { return exp_scaled(t, 0, tab_addr); }
+
+// smallest integer Mq with Mq*ln2 >= m  (so that every term exp(u - Mq*ln2) <= 1 when u <= m)
+__device__ __forceinline__ int shift_for_max(double m) { return (int)ceil(m * c_exp.inv_ln2 + 1e-9); }
+
+// Mq*ln2 + x with the product carried in two pieces (Mq*ln2_hi is exact for |Mq| < 2^20)
+__device__ __forceinline__ double add_shift(int Mq, double x)
+{
+    const double q = (double)Mq;
+    return fma(q, c_exp.ln2_hi, x) + q * c_exp.ln2_lo;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -36,6 +36,7 @@ struct PointEval {
     const unsigned member;  // warp mask of my group
     const unsigned gshift;  // first lane of my group
     const int n, last, w, npad, pmax, R;
+    const uint32_t tab;  // shared-memory address of the 2^(j/64) table
 
     // state point (group-uniform)
     double s, xi[FHMC_MAX_TERMS], ts[FHMC_MAX_TERMS];
@@ -43,11 +44,11 @@ struct PointEval {
     int P, nmin;
     double m, c;
 
-    __device__ PointEval(const SweepArgs &args, const double *smem, int lane)
+    __device__ PointEval(const SweepArgs &args, const double *smem, int lane, const double *exp_table)
         : a(args), sm(smem), g(lane & (G - 1)),
           member(G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)))), gshift(lane & ~(G - 1)),
           n(args.d.n), last(args.d.n - 1), w(args.d.smooth), npad(args.d.n_pad), pmax(args.d.pmax),
-          R((args.d.n + G - 1) / G)
+          R((args.d.n + G - 1) / G), tab(smem_u32(exp_table))
     {
     }
 
@@ -297,7 +298,7 @@ struct PointEval {
 #pragma unroll
         for (int q = 0; q < FHMC_MAX_SEL; ++q) A[q] = 0.0;
         for (int i = left + g; i < right; i += G) {
-            const double e = exp_nonpos(U(i) - shift);
+            const double e = exp_nonpos(U(i) - shift, tab);
             S += e;
 #pragma unroll
             for (int q = 0; q < FHMC_MAX_SEL; ++q)
@@ -371,7 +372,7 @@ struct PointEval {
 #pragma unroll
             for (int q = 0; q < FHMC_MAX_SEL; ++q) X[q] = 0.0;
             if (G == 1 || i < n) {
-                e = exp_nonpos(U(i) - m);
+                e = exp_nonpos(U(i) - m, tab);
 #pragma unroll
                 for (int q = 0; q < FHMC_MAX_SEL; ++q)
                     if (q < a.d.n_sel) X[q] = Xsel(q, i);

@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(FHMC_CTA) k_find_phase_eq(const __grid_constan
     double *sm = reinterpret_cast<double *>(smem_raw);
     const uint32_t blob_bytes = (uint32_t)a.d.n_rows * (uint32_t)a.d.n_pad * 8u;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + blob_bytes);
+    double *s_tab = reinterpret_cast<double *>(smem_raw + blob_bytes + 16);
+    stage_exp_table(s_tab);
     stage_blob(sm, a.blob, blob_bytes, bar);
 
     constexpr int GPC = FHMC_CTA / G;
@@ -36,7 +38,7 @@ __global__ void __launch_bounds__(FHMC_CTA) k_find_phase_eq(const __grid_constan
     const long long ntiles = (T + GPC - 1) / GPC;
     const int pmax = a.d.pmax, nsel = a.d.n_sel;
     const int min_width = 2 * a.d.smooth;  // gc_hist.pyx:652
-    PointEval<G, TAYLOR> pe(a, sm, threadIdx.x & 31);
+    PointEval<G, TAYLOR> pe(a, sm, threadIdx.x & 31, s_tab);
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long rec = tile * GPC + grp;
@@ -163,7 +165,7 @@ extern "C" int fhmc_find_phase_eq_1d(const fhmc_hist_desc *desc, const double *b
     if (((uintptr_t)blob & 15) || (desc->n_pad & 1)) { set_error("blob must be 16-byte aligned with even n_pad"); return 1; }
     DevCaps caps;
     if (get_caps(caps)) return 1;
-    const size_t smem = (size_t)desc->n_rows * desc->n_pad * 8 + 16;
+    const size_t smem = (size_t)desc->n_rows * desc->n_pad * 8 + 16 + 512;
     if (smem > (size_t)caps.smem_optin) { set_error("histogram blob exceeds shared memory"); return 1; }
     SolveArgs sa;
     sa.sw.d = *desc;

@@ -41,6 +41,32 @@ def _stream_ptr(device):
     return ctypes.c_void_p(torch().cuda.current_stream(device).cuda_stream)
 
 
+def upper_hull(x, y):
+    """Upper concave envelope of the points (x_i, y_i), x strictly increasing and finite y: returns
+    (edge slopes, strictly decreasing; vertex indices) or None when the fast mu-sweep path cannot use it.
+    One-time O(n) host setup per histogram (Andrew's monotone chain)."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    n = len(x)
+    if n < 3 or not np.all(np.diff(x) > 0) or not np.all(np.isfinite(y)):
+        return None
+    h = []
+    for i in range(n):
+        while len(h) >= 2:
+            a, b = h[-2], h[-1]
+            # drop b unless slope(a,b) > slope(b,i)
+            if (y[b] - y[a]) * (x[i] - x[b]) <= (y[i] - y[b]) * (x[b] - x[a]):
+                h.pop()
+            else:
+                break
+        h.append(i)
+    verts = np.array(h, dtype=np.float64)
+    slopes = np.array([(y[h[k + 1]] - y[h[k]]) / (x[h[k + 1]] - x[h[k]]) for k in range(len(h) - 1)])
+    if len(slopes) > 1 and not np.all(np.diff(slopes) < 0):
+        return None
+    return slopes, verts
+
+
 class SweepResult(object):
     """Per-state-point records of one sweep (device tensors; ``host()`` copies them to NumPy)."""
 
@@ -134,6 +160,16 @@ class DeviceHistogram(object):
                 continue
             sel_row.append(len(rows))
             rows.extend(np.ascontiguousarray(r, dtype=np.float64) for r in terms)
+        hull_row, hull_len = 0, 0
+        if not coef:
+            hull = upper_hull(ntot, lnpi)
+            if hull is not None:
+                slopes, verts = hull
+                hull_row, hull_len = len(rows), len(verts)
+                srow, vrow = np.zeros(n), np.zeros(n)
+                srow[:len(slopes)] = slopes
+                vrow[:len(verts)] = verts
+                rows.extend([srow, vrow])
         blob = np.zeros((len(rows), n_pad), dtype=np.float64)
         for i, r in enumerate(rows):
             if r.shape != (n,):
@@ -157,6 +193,7 @@ class DeviceHistogram(object):
             d.sel_kind[1 + i] = int(k)
         d.smooth, d.pmax, d.complete, d.compare_raw = int(smooth), 4, 0, 0
         d.cutoff, d.beta_ref, d.mu1_ref, d.dmu_ref = float(cutoff), float(beta_ref), float(mu1_ref), float(dmu_ref)
+        d.hull_row, d.hull_len = hull_row, hull_len
         self.desc = d
 
     # ------------------------------------------------------------------------------------------

@@ -91,6 +91,11 @@ typedef struct fhmc_hist_desc {
     double beta_ref;                /* data['curr_beta'] of the stored histogram                 */
     double mu1_ref;                 /* data['curr_mu'][0]                                        */
     double dmu_ref;                 /* data['curr_mu'][1]-data['curr_mu'][0] (0 for 1 species)   */
+    /* Optional accelerator for pure mu sweeps (n_coef == 0): upper concave envelope of the points
+     * (N_i, lnPI_i).  Row hull_row holds the hull_len-1 edge slopes (strictly decreasing), row
+     * hull_row+1 the hull_len vertex bin indices (as fp64).  hull_len == 0: not provided.          */
+    int hull_row;
+    int hull_len;
 } fhmc_hist_desc;
 
 /*
