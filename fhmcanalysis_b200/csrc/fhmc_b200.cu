@@ -347,7 +347,11 @@ int fhmc_sweep_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_sta
     if (lanes_per_point == -1) G = 1;
     else if (G == 1 && !taylor && !desc->complete && desc->hull_len >= 2 && desc->n >= 3 && desc->hull_row > 1 &&
              desc->hull_row + 2 <= desc->n_rows)
-        return launch_fast_dispatch(args, smem, di, s);
+    {
+        // + packed {lnPI, N, X...} copy the fast kernel builds (fhmc_fast.cuh): up to 6 doubles per bin
+        const size_t smem_fast = smem + (size_t)desc->n_pad * 8 * 6;
+        if (smem_fast <= (size_t)di->smem_optin) return launch_fast_dispatch(args, smem_fast, di, s);
+    }
     switch (G) {
     case 1: return launch_sweep_t<1>(taylor, args, smem, di, s);
     case 4: return launch_sweep_t<4>(taylor, args, smem, di, s);

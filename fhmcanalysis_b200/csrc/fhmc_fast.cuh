@@ -45,9 +45,21 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_mu_fast(const __grid_cons
     const int n = a.d.n, last = n - 1, pmax = a.d.pmax;
     const uint32_t row_bytes = (uint32_t)a.d.n_pad * 8u;
     const uint32_t s_lnpi = smem_u32(sm), s_n = s_lnpi + row_bytes, tab = pe.tab;
-    uint32_t s_sel[NSEL > 0 ? NSEL : 1];
+    // Interleave the rows this kernel walks into one packed array {lnPI_i, N_i, X_a(i), X_b(i), ...} (PK doubles per
+    // bin, 16-byte aligned) so that a bin costs one or two LDS.128 with immediate offsets instead of one LDS.64 and
+    // one address computation per row.  Built once per (persistent) CTA from the TMA-staged blob.
+    constexpr int NX = NSEL - (SEL0N ? 1 : 0);          // quantities that need their own row
+    constexpr int PK = 2 + NX + (NX & 1);               // doubles per packed bin (even)
+    double *pk = s_tab + 64;
+    for (int i = threadIdx.x; i < n; i += FHMC_CTA) {
+        pk[i * PK + 0] = sm[i];
+        pk[i * PK + 1] = sm[a.d.n_pad + i];
 #pragma unroll
-    for (int q = 0; q < NSEL; ++q) s_sel[q] = s_lnpi + (uint32_t)a.d.sel_row[q] * row_bytes;
+        for (int q = 0; q < NX; ++q) pk[i * PK + 2 + q] = sm[a.d.sel_row[q + (SEL0N ? 1 : 0)] * a.d.n_pad + i];
+        if (NX & 1) pk[i * PK + 2 + NX] = 0.0;
+    }
+    __syncthreads();
+    const uint32_t s_pk = smem_u32(pk);
     const uint32_t s_slope = s_lnpi + (uint32_t)a.d.hull_row * row_bytes, s_hidx = s_slope + row_bytes;
     const int H = a.d.hull_len;
 
@@ -75,21 +87,32 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_mu_fast(const __grid_cons
 #pragma unroll
         for (int q = 0; q < NSEL; ++q) A[q] = 0.0;
 
-        auto accumulate = [&](double u, int i, double Ni) {
-            const double e = exp_scaled(u, Mq, tab);
-            Sacc += e;
+        struct Bin {
+            double u, N, x[NX > 0 ? NX : 1];
+        };
+        auto load_bin = [&](int i, Bin &b) {
+            const uint32_t addr = s_pk + (uint32_t)i * (uint32_t)(PK * 8);
+            double l;
+            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(l), "=d"(b.N) : "r"(addr));
+            b.u = __dadd_rn(l, __dmul_rn(s, b.N));   // un-fused, GH:77
 #pragma unroll
-            for (int q = 0; q < NSEL; ++q) {
-                const double x = (SEL0N && q == 0) ? Ni : lds_f64(s_sel[q] + 8u * i);
-                A[q] = fma(e, x, A[q]);
+            for (int q = 0; q < NX; q += 2) {
+                double x0, x1;
+                asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(addr + 16u + 8u * q));
+                b.x[q] = x0;
+                if (q + 1 < NX) b.x[q + 1] = x1;
             }
         };
-        auto load_u = [&](int i, double &Ni) {
-            Ni = lds_f64(s_n + 8u * i);
-            return __dadd_rn(lds_f64(s_lnpi + 8u * i), __dmul_rn(s, Ni));
+        auto accumulate = [&](const Bin &b) {
+            const double e = exp_scaled(b.u, Mq, tab);
+            Sacc += e;
+            if (SEL0N) A[0] = fma(e, b.N, A[0]);
+#pragma unroll
+            for (int q = 0; q < NX; ++q) A[q + (SEL0N ? 1 : 0)] = fma(e, b.x[q], A[q + (SEL0N ? 1 : 0)]);
         };
-        double N0;
-        const double u0 = load_u(0, N0);
+        Bin b0;
+        load_bin(0, b0);
+        const double u0 = b0.u;
         auto flush = [&]() {
             if (P < pmax && Sacc >= 1e-280) {
                 a.out.fe[sp * pmax + P] = -(add_shift(Mq, log(Sacc)) - u0);
@@ -105,7 +128,8 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_mu_fast(const __grid_cons
             ++P;
         };
         // exact strict 1-neighbour test + window test of bin i (values xm, xc, xp), then its contribution
-        auto slow_bin = [&](int i, double xm, double xc, double xp, double Nc) {
+        auto slow_bin = [&](int i, double xm, const Bin &c, double xp) {
+            const double xc = c.u;
             const bool is_max = (xc > xm) && (xc > xp), is_min = (xc < xm) && (xc < xp);
             if ((is_max || is_min) && pe.window_ok(i, xc, is_max, false, 0.0, 2)) {
                 if (is_max) {
@@ -117,46 +141,48 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_mu_fast(const __grid_cons
                     flush();  // a minimum bin opens the phase to its right (GH:498-520)
                 }
             }
-            accumulate(xc, i, Nc);
+            accumulate(c);
         };
 
         if (n >= 3) {
-            accumulate(u0, 0, N0);
-            double Nc, xm = u0;
-            double xc = load_u(1, Nc);
-            double dc = __dsub_rn(xc, xm);  // sign(dc) is the exact order of (xm, xc)
+            accumulate(b0);
+            Bin c;
+            load_bin(1, c);
+            double xm = u0;
+            double dc = __dsub_rn(c.u, xm);  // sign(dc) is the exact order of (xm, xc)
             int i = 1;
             for (; i + 3 < last; i += 4) {   // bins i..i+3 are interior, i+4 <= last exists
-                double N1, N2, N3, N4;
-                const double x1 = load_u(i + 1, N1), x2 = load_u(i + 2, N2), x3 = load_u(i + 3, N3), x4 = load_u(i + 4, N4);
-                const double d1 = __dsub_rn(x1, xc), d2 = __dsub_rn(x2, x1), d3 = __dsub_rn(x3, x2), d4 = __dsub_rn(x4, x3);
+                Bin b1, b2, b3, b4;
+                load_bin(i + 1, b1);
+                load_bin(i + 2, b2);
+                load_bin(i + 3, b3);
+                load_bin(i + 4, b4);
+                const double d1 = __dsub_rn(b1.u, c.u), d2 = __dsub_rn(b2.u, b1.u), d3 = __dsub_rn(b3.u, b2.u), d4 = __dsub_rn(b4.u, b3.u);
                 const int flip = (__double2hiint(dc) ^ __double2hiint(d1)) | (__double2hiint(d1) ^ __double2hiint(d2)) |
                                  (__double2hiint(d2) ^ __double2hiint(d3)) | (__double2hiint(d3) ^ __double2hiint(d4));
                 if (flip < 0) {   // some pair of successive differences changes sign: look closely
-                    slow_bin(i, xm, xc, x1, Nc);
-                    slow_bin(i + 1, xc, x1, x2, N1);
-                    slow_bin(i + 2, x1, x2, x3, N2);
-                    slow_bin(i + 3, x2, x3, x4, N3);
+                    slow_bin(i, xm, c, b1.u);
+                    slow_bin(i + 1, c.u, b1, b2.u);
+                    slow_bin(i + 2, b1.u, b2, b3.u);
+                    slow_bin(i + 3, b2.u, b3, b4.u);
                 } else {
-                    accumulate(xc, i, Nc);
-                    accumulate(x1, i + 1, N1);
-                    accumulate(x2, i + 2, N2);
-                    accumulate(x3, i + 3, N3);
+                    accumulate(c);
+                    accumulate(b1);
+                    accumulate(b2);
+                    accumulate(b3);
                 }
-                xm = x3;
-                xc = x4;
-                Nc = N4;
+                xm = b3.u;
+                c = b4;
                 dc = d4;
             }
             for (; i < last; ++i) {
-                double Np;
-                const double xp = load_u(i + 1, Np);
-                slow_bin(i, xm, xc, xp, Nc);
-                xm = xc;
-                xc = xp;
-                Nc = Np;
+                Bin nx;
+                load_bin(i + 1, nx);
+                slow_bin(i, xm, c, nx.u);
+                xm = c.u;
+                c = nx;
             }
-            accumulate(xc, last, Nc);
+            accumulate(c);
             flush();
         } else {
             bad = true;
