@@ -1,0 +1,113 @@
+"""GPU: isopleth grid, joint (2-D) histogram reweighting, sharded sweep helper, compare fast vs generic kernels."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_isopleth_make_grid_multi_matches_reference(golden, golden_meta):
+    """gc_binary.isopleth.make_grid_multi (GB:173-290; untested upstream) against the compiled reference."""
+    import FHMCAnalysis.moments.histogram.one_dim.ntot.gc_hist as oneDH
+    import FHMCAnalysis.moments.histogram.one_dim.ntot.gc_binary as gcB
+    meta = golden_meta["iso"]
+    assert meta["status"] == "ok"
+    hists = []
+    for k, d2 in enumerate(meta["dmu2"]):
+        hists.append(oneDH.histogram.from_arrays(golden["iso/lnpi"][k], golden["c3/mom"], meta["beta_ref"],
+                                                 [meta["mu1_ref"], meta["mu1_ref"] + d2], meta["smooth"], volume=meta["volume"]))
+    iso = gcB.isopleth(hists, meta["beta_ref"], meta["order"])
+    Z, (X, Y) = iso.make_grid_multi(meta["mu1_bounds"], meta["dmu2_bounds"], meta["delta"], meta["m"])
+    assert np.allclose(X, golden["iso/X"]) and np.allclose(Y, golden["iso/Y"])
+    assert np.array_equal(Z == 0, golden["iso/x1"] == 0)   # same cells skipped
+    assert np.allclose(Z, golden["iso/x1"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(iso.data["density"], golden["iso/density"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(iso.data["F.E./kT"], golden["iso/fe"], rtol=1e-9, atol=1e-12)
+
+
+def test_combine_isopleth_grids():
+    """unittests/moments_histogram_one_dim_gc_ntot_isopleth.py:27-91 (pure host bookkeeping)."""
+    import FHMCAnalysis.moments.histogram.one_dim.ntot.gc_binary as gcB
+    dmu2 = np.linspace(-5, -3, 5)
+    x1, y1 = np.meshgrid(np.linspace(-15, -10, 10), dmu2)
+    x2, y2 = np.meshgrid(np.linspace(-10, -5, 10), dmu2)
+    z1, z2 = x1 ** 2 + y1 ** 2, x2 ** 2 + y2 ** 2
+    x3, y3 = np.meshgrid(np.concatenate((np.linspace(-15, -10, 10), np.linspace(-10, -5, 10)[1:])), dmu2)
+    Z, (X, Y) = gcB.combine_isopleth_grids([x2, x1], [y2, y1], [z2, z1])
+    assert np.all(np.abs(X - x3) < 1e-9) and np.all(np.abs(Y - y3) < 1e-9) and np.all(np.abs(Z - (x3 ** 2 + y3 ** 2)) < 1e-9)
+    xb, yb = np.meshgrid(np.linspace(-10, -5, 10), np.linspace(-5, -4, 5))
+    with pytest.raises(Exception):
+        gcB.combine_isopleth_grids([xb, x1], [yb, y1], [xb ** 2, z1])
+
+
+def test_joint_hist_container_and_reweight(golden, golden_meta, oracle):
+    """unittests/moments_histogram_two_dim_joint.py:238-244 layout (-inf padding, inclusive bounds) + K5 vs the oracle."""
+    import FHMCAnalysis.moments.histogram.two_dim.joint_hist as jh
+    J = jh.joint_hist()
+    for op1, dct in golden_meta["joint"]["entries"]:
+        J.enter(op1, np.array(dct["lnPI"]), np.array(dct["op2"]), {k: np.array(v) for k, v in dct["props"].items()})
+    J.make()
+    assert np.array_equal(J.data["ln(PI)"], golden["joint/lnpi"])
+    assert J.data["bounds_idx"].tolist() == golden["joint/bounds"].tolist() == [[1, 3], [0, 4]]
+    assert np.array_equal(J.data["op_1"], golden["joint/op1"]) and np.array_equal(J.data["op_2"], golden["joint/op2"])
+    assert np.array_equal(J.data["props"]["e"], golden["joint/prop_e"])
+    a1, a2 = np.array([0.0, 0.3, -1.0]), np.array([0.0, -0.2, 0.5])
+    out = J.reweight_batch(a1, a2, props=("e",))
+    b = J.data["bounds_idx"].astype(np.int32).copy()
+    b[:, 1] += 1
+    for s in range(3):
+        ref = oracle.reweight_2d(J.data["ln(PI)"], b, J.data["op_1"], J.data["op_2"], a1[s], a2[s], J.data["props"]["e"][None])
+        assert np.allclose(out[s], ref, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("n1,n2,nprop", [(64, 48, 0), (129, 77, 1), (512, 512, 2)])
+def test_reweight_2d_vs_oracle(oracle, n1, n2, nprop):
+    """BASELINE config 5 generator (two anisotropic Gaussians, triangular -inf region) at three sizes."""
+    from fhmcanalysis_b200 import engine, synth
+    lnpi, bounds = synth.joint_2d(n1, n2, cut=int(0.625 * (n1 + n2)))
+    op1, op2 = np.arange(n1, dtype=float), np.arange(n2, dtype=float)
+    rng = np.random.default_rng(5)
+    props = rng.random((nprop, n1, n2)) if nprop else None
+    S = 300
+    a1, a2 = rng.uniform(-0.05, 0.05, S), rng.uniform(-0.05, 0.05, S)
+    out = engine.reweight_2d(lnpi, bounds, op1, op2, a1, a2, props)
+    for s in range(0, S, 37):
+        ref = oracle.reweight_2d(lnpi, bounds, op1, op2, a1[s], a2[s], props)
+        assert np.allclose(out[s], ref, rtol=1e-10, atol=0)
+    # linearity property at full batch: <op1> is non-decreasing in a1 at fixed a2
+    a1s = np.linspace(-0.05, 0.05, 257)
+    o = engine.reweight_2d(lnpi, bounds, op1, op2, a1s, np.zeros_like(a1s))
+    assert np.all(np.diff(o[:, 1]) > -1e-9)
+
+
+def test_fast_and_generic_kernels_agree():
+    """The one-pass mu-sweep kernel and the generic two-pass kernel must give identical integers and fp64 to 1e-10."""
+    from fhmcanalysis_b200 import engine, synth
+    for n, smooth, noise in ((1001, 10, 1e-3), (573, 3, 5e-2), (2001, 30, 0.0)):
+        lnpi = synth.two_peak_lnpi(n, noise=noise, scale=n / 1001.0)
+        N = np.arange(n, dtype=float)
+        dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=smooth, sel=["N", N * N])
+        mus = np.linspace(-0.05, 0.05, 5000)
+        a = dh.sweep_auto(mus, pmax=4, lanes=1).host()      # fast path
+        b = dh.sweep_auto(mus, pmax=a["fe"].shape[1], lanes=-1).host()     # generic one-lane kernel
+        for k in ("code", "nphase", "nmin", "safe", "bounds", "max_idx", "min_idx"):
+            assert np.array_equal(a[k], b[k]), (n, k)
+        mask = np.arange(a["fe"].shape[1])[None, :] < a["nphase"][:, None]
+        assert np.allclose(a["fe"][mask], b["fe"][mask], rtol=1e-10, atol=1e-11)
+        assert np.allclose(a["avg"][mask], b["avg"][mask], rtol=1e-10, atol=0)
+        assert np.allclose(a["lnnorm"], b["lnnorm"], rtol=1e-13, atol=1e-13)
+
+
+def test_sharded_sweep_single_process(golden, golden_meta):
+    """parallel.sweep_sharded without an initialised process group == plain sweep."""
+    from fhmcanalysis_b200 import engine, parallel
+    lnpi, mus = golden["c2/lnpi"], golden["c2/mu"]
+    n = len(lnpi)
+    N = np.arange(n, dtype=float)
+
+    def mk():
+        return engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=golden_meta["c2"]["smooth"], sel=["N", N * N])
+    out = parallel.sweep_sharded(mk, mus, pmax=4, gather=True)
+    ref = mk().sweep(mus, pmax=4).host()
+    for k in ("nphase", "max_idx", "min_idx", "bounds"):
+        assert np.array_equal(out[k], ref[k])
+    assert np.allclose(out["fe"][:, :2], ref["fe"][:, :2], rtol=0, atol=0)
