@@ -251,14 +251,8 @@ def run_gpu_arm(args, rank, world, local_rank):
     h2d = mu_host.numel() * 8 + dh.h2d_bytes
 
     def e2e_step():
-        mu_d = mu_host.to(dev, non_blocking=True)
-        blob_d = torch.from_numpy(dh.blob_host).to(dev, non_blocking=True)
-        dh.blob = blob_d
-        st = dh.make_states(mu_d)
-        r = dh.sweep(None, states=st, out=out, pmax=PMAX, lanes=args.lanes)
-        for k, v in host_out.items():
-            v.copy_(getattr(r, k), non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        # public host-buffer entry point: chunked, double-buffered H2D(mu) -> kernel -> D2H(results) pipeline
+        dh.sweep_host(mu_host, pmax=PMAX, lanes=args.lanes, out=host_out)
 
     for _ in range(2):
         e2e_step()

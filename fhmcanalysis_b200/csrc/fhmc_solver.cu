@@ -49,8 +49,9 @@ __global__ void __launch_bounds__(FHMC_CTA) k_find_phase_eq(const __grid_constan
         beta = st.beta ? st.beta[(rec / st.beta_div) % st.n_beta] : a.d.beta_ref;
         dmu = st.dmu ? st.dmu[(rec / st.dmu_div) % st.n_dmu] : a.d.dmu_ref;
 
-        bool have_lo = false, have_hi = false, converged = false;
-        double lo = 0.0, hi = 0.0, mu_good = mu, d = 0.0;
+        bool have_lo = false, have_hi = false, converged = false, located = false, have_glo = false, have_ghi = false;
+        double lo = 0.0, hi = 0.0, mu_good = mu, d = 0.0, glo = 0.0, ghi = 0.0, step = sa.mu_step;
+        const double n_mid = 0.5 * (sm[a.d.n_pad] + sm[a.d.n_pad + a.d.n - 1]);
         unsigned status = 0;
         int code = FHMC_E_NO_COEX, it = 0, nevals = 0;
         for (it = 0; it < sa.max_iter; ++it) {
@@ -81,10 +82,35 @@ __global__ void __launch_bounds__(FHMC_CTA) k_find_phase_eq(const __grid_constan
                 }
             }
             if (!ok) {
-                if (it == 0) { code = ((status & FHMC_ST_CODE_MASK) != FHMC_OK) ? (int)(status & FHMC_ST_CODE_MASK) : FHMC_E_NO_COEX; break; }
-                mu = 0.5 * (mu + mu_good);  // stepped out of the two-phase window: come back half way
+                if ((status & FHMC_ST_CODE_MASK) != FHMC_OK) { code = (int)(status & FHMC_ST_CODE_MASK); break; }
+                if (located) {
+                    mu = 0.5 * (mu + mu_good);  // stepped out of the two-phase window: come back half way
+                    continue;
+                }
+                // ---- locate the two-phase window: <N>_total(mu) is monotone, the window is where it crosses the
+                // middle of the N range.  Expand geometrically from the guess until bracketed, then bisect.
+                const double *fe = a.out.fe + rec * pmax;
+                const double *av = a.out.avg + rec * pmax * nsel;
+                double fmin_ = fe[0];
+                for (int p = 1; p < pe.P; ++p) fmin_ = fmin(fmin_, fe[p]);
+                double wsum = 0.0, nsum = 0.0;
+                for (int p = 0; p < pe.P; ++p) {
+                    const double wgt = exp(-(fe[p] - fmin_));
+                    wsum += wgt;
+                    nsum += wgt * av[p * nsel];
+                }
+                const double g = nsum / wsum - n_mid;
+                if (g < 0.0) { glo = mu; have_glo = true; } else { ghi = mu; have_ghi = true; }
+                if (have_glo && have_ghi) {
+                    if (fabs(ghi - glo) <= 1e-13 * fmax(1.0, fmax(fabs(glo), fabs(ghi)))) { code = FHMC_E_NO_COEX; break; }
+                    mu = 0.5 * (glo + ghi);
+                } else {
+                    mu += (g < 0.0) ? step : -step;
+                    step *= 2.0;
+                }
                 continue;
             }
+            located = true;
             mu_good = mu;
             if (fabs(d) <= sa.lnz_tol) { converged = true; code = FHMC_OK; break; }
             const bool below = (slope >= 0.0) ? (d < 0.0) : (d > 0.0);
@@ -92,8 +118,9 @@ __global__ void __launch_bounds__(FHMC_CTA) k_find_phase_eq(const __grid_constan
             double mu_n = mu;
             if (slope != 0.0) {
                 double dm = -d / slope;
-                if (dm > sa.mu_step) dm = sa.mu_step;
-                if (dm < -sa.mu_step) dm = -sa.mu_step;
+                const double cap = 16.0 * sa.mu_step;  // Newton steps are trusted further than the blind search step
+                if (dm > cap) dm = cap;
+                if (dm < -cap) dm = -cap;
                 mu_n = mu + dm;
             } else {
                 mu_n = mu + (below ? sa.mu_step : -sa.mu_step);

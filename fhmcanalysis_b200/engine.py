@@ -44,62 +44,83 @@ def _stream_ptr(device):
 def upper_hull(x, y):
     """Upper concave envelope of the points (x_i, y_i), x strictly increasing and finite y: returns
     (edge slopes, strictly decreasing; vertex indices) or None when the fast mu-sweep path cannot use it.
-    One-time O(n) host setup per histogram (Andrew's monotone chain)."""
+    One-time host setup per histogram (qhull through scipy when available, else Andrew's monotone chain)."""
     x = np.asarray(x, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64)
     n = len(x)
     if n < 3 or not np.all(np.diff(x) > 0) or not np.all(np.isfinite(y)):
         return None
-    h = []
-    for i in range(n):
-        while len(h) >= 2:
-            a, b = h[-2], h[-1]
-            # drop b unless slope(a,b) > slope(b,i)
-            if (y[b] - y[a]) * (x[i] - x[b]) <= (y[i] - y[b]) * (x[b] - x[a]):
-                h.pop()
-            else:
-                break
-        h.append(i)
-    verts = np.array(h, dtype=np.float64)
-    slopes = np.array([(y[h[k + 1]] - y[h[k]]) / (x[h[k + 1]] - x[h[k]]) for k in range(len(h) - 1)])
-    if len(slopes) > 1 and not np.all(np.diff(slopes) < 0):
-        return None
-    return slopes, verts
+    h = None
+    try:
+        from scipy.spatial import ConvexHull
+        v = np.sort(ConvexHull(np.column_stack([x, y])).vertices)
+        # keep the vertices on or above the chord from the first to the last point
+        chord = y[0] + (y[-1] - y[0]) * (x[v] - x[0]) / (x[-1] - x[0])
+        h = [int(i) for i in v[(y[v] >= chord) | (v == 0) | (v == n - 1)]]
+    except Exception:
+        h = None
+    if h is None or len(h) < 2:
+        h = []
+        for i in range(n):
+            while len(h) >= 2:
+                a, b = h[-2], h[-1]
+                if (y[b] - y[a]) * (x[i] - x[b]) <= (y[i] - y[b]) * (x[b] - x[a]):
+                    h.pop()
+                else:
+                    break
+            h.append(i)
+    h = np.asarray(h, dtype=np.int64)
+    slopes = np.diff(y[h]) / np.diff(x[h])
+    while len(slopes) > 1 and not np.all(np.diff(slopes) < 0):   # drop collinear / numerically reflex vertices
+        keep = np.concatenate([[True], np.diff(slopes) < 0, [True]])
+        h = h[keep]
+        slopes = np.diff(y[h]) / np.diff(x[h])
+    return slopes, h.astype(np.float64)
 
 
 class SweepResult(object):
-    """Per-state-point records of one sweep (device tensors; ``host()`` copies them to NumPy)."""
+    """Per-state-point records of one sweep.  All fields live in ONE device allocation (typed views), so the whole
+    result comes back with a single device-to-host copy (``host()``)."""
 
     FIELDS = ("status", "nphase", "nmin", "lnnorm", "fe", "avg", "bounds", "max_idx", "min_idx")
+
+    @staticmethod
+    def layout(S, pmax, n_sel):
+        spec = [("lnnorm", np.float64, (S,)), ("fe", np.float64, (S, pmax)), ("avg", np.float64, (S, pmax, n_sel)),
+                ("status", np.int32, (S,)), ("nphase", np.int32, (S,)), ("nmin", np.int32, (S,)),
+                ("bounds", np.int32, (S, pmax, 2)), ("max_idx", np.int32, (S, pmax)), ("min_idx", np.int32, (S, pmax + 1))]
+        off, out = 0, []
+        for name, dt, shape in spec:
+            nb = int(np.prod(shape)) * np.dtype(dt).itemsize
+            if name == "avg" and n_sel == 0:
+                continue
+            out.append((name, dt, shape, off, nb))
+            off += (nb + 15) & ~15
+        return out, max(off, 16)
 
     def __init__(self, n_states, pmax, n_sel, device, pinned=False):
         t = torch()
         S = int(n_states)
         self.n_states, self.pmax, self.n_sel, self.device = S, int(pmax), int(n_sel), device
-        kw = dict(device=device)
-        self.status = t.empty(S, dtype=t.int32, **kw)   # bit pattern of the unsigned status word
-        self.nphase = t.empty(S, dtype=t.int32, **kw)
-        self.nmin = t.empty(S, dtype=t.int32, **kw)
-        self.lnnorm = t.empty(S, dtype=t.float64, **kw)
-        self.fe = t.empty((S, pmax), dtype=t.float64, **kw)
-        self.avg = t.empty((S, pmax, max(n_sel, 1)), dtype=t.float64, **kw) if n_sel else None
-        self.bounds = t.empty((S, pmax, 2), dtype=t.int32, **kw)
-        self.max_idx = t.empty((S, pmax), dtype=t.int32, **kw)
-        self.min_idx = t.empty((S, pmax + 1), dtype=t.int32, **kw)
+        self._layout, total = self.layout(S, self.pmax, self.n_sel)
+        self.buf = t.empty(total, dtype=t.uint8, device=device)
+        self.avg = None
+        tdt = {np.float64: t.float64, np.int32: t.int32}
+        for name, dt, shape, off, nb in self._layout:
+            setattr(self, name, self.buf[off:off + nb].view(tdt[dt]).view(shape))
         self.extra = {}
 
     def c_struct(self):
         return _lib.SweepOut(*[_ptr(getattr(self, k)) for k in self.FIELDS])
 
     def nbytes(self):
-        return sum(getattr(self, k).numel() * getattr(self, k).element_size()
-                   for k in self.FIELDS if getattr(self, k) is not None)
+        return sum(nb for _, _, _, _, nb in self._layout)
 
     def host(self):
-        out = {}
-        for k in self.FIELDS:
-            v = getattr(self, k)
-            out[k] = v.cpu().numpy() if v is not None else None
+        hb = self.buf.cpu().numpy()
+        out = {"avg": None}
+        for name, dt, shape, off, nb in self._layout:
+            out[name] = hb[off:off + nb].view(dt).reshape(shape)
         out["status"] = out["status"].view(np.uint32)
         out["code"] = (out["status"] & ST_CODE_MASK).astype(np.int32)
         out["safe"] = (out["status"] & ST_SAFE) != 0
@@ -160,16 +181,8 @@ class DeviceHistogram(object):
                 continue
             sel_row.append(len(rows))
             rows.extend(np.ascontiguousarray(r, dtype=np.float64) for r in terms)
-        hull_row, hull_len = 0, 0
-        if not coef:
-            hull = upper_hull(ntot, lnpi)
-            if hull is not None:
-                slopes, verts = hull
-                hull_row, hull_len = len(rows), len(verts)
-                srow, vrow = np.zeros(n), np.zeros(n)
-                srow[:len(slopes)] = slopes
-                vrow[:len(verts)] = verts
-                rows.extend([srow, vrow])
+        hull_row, hull_len = 0, 0          # the hull rows are added lazily (ensure_hull) by large mu sweeps only
+        self._hull_possible = not coef
         blob = np.zeros((len(rows), n_pad), dtype=np.float64)
         for i, r in enumerate(rows):
             if r.shape != (n,):
@@ -195,6 +208,30 @@ class DeviceHistogram(object):
         d.cutoff, d.beta_ref, d.mu1_ref, d.dmu_ref = float(cutoff), float(beta_ref), float(mu1_ref), float(dmu_ref)
         d.hull_row, d.hull_len = hull_row, hull_len
         self.desc = d
+
+    FAST_PATH_MIN_STATES = 100000   # below this the generic multi-lane kernels are used and no hull is needed
+
+    def ensure_hull(self):
+        """Append the two hull rows the one-pass mu-sweep kernel needs (upper concave envelope of (N, lnPI)) and
+        re-upload the blob.  Done once, on the first large pure-mu sweep."""
+        if self.desc.hull_len or not self._hull_possible:
+            return
+        self._hull_possible = False
+        hull = upper_hull(self.blob_host[1, :self.n], self.blob_host[0, :self.n])
+        if hull is None:
+            return
+        slopes, verts = hull
+        extra = np.zeros((2, self.n_pad), dtype=np.float64)
+        extra[0, :len(slopes)] = slopes
+        extra[1, :len(verts)] = verts
+        self.desc.hull_row, self.desc.hull_len = self.n_rows, len(verts)
+        self.blob_host = np.ascontiguousarray(np.vstack([self.blob_host, extra]))
+        self.n_rows += 2
+        self.desc.n_rows = self.n_rows
+        self.blob = torch().from_numpy(self.blob_host).to(self.device)
+        self.h2d_bytes = self.blob_host.nbytes
+        if hasattr(self, "_blob_pin"):
+            del self._blob_pin
 
     # ------------------------------------------------------------------------------------------
     def _desc(self, pmax, complete=False, compare_raw=False, cutoff=None, smooth=None):
@@ -248,10 +285,12 @@ class DeviceHistogram(object):
         """K1+K3+K2 over all state points; returns a SweepResult of device tensors (asynchronous)."""
         L = _lib.load()
         st = states if states is not None else self.make_states(mu1, beta, dmu, grid)
+        if st.n_states >= self.FAST_PATH_MIN_STATES and lanes in (0, 1) and not complete:
+            self.ensure_hull()
         d = self._desc(pmax, complete, compare_raw, cutoff, smooth)
         if out is None:
             out = SweepResult(st.n_states, pmax, self.n_sel, self.device)
-        elif out.n_states != st.n_states or out.pmax != pmax or out.n_sel != self.n_sel:
+        elif out.n_states < st.n_states or out.pmax != pmax or out.n_sel != self.n_sel:
             raise ValueError("output buffers do not match the sweep")
         cs = out.c_struct()
         with torch().cuda.device(self.device):
@@ -259,6 +298,69 @@ class DeviceHistogram(object):
                                  _stream_ptr(self.device))
         _lib.check(rc, "fhmc_sweep_1d")
         out._states = st
+        return out
+
+    def sweep_host(self, mu1, pmax=4, lanes=0, chunk=1 << 18, out=None, fields=None):
+        """End-to-end mu sweep with HOST buffers (what `bench.py`'s e2e times): the state points are cut into chunks
+        that alternate between two CUDA streams so that the pinned-host -> device copy of chunk k+1, the kernel of
+        chunk k and the device -> pinned-host copy of the results of chunk k-1 overlap.  The histogram blob is
+        uploaded on every call.
+
+        mu1: 1-D float64 NumPy array or CPU tensor (pinned memory avoids one staging copy).
+        out: optional dict of pinned CPU tensors [S, ...] (as returned by a previous call) to reuse.
+        Returns the dict of CPU tensors (fields of SweepResult.FIELDS, or the subset `fields`)."""
+        t = torch()
+        L = _lib.load()
+        dev = self.device
+        mu_h = mu1 if isinstance(mu1, t.Tensor) else t.from_numpy(np.ascontiguousarray(mu1, dtype=np.float64))
+        if not mu_h.is_pinned():
+            mu_h = mu_h.pin_memory()
+        S = mu_h.numel()
+        names = [k for k in SweepResult.FIELDS if (fields is None or k in fields) and (k != "avg" or self.n_sel)]
+        chunk = int(min(chunk, max(S, 1)))
+        if S >= self.FAST_PATH_MIN_STATES and lanes in (0, 1):
+            self.ensure_hull()
+        if not hasattr(self, "_pipe") or self._pipe[0] != (chunk, pmax):
+            self._pipe = ((chunk, pmax), [t.cuda.Stream(dev), t.cuda.Stream(dev)],
+                          [t.empty(chunk, dtype=t.float64, device=dev) for _ in range(2)],
+                          [SweepResult(chunk, pmax, self.n_sel, dev) for _ in range(2)])
+        _, streams, mu_d, res = self._pipe
+        if out is None:
+            out = {}
+            for k in names:
+                ref = getattr(res[0], k)
+                out[k] = t.empty((S,) + tuple(ref.shape[1:]), dtype=ref.dtype).pin_memory()
+        d = self._desc(pmax)
+        cur = t.cuda.current_stream(dev)
+        if not hasattr(self, "_blob_pin"):
+            self._blob_pin = t.from_numpy(self.blob_host).pin_memory()
+        blob_d = t.empty_like(self.blob)
+        blob_d.copy_(self._blob_pin, non_blocking=True)
+        ready = t.cuda.Event()
+        ready.record(cur)
+        for st_ in streams:
+            st_.wait_event(ready)
+        for k, lo in enumerate(range(0, S, chunk)):
+            hi = min(S, lo + chunk)
+            b = k & 1
+            with t.cuda.stream(streams[b]):
+                mu_d[b][:hi - lo].copy_(mu_h[lo:hi], non_blocking=True)
+                st = _lib.States()
+                st.n_states = hi - lo
+                st.mu1, st.n_mu1, st.mu1_div = _ptr(mu_d[b]), hi - lo, 1
+                st.beta, st.n_beta, st.beta_div = None, 1, 1
+                st.dmu, st.n_dmu, st.dmu_div = None, 1, 1
+                cs = res[b].c_struct()
+                rc = L.fhmc_sweep_1d(ctypes.byref(d), _ptr(blob_d), ctypes.byref(st), ctypes.byref(cs), int(lanes),
+                                     ctypes.c_void_p(streams[b].cuda_stream))
+                _lib.check(rc, "fhmc_sweep_1d")
+                for name in names:
+                    out[name][lo:hi].copy_(getattr(res[b], name)[:hi - lo], non_blocking=True)
+        for st_ in streams:
+            cur.wait_stream(st_)
+        blob_d.record_stream(streams[0])
+        blob_d.record_stream(streams[1])
+        cur.synchronize()
         return out
 
     def sweep_auto(self, mu1, beta=None, dmu=None, grid=False, pmax=4, **kw):
@@ -299,7 +401,7 @@ class DeviceHistogram(object):
         dfe = t.empty(T, dtype=t.float64, device=self.device)
         iters = t.empty(T, dtype=t.int32, device=self.device)
         if mu_step is None:
-            mu_step = 1.0 / abs(self.desc.beta_ref)
+            mu_step = 0.05 / abs(self.desc.beta_ref)   # first blind search step (doubles until <N> brackets the window)
         cs = out.c_struct()
         with t.cuda.device(self.device):
             rc = L.fhmc_find_phase_eq_1d(ctypes.byref(d), _ptr(self.blob), ctypes.byref(st), float(lnz_tol),

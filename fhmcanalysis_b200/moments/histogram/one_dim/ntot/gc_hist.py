@@ -711,6 +711,13 @@ class histogram(TaylorMixin):
         avg[S,pmax,len(moments)], bounds[S,pmax,2], max_idx, min_idx (or the device SweepResult)."""
         if dh is None:
             dh = self.device_histogram(beta, dmu, order, moments, cutoff, device)
+        if beta is None and dmu is None and not grid and not return_device and isinstance(mu, np.ndarray) and mu.size >= (1 << 16):
+            # large host-resident mu sweep: chunked, double-buffered H2D -> kernel -> D2H pipeline
+            out = {k: v.numpy() for k, v in dh.sweep_host(mu, pmax=pmax, lanes=lanes).items()}
+            out["status"] = out["status"].view(np.uint32)
+            out["code"] = (out["status"] & _lib.ST_CODE_MASK).astype(np.int32)
+            out["safe"] = (out["status"] & _lib.ST_SAFE) != 0
+            return out
         res = dh.sweep(mu, beta, dmu, grid=grid, pmax=pmax, lanes=lanes)
         return res if return_device else res.host()
 

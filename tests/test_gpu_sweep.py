@@ -13,7 +13,9 @@ def _dh(lnpi, mom, beta_ref, mu1_ref, smooth, **kw):
     from fhmcanalysis_b200 import engine
     n = len(lnpi)
     s = sel_rows(n, mom)
-    return engine.DeviceHistogram(lnpi, np.arange(n), beta_ref, mu1_ref, smooth=smooth, sel=["N", s[1], s[2]], **kw)
+    dh = engine.DeviceHistogram(lnpi, np.arange(n), beta_ref, mu1_ref, smooth=smooth, sel=["N", s[1], s[2]], **kw)
+    dh.ensure_hull()  # lanes=1 -> one-pass fast kernel, lanes=-1 -> generic one-lane kernel
+    return dh
 
 
 def _check_record(h, k, r, nsel=3):
@@ -31,7 +33,7 @@ def _check_record(h, k, r, nsel=3):
         assert np.allclose(h["avg"][k, :P, :nsel], r["avg"][:, :nsel], rtol=RTOL, atol=1e-300)
 
 
-@pytest.mark.parametrize("lanes", [1, 4, 32])
+@pytest.mark.parametrize("lanes", [1, -1, 4, 32])
 def test_golden_config2_sweep(golden, golden_meta, lanes):
     lnpi, mom, mus = golden["c2/lnpi"], golden["c2/mom"], golden["c2/mu"]
     dh = _dh(lnpi, mom, 1.0, 0.0, golden_meta["c2"]["smooth"])
@@ -53,7 +55,7 @@ def test_golden_config2_sweep(golden, golden_meta, lanes):
         assert np.max(np.abs(rows[k] - g["lnpi"])) < 1e-11
 
 
-@pytest.mark.parametrize("lanes", [1, 4, 32])
+@pytest.mark.parametrize("lanes", [1, -1, 4, 32])
 def test_stress_cases_match_reference_and_oracle(golden, golden_meta, oracle, lanes):
     from fhmcanalysis_b200 import engine
     for key, smooth, noise, mu, outcome in golden_meta["stress"]:
@@ -128,7 +130,7 @@ def test_square_well_real_data(golden, golden_meta):
             assert np.allclose(h["avg"][k, :P, 2], golden[pre + "/mom"][:, 0, 0, 0, 0, 1], rtol=RTOL, atol=0)
 
 
-@pytest.mark.parametrize("lanes,S", [(1, 4096), (4, 1024), (32, 256)])
+@pytest.mark.parametrize("lanes,S", [(1, 4096), (-1, 2048), (4, 1024), (32, 256)])
 def test_seeded_sweep_vs_oracle(oracle, lanes, S):
     """BASELINE config 2 generator at full N=1001; every 13th state point checked against the oracle."""
     from fhmcanalysis_b200 import synth
