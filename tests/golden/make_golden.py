@@ -238,6 +238,86 @@ def main():
     except Exception as e:
         meta["joint"] = {"status": "reference API differs: %r" % (e,)}
 
+    # ---- H. derivative builders and every extrapolation entry point on a max_order-4, 2-species tensor (like
+    #         unittests/reference/test2.nc), with and without the kinetic-energy terms -----------------------------
+    n4 = 61
+    rng = np.random.default_rng(4)
+    x4 = np.arange(n4, dtype=np.float64)
+    lnpi4 = synth.two_peak_lnpi(n4, noise=1e-3, scale=0.06, seed=11) * 1.0
+    base = [0.4 * x4 + 0.3, 0.6 * x4 + 0.2]
+    uu = -1.5 * x4 - 0.01 * x4 * x4 - 0.5
+    mom4 = np.zeros((2, 5, 2, 5, 5, n4))
+    for i in range(2):
+        for j in range(5):
+            for k in range(2):
+                for m_ in range(5):
+                    for p in range(5):
+                        mom4[i, j, k, m_, p] = base[i] ** j * base[k] ** m_ * uu ** p * (1.0 + 0.02 * (j + m_ + p) * rng.random(n4))
+    out["h/lnpi"], out["h/mom"] = lnpi4, mom4
+    meta["h"] = {"beta_ref": 1.0, "mu_ref": [-2.0, -1.6], "smooth": 3, "mu1": -1.9, "beta": 1.04, "dmu": 0.55}
+    sample = [[0, 1, 0, 0, 0], [1, 1, 0, 0, 0], [0, 0, 0, 0, 1], [0, 1, 1, 1, 0], [1, 2, 0, 0, 1], [0, 1, 0, 1, 1], [1, 1, 1, 1, 1]]
+    meta["h"]["sample"] = sample
+
+    def pick(t, lead=()):
+        return np.array([t[tuple(lead) + tuple(a)] for a in sample])
+
+    for ke in (False, True):
+        tag = "h/ke%d" % int(ke)
+        hh = ref.make_histogram(lnpi4, mom4, 1.0, [-2.0, -1.6], 3, ke=ke)
+        hh.reweight(-1.9)
+        d1, dm1 = hh._dB(False)
+        d2, dm2 = hh._dB2(False)
+        out[tag + "/dB"], out[tag + "/dB_mom"], out[tag + "/dB_sum"] = d1, pick(dm1), np.array(np.sum(np.abs(dm1)))
+        out[tag + "/dB2"], out[tag + "/dB2_mom"], out[tag + "/dB2_sum"] = d2, pick(dm2), np.array(np.sum(np.abs(dm2)))
+        dmu1, dmm1 = hh._dMU(False)
+        H2, Hm2 = hh._dMU2(False)
+        out[tag + "/dMU"], out[tag + "/dMU_mom"] = dmu1, pick(dmm1, (0,))
+        out[tag + "/dMU2"], out[tag + "/dMU2_mom"] = H2, pick(Hm2, (0, 0))
+        Hl, Hm = hh._dBMU2(False)
+        out[tag + "/dBMU2"], out[tag + "/dBMU2_mom01"], out[tag + "/dBMU2_sum"] = Hl, pick(Hm, (0, 1)), np.array(np.sum(np.abs(Hm)))
+        out[tag + "/gc"] = np.array([hh._gc_dX_dB([0, 1, 0, 0, 0], 0), hh._gc_dX_dB([0, 0, 0, 0, 1], 1), hh._gc_d2X_dB2([1, 1, 0, 0, 0], 0),
+                                     hh._gc_df_dB_ii(([0, 1, 0, 0, 0], 0), ([0, 0, 0, 0, 1], 0)), hh._gc_df_dB_in(([1, 1, 0, 0, 0], 0), 1),
+                                     hh._gc_fluct_ii([0, 1, 0, 0, 0], [1, 1, 0, 0, 0])])
+        if not ke:
+            d3, dm3 = hh._dB3(False)
+            out[tag + "/dB3"], out[tag + "/dB3_mom"] = d3, pick(dm3)
+        for order in ((1, 2, 3) if not ke else (1, 2)):
+            hn = hh.temp_extrap(1.04, order, 10.0, True, True, False)
+            out[tag + "/temp%d/lnpi" % order], out[tag + "/temp%d/mom" % order] = hn.data["ln(PI)"].copy(), pick(hn.data["mom"])
+        for order in (1, 2):
+            hn = hh.dmu_extrap(np.array([0.55]), order, 10.0, True, True, False)
+            out[tag + "/dmu%d/lnpi" % order], out[tag + "/dmu%d/mom" % order] = hn.data["ln(PI)"].copy(), pick(hn.data["mom"])
+            for fom in (False, True):
+                hn = hh.temp_dmu_extrap(1.04, np.array([0.55]), order, 10.0, True, True, False, fom)
+                out[tag + "/tdmu%d_%d/lnpi" % (order, int(fom))] = hn.data["ln(PI)"].copy()
+                out[tag + "/tdmu%d_%d/mom" % (order, int(fom))] = pick(hn.data["mom"])
+    # find_phase_eq at another temperature / dmu (reference Nelder-Mead), orders 1 and 2, on a wider two-peak surface
+    n5 = 241
+    lnpi5 = synth.two_peak_lnpi(n5, noise=0.0, scale=0.24)
+    mom5 = synth.two_comp_moments(n5)
+    mom5b = np.zeros((2, 4, 2, 4, 4, n5))
+    mom5b[:, :3, :, :3, :3] = mom5
+    for i in range(2):   # third-order entries so that order-2 moment extrapolation is defined (max_order 3)
+        for j in range(4):
+            for k in range(2):
+                for m_ in range(4):
+                    for p in range(4):
+                        if j + m_ + p >= 3 or j == 3 or m_ == 3 or p == 3:
+                            mom5b[i, j, k, m_, p] = (mom5[i, 1, 0, 0, 0] ** j) * (mom5[k, 1, 0, 0, 0] ** m_) * (mom5[0, 0, 0, 0, 1] ** p)
+    out["eq/lnpi"], out["eq/mom"] = lnpi5, mom5b
+    meta["eq"] = {"beta_ref": 1.0, "mu_ref": [-3.0, -2.5], "smooth": 5, "cases": []}
+    for order, beta, dmu in ((1, 1.01, 0.5), (2, 0.985, 0.52), (1, 1.0, 0.5)):
+        hh = ref.make_histogram(lnpi5, mom5b, 1.0, [-3.0, -2.5], 5)
+        try:
+            with redirect_stdout(io.StringIO()):
+                eq, err = hh.find_phase_eq(1e-8, -3.0, beta, [dmu], order, 10.0, True, True)
+            key = "eq/o%d_b%g_d%g" % (order, beta, dmu)
+            out[key + "/mu"], out[key + "/err"] = eq.data["curr_mu"].copy(), np.array(err)
+            pack(key, thermo_record(eq), out)
+            meta["eq"]["cases"].append([key, order, beta, dmu, "ok"])
+        except Exception as e:
+            meta["eq"]["cases"].append(["", order, beta, dmu, "reference raised: " + str(e)[:80]])
+
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     with open(os.path.join(HERE, "reference_vectors.json"), "w") as fh:
         json.dump(meta, fh, indent=1, sort_keys=True, default=str)

@@ -1,0 +1,94 @@
+"""GPU: every Taylor-extrapolation entry point of the drop-in class (temp_extrap orders 1-3, dmu_extrap, temp_dmu_extrap with
+and without first_order_mom, kinetic-energy variant) and find_phase_eq at another (beta, dMu), against the compiled reference."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _hist(golden, golden_meta, ke):
+    from fhmcanalysis_b200.moments.histogram.one_dim.ntot.gc_hist import histogram
+    meta = golden_meta["h"]
+    h = histogram.from_arrays(golden["h/lnpi"], golden["h/mom"], meta["beta_ref"], meta["mu_ref"], meta["smooth"], ke=ke)
+    h.reweight(meta["mu1"])
+    return h
+
+
+def _pick(t, sample):
+    return np.array([t[tuple(a)] for a in sample])
+
+
+def _mom_close(a, b, rtol=1e-9):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6 * np.max(np.abs(b)))) < rtol
+
+
+@pytest.mark.parametrize("ke", [False, True])
+def test_extrapolation_entry_points(golden, golden_meta, ke):
+    meta = golden_meta["h"]
+    sample = meta["sample"]
+    tag = "h/ke%d" % int(ke)
+    h = _hist(golden, golden_meta, ke)
+    for order in ((1, 2, 3) if not ke else (1, 2)):
+        hn = h.temp_extrap(meta["beta"], order, 10.0, True, True, False)
+        assert np.max(np.abs(hn.data["ln(PI)"] - golden[tag + "/temp%d/lnpi" % order])) < 1e-9, order
+        assert _mom_close(_pick(hn.data["mom"], sample), golden[tag + "/temp%d/mom" % order]), order
+        assert hn.data["curr_beta"] == meta["beta"] and h.data["curr_beta"] == meta["beta_ref"]
+    if ke:
+        with pytest.raises(Exception):
+            h.temp_extrap(meta["beta"], 3, 10.0, True, True, False)
+    for order in (1, 2):
+        hn = h.dmu_extrap(np.array([meta["dmu"]]), order, 10.0, True, True, False)
+        assert np.max(np.abs(hn.data["ln(PI)"] - golden[tag + "/dmu%d/lnpi" % order])) < 1e-9
+        assert _mom_close(_pick(hn.data["mom"], sample), golden[tag + "/dmu%d/mom" % order])
+        assert abs(hn.data["curr_mu"][1] - hn.data["curr_mu"][0] - meta["dmu"]) < 1e-14
+        for fom in (False, True):
+            hn = h.temp_dmu_extrap(meta["beta"], np.array([meta["dmu"]]), order, 10.0, True, True, False, fom)
+            assert np.max(np.abs(hn.data["ln(PI)"] - golden[tag + "/tdmu%d_%d/lnpi" % (order, int(fom))])) < 1e-9
+            assert _mom_close(_pick(hn.data["mom"], sample), golden[tag + "/tdmu%d_%d/mom" % (order, int(fom))])
+    with pytest.raises(Exception, match="twice"):
+        h.temp_extrap(meta["beta"], 1, 10.0, True, False, True).temp_extrap(1.1, 1, 10.0, True, True, True)
+
+
+def test_batched_taylor_sweep_matches_dropin(golden, golden_meta):
+    """reweight_batch(beta=, dmu=) (coefficient rows inside the kernel) == the drop-in temp_dmu_extrap + thermo per point."""
+    import copy
+    from fhmcanalysis_b200.moments.histogram.one_dim.ntot.gc_hist import histogram
+    meta = golden_meta["h"]
+    h0 = histogram.from_arrays(golden["h/lnpi"], golden["h/mom"], meta["beta_ref"], meta["mu_ref"], meta["smooth"])
+    mus = np.array([-1.95, -1.9, -1.85])
+    betas = np.array([0.98, 1.0, 1.03])
+    dmus = np.array([0.35, 0.4, 0.5])
+    for order in (1, 2):
+        out = h0.reweight_batch(mus, betas, dmus, order=order, moments=("N1", "N2", "U"), pmax=8)
+        for k in range(3):
+            h = copy.deepcopy(h0)
+            h.reweight(mus[k])
+            hn = h.temp_dmu_extrap(betas[k], np.array([dmus[k]]), order, 10.0, True, True, False, True)
+            hn.thermo()
+            P = len(hn.data["thermo"])
+            assert out["code"][k] == 0 and out["nphase"][k] == P
+            assert out["max_idx"][k, :P].tolist() == hn.data["ln(PI)_maxima_idx"].tolist()
+            fe = np.array([hn.data["thermo"][p]["F.E./kT"] for p in range(P)])
+            assert np.allclose(out["fe"][k, :P], fe, rtol=1e-9, atol=1e-9)
+            n1 = np.array([hn.data["thermo"][p]["n1"] for p in range(P)])
+            uu = np.array([hn.data["thermo"][p]["u"] for p in range(P)])
+            assert np.allclose(out["avg"][k, :P, 0], n1, rtol=1e-8, atol=1e-10)
+            assert np.allclose(out["avg"][k, :P, 2], uu, rtol=1e-8, atol=1e-10)
+
+
+def test_find_phase_eq_other_conditions(golden, golden_meta):
+    """find_phase_eq(lnZ_tol, mu_guess, beta, dMu, order) vs the reference's Nelder-Mead result: same extrema at coexistence,
+    mu within the reference solver's x-tolerance (1e-4), residual far below the reference's."""
+    from fhmcanalysis_b200.moments.histogram.one_dim.ntot.gc_hist import histogram
+    meta = golden_meta["eq"]
+    for key, order, beta, dmu, status in meta["cases"]:
+        assert status == "ok"
+        h = histogram.from_arrays(golden["eq/lnpi"], golden["eq/mom"], meta["beta_ref"], meta["mu_ref"], meta["smooth"])
+        eq, err = h.find_phase_eq(1e-8, -3.0, beta, [dmu], order, 10.0, True, True)
+        assert abs(eq.data["curr_mu"][0] - golden[key + "/mu"][0]) < 2e-4, key
+        assert eq.data["ln(PI)_maxima_idx"].tolist() == golden[key + "/maxima"].tolist(), key
+        assert eq.data["ln(PI)_minima_idx"].tolist() == golden[key + "/minima"].tolist(), key
+        fe = [eq.data["thermo"][p]["F.E./kT"] for p in range(len(eq.data["thermo"]))]
+        assert abs(fe[0] - fe[1]) < 1e-8 and err < 1e-16
+        assert np.allclose(fe, golden[key + "/fe"], rtol=0, atol=5e-2)      # the reference stops ~1e-4 away in mu
+        assert h.data["curr_mu"][0] == meta["mu_ref"][0]                     # self untouched
