@@ -91,6 +91,36 @@ __device__ __forceinline__ double exp_scaled(double u, int Mq, uint32_t tab_addr
     return __hiloint2double(hi, __double2loint(v));
 }
 
+// Same function with the seven constants held in (opaque) registers: the compiler otherwise re-materialises them
+// from the constant bank through uniform registers on every use (LDCU + IMAD.U32 per constant per block).
+struct ExpRegs {
+    double inv, nhi, nlo, c5, c4, c3, c2;
+};
+__device__ __forceinline__ ExpRegs load_exp_regs()
+{
+    ExpRegs r = {c_exp.inv, -c_exp.hi, -c_exp.lo, c_exp.c5, c_exp.c4, c_exp.c3, c_exp.c2};
+    asm volatile("" : "+d"(r.inv), "+d"(r.nhi), "+d"(r.nlo), "+d"(r.c5), "+d"(r.c4), "+d"(r.c3), "+d"(r.c2));
+    return r;
+}
+__device__ __forceinline__ double exp_scaled_r(double u, int Mq, uint32_t tab_addr, const ExpRegs &c)
+{
+    const double kd0 = fma(u, c.inv, FHMC_EXP_MAGIC);
+    const int k = __double2loint(kd0);
+    const double kd = kd0 - FHMC_EXP_MAGIC;
+    double r = fma(kd, c.nhi, u);
+    r = fma(kd, c.nlo, r);
+    double p = fma(r, c.c5, c.c4);
+    p = fma(p, r, c.c3);
+    p = fma(p, r, c.c2);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double T = lds_f64(tab_addr + ((k & 63) << 3));
+    const double v = T * p;
+    const int q = max((k >> 6) - Mq, -1022);
+    const int hi = __double2hiint(v) + (q << 20);
+    return __hiloint2double(hi, __double2loint(v));
+}
+
 // exp(t) for t <= ~0 (generic paths): same algorithm, no exponent offset
 __device__ __forceinline__ double exp_nonpos(double t, uint32_t tab_addr) { return exp_scaled(t, 0, tab_addr); }
 

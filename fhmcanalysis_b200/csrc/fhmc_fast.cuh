@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_mu_fast(const __grid_cons
     const uint32_t s_slope = s_lnpi + (uint32_t)a.d.hull_row * row_bytes, s_hidx = s_slope + row_bytes;
     const int H = a.d.hull_len;
 
+    const ExpRegs ec = load_exp_regs();   // reduction / polynomial constants pinned in registers for the hot loop
     const long long S = a.st.n_states;
     for (long long sp = (long long)blockIdx.x * FHMC_CTA + threadIdx.x; sp < S; sp += (long long)gridDim.x * FHMC_CTA) {
         const double mu1 = a.st.mu1[(sp / a.st.mu1_div) % a.st.n_mu1];
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_mu_fast(const __grid_cons
             }
         };
         auto accumulate = [&](const Bin &b) {
-            const double e = exp_scaled(b.u, Mq, tab);
+            const double e = exp_scaled_r(b.u, Mq, tab, ec);
             Sacc += e;
             if (SEL0N) A[0] = fma(e, b.N, A[0]);
 #pragma unroll
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_mu_fast(const __grid_cons
             double xm = u0;
             double dc = __dsub_rn(c.u, xm);  // sign(dc) is the exact order of (xm, xc)
             int i = 1;
+#pragma unroll 2
             for (; i + 3 < last; i += 4) {   // bins i..i+3 are interior, i+4 <= last exists
                 Bin b1, b2, b3, b4;
                 load_bin(i + 1, b1);
