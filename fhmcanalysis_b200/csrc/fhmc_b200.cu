@@ -51,12 +51,8 @@ template <int G, bool TAYLOR>
 __global__ void __launch_bounds__(FHMC_CTA) k_sweep_1d(const __grid_constant__ SweepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *sm = reinterpret_cast<double *>(smem_raw);
-    const uint32_t blob_bytes = (uint32_t)a.d.n_rows * (uint32_t)a.d.n_pad * 8u;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + blob_bytes);
-    double *s_tab = reinterpret_cast<double *>(smem_raw + blob_bytes + 16);
-    stage_exp_table(s_tab);
-    stage_blob(sm, a.blob, blob_bytes, bar);  // contains a __syncthreads after the table stores
+    double *s_tab;
+    const double *sm = stage_histogram(a, smem_raw, s_tab);
 
     constexpr int GPC = FHMC_CTA / G;  // state points per CTA tile
     const int grp = threadIdx.x / G;
@@ -332,20 +328,24 @@ int fhmc_sweep_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_sta
     if (states->n_states == 0) return 0;
     const DevInfo *di = dev_info();
     if (!di) { set_error("no CUDA device"); return 1; }
-    const size_t smem = (size_t)desc->n_rows * desc->n_pad * 8 + 16 + 512;
-    if (smem > (size_t)di->smem_optin) { set_error("histogram blob (%zu bytes) exceeds shared memory (%d bytes)", smem, di->smem_optin); return 1; }
+    size_t smem = (size_t)desc->n_rows * desc->n_pad * 8 + 16 + 512;
     SweepArgs args;
     args.d = *desc;
     args.blob = blob;
     args.st = *states;
     args.out = *out;
+    args.blob_global = 0;
+    if (smem > (size_t)di->smem_optin) {  // histogram larger than shared memory: read the rows through L1/L2
+        args.blob_global = 1;
+        smem = 16 + 512;
+    }
     const bool taylor = desc->n_coef > 0 || desc->n_term > 1;
     int G = lanes_per_point > 0 ? lanes_per_point : choose_lanes(states->n_states, di);
     cudaStream_t s = (cudaStream_t)stream;
     // pure mu sweep with a precomputed hull, one lane per point: the one-pass kernel.  lanes_per_point = -1 forces
     // the generic one-lane kernel (tests compare the two).
     if (lanes_per_point == -1) G = 1;
-    else if (G == 1 && !taylor && !desc->complete && desc->hull_len >= 2 && desc->n >= 3 && desc->hull_row > 1 &&
+    else if (G == 1 && !taylor && !args.blob_global && !desc->complete && desc->hull_len >= 2 && desc->n >= 3 && desc->hull_row > 1 &&
              desc->hull_row + 2 <= desc->n_rows)
     {
         // + packed {lnPI, N, X...} copy the fast kernel builds (fhmc_fast.cuh): up to 6 doubles per bin

@@ -24,7 +24,24 @@ struct SweepArgs {
     const double *blob;
     fhmc_states st;
     fhmc_sweep_out out;
+    int blob_global;  // histogram too large for shared memory: rows are read from HBM/L2 (all lanes read the same bin)
 };
+
+// Shared-memory prologue of the 1-D kernels: [blob | mbarrier(16 B) | 2^(j/64) table(512 B) | ...].  Returns the
+// pointer the evaluator reads rows through (shared copy, or the global blob when it does not fit).
+__device__ __forceinline__ const double *stage_histogram(const SweepArgs &a, unsigned char *smem_raw, double *&s_tab)
+{
+    const uint32_t blob_bytes = a.blob_global ? 0u : (uint32_t)a.d.n_rows * (uint32_t)a.d.n_pad * 8u;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + blob_bytes);
+    s_tab = reinterpret_cast<double *>(smem_raw + blob_bytes + 16);
+    stage_exp_table(s_tab);
+    if (a.blob_global) {
+        __syncthreads();
+        return a.blob;
+    }
+    stage_blob(smem_raw, a.blob, blob_bytes, bar);
+    return reinterpret_cast<const double *>(smem_raw);
+}
 
 #define FHMC_NEED_SLOW 0x7fffffff
 

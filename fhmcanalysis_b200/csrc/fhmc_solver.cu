@@ -25,12 +25,8 @@ __global__ void __launch_bounds__(FHMC_CTA) k_find_phase_eq(const __grid_constan
 {
     const SweepArgs &a = sa.sw;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *sm = reinterpret_cast<double *>(smem_raw);
-    const uint32_t blob_bytes = (uint32_t)a.d.n_rows * (uint32_t)a.d.n_pad * 8u;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + blob_bytes);
-    double *s_tab = reinterpret_cast<double *>(smem_raw + blob_bytes + 16);
-    stage_exp_table(s_tab);
-    stage_blob(sm, a.blob, blob_bytes, bar);
+    double *s_tab;
+    const double *sm = stage_histogram(a, smem_raw, s_tab);
 
     constexpr int GPC = FHMC_CTA / G;
     const int grp = threadIdx.x / G;
@@ -192,9 +188,13 @@ extern "C" int fhmc_find_phase_eq_1d(const fhmc_hist_desc *desc, const double *b
     if (((uintptr_t)blob & 15) || (desc->n_pad & 1)) { set_error("blob must be 16-byte aligned with even n_pad"); return 1; }
     DevCaps caps;
     if (get_caps(caps)) return 1;
-    const size_t smem = (size_t)desc->n_rows * desc->n_pad * 8 + 16 + 512;
-    if (smem > (size_t)caps.smem_optin) { set_error("histogram blob exceeds shared memory"); return 1; }
+    size_t smem = (size_t)desc->n_rows * desc->n_pad * 8 + 16 + 512;
     SolveArgs sa;
+    sa.sw.blob_global = 0;
+    if (smem > (size_t)caps.smem_optin) {
+        sa.sw.blob_global = 1;
+        smem = 16 + 512;
+    }
     sa.sw.d = *desc;
     sa.sw.blob = blob;
     sa.sw.st = *states;

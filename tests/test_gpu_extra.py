@@ -117,3 +117,26 @@ def test_sharded_sweep_single_process(golden, golden_meta):
     for k in ("nphase", "max_idx", "min_idx", "bounds"):
         assert np.array_equal(out[k], ref[k])
     assert np.allclose(out["fe"][:, :2], ref["fe"][:, :2], rtol=0, atol=0)
+
+
+def test_histogram_larger_than_shared_memory(oracle):
+    """N_max = 40000: the blob (3 rows x 320 KB) cannot be staged in 227 KB of shared memory; the generic kernels read the
+    rows through L1/L2 instead.  Same outputs as the oracle."""
+    from fhmcanalysis_b200 import engine, synth
+    n = 40001
+    lnpi = synth.two_peak_lnpi(n, noise=0.0, scale=40.0)
+    N = np.arange(n, dtype=float)
+    dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=50, sel=["N"])
+    mus = np.array([-1e-3, 0.0, 2e-4])
+    for lanes in (32, 4, -1):
+        h = dh.sweep(mus, pmax=4, lanes=lanes).host()
+        for k, mu in enumerate(mus):
+            r = oracle.state_point(lnpi, np.arange(n), 1.0, 0.0, mu, 50, sel=N[None])
+            P = r["nphase"]
+            assert h["code"][k] == r["status"] == 0 and h["nphase"][k] == P
+            assert h["max_idx"][k, :P].tolist() == r["max_idx"].tolist()
+            assert h["min_idx"][k, :h["nmin"][k]].tolist() == r["min_idx"].tolist()
+            assert np.allclose(h["fe"][k, :P], r["fe"], rtol=1e-10, atol=0)
+            assert np.allclose(h["avg"][k, :P, 0], r["avg"][:, 0], rtol=1e-10, atol=0)
+    res = dh.find_phase_eq(np.array([0.0]), lnz_tol=1e-10).host()
+    assert res["code"][0] == 0 and abs(res["dfe"][0]) < 1e-9
