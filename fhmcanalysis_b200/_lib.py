@@ -20,6 +20,7 @@ ST_SAFE = 0x100
 ST_GAP_FILL = 0x200
 ST_SLOW_PATH = 0x400
 ST_RESCUED = 0x800
+ST_FAST = 0x1000
 E_CAPACITY = 8
 E_NO_COEX = 100
 

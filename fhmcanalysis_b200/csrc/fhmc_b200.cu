@@ -262,31 +262,16 @@ static int launch_sweep_t(bool taylor, const SweepArgs &args, size_t smem, const
     return taylor ? launch_sweep<G, true>(args, smem, di, stream) : launch_sweep<G, false>(args, smem, di, stream);
 }
 
-// one-pass mu-sweep kernel (fhmc_fast.cuh): one thread per state point
-template <int NSEL, bool SEL0N>
-static int launch_fast(const SweepArgs &args, size_t smem, const DevInfo *di, cudaStream_t stream)
-{
-    auto kern = k_sweep_mu_fast<NSEL, SEL0N>;
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return 1;
-    int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FHMC_CTA, smem), "occupancy query")) return 1;
-    if (occ < 1) { set_error("fast sweep kernel does not fit on an SM (smem %zu bytes)", smem); return 1; }
-    const long long ntiles = (args.st.n_states + FHMC_CTA - 1) / FHMC_CTA;
-    long long grid = (long long)di->sm_count * occ;
-    if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, FHMC_CTA, smem, stream>>>(args);
-    return check_cuda(cudaGetLastError(), "k_sweep_mu_fast launch");
-}
-
-static int launch_fast_dispatch(const SweepArgs &args, size_t smem, const DevInfo *di, cudaStream_t stream)
+// one-pass mu-sweep kernel (fhmc_fast.cuh, NC = 0): one thread per state point
+static int launch_fast_mu(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream)
 {
     const bool s0n = args.d.n_sel > 0 && args.d.sel_row[0] == 1;
     switch (args.d.n_sel) {
-    case 0: return launch_fast<0, false>(args, smem, di, stream);
-    case 1: return s0n ? launch_fast<1, true>(args, smem, di, stream) : launch_fast<1, false>(args, smem, di, stream);
-    case 2: return s0n ? launch_fast<2, true>(args, smem, di, stream) : launch_fast<2, false>(args, smem, di, stream);
-    case 3: return s0n ? launch_fast<3, true>(args, smem, di, stream) : launch_fast<3, false>(args, smem, di, stream);
-    default: return s0n ? launch_fast<4, true>(args, smem, di, stream) : launch_fast<4, false>(args, smem, di, stream);
+    case 0: return launch_fast<0, false, 0, 1>(args, sm_count, smem_optin, stream);
+    case 1: return s0n ? launch_fast<1, true, 0, 1>(args, sm_count, smem_optin, stream) : launch_fast<1, false, 0, 1>(args, sm_count, smem_optin, stream);
+    case 2: return s0n ? launch_fast<2, true, 0, 1>(args, sm_count, smem_optin, stream) : launch_fast<2, false, 0, 1>(args, sm_count, smem_optin, stream);
+    case 3: return s0n ? launch_fast<3, true, 0, 1>(args, sm_count, smem_optin, stream) : launch_fast<3, false, 0, 1>(args, sm_count, smem_optin, stream);
+    default: return s0n ? launch_fast<4, true, 0, 1>(args, sm_count, smem_optin, stream) : launch_fast<4, false, 0, 1>(args, sm_count, smem_optin, stream);
     }
 }
 
@@ -342,15 +327,19 @@ int fhmc_sweep_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_sta
     const bool taylor = desc->n_coef > 0 || desc->n_term > 1;
     int G = lanes_per_point > 0 ? lanes_per_point : choose_lanes(states->n_states, di);
     cudaStream_t s = (cudaStream_t)stream;
-    // pure mu sweep with a precomputed hull, one lane per point: the one-pass kernel.  lanes_per_point = -1 forces
-    // the generic one-lane kernel (tests compare the two).
+    // One thread per state point + one exp pass (fhmc_fast.cuh): large pure-mu sweeps with a precomputed hull, and
+    // Taylor-extrapolated sweeps whose term pattern has an instantiation.  lanes_per_point = -1 forces the generic
+    // one-lane kernel (tests compare the two).  -1 from the launchers means "not applicable": fall through.
     if (lanes_per_point == -1) G = 1;
-    else if (G == 1 && !taylor && !args.blob_global && !desc->complete && desc->hull_len >= 2 && desc->n >= 3 && desc->hull_row > 1 &&
-             desc->hull_row + 2 <= desc->n_rows)
-    {
-        // + packed {lnPI, N, X...} copy the fast kernel builds (fhmc_fast.cuh): up to 6 doubles per bin
-        const size_t smem_fast = smem + (size_t)desc->n_pad * 8 * 6;
-        if (smem_fast <= (size_t)di->smem_optin) return launch_fast_dispatch(args, smem_fast, di, s);
+    else if (G == 1 && !desc->complete && desc->n >= 3) {
+        int rc = -1;
+        if (!taylor) {
+            if (desc->hull_len >= 2 && desc->hull_row > 1 && desc->hull_row + 2 <= desc->n_rows)
+                rc = launch_fast_mu(args, di->sm_count, di->smem_optin, s);
+        } else {
+            rc = launch_fast_taylor(args, di->sm_count, di->smem_optin, s);
+        }
+        if (rc >= 0) return rc;
     }
     switch (G) {
     case 1: return launch_sweep_t<1>(taylor, args, smem, di, s);

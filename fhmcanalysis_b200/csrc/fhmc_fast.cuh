@@ -1,83 +1,198 @@
-// fhmc_fast.cuh -- the headline path: pure chemical-potential sweeps (no Taylor terms), one state
-// point per thread, ONE pass over the bins.
+// fhmc_fast.cuh -- the throughput path for large sweeps: one state point per THREAD, one exp pass over the bins.
 //
-// What makes one pass possible:
-//  (1) the maximum of u_i = lnPI_i + s*N_i over i is attained on the upper concave envelope of the points
-//      (N_i, lnPI_i); the host precomputes that hull once per histogram (two extra blob rows: edge slopes and
-//      vertex indices) and each state point finds its vertex by a <= 11-step binary search, so the shift of the
-//      max-shifted sums is known before the bins are touched;
-//  (2) the phase boundaries are the windowed local minima (GH:329-330, 498-520); a sequential walk finds
-//      them on the fly, so the per-phase sums can be flushed the moment a minimum is confirmed.  Bins are
-//      handled four at a time: the sign bits of the four successive differences u_{k+1}-u_k (exact in sign)
-//      say whether the block can contain a strict 1-neighbour extremum at all; only then (rare) are the exact
-//      comparisons and the full +-smooth window test run, bin by bin.  Otherwise the four exp chains are
-//      independent and interleave, which is what hides the fp64 pipe latency.
-// Per bin: 2 fp64 ops for u (un-fused, bit-identical to GH:77), 1 difference, 10 for exp, 1 + NSEL accumulates.
+//   k_sweep_fast<NSEL, SEL0N, NC, NT>
+//     NC = 0   pure chemical-potential sweep (the headline metric).  The shift of the max-shifted sums is known before
+//              the bins are touched: max_i(lnPI_i + s*N_i) lies on the upper concave envelope of the points
+//              (N_i, lnPI_i), precomputed by the host (two blob rows: edge slopes, vertex indices); <= 11-step binary search.
+//     NC > 0   Taylor-extrapolated state points (beta and/or dmu_2 differ): lnPI' = lnPI + fl(s*N) + xi_0*N + sum_c xi_c*A_c
+//              (term 0 is the dB*mu_1*N term, terms 1..NC-1 own a coefficient row).  No hull exists for a shift that is
+//              nonlinear in the state variables, so a cheap max-only pre-pass (no exp) runs first.
+//     NT       rows per averaged quantity (1 = no extrapolation of the quantity, 2/3 = first-order terms in dB [, dD]).
+//
+// Shared memory holds ONE packed, interleaved copy of the rows this kernel walks, {lnPI_i, N_i, A_1(i).., X..(i)}
+// (PK doubles per bin, 16-byte aligned), so a bin costs one or a few LDS.128 with immediate offsets, and every lane
+// of a warp reads the same bin (broadcast).  The packed copy is built once per persistent CTA: each needed blob row is
+// staged by a 1-D TMA bulk copy (cp.async.bulk + mbarrier, SASS UBLKCP) into a one-row buffer and scattered.
+//
+// The walk: four bins per iteration; u_i = fl(lnPI_i + fl(s*N_i)) un-fused (bit-identical to GH:77) [+ fma terms in the
+// same order as the generic evaluator]; the sign bits of the four successive differences (exact in sign) tell whether a
+// strict 1-neighbour extremum can sit inside the block; only then (rare) the exact comparisons and the +-smooth window
+// test of argrelextrema (GH:329-330) run, bin by bin, and a confirmed minimum flushes the running per-phase sums (a
+// minimum bin opens the phase to its right, GH:498-520).  Otherwise four independent exp chains interleave, which is what
+// hides the fp64 latency.  Per bin (NC = 0): 2 fp64 ops for u, 1 difference, 10 for exp, 1 + NSEL accumulates.
+//
 // Everything that decides an index is afterwards validated exactly like the generic path (repair(), verify() on
-// fl(u - c)); any state point that is not a plain "maxima and minima alternate, phases tile [0,n)" case, that
-// overflows pmax or that contains a phase of negligible weight is re-run by the generic PointEval::run().
+// fl(u - c)); any state point that is not a plain "maxima and minima alternate, phases tile [0,n)" case, that overflows
+// pmax or that contains a phase of negligible weight is re-run by the generic evaluator (rows read from HBM/L2).
 #pragma once
 #include "fhmc_point.cuh"
 
+#define FHMC_FAST_QUEUE 2048  // deferred-fallback queue entries per CTA (drained when fewer than one tile is free)
+
 namespace fhmc {
 
-// out-of-line generic evaluation (own PointEval, so the hot loop's evaluator never has its address taken)
-__device__ __noinline__ void run_generic_point(const SweepArgs &a, const double *sm, const double *s_tab, int lane,
-                                               double mu1, long long sp)
+template <bool TAYLOR>
+__device__ __noinline__ void run_generic_point(const SweepArgs &a, const double *s_tab, int lane, double mu1, double beta,
+                                               double dmu, long long sp)
 {
-    PointEval<1, false> pe(a, sm, lane, s_tab);
-    pe.setup(mu1, a.d.beta_ref, a.d.dmu_ref);
+    PointEval<1, TAYLOR> pe(a, a.blob, lane, s_tab);  // own evaluator: the hot loop's one never has its address taken
+    pe.setup(mu1, beta, dmu);
     pe.run(sp);
 }
 
-template <int NSEL, bool SEL0N>
-__global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_mu_fast(const __grid_constant__ SweepArgs a)
+template <int NSEL, bool SEL0N, int NC, int NT>
+struct FastLayout {
+    static constexpr int NX = NSEL - (SEL0N ? 1 : 0);   // quantities that need their own rows
+    static constexpr int NCR = NC > 0 ? NC - 1 : 0;     // coefficient rows (term 0 re-uses the N row)
+    static constexpr int RAW = 2 + NCR + NX * NT;
+    static constexpr int PK = RAW + (RAW & 1);          // doubles per packed bin (even -> 16-byte aligned)
+    static constexpr int XOFF = 2 + NCR;
+};
+
+template <int NSEL, bool SEL0N, int NC, int NT>
+__global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constant__ SweepArgs a)
 {
+    using LY = FastLayout<NSEL, SEL0N, NC, NT>;
+    constexpr int NX = LY::NX, PK = LY::PK, XOFF = LY::XOFF;
+    constexpr bool TAYLOR = (NC > 0) || (NT > 1);
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *sm = reinterpret_cast<double *>(smem_raw);
-    const uint32_t blob_bytes = (uint32_t)a.d.n_rows * (uint32_t)a.d.n_pad * 8u;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + blob_bytes);
-    double *s_tab = reinterpret_cast<double *>(smem_raw + blob_bytes + 16);
+    const int n = a.d.n, last = n - 1, pmax = a.d.pmax, npad = a.d.n_pad;
+    double *pk = reinterpret_cast<double *>(smem_raw);
+    double *stage = pk + (size_t)npad * PK;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(stage + npad);
+    double *s_tab = reinterpret_cast<double *>(bar + 2);
     stage_exp_table(s_tab);
-    stage_blob(sm, a.blob, blob_bytes, bar);
-
-    PointEval<1, false> pe(a, sm, threadIdx.x & 31, s_tab);
-    const int n = a.d.n, last = n - 1, pmax = a.d.pmax;
-    const uint32_t row_bytes = (uint32_t)a.d.n_pad * 8u;
-    const uint32_t s_lnpi = smem_u32(sm), s_n = s_lnpi + row_bytes, tab = pe.tab;
-    // Interleave the rows this kernel walks into one packed array {lnPI_i, N_i, X_a(i), X_b(i), ...} (PK doubles per
-    // bin, 16-byte aligned) so that a bin costs one or two LDS.128 with immediate offsets instead of one LDS.64 and
-    // one address computation per row.  Built once per (persistent) CTA from the TMA-staged blob.
-    constexpr int NX = NSEL - (SEL0N ? 1 : 0);          // quantities that need their own row
-    constexpr int PK = 2 + NX + (NX & 1);               // doubles per packed bin (even)
-    double *pk = s_tab + 64;
-    for (int i = threadIdx.x; i < n; i += FHMC_CTA) {
-        pk[i * PK + 0] = sm[i];
-        pk[i * PK + 1] = sm[a.d.n_pad + i];
-#pragma unroll
-        for (int q = 0; q < NX; ++q) pk[i * PK + 2 + q] = sm[a.d.sel_row[q + (SEL0N ? 1 : 0)] * a.d.n_pad + i];
-        if (NX & 1) pk[i * PK + 2 + NX] = 0.0;
-    }
-    __syncthreads();
-    const uint32_t s_pk = smem_u32(pk);
-    const uint32_t s_slope = s_lnpi + (uint32_t)a.d.hull_row * row_bytes, s_hidx = s_slope + row_bytes;
-    const int H = a.d.hull_len;
-
-    const ExpRegs ec = load_exp_regs();   // reduction / polynomial constants pinned in registers for the hot loop
-    const long long S = a.st.n_states;
-    for (long long sp = (long long)blockIdx.x * FHMC_CTA + threadIdx.x; sp < S; sp += (long long)gridDim.x * FHMC_CTA) {
-        const double mu1 = a.st.mu1[(sp / a.st.mu1_div) % a.st.n_mu1];
-        pe.setup(mu1, a.d.beta_ref, a.d.dmu_ref);
-        const double s = pe.s;
-        // ---- shift: hull vertex maximising lnPI + s*N ------------------------------------------
-        int lo = 0, hi = H - 1;
-        const double neg_s = -s;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (lds_f64(s_slope + 8u * mid) > neg_s) lo = mid + 1; else hi = mid;
+    // ---- build the packed copy: TMA-stage one blob row at a time, scatter it to its slot ----------------
+    {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        uint32_t parity = 0;
+        for (int slot = 0; slot < LY::RAW; ++slot) {
+            int row;
+            if (slot < 2) row = slot;
+            else if (slot < XOFF) row = a.d.coef_row[slot - 1];                      // terms 1..NC-1
+            else row = a.d.sel_row[(slot - XOFF) / NT + (SEL0N ? 1 : 0)] + (slot - XOFF) % NT;
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(bar, (uint32_t)npad * 8u);
+                tma_bulk_g2s(stage, a.blob + (size_t)row * npad, (uint32_t)npad * 8u, bar);
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            for (int i = threadIdx.x; i < n; i += FHMC_CTA) pk[(size_t)i * PK + slot] = stage[i];
+            __syncthreads();
         }
-        const int i_max = (int)lds_f64(s_hidx + 8u * lo);
-        const int Mq = shift_for_max(pe.U(i_max));
+        if (LY::RAW & 1)
+            for (int i = threadIdx.x; i < n; i += FHMC_CTA) pk[(size_t)i * PK + LY::RAW] = 0.0;
+        if (NC == 0) {  // the one-row staging buffer is free now: keep the hull edge slopes in it for the binary search
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(bar, (uint32_t)npad * 8u);
+                tma_bulk_g2s(stage, a.blob + (size_t)a.d.hull_row * npad, (uint32_t)npad * 8u, bar);
+            }
+            mbar_wait(bar, parity);
+        }
+        __syncthreads();
+    }
+    const uint32_t s_slope = smem_u32(stage);
+    const uint32_t s_pk = smem_u32(pk);
+    PointEval<1, TAYLOR> pe(a, a.blob, threadIdx.x & 31, s_tab);   // rare paths (window test, repair) read HBM/L2
+    const uint32_t tab = pe.tab;
+    const double *g_slope = a.blob + (size_t)a.d.hull_row * npad, *g_hidx = g_slope + npad;
+    const int H = a.d.hull_len;
+    const ExpRegs ec = load_exp_regs();   // reduction / polynomial constants pinned in registers for the hot loop
+
+    // Irregular state points are not re-run on the spot (one such lane would stall its whole warp for a full generic
+    // evaluation): they are queued in shared memory and drained by all threads of the CTA, one queued point per thread.
+    // The queue is inspected (one CTA barrier) only every fourth tile.
+    long long *queue = reinterpret_cast<long long *>(s_tab + 64);
+    int *q_count = reinterpret_cast<int *>(queue + FHMC_FAST_QUEUE);
+    if (threadIdx.x == 0) *q_count = 0;
+    __syncthreads();
+    auto drain = [&]() {
+        const int cnt = *q_count;
+        for (int k = threadIdx.x; k < cnt; k += FHMC_CTA) {
+            const long long qs = queue[k];
+            const double qm = a.st.mu1[(qs / a.st.mu1_div) % a.st.n_mu1];
+            const double qb = (TAYLOR && a.st.beta) ? a.st.beta[(qs / a.st.beta_div) % a.st.n_beta] : a.d.beta_ref;
+            const double qd = (TAYLOR && a.st.dmu) ? a.st.dmu[(qs / a.st.dmu_div) % a.st.n_dmu] : a.d.dmu_ref;
+            run_generic_point<TAYLOR>(a, s_tab, threadIdx.x & 31, qm, qb, qd, qs);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *q_count = 0;
+        __syncthreads();
+    };
+    int tile_no = 0;
+
+    const long long S = a.st.n_states;
+    for (long long base = (long long)blockIdx.x * FHMC_CTA; base < S; base += (long long)gridDim.x * FHMC_CTA) {
+      const long long sp = base + threadIdx.x;
+      if (sp < S) {
+        const double mu1 = a.st.mu1[(sp / a.st.mu1_div) % a.st.n_mu1];
+        const double beta = (TAYLOR && a.st.beta) ? a.st.beta[(sp / a.st.beta_div) % a.st.n_beta] : a.d.beta_ref;
+        const double dmu = (TAYLOR && a.st.dmu) ? a.st.dmu[(sp / a.st.dmu_div) % a.st.n_dmu] : a.d.dmu_ref;
+        pe.setup(mu1, beta, dmu);
+        const double s = pe.s;
+        double xi[NC > 0 ? NC : 1], ts[NT];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) xi[c] = pe.xi[c];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) ts[t] = TAYLOR ? pe.ts[t] : 1.0;
+
+        struct Bin {
+            double u, N, x[NX > 0 ? NX : 1];
+        };
+        // u in the generic evaluator's order: fl(lnPI + fl(s*N)), then fma per Taylor term
+        auto load_u = [&](int i, double &Ni) {
+            const uint32_t addr = s_pk + (uint32_t)i * (uint32_t)(PK * 8);
+            double l;
+            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(l), "=d"(Ni) : "r"(addr));
+            double u = __dadd_rn(l, __dmul_rn(s, Ni));
+            if (NC > 0) {
+                u = fma(xi[0], Ni, u);
+#pragma unroll
+                for (int c = 1; c < NC; c += 2) {
+                    double a0, a1;
+                    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a0), "=d"(a1) : "r"(addr + 8u * (1 + c)));
+                    u = fma(xi[c], a0, u);
+                    if (c + 1 < NC) u = fma(xi[c + 1], a1, u);
+                }
+            }
+            return u;
+        };
+        auto load_bin = [&](int i, Bin &b) {
+            b.u = load_u(i, b.N);
+            const uint32_t addr = s_pk + (uint32_t)i * (uint32_t)(PK * 8) + 8u * XOFF;
+#pragma unroll
+            for (int q = 0; q < NX; ++q) {
+                double x = lds_f64(addr + 8u * (q * NT));
+#pragma unroll
+                for (int t = 1; t < NT; ++t) x = fma(ts[t], lds_f64(addr + 8u * (q * NT + t)), x);
+                b.x[q] = x;
+            }
+        };
+
+        // ---- shift -------------------------------------------------------------------------------------
+        int Mq;
+        if (NC == 0) {   // hull vertex maximising lnPI + s*N
+            int lo = 0, hi = H - 1;
+            const double neg_s = -s;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (lds_f64(s_slope + 8u * mid) > neg_s) lo = mid + 1; else hi = mid;
+            }
+            double Nm;
+            Mq = shift_for_max(load_u((int)g_hidx[lo], Nm));
+        } else {         // max-only pre-pass
+            double m0 = -CUDART_INF, m1 = -CUDART_INF, m2 = -CUDART_INF, m3 = -CUDART_INF, Nd;
+            int i = 0;
+            for (; i + 3 < n; i += 4) {
+                m0 = fmax(m0, load_u(i, Nd));
+                m1 = fmax(m1, load_u(i + 1, Nd));
+                m2 = fmax(m2, load_u(i + 2, Nd));
+                m3 = fmax(m3, load_u(i + 3, Nd));
+            }
+            for (; i < n; ++i) m0 = fmax(m0, load_u(i, Nd));
+            Mq = shift_for_max(fmax(fmax(m0, m1), fmax(m2, m3)));
+        }
 
         int *maxl = a.out.max_idx + sp * pmax;
         int *minl = a.out.min_idx + sp * (pmax + 1);
@@ -88,22 +203,6 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_mu_fast(const __grid_cons
 #pragma unroll
         for (int q = 0; q < NSEL; ++q) A[q] = 0.0;
 
-        struct Bin {
-            double u, N, x[NX > 0 ? NX : 1];
-        };
-        auto load_bin = [&](int i, Bin &b) {
-            const uint32_t addr = s_pk + (uint32_t)i * (uint32_t)(PK * 8);
-            double l;
-            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(l), "=d"(b.N) : "r"(addr));
-            b.u = __dadd_rn(l, __dmul_rn(s, b.N));   // un-fused, GH:77
-#pragma unroll
-            for (int q = 0; q < NX; q += 2) {
-                double x0, x1;
-                asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(addr + 16u + 8u * q));
-                b.x[q] = x0;
-                if (q + 1 < NX) b.x[q + 1] = x1;
-            }
-        };
         auto accumulate = [&](const Bin &b) {
             const double e = exp_scaled_r(b.u, Mq, tab, ec);
             Sacc += e;
@@ -204,7 +303,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_mu_fast(const __grid_cons
                 if (a.d.compare_raw || !pe.verify(maxl, minl, c)) {
                     const double xM = __dsub_rn(pe.U(maxl[nM - 1]), c), xl = __dsub_rn(pe.U(last), c);
                     if (!(__dsub_rn(xM, xl) < a.d.cutoff)) flags |= FHMC_ST_SAFE;
-                    a.out.status[sp] = flags;
+                    a.out.status[sp] = flags | FHMC_ST_FAST;
                     a.out.nphase[sp] = nM;
                     a.out.nmin[sp] = nm;
                     a.out.lnnorm[sp] = c;
@@ -212,8 +311,50 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_mu_fast(const __grid_cons
                 }
             }
         }
-        if (!done) run_generic_point(a, sm, s_tab, threadIdx.x & 31, mu1, sp);  // anything unusual: the generic evaluator redoes this state point
+        if (!done) queue[atomicAdd(q_count, 1)] = sp;  // anything unusual: defer to the generic evaluator
+      }
+      if ((++tile_no & 3) == 0) {
+          __syncthreads();
+          if (*q_count > FHMC_FAST_QUEUE - 4 * FHMC_CTA) drain();   // uniform across the CTA (read after the barrier)
+      }
     }
+    __syncthreads();
+    drain();
 }
+
+// shared memory the fast kernel needs for this histogram
+template <int NSEL, bool SEL0N, int NC, int NT>
+static size_t fast_smem_bytes(int n_pad)
+{
+    return (size_t)n_pad * 8 * (FastLayout<NSEL, SEL0N, NC, NT>::PK + 1) + 16 + 512 + FHMC_FAST_QUEUE * 8 + 64;
+}
+
+}  // namespace fhmc
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: launch helpers shared by fhmc_b200.cu (NC = 0 instantiations) and fhmc_fast_taylor.cu (NC > 0)
+// ---------------------------------------------------------------------------------------------------------
+namespace fhmc {
+
+// returns 0 ok, 1 error, -1 "does not fit / not applicable" (caller falls back to the generic kernel)
+template <int NSEL, bool SEL0N, int NC, int NT>
+static int launch_fast(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream)
+{
+    const size_t smem = fast_smem_bytes<NSEL, SEL0N, NC, NT>(args.d.n_pad);
+    if (smem > (size_t)smem_optin) return -1;
+    auto kern = k_sweep_fast<NSEL, SEL0N, NC, NT>;
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return 1;
+    int occ = 0;
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FHMC_CTA, smem), "occupancy query")) return 1;
+    if (occ < 1) return -1;
+    const long long ntiles = (args.st.n_states + FHMC_CTA - 1) / FHMC_CTA;
+    long long grid = (long long)sm_count * occ;
+    if (grid > ntiles) grid = ntiles;
+    kern<<<(unsigned)grid, FHMC_CTA, smem, stream>>>(args);
+    return check_cuda(cudaGetLastError(), "k_sweep_fast launch");
+}
+
+// Taylor-extrapolated sweeps (fhmc_fast_taylor.cu)
+int launch_fast_taylor(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream);
 
 }  // namespace fhmc

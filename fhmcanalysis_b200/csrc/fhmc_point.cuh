@@ -221,7 +221,9 @@ struct PointEval {
             else if (lM > lm) { if (nm >= pmax + 1) return FHMC_E_CAPACITY; minl[nm++] = last; }
             else return FHMC_E_BAD_BACK;
         } else {
-            if (!use_c) return FHMC_NEED_SLOW;
+            // exactly one interior extremum of one kind needs no value of the normalised array (GH:364-366, 379-381);
+            // gap filling and the "all tied with the max/min" branch do
+            if (!use_c && !((cntM == 1 && cntm == 0) || (cntM == 0 && cntm == 1))) return FHMC_NEED_SLOW;
             if (cntM > 0) {  // GH:352-366
                 compact(maxl, cntM);
                 nM = cntM;

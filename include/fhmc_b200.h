@@ -48,6 +48,7 @@ enum fhmc_monomial {
 #define FHMC_ST_GAP_FILL    0x200u  /* GH:355-363 / 370-378 branch taken (unique gap extremum)    */
 #define FHMC_ST_SLOW_PATH   0x400u  /* extrema had to be re-evaluated on the normalised array     */
 #define FHMC_ST_RESCUED     0x800u  /* a phase with negligible weight was re-summed about its own max */
+#define FHMC_ST_FAST        0x1000u /* produced by the one-thread-per-point, one-exp-pass kernel (diagnostic)     */
 enum fhmc_status_code {
     FHMC_OK = 0,
     FHMC_E_TOO_SHORT = 1,       /* GH:326-327                                                    */

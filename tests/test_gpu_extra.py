@@ -140,3 +140,44 @@ def test_histogram_larger_than_shared_memory(oracle):
             assert np.allclose(h["avg"][k, :P, 0], r["avg"][:, 0], rtol=1e-10, atol=0)
     res = dh.find_phase_eq(np.array([0.0]), lnz_tol=1e-10).host()
     assert res["code"][0] == 0 and abs(res["dfe"][0]) < 1e-9
+
+
+def _agree(a, b, tag):
+    for k in ("code", "nphase", "nmin", "safe"):
+        assert np.array_equal(a[k], b[k]), (tag, k)
+    ok = a["code"] == 0
+    P = a["nphase"]
+    for k in ("max_idx", "min_idx"):
+        pm = np.arange(a[k].shape[1])[None, :] < (P + (1 if k == "min_idx" else 0))[:, None]
+        assert np.array_equal(a[k][pm & ok[:, None]], b[k][pm & ok[:, None]]), (tag, k)
+    mask = (np.arange(a["fe"].shape[1])[None, :] < P[:, None]) & ok[:, None]
+    assert np.allclose(a["fe"][mask], b["fe"][mask], rtol=1e-10, atol=1e-11), tag
+    if a["avg"] is not None:
+        assert np.allclose(a["avg"][mask], b["avg"][mask], rtol=1e-10, atol=1e-12), tag
+    assert np.allclose(a["lnnorm"], b["lnnorm"], rtol=1e-13, atol=1e-12), tag
+
+
+def test_fast_taylor_kernel_agrees_with_generic(golden, golden_meta):
+    """One-thread-per-point Taylor kernel (NC > 0 instantiations) vs the generic evaluator on (beta x dmu) grids and on a
+    1-species beta sweep of the real square-well data."""
+    from fhmcanalysis_b200.moments.histogram.one_dim.ntot.gc_hist import histogram
+    meta = golden_meta["c3"]
+    h = histogram.from_arrays(golden["c3/lnpi"], golden["c3/mom"], meta["beta_ref"], meta["mu_ref"], meta["smooth"])
+    h.reweight(meta["mu1"])
+    betas, dmus = np.linspace(0.96, 1.04, 48), np.linspace(0.25, 0.75, 40)
+    for order, moments in ((2, ()), (1, ("N1", "N2", "U")), (1, ())):
+        dh = h.device_histogram(beta=betas, dmu=dmus, order=order, moments=moments)
+        st = dh.make_states(np.array([meta["mu1"]]), betas, dmus, grid=True)
+        a = dh.sweep(None, states=st, pmax=8, lanes=1).host()
+        b = dh.sweep(None, states=st, pmax=8, lanes=-1).host()
+        assert np.mean(a["code"] == 0) > 0.9
+        _agree(a, b, ("c3", order, moments))
+    sw = golden_meta["sw"]
+    h1 = histogram.from_arrays(golden["sw/lnpi"], golden["sw/mom"], sw["beta_ref"], sw["mu_ref"], sw["smooth"])
+    b1 = sw["beta_ref"] * np.linspace(0.99, 1.01, 300)
+    for order, moments in ((1, ("N", "N2", "U")), (2, ())):
+        dh = h1.device_histogram(beta=b1, order=order, moments=moments)
+        mu = np.full(300, -4.02)
+        a = dh.sweep(mu, b1, pmax=4, lanes=1).host()
+        b = dh.sweep(mu, b1, pmax=4, lanes=-1).host()
+        _agree(a, b, ("sw", order, moments))
