@@ -8,6 +8,8 @@
 //     d'(mu) = beta * (<N>_j - <N>_i)          (averages of the N row, free from K2)
 // so a bracketed Newton iteration converges in a handful of evaluations; each evaluation is the
 // full fused state-point pass of fhmc_point.cuh (reweight + Taylor + phase split + thermo).
+#include <stdlib.h>
+
 #include "fhmc_point.cuh"
 
 namespace fhmc {
@@ -209,7 +211,11 @@ extern "C" int fhmc_find_phase_eq_1d(const fhmc_hist_desc *desc, const double *b
     const long long T = states->n_states;
     cudaStream_t s = (cudaStream_t)stream;
     // a solve is ~10 dependent state-point passes: prefer wide groups unless there are very many solves
-    if (T * 32 <= (long long)caps.sm_count * 2048 * 4)
+    const char *force = getenv("FHMC_SOLVER_LANES");  // tuning/debug override
+    const int forced = force ? atoi(force) : 0;
+    if (forced == 1) return taylor ? launch_solver<1, true>(sa, smem, caps, s) : launch_solver<1, false>(sa, smem, caps, s);
+    if (forced == 4) return taylor ? launch_solver<4, true>(sa, smem, caps, s) : launch_solver<4, false>(sa, smem, caps, s);
+    if (forced == 32 || T * 32 <= (long long)caps.sm_count * 2048 * 4)
         return taylor ? launch_solver<32, true>(sa, smem, caps, s) : launch_solver<32, false>(sa, smem, caps, s);
     if (T * 4 <= (long long)caps.sm_count * 2048 * 4)
         return taylor ? launch_solver<4, true>(sa, smem, caps, s) : launch_solver<4, false>(sa, smem, caps, s);
