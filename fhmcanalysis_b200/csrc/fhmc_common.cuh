@@ -109,11 +109,22 @@ __device__ __forceinline__ double exp_scaled_r(double u, int Mq, uint32_t tab_ad
     const double kd = kd0 - FHMC_EXP_MAGIC;
     double r = fma(kd, c.nhi, u);
     r = fma(kd, c.nlo, r);
+#ifdef FHMC_EXP_ESTRIN
+    // Estrin evaluation: 2 more fp64 ops than Horner but a dependency chain that is 2 levels shorter
+    const double r2 = r * r;
+    const double pa = fma(c.c3, r, c.c2);
+    const double pb = fma(c.c5, r, c.c4);
+    const double pq = r + 1.0;
+    const double r4 = r2 * r2;
+    double p = fma(r2, pa, pq);
+    p = fma(r4, pb, p);
+#else
     double p = fma(r, c.c5, c.c4);
     p = fma(p, r, c.c3);
     p = fma(p, r, c.c2);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
+#endif
     const double T = lds_f64(tab_addr + ((k & 63) << 3));
     const double v = T * p;
     const int q = max((k >> 6) - Mq, -1022);
