@@ -265,6 +265,10 @@ static int launch_sweep_t(bool taylor, const SweepArgs &args, size_t smem, const
 // one-pass mu-sweep kernel (fhmc_fast.cuh, NC = 0): one thread per state point
 static int launch_fast_mu(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream)
 {
+    if (args.d.mu_recurrence) {
+        const int rc = launch_fast_mu_rec(args, sm_count, smem_optin, stream);   // fhmc_fast_rec.cu
+        if (rc >= 0) return rc;
+    }
     const bool s0n = args.d.n_sel > 0 && args.d.sel_row[0] == 1;
     switch (args.d.n_sel) {
     case 0: return launch_fast<0, false, 0, 1>(args, sm_count, smem_optin, stream);

@@ -40,19 +40,22 @@ __device__ __noinline__ void run_generic_point(const SweepArgs &a, const double 
     pe.run(sp);
 }
 
-template <int NSEL, bool SEL0N, int NC, int NT>
+template <int NSEL, bool SEL0N, int NC, int NT, bool REC = false>
 struct FastLayout {
     static constexpr int NX = NSEL - (SEL0N ? 1 : 0);   // quantities that need their own rows
     static constexpr int NCR = NC > 0 ? NC - 1 : 0;     // coefficient rows (term 0 re-uses the N row)
-    static constexpr int RAW = 2 + NCR + NX * NT;
+    static constexpr int ROWS = 2 + NCR + NX * NT;      // slots copied from blob rows
+    static constexpr int RAW = ROWS + (REC ? 1 : 0);    // + the 4-bin ratio exp(lnPI_i - lnPI_{i-4}) of the recurrence
     static constexpr int PK = RAW + (RAW & 1);          // doubles per packed bin (even -> 16-byte aligned)
     static constexpr int XOFF = 2 + NCR;
+    static constexpr int DOFF = ROWS;
 };
 
-template <int NSEL, bool SEL0N, int NC, int NT>
+template <int NSEL, bool SEL0N, int NC, int NT, bool REC = false>
 __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constant__ SweepArgs a)
 {
-    using LY = FastLayout<NSEL, SEL0N, NC, NT>;
+    static_assert(!REC || NC == 0, "the exp recurrence only exists for pure mu sweeps");
+    using LY = FastLayout<NSEL, SEL0N, NC, NT, REC>;
     constexpr int NX = LY::NX, PK = LY::PK, XOFF = LY::XOFF;
     constexpr bool TAYLOR = (NC > 0) || (NT > 1);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
         if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();
         uint32_t parity = 0;
-        for (int slot = 0; slot < LY::RAW; ++slot) {
+        for (int slot = 0; slot < LY::ROWS; ++slot) {
             int row;
             if (slot < 2) row = slot;
             else if (slot < XOFF) row = a.d.coef_row[slot - 1];                      // terms 1..NC-1
@@ -81,6 +84,9 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
             for (int i = threadIdx.x; i < n; i += FHMC_CTA) pk[(size_t)i * PK + slot] = stage[i];
             __syncthreads();
         }
+        if (REC)   // G_i = exp(lnPI_i - lnPI_{i-4}): e_i = e_{i-4} * exp(4 s dN) * G_i along each of the four bin chains
+            for (int i = threadIdx.x; i < n; i += FHMC_CTA)
+                pk[(size_t)i * PK + LY::DOFF] = (i >= 4) ? exp(pk[(size_t)i * PK] - pk[(size_t)(i - 4) * PK]) : 1.0;
         if (LY::RAW & 1)
             for (int i = threadIdx.x; i < n; i += FHMC_CTA) pk[(size_t)i * PK + LY::RAW] = 0.0;
         if (NC == 0) {  // the one-row staging buffer is free now: keep the hull edge slopes in it for the binary search
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
         for (int t = 0; t < NT; ++t) ts[t] = TAYLOR ? pe.ts[t] : 1.0;
 
         struct Bin {
-            double u, N, x[NX > 0 ? NX : 1];
+            double u, N, x[NX > 0 ? NX : 1], g;
         };
         // u in the generic evaluator's order: fl(lnPI + fl(s*N)), then fma per Taylor term
         auto load_u = [&](int i, double &Ni) {
@@ -168,6 +174,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
                 for (int t = 1; t < NT; ++t) x = fma(ts[t], lds_f64(addr + 8u * (q * NT + t)), x);
                 b.x[q] = x;
             }
+            if (REC) b.g = lds_f64(s_pk + (uint32_t)i * (uint32_t)(PK * 8) + 8u * LY::DOFF);
         };
 
         // ---- shift -------------------------------------------------------------------------------------
@@ -203,12 +210,16 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
 #pragma unroll
         for (int q = 0; q < NSEL; ++q) A[q] = 0.0;
 
-        auto accumulate = [&](const Bin &b) {
-            const double e = exp_scaled_r(b.u, Mq, tab, ec);
+        auto add_term = [&](const Bin &b, double e) {
             Sacc += e;
             if (SEL0N) A[0] = fma(e, b.N, A[0]);
 #pragma unroll
             for (int q = 0; q < NX; ++q) A[q + (SEL0N ? 1 : 0)] = fma(e, b.x[q], A[q + (SEL0N ? 1 : 0)]);
+        };
+        auto accumulate = [&](const Bin &b) {
+            const double e = exp_scaled_r(b.u, Mq, tab, ec);
+            add_term(b, e);
+            return e;
         };
         Bin b0;
         load_bin(0, b0);
@@ -241,10 +252,20 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
                     flush();  // a minimum bin opens the phase to its right (GH:498-520)
                 }
             }
-            accumulate(c);
+            return accumulate(c);
         };
+        // exp recurrence (REC): four chains, one per bin position in the block; e_i = (e_{i-4} * r4) * G_i.  Chains are
+        // re-anchored with true exps every 16 blocks and in every block that takes the slow (exact-test) path, which
+        // bounds the accumulated rounding at ~3e-15 relative.
+        double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0, r4 = 1.0;
+        int since_anchor = 16;
+        if (REC) {
+            const double t4 = 4.0 * s * (lds_f64(s_pk + (uint32_t)(PK * 8) + 8u) - lds_f64(s_pk + 8u));   // 4 s dN
+            if (!(fabs(t4) < 200.0)) bad = true;   // extreme tilt: leave it to the generic evaluator
+            r4 = exp(t4);
+        }
 
-        if (n >= 3) {
+        if (n >= 3 && !bad) {
             accumulate(b0);
             Bin c;
             load_bin(1, c);
@@ -262,16 +283,28 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
                 const int flip = (__double2hiint(dc) ^ __double2hiint(d1)) | (__double2hiint(d1) ^ __double2hiint(d2)) |
                                  (__double2hiint(d2) ^ __double2hiint(d3)) | (__double2hiint(d3) ^ __double2hiint(d4));
                 if (flip < 0) {   // some pair of successive differences changes sign: look closely
-                    slow_bin(i, xm, c, b1.u);
-                    slow_bin(i + 1, c.u, b1, b2.u);
-                    slow_bin(i + 2, b1.u, b2, b3.u);
-                    slow_bin(i + 3, b2.u, b3, b4.u);
+                    e0 = slow_bin(i, xm, c, b1.u);
+                    e1 = slow_bin(i + 1, c.u, b1, b2.u);
+                    e2 = slow_bin(i + 2, b1.u, b2, b3.u);
+                    e3 = slow_bin(i + 3, b2.u, b3, b4.u);
+                    since_anchor = 0;
+                } else if (!REC || since_anchor >= 16) {
+                    e0 = accumulate(c);
+                    e1 = accumulate(b1);
+                    e2 = accumulate(b2);
+                    e3 = accumulate(b3);
+                    since_anchor = 0;
                 } else {
-                    accumulate(c);
-                    accumulate(b1);
-                    accumulate(b2);
-                    accumulate(b3);
+                    e0 = (e0 * r4) * c.g;
+                    e1 = (e1 * r4) * b1.g;
+                    e2 = (e2 * r4) * b2.g;
+                    e3 = (e3 * r4) * b3.g;
+                    add_term(c, e0);
+                    add_term(b1, e1);
+                    add_term(b2, e2);
+                    add_term(b3, e3);
                 }
+                ++since_anchor;
                 xm = b3.u;
                 c = b4;
                 dc = d4;
@@ -323,10 +356,10 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
 }
 
 // shared memory the fast kernel needs for this histogram
-template <int NSEL, bool SEL0N, int NC, int NT>
+template <int NSEL, bool SEL0N, int NC, int NT, bool REC = false>
 static size_t fast_smem_bytes(int n_pad)
 {
-    return (size_t)n_pad * 8 * (FastLayout<NSEL, SEL0N, NC, NT>::PK + 1) + 16 + 512 + FHMC_FAST_QUEUE * 8 + 64;
+    return (size_t)n_pad * 8 * (FastLayout<NSEL, SEL0N, NC, NT, REC>::PK + 1) + 16 + 512 + FHMC_FAST_QUEUE * 8 + 64;
 }
 
 }  // namespace fhmc
@@ -337,12 +370,12 @@ static size_t fast_smem_bytes(int n_pad)
 namespace fhmc {
 
 // returns 0 ok, 1 error, -1 "does not fit / not applicable" (caller falls back to the generic kernel)
-template <int NSEL, bool SEL0N, int NC, int NT>
+template <int NSEL, bool SEL0N, int NC, int NT, bool REC = false>
 static int launch_fast(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream)
 {
-    const size_t smem = fast_smem_bytes<NSEL, SEL0N, NC, NT>(args.d.n_pad);
+    const size_t smem = fast_smem_bytes<NSEL, SEL0N, NC, NT, REC>(args.d.n_pad);
     if (smem > (size_t)smem_optin) return -1;
-    auto kern = k_sweep_fast<NSEL, SEL0N, NC, NT>;
+    auto kern = k_sweep_fast<NSEL, SEL0N, NC, NT, REC>;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return 1;
     int occ = 0;
     if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FHMC_CTA, smem), "occupancy query")) return 1;
@@ -356,5 +389,7 @@ static int launch_fast(const SweepArgs &args, int sm_count, int smem_optin, cuda
 
 // Taylor-extrapolated sweeps (fhmc_fast_taylor.cu)
 int launch_fast_taylor(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream);
+// pure mu sweeps with the exp recurrence (fhmc_fast_rec.cu)
+int launch_fast_mu_rec(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream);
 
 }  // namespace fhmc

@@ -183,6 +183,7 @@ class DeviceHistogram(object):
             rows.extend(np.ascontiguousarray(r, dtype=np.float64) for r in terms)
         hull_row, hull_len = 0, 0          # the hull rows are added lazily (ensure_hull) by large mu sweeps only
         self._hull_possible = not coef
+        self.use_recurrence = True   # set False before the first large sweep to force one true exp per bin
         blob = np.zeros((len(rows), n_pad), dtype=np.float64)
         for i, r in enumerate(rows):
             if r.shape != (n,):
@@ -225,6 +226,11 @@ class DeviceHistogram(object):
         extra[0, :len(slopes)] = slopes
         extra[1, :len(verts)] = verts
         self.desc.hull_row, self.desc.hull_len = self.n_rows, len(verts)
+        # exp recurrence of the one-pass kernel: uniform N spacing and moderate 4-bin steps of lnPI
+        Nrow, lrow = self.blob_host[1, :self.n], self.blob_host[0, :self.n]
+        dN = np.diff(Nrow)
+        if self.n > 8 and np.all(dN == dN[0]) and dN[0] > 0 and np.max(np.abs(lrow[4:] - lrow[:-4])) < 300.0 and self.use_recurrence:
+            self.desc.mu_recurrence = 1
         self.blob_host = np.ascontiguousarray(np.vstack([self.blob_host, extra]))
         self.n_rows += 2
         self.desc.n_rows = self.n_rows

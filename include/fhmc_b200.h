@@ -97,6 +97,11 @@ typedef struct fhmc_hist_desc {
      * hull_row+1 the hull_len vertex bin indices (as fp64).  hull_len == 0: not provided.          */
     int hull_row;
     int hull_len;
+    /* Caller's promise that row 1 (N) is uniformly spaced and |lnPI_{i+4} - lnPI_i| < 300 for all i: pure mu sweeps may
+     * then advance exp(lnPI_i + s N_i - shift) along four interleaved bin chains by two multiplications per bin
+     * (e_i = e_{i-4} * exp(4 s dN) * exp(lnPI_i - lnPI_{i-4})), re-anchored with a true exp every 64 bins.          */
+    int mu_recurrence;
+    int reserved;
 } fhmc_hist_desc;
 
 /*

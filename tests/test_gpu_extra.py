@@ -80,27 +80,33 @@ def test_reweight_2d_vs_oracle(oracle, n1, n2, nprop):
 
 
 def test_fast_and_generic_kernels_agree():
-    """The one-pass mu-sweep kernel and the generic two-pass kernel must give identical integers and fp64 to 1e-10."""
+    """The one-pass mu-sweep kernel (with and without the exp recurrence) and the generic two-pass kernel must give
+    identical integers and fp64 to 1e-10."""
     from fhmcanalysis_b200 import engine, synth
     for n, smooth, noise in ((1001, 10, 1e-3), (573, 3, 5e-2), (2001, 30, 0.0)):
         lnpi = synth.two_peak_lnpi(n, noise=noise, scale=n / 1001.0)
         N = np.arange(n, dtype=float)
-        dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=smooth, sel=["N", N * N])
-        dh.ensure_hull()
-        mus = np.linspace(-0.05, 0.05, 5000)
-        a = dh.sweep_auto(mus, pmax=4, lanes=1).host()      # one-pass fast kernel
-        b = dh.sweep_auto(mus, pmax=a["fe"].shape[1], lanes=-1).host()     # generic one-lane kernel
-        for k in ("code", "nphase", "nmin", "safe"):
-            assert np.array_equal(a[k], b[k]), (n, k)
-        ok = a["code"] == 0                                   # records of raised state points carry no thermo
-        for k in ("bounds", "max_idx", "min_idx"):
-            pm = np.arange(a[k].shape[1])[None, :] < (a["nphase"] + (1 if k == "min_idx" else 0))[:, None]
-            m2 = (pm & ok[:, None]) if a[k].ndim == 2 else (pm & ok[:, None])[:, :, None].repeat(2, 2)
-            assert np.array_equal(a[k][m2], b[k][m2]), (n, k)
-        mask = (np.arange(a["fe"].shape[1])[None, :] < a["nphase"][:, None]) & ok[:, None]
-        assert np.allclose(a["fe"][mask], b["fe"][mask], rtol=1e-10, atol=1e-11)
-        assert np.allclose(a["avg"][mask], b["avg"][mask], rtol=1e-10, atol=0)
-        assert np.allclose(a["lnnorm"], b["lnnorm"], rtol=1e-13, atol=1e-13)
+        for rec in (True, False):
+            dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=smooth, sel=["N", N * N])
+            dh.use_recurrence = rec
+            dh.ensure_hull()
+            assert dh.desc.mu_recurrence == int(rec)
+            mus = np.linspace(-0.05, 0.05, 5000)
+            a = dh.sweep_auto(mus, pmax=4, lanes=1).host()      # one-pass fast kernel
+            if n == 1001:
+                assert np.mean((a["status"] & 0x1000) != 0) > 0.99   # really produced by the fast kernel
+            b = dh.sweep_auto(mus, pmax=a["fe"].shape[1], lanes=-1).host()     # generic one-lane kernel
+            for k in ("code", "nphase", "nmin", "safe"):
+                assert np.array_equal(a[k], b[k]), (n, k)
+            ok = a["code"] == 0                                   # records of raised state points carry no thermo
+            for k in ("bounds", "max_idx", "min_idx"):
+                pm = np.arange(a[k].shape[1])[None, :] < (a["nphase"] + (1 if k == "min_idx" else 0))[:, None]
+                m2 = (pm & ok[:, None]) if a[k].ndim == 2 else (pm & ok[:, None])[:, :, None].repeat(2, 2)
+                assert np.array_equal(a[k][m2], b[k][m2]), (n, k)
+            mask = (np.arange(a["fe"].shape[1])[None, :] < a["nphase"][:, None]) & ok[:, None]
+            assert np.allclose(a["fe"][mask], b["fe"][mask], rtol=1e-10, atol=1e-11)
+            assert np.allclose(a["avg"][mask], b["avg"][mask], rtol=1e-10, atol=0)
+            assert np.allclose(a["lnnorm"], b["lnnorm"], rtol=1e-13, atol=1e-13)
 
 
 def test_sharded_sweep_single_process(golden, golden_meta):
