@@ -39,6 +39,7 @@ MU_LO, MU_HI = -0.03, 0.03
 PMAX = 4
 METRIC = "reweighted state points/sec (lnPI+thermo) at N_max=1000"
 UNIT = "state points/s"
+E2E_FIELDS = ("status", "nphase", "bounds", "fe", "avg")   # what the e2e arm copies back to the host every step
 
 
 def workload_arrays():
@@ -246,13 +247,15 @@ def run_gpu_arm(args, rank, world, local_rank):
     value = world * S / (ms_per_step * 1e-3)
 
     # ---- e2e through the public batched API with host buffers ------------------------------------
-    host_out = {k: torch.empty_like(getattr(out, k), device="cpu").pin_memory() for k in out.FIELDS if getattr(out, k) is not None}
+    # the per-state-point outputs SURVEY 8(d) config 2 lists: nphase, bounds, is_safe (status bit), lnZ per phase,
+    # <N>, <N^2> per phase.  (extrema index lists and the normalisation constant stay on the device.)
+    host_out = {k: torch.empty_like(getattr(out, k), device="cpu").pin_memory() for k in E2E_FIELDS}
     d2h = sum(v.numel() * v.element_size() for v in host_out.values())
     h2d = mu_host.numel() * 8 + dh.h2d_bytes
 
     def e2e_step():
         # public host-buffer entry point: chunked, double-buffered H2D(mu) -> kernel -> D2H(results) pipeline
-        dh.sweep_host(mu_host, pmax=PMAX, lanes=args.lanes, out=host_out)
+        dh.sweep_host(mu_host, pmax=PMAX, lanes=args.lanes, out=host_out, fields=E2E_FIELDS)
 
     for _ in range(2):
         e2e_step()
@@ -342,7 +345,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             "config": {"workload": "config2: synthetic 1-comp N_tot lnPI, N_max=1000 (1001 bins), smooth=10, 10^6-point mu sweep per GPU with thermo "
                                    "(<N>, <N^2>, per-phase lnZ, phase split, is_safe)",
                        "state_points_per_gpu": S, "bins": N_BINS, "smooth": SMOOTH, "pmax": PMAX, "moments": list(moments),
-                       "lanes_per_point": args.lanes or "auto", "l2": "flushed (256 MiB memset) before every timed step",
+                       "lanes_per_point": args.lanes or "auto", "e2e_outputs": list(E2E_FIELDS), "l2": "flushed (256 MiB memset) before every timed step",
                        "parallelism": "dp%d over state points, no data-path collective" % world,
                        "final_gather_ms": gather_ms, "ok_fraction": ok_frac, "fast_kernel_fraction": fast_frac, "wall_s_timed_region": wall},
             "clocks": clocks,

@@ -129,6 +129,29 @@ class SweepResult(object):
         return out
 
 
+def save_results(fname, host, attrs=None):
+    """Write the dict of per-state-point arrays returned by ``SweepResult.host()`` / ``sweep_host`` /
+    ``reweight_batch`` as variables of one HDF5 file (``io.hdf5_min.write_hdf5``); ``load_results`` reads it back."""
+    from .io.hdf5_min import write_hdf5
+    v = {}
+    for k, a in host.items():
+        if a is None:
+            continue
+        a = a.numpy() if hasattr(a, "numpy") else np.asarray(a)
+        if a.dtype.kind in "fiub":
+            v[k] = a
+    write_hdf5(fname, v, dict(attrs or {}, producer="fhmcanalysis_b200"))
+
+
+def load_results(fname):
+    from .io.hdf5_min import File
+    f = File(fname)
+    out = {k: v.read() for k, v in f.variables.items()}
+    if "safe" in out:
+        out["safe"] = out["safe"].astype(bool)
+    return out, dict(f.attrs)
+
+
 class DeviceHistogram(object):
     """One histogram resident in HBM as the row blob the kernels stage in shared memory.
 

@@ -12,6 +12,10 @@ group links in dense storage (LinkInfo -> fractal heap ``FRHP`` -> ``FHIB``/``FH
 Link messages, contiguous or compact dataset layout, little/big-endian fixed-point and IEEE float
 element types, fixed-length string / numeric scalar attributes.  Chunked or filtered datasets raise
 ``NotImplementedError`` (the reference never writes them for the variables the hot path reads).
+
+``write_hdf5`` / ``write_composite`` (bottom of the file) write the same subset; their metadata checksums (lookup3) are
+verified against the values stored in the reference's own fixtures.  No libhdf5 exists in this image, so acceptance of
+the written files by libhdf5/netCDF-4 itself is untested here.
 """
 
 import struct
@@ -417,3 +421,172 @@ class Dataset(object):
 
     def close(self):
         self._f.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Writer: the smallest HDF5 layout the reader above, libhdf5 >= 1.8 and netCDF-4 accept.
+# Superblock v2, version-2 object headers, root links as compact Link messages, contiguous little-endian datasets,
+# scalar/1-element attributes.  No dimension scales are written, so a netCDF-4 reader names the dimensions
+# ``phony_dim_k``; ``histogram.reload`` (reference gc_hist.pyx:143-182) only indexes ``.variables[name][:]`` and reads
+# the four global attributes, which is what this layout provides.
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _rot(x, k):
+    return ((x << k) | (x >> (32 - k))) & 0xFFFFFFFF
+
+
+def lookup3(data, initval=0):
+    """Bob Jenkins' lookup3 ``hashlittle`` — the metadata checksum of HDF5 v2 superblocks and object headers."""
+    M = 0xFFFFFFFF
+    n = len(data)
+    a = b = c = (0xDEADBEEF + n + initval) & M
+    p = 0
+    while n > 12:
+        a = (a + int.from_bytes(data[p:p + 4], "little")) & M
+        b = (b + int.from_bytes(data[p + 4:p + 8], "little")) & M
+        c = (c + int.from_bytes(data[p + 8:p + 12], "little")) & M
+        a = (a - c) & M; a ^= _rot(c, 4); c = (c + b) & M
+        b = (b - a) & M; b ^= _rot(a, 6); a = (a + c) & M
+        c = (c - b) & M; c ^= _rot(b, 8); b = (b + a) & M
+        a = (a - c) & M; a ^= _rot(c, 16); c = (c + b) & M
+        b = (b - a) & M; b ^= _rot(a, 19); a = (a + c) & M
+        c = (c - b) & M; c ^= _rot(b, 4); b = (b + a) & M
+        p += 12
+        n -= 12
+    if n == 0:
+        return c
+    tail = bytes(data[p:p + n]) + b"\x00" * (12 - n)
+    a = (a + int.from_bytes(tail[0:4], "little")) & M
+    b = (b + int.from_bytes(tail[4:8], "little")) & M
+    c = (c + int.from_bytes(tail[8:12], "little")) & M
+    c ^= b; c = (c - _rot(b, 14)) & M
+    a ^= c; a = (a - _rot(c, 11)) & M
+    b ^= a; b = (b - _rot(a, 25)) & M
+    c ^= b; c = (c - _rot(b, 16)) & M
+    a ^= c; a = (a - _rot(c, 4)) & M
+    b ^= a; b = (b - _rot(a, 14)) & M
+    c ^= b; c = (c - _rot(b, 24)) & M
+    return c
+
+
+def _dtype_message(dt):
+    dt = np.dtype(dt)
+    if dt.kind == "f" and dt.itemsize == 8:
+        return bytes([0x11, 0x20, 0x3F, 0x00]) + struct.pack("<I", 8) + struct.pack("<HHBBBBI", 0, 64, 52, 11, 0, 52, 1023)
+    if dt.kind == "f" and dt.itemsize == 4:
+        return bytes([0x11, 0x20, 0x1F, 0x00]) + struct.pack("<I", 4) + struct.pack("<HHBBBBI", 0, 32, 23, 8, 0, 23, 127)
+    if dt.kind in "iu":
+        return bytes([0x10, 0x08 if dt.kind == "i" else 0x00, 0, 0]) + struct.pack("<I", dt.itemsize) + \
+            struct.pack("<HH", 0, 8 * dt.itemsize)
+    if dt.kind == "S":
+        return bytes([0x13, 0x00, 0x00, 0x00]) + struct.pack("<I", dt.itemsize)
+    raise TypeError("cannot store dtype %s" % dt)
+
+
+def _dataspace_message(shape):
+    if shape == ():
+        return bytes([2, 0, 0, 0])
+    return bytes([2, len(shape), 0, 1]) + b"".join(struct.pack("<Q", int(d)) for d in shape)
+
+
+def _message(mtype, body, flags=0):
+    return bytes([mtype]) + struct.pack("<H", len(body)) + bytes([flags]) + body
+
+
+def _attribute_message(name, value):
+    if isinstance(value, (bytes, str)):
+        raw = value.encode("utf-8") if isinstance(value, str) else value
+        raw += b"\x00"
+        dt, ds = _dtype_message(np.dtype("S%d" % len(raw))), _dataspace_message(())
+    else:
+        arr = np.atleast_1d(np.asarray(value))
+        if arr.dtype.kind == "b":
+            arr = arr.astype(np.int64)
+        arr = np.ascontiguousarray(arr.astype(arr.dtype.newbyteorder("<")))
+        raw, dt, ds = arr.tobytes(), _dtype_message(arr.dtype), _dataspace_message(arr.shape)
+    nm = name.encode("utf-8") + b"\x00"
+    body = bytes([3, 0]) + struct.pack("<HHH", len(nm), len(dt), len(ds)) + b"\x00" + nm + dt + ds + raw
+    return _message(0x0C, body)
+
+
+def _object_header(messages):
+    body = b"".join(messages)
+    head = b"OHDR" + bytes([2, 0x02]) + struct.pack("<I", len(body)) + body
+    return head + struct.pack("<I", lookup3(head))
+
+
+def write_hdf5(fname, variables, attrs=None, var_attrs=None):
+    """Write ``variables`` (name -> ndarray) and global ``attrs`` (name -> str | number) to a new HDF5 file."""
+    attrs = attrs or {}
+    var_attrs = var_attrs or {}
+    names = list(variables.keys())
+    arrays = []
+    for n in names:
+        a = np.asarray(variables[n])
+        if a.dtype.kind == "b":
+            a = a.astype(np.int8)
+        arrays.append(np.array(a.astype(a.dtype.newbyteorder("<")), order="C"))   # keeps 0-d arrays 0-d
+
+    def dataset_header(a, addr, extra):
+        msgs = [_message(0x01, _dataspace_message(a.shape)), _message(0x03, _dtype_message(a.dtype), 1),
+                _message(0x05, bytes([3, 0x0A]), 1),
+                _message(0x08, bytes([3, 1]) + struct.pack("<QQ", addr, a.nbytes), 0)]
+        msgs += [_attribute_message(k, v) for k, v in extra.items()]
+        return _object_header(msgs)
+
+    def root_header(addrs):
+        msgs = [_message(0x02, bytes([0, 0]) + struct.pack("<QQ", _UNDEF, _UNDEF)), _message(0x0A, bytes([0, 0]), 1)]
+        for n, ad in zip(names, addrs):
+            nm = n.encode("utf-8")
+            if len(nm) > 255:
+                raise ValueError("link name too long: %r" % n)
+            msgs.append(_message(0x06, bytes([1, 0, len(nm)]) + nm + struct.pack("<Q", ad)))
+        msgs += [_attribute_message(k, v) for k, v in attrs.items()]
+        return _object_header(msgs)
+
+    # header sizes do not depend on the addresses they hold: lay out with placeholders first
+    root_len = len(root_header([0] * len(names)))
+    hdr_len = [len(dataset_header(a, 0, var_attrs.get(n, {}))) for n, a in zip(names, arrays)]
+    pos = 48 + root_len
+    hdr_addr = []
+    for ln in hdr_len:
+        hdr_addr.append(pos)
+        pos += ln
+    data_addr = []
+    for a in arrays:
+        pos = (pos + 7) & ~7
+        data_addr.append(pos if a.nbytes else _UNDEF)
+        pos += a.nbytes
+    eof = pos
+    sb = _SIG + bytes([2, 8, 8, 0]) + struct.pack("<QQQQ", 0, _UNDEF, eof, 48)
+    sb += struct.pack("<I", lookup3(sb))
+    out = bytearray(eof)
+    out[0:48] = sb
+    rh = root_header(hdr_addr)
+    out[48:48 + len(rh)] = rh
+    for n, a, ha, da in zip(names, arrays, hdr_addr, data_addr):
+        dh = dataset_header(a, da, var_attrs.get(n, {}))
+        out[ha:ha + len(dh)] = dh
+        if a.nbytes:
+            out[da:da + a.nbytes] = a.tobytes()
+    with open(fname, "wb") as fh:
+        fh.write(out)
+
+
+def write_composite(fname, lnpi, ntot, mom, volume, nspec, max_order, history="", histograms=None, op_name="N_{tot}"):
+    """Write a ``composite.nc`` with the variable/attribute names of ``window.to_nc`` (reference
+    moments/win_patch/fhmc_patch.pyx:551-634) so that ``histogram(fname, ...)`` — here or in the reference — loads it.
+    ``histograms``: optional dict of the ``P_{N_i}(N_{tot})`` / ``P_{U}(N_{tot})`` families, written as given."""
+    lnpi = np.asarray(lnpi, dtype=np.float64)
+    ntot = np.asarray(ntot, dtype=np.int64)
+    mom = np.asarray(mom, dtype=np.float64)
+    n = len(lnpi)
+    if ntot.shape != (n,) or mom.shape != (nspec, max_order + 1, nspec, max_order + 1, max_order + 1, n):
+        raise ValueError("inconsistent composite shapes")
+    v = {op_name: ntot, "ln(PI)": lnpi,
+         "i": np.arange(1, nspec + 1, dtype=np.int64), "j": np.arange(max_order + 1, dtype=np.int64),
+         "k": np.arange(1, nspec + 1, dtype=np.int64), "m": np.arange(max_order + 1, dtype=np.int64),
+         "p": np.arange(max_order + 1, dtype=np.int64), "N_{i}^{j}*N_{k}^{m}*U^{p}": mom}
+    for k, a in (histograms or {}).items():
+        v[k] = np.asarray(a)
+    write_hdf5(fname, v, {"history": history, "volume": float(volume), "nspec": int(nspec), "max_order": int(max_order)})

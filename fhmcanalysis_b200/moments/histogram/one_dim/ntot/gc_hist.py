@@ -93,6 +93,21 @@ class histogram(TaylorMixin):
                   "pk_hist": {}, "e_hist": {}, "mom": mom}
         return h
 
+    def to_nc(self, fname):
+        """Write the CURRENT state as a ``composite.nc`` (names and attributes of ``window.to_nc``,
+        win_patch/fhmc_patch.pyx:551-634) with the built-in HDF5 writer, so that ``histogram(fname, ...)`` reloads it."""
+        from fhmcanalysis_b200.io.hdf5_min import write_composite
+        extra = {}
+        for fam, key in (("P_{N_i}(N_{tot})", "pk_hist"), ("P_{U}(N_{tot})", "e_hist")):
+            hst = self.data.get(key, {})
+            if "hist" in hst:
+                extra[fam] = hst["hist"]
+                for sfx in ("lb", "ub", "bw"):
+                    extra[fam + "_{" + sfx + "}"] = hst[sfx]
+        write_composite(fname, self.data["ln(PI)"], self.data["ntot"], self.data["mom"], self.data["volume"],
+                        self.data["nspec"], self.data["max_order"],
+                        history=str(self.metadata.get("file_history", "")), histograms=extra)
+
     def clear(self):
         self.data = {}
 
