@@ -6,7 +6,8 @@ import sys
 _MODULES = [
     "moments", "moments.histogram", "moments.histogram.one_dim", "moments.histogram.one_dim.ntot",
     "moments.histogram.one_dim.ntot.gc_hist", "moments.histogram.one_dim.ntot.gc_binary",
-    "moments.histogram.one_dim.ntot.collect", "moments.histogram.two_dim", "moments.histogram.two_dim.joint_hist",
+    "moments.histogram.one_dim.ntot.collect", "moments.histogram.one_dim.n1", "moments.histogram.one_dim.n1.gc_hist",
+    "moments.histogram.two_dim", "moments.histogram.two_dim.joint_hist",
 ]
 for _m in _MODULES:
     try:

@@ -47,7 +47,7 @@ class HistDesc(ctypes.Structure):
         ("smooth", ctypes.c_int), ("pmax", ctypes.c_int), ("complete", ctypes.c_int), ("compare_raw", ctypes.c_int),
         ("cutoff", ctypes.c_double), ("beta_ref", ctypes.c_double), ("mu1_ref", ctypes.c_double),
         ("dmu_ref", ctypes.c_double),
-        ("hull_row", ctypes.c_int), ("hull_len", ctypes.c_int), ("mu_recurrence", ctypes.c_int), ("reserved", ctypes.c_int),
+        ("hull_row", ctypes.c_int), ("hull_len", ctypes.c_int), ("mu_recurrence", ctypes.c_int), ("min_width", ctypes.c_int),
     ]
 
 

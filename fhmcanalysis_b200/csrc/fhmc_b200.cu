@@ -47,14 +47,14 @@ __device__ __forceinline__ void load_state(const SweepArgs &a, long long sp, dou
 // K1+K3+K2: persistent CTAs; the histogram blob is staged ONCE per CTA by a TMA bulk copy, then the
 // CTA walks tiles of FHMC_CTA/G state points.
 // ---------------------------------------------------------------------------------------------
-template <int G, bool TAYLOR>
-__global__ void __launch_bounds__(FHMC_CTA) k_sweep_1d(const __grid_constant__ SweepArgs a)
+template <int G, bool TAYLOR, int CTA>
+__global__ void __launch_bounds__(CTA) k_sweep_1d(const __grid_constant__ SweepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_tab;
     const double *sm = stage_histogram(a, smem_raw, s_tab);
 
-    constexpr int GPC = FHMC_CTA / G;  // state points per CTA tile
+    constexpr int GPC = CTA / G;  // state points per CTA tile
     const int grp = threadIdx.x / G;
     const long long S = a.st.n_states;
     const long long ntiles = (S + GPC - 1) / GPC;
@@ -239,21 +239,39 @@ static int validate_states(const fhmc_states *st)
     return 0;
 }
 
-template <int G, bool TAYLOR>
-static int launch_sweep(const SweepArgs &args, size_t smem, const DevInfo *di, cudaStream_t stream)
+template <int G, bool TAYLOR, int CTA>
+static int launch_sweep_cta(const SweepArgs &args, size_t smem, const DevInfo *di, cudaStream_t stream, int *occ_out, bool dry)
 {
-    auto kern = k_sweep_1d<G, TAYLOR>;
+    auto kern = k_sweep_1d<G, TAYLOR, CTA>;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return 1;
     int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FHMC_CTA, smem), "occupancy query")) return 1;
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA, smem), "occupancy query")) return 1;
+    *occ_out = occ;
+    if (dry) return 0;
     if (occ < 1) { set_error("sweep kernel does not fit on an SM (smem %zu bytes)", smem); return 1; }
-    const long long gpc = FHMC_CTA / G;
+    const long long gpc = CTA / G;
     const long long ntiles = (args.st.n_states + gpc - 1) / gpc;
     long long grid = (long long)di->sm_count * occ;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, FHMC_CTA, smem, stream>>>(args);
+    kern<<<(unsigned)grid, CTA, smem, stream>>>(args);
     return check_cuda(cudaGetLastError(), "k_sweep_1d launch");
+}
+
+template <int G, bool TAYLOR>
+static int launch_sweep(const SweepArgs &args, size_t smem, const DevInfo *di, cudaStream_t stream)
+{
+    // a histogram blob that leaves room for one 256-thread CTA per SM only (Taylor sweeps at 2001 bins) runs as one
+    // 512-thread CTA instead: twice the warps to hide the fp64 latencies behind
+    int occ = 0;
+    if (launch_sweep_cta<G, TAYLOR, FHMC_CTA>(args, smem, di, stream, &occ, true)) return 1;
+    const long long tiles512 = (args.st.n_states + 512 / G - 1) / (512 / G);
+    if (occ == 1 && tiles512 >= di->sm_count) {
+        int occ2 = 0;
+        if (launch_sweep_cta<G, TAYLOR, 512>(args, smem, di, stream, &occ2, true)) return 1;
+        if (occ2 >= 1) return launch_sweep_cta<G, TAYLOR, 512>(args, smem, di, stream, &occ2, false);
+    }
+    return launch_sweep_cta<G, TAYLOR, FHMC_CTA>(args, smem, di, stream, &occ, false);
 }
 
 template <int G>
@@ -279,9 +297,16 @@ static int launch_fast_mu(const SweepArgs &args, int sm_count, int smem_optin, c
     }
 }
 
-int choose_lanes(long long n_states, const DevInfo *di)
+#define FHMC_FAST_MIN_STATES 4096
+
+int choose_lanes(long long n_states, int bins, const DevInfo *di)
 {
-    // enough groups to give every SM >= 1024 busy threads, otherwise widen the groups
+    if (bins >= 512) {
+        // measured on B200 at 1001 bins (scripts/probe_threshold.py): a warp per state point wins up to ~2.4e4 state
+        // points, one lane per state point beyond; four lanes never win
+        return n_states >= (long long)di->sm_count * 160 ? 1 : 32;
+    }
+    // short histograms: enough groups to give every SM >= 1024 busy threads, otherwise widen the groups
     const long long target = (long long)di->sm_count * 1024;
     if (n_states >= target) return 1;
     if (n_states * 4 >= target) return 4;
@@ -329,13 +354,19 @@ int fhmc_sweep_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_sta
         smem = 16 + 512;
     }
     const bool taylor = desc->n_coef > 0 || desc->n_term > 1;
-    int G = lanes_per_point > 0 ? lanes_per_point : choose_lanes(states->n_states, di);
+    int G = lanes_per_point > 0 ? lanes_per_point : choose_lanes(states->n_states, desc->n, di);
+    // the one-thread-per-point kernel has a latency floor of one walk over the bins (~0.15 ms at 1001 bins) and beats
+    // the generic kernels from a few thousand state points on (scripts/probe_threshold.py)
+    // (pure mu sweeps; the Taylor variant walks the bins twice with a true exp per bin: 4 ms for 10^4 state points at
+    // 2001 bins against 0.6 ms for the warp-per-point kernel, so it waits for two full CTAs per SM)
+    const long long fast_min = taylor ? (long long)di->sm_count * 512 : FHMC_FAST_MIN_STATES;
+    const bool try_fast = lanes_per_point == 1 || (lanes_per_point == 0 && states->n_states >= fast_min);
     cudaStream_t s = (cudaStream_t)stream;
     // One thread per state point + one exp pass (fhmc_fast.cuh): large pure-mu sweeps with a precomputed hull, and
     // Taylor-extrapolated sweeps whose term pattern has an instantiation.  lanes_per_point = -1 forces the generic
     // one-lane kernel (tests compare the two).  -1 from the launchers means "not applicable": fall through.
     if (lanes_per_point == -1) G = 1;
-    else if (G == 1 && !desc->complete && desc->n >= 3) {
+    else if (try_fast && !desc->complete && desc->n >= 3) {
         int rc = -1;
         if (!taylor) {
             if (desc->hull_len >= 2 && desc->hull_row > 1 && desc->hull_row + 2 <= desc->n_rows)

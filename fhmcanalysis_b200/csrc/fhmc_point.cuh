@@ -87,9 +87,19 @@ struct PointEval {
     {
         double u = __dadd_rn(sm[i], __dmul_rn(s, sm[npad + i]));
         if (TAYLOR) {
+            // fully unrolled so that xi[] stays in registers.  Multi-lane groups (few registers to spare, short
+            // Taylor series in the solver) leave at the first unused term; the one-lane evaluator that is inlined into
+            // the thread-per-state-point kernel keeps the branch-free predicated form (measured: the early exit
+            // costs that kernel spills and 30 % at n_coef = 6).
 #pragma unroll
-            for (int t = 0; t < FHMC_MAX_TERMS; ++t)
-                if (t < a.d.n_coef) u = fma(xi[t], sm[a.d.coef_row[t] * npad + i], u);
+            for (int t = 0; t < FHMC_MAX_TERMS; ++t) {
+                if (G > 1) {
+                    if (t >= a.d.n_coef) break;
+                    u = fma(xi[t], sm[a.d.coef_row[t] * npad + i], u);
+                } else {
+                    if (t < a.d.n_coef) u = fma(xi[t], sm[a.d.coef_row[t] * npad + i], u);
+                }
+            }
         }
         return u;
     }
@@ -99,8 +109,14 @@ struct PointEval {
         double x = row[0];
         if (TAYLOR) {
 #pragma unroll
-            for (int t = 1; t < FHMC_MAX_TERMS; ++t)
-                if (t < a.d.n_term) x = fma(ts[t], row[t * npad], x);
+            for (int t = 1; t < FHMC_MAX_TERMS; ++t) {
+                if (G > 1) {
+                    if (t >= a.d.n_term) break;
+                    x = fma(ts[t], row[t * npad], x);
+                } else {
+                    if (t < a.d.n_term) x = fma(ts[t], row[t * npad], x);
+                }
+            }
         }
         return x;
     }
@@ -163,20 +179,34 @@ struct PointEval {
         } else {
             const unsigned gmask = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
             const unsigned below = (1u << g) - 1u;
+            // every u_i is evaluated once: the neighbours i-1 / i+1 live in the adjacent lanes, the left neighbour of
+            // lane 0 is the last lane's value of the previous round, the right neighbour of the last lane is lane 0's
+            // value of the next round (computed one round ahead)
+            const int lane = gshift + g;
+            double u_cur = (g < n) ? U(g) : 0.0, u_prev_last = 0.0;
             for (int r = 0; r < R; ++r) {
                 const int i = r * G + g;
+                const double u_next = (i + G < n) ? U(i + G) : 0.0;
+                double ul = __shfl_sync(member, u_cur, (lane + 31) & 31);
+                double ur = __shfl_sync(member, u_cur, (lane + 1) & 31);
+                const double u_next0 = __shfl_sync(member, u_next, gshift);
+                const double u_last = __shfl_sync(member, u_cur, gshift + G - 1);
+                if (g == 0) ul = u_prev_last;
+                if (g == G - 1) ur = u_next0;
                 bool isM = false, ism = false;
                 if (i < n) {
-                    const double u = U(i);
+                    const double u = u_cur;
                     mx = fmax(mx, u);
                     mn = fmin(mn, u);
                     if (i > 0 && i < last) {
                         const double xc = use_c ? __dsub_rn(u, cc) : u;
-                        const double xl = V(i - 1, use_c, cc), xr = V(i + 1, use_c, cc);
+                        const double xl = use_c ? __dsub_rn(ul, cc) : ul, xr = use_c ? __dsub_rn(ur, cc) : ur;
                         if (xc > xl && xc > xr) isM = window_ok(i, xc, true, use_c, cc, 2);
                         else if (xc < xl && xc < xr) ism = window_ok(i, xc, false, use_c, cc, 2);
                     }
                 }
+                u_prev_last = u_last;
+                u_cur = u_next;
                 const unsigned bM = (__ballot_sync(member, isM) >> gshift) & gmask;
                 const unsigned bm = (__ballot_sync(member, ism) >> gshift) & gmask;
                 if (isM) {
@@ -201,8 +231,30 @@ struct PointEval {
     // ---- K3b: endpoint insertion / repair (GH:333-386), validation (GH:403-415), bounds (GH:498-520).
     // Leader lane only.  Returns the status code, FHMC_NEED_SLOW when the branch needs values on the
     // normalised array and c is not known yet.  Lists end up starting at position 0. -------------
+    // All lanes of the group: how many bins tie with the max / min of the normalised array, and the first of each.
+    __device__ void tie_scan(double cc, double umax, double umin, int &cM, int &cm, int &pM, int &pm) const
+    {
+        const double vmax = __dsub_rn(umax, cc), vmin = __dsub_rn(umin, cc);
+        cM = 0; cm = 0; pM = 0x7fffffff; pm = 0x7fffffff;
+        for (int j = g; j < n; j += G) {
+            const double v = V(j, true, cc);
+            if (v == vmax) { ++cM; pM = min(pM, j); }
+            if (v == vmin) { ++cm; pm = min(pm, j); }
+        }
+        if (G > 1) {
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                cM += __shfl_xor_sync(member, cM, o);
+                cm += __shfl_xor_sync(member, cm, o);
+                pM = min(pM, __shfl_xor_sync(member, pM, o));
+                pm = min(pm, __shfl_xor_sync(member, pm, o));
+            }
+        }
+    }
+
     __device__ int repair(bool use_c, double cc, int cntM, int cntm, double umax, double umin, int *maxl, int *minl,
-                          int *bl, int &nM_out, int &nm_out, unsigned &flags, bool &partition) const
+                          int *bl, int &nM_out, int &nm_out, unsigned &flags, bool &partition,
+                          int tcM = -1, int tcm = -1, int tpM = 0, int tpm = 0) const
     {
         int nM = 0, nm = 0;
         nM_out = 0;
@@ -266,10 +318,19 @@ struct PointEval {
             } else {  // GH:382-386: all positions tied with the max / min of the normalised array
                 const double vmax = __dsub_rn(umax, cc), vmin = __dsub_rn(umin, cc);
                 bool over = false;
-                for (int j = 0; j < n; ++j) {
-                    const double v = V(j, true, cc);
-                    if (v == vmax) { if (nM < pmax) maxl[nM] = j; else over = true; ++nM; }
-                    if (v == vmin) { if (nm < pmax + 1) minl[nm] = j; else over = true; ++nm; }
+                // a unique argmax and a unique argmin (the usual case) come from the group-wide tie_scan() of run();
+                // ties (or no scan) take the ordered serial scan
+                if (tcM == 1 && tcm == 1) {
+                    if (nM < pmax) maxl[nM] = tpM; else over = true;
+                    ++nM;
+                    if (nm < pmax + 1) minl[nm] = tpm; else over = true;
+                    ++nm;
+                } else {
+                    for (int j = 0; j < n; ++j) {
+                        const double v = V(j, true, cc);
+                        if (v == vmax) { if (nM < pmax) maxl[nM] = j; else over = true; ++nM; }
+                        if (v == vmin) { if (nm < pmax + 1) minl[nm] = j; else over = true; ++nm; }
+                    }
                 }
                 if (over) return FHMC_E_CAPACITY;
             }
@@ -515,10 +576,12 @@ struct PointEval {
                 detect(true, cc, maxl, minl, cntM, cntm, m, umin);
                 packed = 0;
                 unsigned f = 0;
+                int tcM = -1, tcm = -1, tpM = 0, tpm = 0;
+                if (cntM == 0 && cntm == 0) tie_scan(cc, m, umin, tcM, tcm, tpM, tpm);  // GH:382-386, group-wide
                 if (g == 0) {
                     int nM, nm;
                     bool part;
-                    const int rc = repair(true, cc, cntM, cntm, m, umin, maxl, minl, bl, nM, nm, f, part);
+                    const int rc = repair(true, cc, cntM, cntm, m, umin, maxl, minl, bl, nM, nm, f, part, tcM, tcm, tpM, tpm);
                     packed = rc | (part ? 0x100 : 0) | (nM << 9);
                     nmin = nm;
                 }

@@ -22,20 +22,20 @@ struct SolveArgs {
     int *iters;
 };
 
-template <int G, bool TAYLOR>
-__global__ void __launch_bounds__(FHMC_CTA) k_find_phase_eq(const __grid_constant__ SolveArgs sa)
+template <int G, bool TAYLOR, int CTA>
+__global__ void __launch_bounds__(CTA) k_find_phase_eq(const __grid_constant__ SolveArgs sa)
 {
     const SweepArgs &a = sa.sw;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_tab;
     const double *sm = stage_histogram(a, smem_raw, s_tab);
 
-    constexpr int GPC = FHMC_CTA / G;
+    constexpr int GPC = CTA / G;
     const int grp = threadIdx.x / G;
     const long long T = a.st.n_states;
     const long long ntiles = (T + GPC - 1) / GPC;
     const int pmax = a.d.pmax, nsel = a.d.n_sel;
-    const int min_width = 2 * a.d.smooth;  // gc_hist.pyx:652
+    const int min_width = a.d.min_width > 0 ? a.d.min_width : 2 * a.d.smooth;  // ntot/gc_hist.pyx:652, n1/gc_hist.pyx:1479
     PointEval<G, TAYLOR> pe(a, sm, threadIdx.x & 31, s_tab);
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -156,20 +156,37 @@ static int get_caps(DevCaps &c)
     return 0;
 }
 
-template <int G, bool TAYLOR>
-static int launch_solver(const SolveArgs &sa, size_t smem, const DevCaps &caps, cudaStream_t stream)
+template <int G, bool TAYLOR, int CTA>
+static int launch_solver_cta(const SolveArgs &sa, size_t smem, const DevCaps &caps, cudaStream_t stream, int *occ_out, bool dry)
 {
-    auto kern = k_find_phase_eq<G, TAYLOR>;
+    auto kern = k_find_phase_eq<G, TAYLOR, CTA>;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return 1;
     int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FHMC_CTA, smem), "occupancy query")) return 1;
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA, smem), "occupancy query")) return 1;
+    *occ_out = occ;
+    if (dry) return 0;
     if (occ < 1) { set_error("solver kernel does not fit on an SM"); return 1; }
-    const long long gpc = FHMC_CTA / G;
+    const long long gpc = CTA / G;
     const long long ntiles = (sa.sw.st.n_states + gpc - 1) / gpc;
     long long grid = (long long)caps.sm_count * occ;
     if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, FHMC_CTA, smem, stream>>>(sa);
+    kern<<<(unsigned)grid, CTA, smem, stream>>>(sa);
     return check_cuda(cudaGetLastError(), "k_find_phase_eq launch");
+}
+
+template <int G, bool TAYLOR>
+static int launch_solver(const SolveArgs &sa, size_t smem, const DevCaps &caps, cudaStream_t stream)
+{
+    // shared memory leaves room for one 256-thread CTA per SM (config 4: 2001 bins x 10 rows): run 512 threads
+    int occ = 0;
+    if (launch_solver_cta<G, TAYLOR, FHMC_CTA>(sa, smem, caps, stream, &occ, true)) return 1;
+    const long long tiles512 = (sa.sw.st.n_states + 512 / G - 1) / (512 / G);
+    if (occ == 1 && tiles512 >= caps.sm_count) {
+        int occ2 = 0;
+        if (launch_solver_cta<G, TAYLOR, 512>(sa, smem, caps, stream, &occ2, true)) return 1;
+        if (occ2 >= 1) return launch_solver_cta<G, TAYLOR, 512>(sa, smem, caps, stream, &occ2, false);
+    }
+    return launch_solver_cta<G, TAYLOR, FHMC_CTA>(sa, smem, caps, stream, &occ, false);
 }
 
 }  // namespace fhmc

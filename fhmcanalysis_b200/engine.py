@@ -233,7 +233,7 @@ class DeviceHistogram(object):
         d.hull_row, d.hull_len = hull_row, hull_len
         self.desc = d
 
-    FAST_PATH_MIN_STATES = 100000   # below this the generic multi-lane kernels are used and no hull is needed
+    FAST_PATH_MIN_STATES = 4096   # = FHMC_FAST_MIN_STATES: below this the generic multi-lane kernels win and no hull is needed
 
     def ensure_hull(self):
         """Append the two hull rows the one-pass mu-sweep kernel needs (upper concave envelope of (N, lnPI)) and
@@ -415,7 +415,7 @@ class DeviceHistogram(object):
         return out
 
     def find_phase_eq(self, mu_guess, beta=None, dmu=None, lnz_tol=1e-10, mu_step=None, max_iter=200, pmax=4,
-                      smooth=None, cutoff=None):
+                      smooth=None, cutoff=None, min_width=None):
         """K4: one coexistence solve per entry of (mu_guess, beta, dmu) (flat lists).  Returns
         (SweepResult at coexistence with extra['mu_coex','dfe','iters'])."""
         L = _lib.load()
@@ -424,6 +424,7 @@ class DeviceHistogram(object):
             raise ValueError("the solver needs quantity 0 to be N_tot (construct DeviceHistogram with sel=['N', ...])")
         st = self.make_states(mu_guess, beta, dmu, grid=False)
         d = self._desc(max(pmax, 2), False, False, cutoff, smooth)
+        d.min_width = int(min_width) if min_width else 0    # 0: 2*smooth (N_tot histograms); the N_1 class passes smooth
         out = SweepResult(st.n_states, d.pmax, self.n_sel, self.device)
         T = st.n_states
         mu_coex = t.empty(T, dtype=t.float64, device=self.device)

@@ -66,6 +66,11 @@ def mom_prod(x_idx, y_idx, max_order, nspec):
 class TaylorMixin(object):
     """Private derivative builders of ``histogram`` (operate on self.data / self.metadata)."""
 
+    _first_species = 0   # first species whose N_s enters the pointwise derivatives (1 for the N_1 class)
+
+    def _ke(self):
+        return bool(self.metadata.get("used_ke", False))
+
     # ---- helpers -------------------------------------------------------------------------------
     def _m(self, x):
         return self.data["mom"][int(x[0]), int(x[1]), int(x[2]), int(x[3]), int(x[4])]
@@ -154,7 +159,7 @@ class TaylorMixin(object):
         der -= self._gc_fluct_vi(X, [0, 0, 0, 0, 1])
         for i in range(self.data["nspec"]):
             der += self._d(i) * self._gc_fluct_vi(X, [i, 1, 0, 0, 0])
-        if self.metadata["used_ke"] and x_idx[4] > 0:
+        if self._ke() and x_idx[4] > 0:
             y = list(x_idx)
             y[4] -= 1
             der -= 1.5 * x_idx[4] / self.data["curr_beta"] ** 2 * self._gc_ave_v(self._m(y) * self._npow(n + 1))
@@ -179,7 +184,7 @@ class TaylorMixin(object):
         der = self.data["curr_mu"][0] * self._gc_df_dB_in((x_idx, n), 1) - self._gc_df_dB_ii((x_idx, n), ([0, 0, 0, 0, 1], 0))
         for i in range(self.data["nspec"]):
             der += self._d(i) * self._gc_df_dB_ii((x_idx, n), ([i, 1, 0, 0, 0], 0))
-        if self.metadata["used_ke"] and x_idx[4] > 0:
+        if self._ke() and x_idx[4] > 0:
             y = list(x_idx)
             y[4] -= 1
             beta = self.data["curr_beta"]
@@ -198,10 +203,10 @@ class TaylorMixin(object):
         up = list(x)
         up[4] += 1
         der = -(self._m(up) * npw - X * self._m([0, 0, 0, 0, 1]))
-        for s in range(self.data["nspec"]):
+        for s in range(self._first_species, self.data["nspec"]):
             f = self._times_species(x, s) * npw - X * self._m([s, 1, 0, 0, 0])
             der = der + self._d(s) * f
-        if self.metadata["used_ke"] and x[4] > 0:
+        if self._ke() and x[4] > 0:
             dn = list(x)
             dn[4] -= 1
             der = der - 1.5 * x[4] / self.data["curr_beta"] ** 2 * self.data["ntot"] * (self._m(dn) * npw)
@@ -234,9 +239,9 @@ class TaylorMixin(object):
             return self._zeros()
         x = [int(v) for v in x_idx]
         der = -self._sg_df_dB((x, n), ([0, 0, 0, 0, 1], 0))
-        for s in range(self.data["nspec"]):
+        for s in range(self._first_species, self.data["nspec"]):
             der = der + self._d(s) * self._sg_df_dB((x, n), ([s, 1, 0, 0, 0], 0))
-        if self.metadata["used_ke"] and x[4] > 0:
+        if self._ke() and x[4] > 0:
             y = list(x)
             y[4] -= 1
             beta = self.data["curr_beta"]
@@ -263,9 +268,9 @@ class TaylorMixin(object):
             return self._zeros()
         x = [int(v) for v in x_idx]
         der = -self._sg_d2f_dB2((x, n), ([0, 0, 0, 0, 1], 0))
-        for s in range(self.data["nspec"]):
+        for s in range(self._first_species, self.data["nspec"]):
             der = der + self._d(s) * self._sg_d2f_dB2((x, n), ([s, 1, 0, 0, 0], 0))
-        if self.metadata["used_ke"]:
+        if self._ke():
             raise Exception("No KE correction implemented for _sg_d3X_dB3()")
         return der
 
@@ -322,7 +327,7 @@ class TaylorMixin(object):
 
     def _dB3(self, skip_mom=False):
         """GH:2208-2252."""
-        if self.metadata["used_ke"]:
+        if self._ke():
             raise Exception("KE corrections not implemented for 3rd order beta extrapolation")
         ns = self.data["nspec"]
         d3 = self._zeros()
@@ -452,7 +457,7 @@ class TaylorMixin(object):
         a_b = -U
         for s in range(1, ns):
             a_b = a_b + self._d(s) * self._m([s, 1, 0, 0, 0])
-        if self.metadata["used_ke"]:
+        if self._ke():
             pass  # the first-order KE term enters through _sg_dX_dB at second order only (GH:1717-1720)
         rows.append((L.M_DB, a_b))
         beta = self.data["curr_beta"]

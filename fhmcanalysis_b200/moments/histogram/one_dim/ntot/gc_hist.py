@@ -57,6 +57,9 @@ def phase_eq_error(mu_guess, orig_hist, beta, dMu, order, cutoff, override, min_
 class histogram(TaylorMixin):
     """1-D ln(PI)(N_tot) histogram from grand-canonical flat-histogram simulations (GH:80-2563)."""
 
+    _op_key = "ntot"        # data[] key of the order-parameter vector (the N_1 subclass uses "n1")
+    _op_var = "N_{tot}"     # its name inside composite.nc
+
     def __init__(self, fname, beta_ref, mu_ref, smooth=0, ke=False):
         self.metadata = {}
         self.metadata["beta_ref"] = beta_ref
@@ -89,7 +92,7 @@ class histogram(TaylorMixin):
         ntot = np.array(ntot, dtype=np.int64)
         mom = np.array(mom, dtype=np.float64)
         h.data = {"curr_mu": mu.copy(), "curr_beta": float(beta_ref), "nspec": len(mu), "ln(PI)": lnpi,
-                  "max_order": mom.shape[1] - 1, "volume": float(volume), "ntot": ntot, "lb": ntot[0], "ub": ntot[-1],
+                  "max_order": mom.shape[1] - 1, "volume": float(volume), cls._op_key: ntot, "lb": ntot[0], "ub": ntot[-1],
                   "pk_hist": {}, "e_hist": {}, "mom": mom}
         return h
 
@@ -98,15 +101,15 @@ class histogram(TaylorMixin):
         win_patch/fhmc_patch.pyx:551-634) with the built-in HDF5 writer, so that ``histogram(fname, ...)`` reloads it."""
         from fhmcanalysis_b200.io.hdf5_min import write_composite
         extra = {}
-        for fam, key in (("P_{N_i}(N_{tot})", "pk_hist"), ("P_{U}(N_{tot})", "e_hist")):
+        for fam, key in (("P_{N_i}(" + self._op_var + ")", "pk_hist"), ("P_{U}(" + self._op_var + ")", "e_hist")):
             hst = self.data.get(key, {})
             if "hist" in hst:
                 extra[fam] = hst["hist"]
                 for sfx in ("lb", "ub", "bw"):
                     extra[fam + "_{" + sfx + "}"] = hst[sfx]
-        write_composite(fname, self.data["ln(PI)"], self.data["ntot"], self.data["mom"], self.data["volume"],
+        write_composite(fname, self.data["ln(PI)"], self.data[self._op_key], self.data["mom"], self.data["volume"],
                         self.data["nspec"], self.data["max_order"],
-                        history=str(self.metadata.get("file_history", "")), histograms=extra)
+                        history=str(self.metadata.get("file_history", "")), histograms=extra, op_name=self._op_var)
 
     def clear(self):
         self.data = {}
@@ -129,29 +132,30 @@ class histogram(TaylorMixin):
         assert self.data["max_order"] > 0, "Error, max_order < 1"
         self.data["volume"] = float(dataset.volume)
         assert self.data["volume"] > 0, "Error, volume <= 0"
-        self.data["ntot"] = np.array(dataset.variables["N_{tot}"][:], dtype=np.int64)
-        self.data["lb"] = self.data["ntot"][0]
-        self.data["ub"] = self.data["ntot"][len(self.data["ntot"]) - 1]
+        op, ov = self._op_key, self._op_var
+        self.data[op] = np.array(dataset.variables[ov][:], dtype=np.int64)
+        self.data["lb"] = self.data[op][0]
+        self.data["ub"] = self.data[op][len(self.data[op]) - 1]
         assert self.data["lb"] < self.data["ub"], "Error, bad bounds for N_tot"
         self.data["pk_hist"] = {}
         try:
-            self.data["pk_hist"]["hist"] = np.array(dataset.variables["P_{N_i}(N_{tot})"][:])
-            self.data["pk_hist"]["lb"] = np.array(dataset.variables["P_{N_i}(N_{tot})_{lb}"][:])
-            self.data["pk_hist"]["ub"] = np.array(dataset.variables["P_{N_i}(N_{tot})_{ub}"][:])
-            self.data["pk_hist"]["bw"] = np.array(dataset.variables["P_{N_i}(N_{tot})_{bw}"][:])
+            self.data["pk_hist"]["hist"] = np.array(dataset.variables["P_{N_i}(" + ov + ")"][:])
+            self.data["pk_hist"]["lb"] = np.array(dataset.variables["P_{N_i}(" + ov + ")_{lb}"][:])
+            self.data["pk_hist"]["ub"] = np.array(dataset.variables["P_{N_i}(" + ov + ")_{ub}"][:])
+            self.data["pk_hist"]["bw"] = np.array(dataset.variables["P_{N_i}(" + ov + ")_{bw}"][:])
         except Exception:
             pass
         self.data["e_hist"] = {}
         try:
-            self.data["e_hist"]["hist"] = np.array(dataset.variables["P_{U}(N_{tot})"][:])
-            self.data["e_hist"]["lb"] = np.array(dataset.variables["P_{U}(N_{tot})_{lb}"][:])
-            self.data["e_hist"]["ub"] = np.array(dataset.variables["P_{U}(N_{tot})_{ub}"][:])
-            self.data["e_hist"]["bw"] = np.array(dataset.variables["P_{U}(N_{tot})_{bw}"][:])
+            self.data["e_hist"]["hist"] = np.array(dataset.variables["P_{U}(" + ov + ")"][:])
+            self.data["e_hist"]["lb"] = np.array(dataset.variables["P_{U}(" + ov + ")_{lb}"][:])
+            self.data["e_hist"]["ub"] = np.array(dataset.variables["P_{U}(" + ov + ")_{ub}"][:])
+            self.data["e_hist"]["bw"] = np.array(dataset.variables["P_{U}(" + ov + ")_{bw}"][:])
         except Exception:
             pass
         self.data["mom"] = np.array(dataset.variables["N_{i}^{j}*N_{k}^{m}*U^{p}"][:])
         mo, ns = self.data["max_order"], self.data["nspec"]
-        assert self.data["mom"].shape == (ns, mo + 1, ns, mo + 1, mo + 1, len(self.data["ntot"]))
+        assert self.data["mom"].shape == (ns, mo + 1, ns, mo + 1, mo + 1, len(self.data[op]))
         dataset.close()
 
     # ------------------------------------------------------------------------------------------
@@ -162,7 +166,7 @@ class histogram(TaylorMixin):
         dmu_ref = float(self.data["curr_mu"][1] - self.data["curr_mu"][0]) if self.data["nspec"] > 1 else 0.0
         sm = self.metadata["smooth"] if smooth is None else smooth
         lnpi = np.asarray(self.data["ln(PI)"], dtype=np.float64)
-        ntot = self.data["ntot"]
+        ntot = self.data[self._op_key]
         if len(ntot) != len(lnpi):
             # the reference's tests assign shorter arrays to data['ln(PI)'] (T1:155-198); normalize/relextrema/thermo
             # never touch ntot (no reweighting shift: s = 0), so any N row of the right length will do
@@ -670,7 +674,7 @@ class histogram(TaylorMixin):
 
     def _sel_rows(self, moments, order, extrap):
         """Rows (and their Taylor terms) of the quantities averaged inside the fused sweep."""
-        ntot = self.data["ntot"].astype(np.float64)
+        ntot = self.data[self._op_key].astype(np.float64)
         kinds = []
         if extrap:
             kinds = [_lib.M_DB] + ([_lib.M_DD] if self.data["nspec"] == 2 else [])

@@ -69,3 +69,28 @@ def joint_2d(n1=512, n2=512, cut=640):
         hi = int(min(n2, max(0, cut - i + 1)))
         bounds[i] = (0, hi)
     return lnpi, bounds
+
+
+def n1_two_comp_moments(n=201, max_order=3):
+    """Moment tensor (2, mo+1, 2, mo+1, mo+1, n) for an N_1 order parameter: N_1 = n is sharp in every bin and
+    (N_2, U) follow a discrete two-variable distribution (8x8 Gauss-Hermite nodes of a correlated Gaussian), so every
+    stored moment <N_i^j N_k^m U^p> is an exact moment of one distribution and all index symmetries hold."""
+    i = np.arange(n, dtype=np.float64)
+    z, w = np.polynomial.hermite_e.hermegauss(8)
+    w = w / w.sum()
+    z1, z2 = np.meshgrid(z, z, indexing="ij")
+    ww = (w[:, None] * w[None, :]).ravel()
+    z1, z2 = z1.ravel(), z2.ravel()
+    rho = -0.4
+    n2 = (0.4 * i + 5.0)[:, None] + np.sqrt(0.1 * i + 1.0)[:, None] * z1[None, :]
+    u = (-2.0 * i + 0.01 * i ** 1.5)[:, None] + np.sqrt(0.5 * i + 1.0)[:, None] * (rho * z1 + np.sqrt(1 - rho * rho) * z2)[None, :]
+    x = [np.broadcast_to(i[:, None], n2.shape), n2]
+    mo = max_order
+    mom = np.zeros((2, mo + 1, 2, mo + 1, mo + 1, n))
+    for a in range(2):
+        for j in range(mo + 1):
+            for b in range(2):
+                for m in range(mo + 1):
+                    for p in range(mo + 1):
+                        mom[a, j, b, m, p] = np.sum(ww[None, :] * x[a] ** j * x[b] ** m * u ** p, axis=1)
+    return mom

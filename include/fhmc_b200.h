@@ -101,7 +101,9 @@ typedef struct fhmc_hist_desc {
      * then advance exp(lnPI_i + s N_i - shift) along four interleaved bin chains by two multiplications per bin
      * (e_i = e_{i-4} * exp(4 s dN) * exp(lnPI_i - lnPI_{i-4})), re-anchored with a true exp every 64 bins.          */
     int mu_recurrence;
-    int reserved;
+    /* fhmc_find_phase_eq_1d only: minimum width (bins) of a phase that counts in the coexistence objective.
+     * 0 = 2*smooth (ntot/gc_hist.pyx:652); n1/gc_hist.pyx:1479 passes smooth itself.                                  */
+    int min_width;
 } fhmc_hist_desc;
 
 /*

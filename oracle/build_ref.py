@@ -4,8 +4,9 @@
 TEST INFRASTRUCTURE ONLY.  Nothing under ``fhmcanalysis_b200/`` imports this; only ``tests/``,
 ``__graft_entry__`` and ``bench.py`` (cpu_baseline / --impl reference legs) may use the output.
 
-What it does: copies the three reference Cython sources
-  moments/histogram/one_dim/ntot/gc_hist.pyx, gc_binary.pyx, moments/histogram/two_dim/joint_hist.pyx
+What it does: copies the reference Cython sources
+  moments/histogram/one_dim/ntot/gc_hist.pyx, gc_binary.pyx, moments/histogram/two_dim/joint_hist.pyx,
+  moments/histogram/one_dim/n1/gc_hist.pyx (built as module ``gc_hist_n1``)
 from ``/root/reference`` (or $FHMC_REFERENCE) into a scratch directory, applies the minimal
 Python-2 -> Python-3 / NumPy-2 / Cython-3 *porting* edits listed in ``PATCHES`` below (none of
 them touches arithmetic), cythonizes them with ``language_level=2`` and drops ONLY the compiled
@@ -32,6 +33,7 @@ SOURCES = {
     "gc_hist": "moments/histogram/one_dim/ntot/gc_hist.pyx",
     "gc_binary": "moments/histogram/one_dim/ntot/gc_binary.pyx",
     "joint_hist": "moments/histogram/two_dim/joint_hist.pyx",
+    "gc_hist_n1": "moments/histogram/one_dim/n1/gc_hist.pyx",      # N_1 order parameter
 }
 
 # (module, regex, replacement, expected count or None) -- porting edits only.
@@ -48,6 +50,8 @@ PATCHES = [
     ("gc_hist", r"np\.float, np\.float64", "float, np.float64", 1),
     ("joint_hist", r"dtype=np\.int\)", "dtype=np.int64)", None),
 ]
+# the N_1 module carries the same Py2/NumPy-1 idioms as ntot/gc_hist.pyx (n1/gc_hist.pyx:1734-1735, 1739, 156, 112)
+PATCHES += [("gc_hist_n1",) + p[1:] for p in PATCHES if p[0] == "gc_hist"]
 
 SETUP = r'''
 import numpy as np

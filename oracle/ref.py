@@ -45,6 +45,7 @@ def load(build=True):
             gc_hist=importlib.import_module("gc_hist"),
             gc_binary=importlib.import_module("gc_binary"),
             joint_hist=importlib.import_module("joint_hist"),
+            gc_hist_n1=importlib.import_module("gc_hist_n1"),
         )
     except Exception as e:  # pragma: no cover - depends on environment
         _cache["error"] = repr(e)

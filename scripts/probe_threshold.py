@@ -30,7 +30,7 @@ def timed(fn, reps=20, warm=3):
 
 def main():
     lnpi = synth.two_peak_lnpi(1001)
-    dh = engine.DeviceHistogram(lnpi, np.arange(1001), 1.0, 0.0, smooth=10, sel=["N", "N2"])
+    dh = engine.DeviceHistogram(lnpi, np.arange(1001), 1.0, 0.0, smooth=10, sel=[np.arange(1001.0), np.arange(1001.0) ** 2])
     dh.ensure_hull()
     for S in (300, 1000, 3000, 10000, 30000, 100000, 300000):
         mu = dh._dev_array(np.linspace(-0.03, 0.03, S))
