@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
 
         // ---- shift -------------------------------------------------------------------------------------
         int Mq;
+        double approx_max = 0.0, seen_max = -CUDART_INF;
         if (NC == 0) {   // hull vertex maximising lnPI + s*N
             int lo = 0, hi = H - 1;
             const double neg_s = -s;
@@ -188,17 +189,20 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
             }
             double Nm;
             Mq = shift_for_max(load_u((int)g_hidx[lo], Nm));
-        } else {         // max-only pre-pass
-            double m0 = -CUDART_INF, m1 = -CUDART_INF, m2 = -CUDART_INF, m3 = -CUDART_INF, Nd;
+        } else {
+            // Max-only pre-pass over every 8th bin: the exponent shift need not sit on the exact maximum, only close
+            // enough that nothing overflows.  The walk tracks the true maximum; a state point whose subsample missed
+            // it by more than e^400 (pathologically spiky input) is handed to the generic evaluator.
+            double m0 = -CUDART_INF, m1 = -CUDART_INF, Nd;
             int i = 0;
-            for (; i + 3 < n; i += 4) {
+            for (; i + 8 < n; i += 16) {
                 m0 = fmax(m0, load_u(i, Nd));
-                m1 = fmax(m1, load_u(i + 1, Nd));
-                m2 = fmax(m2, load_u(i + 2, Nd));
-                m3 = fmax(m3, load_u(i + 3, Nd));
+                m1 = fmax(m1, load_u(i + 8, Nd));
             }
-            for (; i < n; ++i) m0 = fmax(m0, load_u(i, Nd));
-            Mq = shift_for_max(fmax(fmax(m0, m1), fmax(m2, m3)));
+            for (; i < n; i += 8) m0 = fmax(m0, load_u(i, Nd));
+            m0 = fmax(m0, load_u(last, Nd));
+            approx_max = fmax(m0, m1);
+            Mq = shift_for_max(approx_max);
         }
 
         int *maxl = a.out.max_idx + sp * pmax;
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
             for (int q = 0; q < NX; ++q) A[q + (SEL0N ? 1 : 0)] = fma(e, b.x[q], A[q + (SEL0N ? 1 : 0)]);
         };
         auto accumulate = [&](const Bin &b) {
+            if (NC > 0) seen_max = fmax(seen_max, b.u);
             const double e = exp_scaled_r(b.u, Mq, tab, ec);
             add_term(b, e);
             return e;
@@ -318,6 +323,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
             }
             accumulate(c);
             flush();
+            if (NC > 0 && !(seen_max - approx_max < 400.0)) bad = true;
         } else {
             bad = true;
         }
@@ -328,11 +334,27 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
         if (!bad && !a.d.complete) {
             int nM = 0, nm = 0;
             bool part = false;
-            const int rc = pe.repair(false, 0.0, cntM, cntm, 0.0, 0.0, maxl, minl, bl, nM, nm, flags, part);
+            const double c = add_shift(Mq, log(Stot));
+            int rc;
+            if (cntM == 0 && cntm == 0) {
+                // No windowed extremum at all (monotone ln(PI), e.g. far from coexistence on a Taylor grid): the
+                // reference takes the bins tied with the max / min of the NORMALISED array (GH:382-386).  One light
+                // scan on fl(u - c) here; only genuine ties go to the generic evaluator.
+                double vM = -CUDART_INF, vm = CUDART_INF, Nd;
+                int cM = 0, cm = 0, pM = 0, pm = 0;
+                for (int j = 0; j < n; ++j) {
+                    const double v = __dsub_rn(load_u(j, Nd), c);
+                    if (v > vM) { vM = v; cM = 1; pM = j; } else if (v == vM) ++cM;
+                    if (v < vm) { vm = v; cm = 1; pm = j; } else if (v == vm) ++cm;
+                }
+                rc = (cM == 1 && cm == 1) ? pe.repair(true, c, 0, 0, 0.0, 0.0, maxl, minl, bl, nM, nm, flags, part, 1, 1, pM, pm)
+                                          : FHMC_NEED_SLOW;
+            } else {
+                rc = pe.repair(false, 0.0, cntM, cntm, 0.0, 0.0, maxl, minl, bl, nM, nm, flags, part);
+            }
             if (rc == FHMC_OK && part && nM == P) {
                 pe.P = nM;
                 pe.nmin = nm;
-                const double c = add_shift(Mq, log(Stot));
                 if (a.d.compare_raw || !pe.verify(maxl, minl, c)) {
                     const double xM = __dsub_rn(pe.U(maxl[nM - 1]), c), xl = __dsub_rn(pe.U(last), c);
                     if (!(__dsub_rn(xM, xl) < a.d.cutoff)) flags |= FHMC_ST_SAFE;
