@@ -243,11 +243,25 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
             for (int q = 0; q < NSEL; ++q) A[q] = 0.0;
             ++P;
         };
+        // remaining shifts d0..smooth of the argrelextrema test, on the packed shared-memory rows (the generic
+        // evaluator's window_ok()/verify() would read the blob through global memory here)
+        auto window_fast = [&](int i, double xc, bool is_max, bool use_c, double cc, int d0) {
+            double Nd;
+            for (int d = d0; d <= pe.w; ++d) {
+                const int jl = (i - d < 0) ? 0 : i - d;
+                const int jr = (i + d > last) ? last : i + d;
+                double xl = load_u(jl, Nd), xr = load_u(jr, Nd);
+                if (use_c) { xl = __dsub_rn(xl, cc); xr = __dsub_rn(xr, cc); }
+                const bool ok = is_max ? (xc > xl && xc > xr) : (xc < xl && xc < xr);
+                if (!ok) return false;
+            }
+            return true;
+        };
         // exact strict 1-neighbour test + window test of bin i (values xm, xc, xp), then its contribution
         auto slow_bin = [&](int i, double xm, const Bin &c, double xp) {
             const double xc = c.u;
             const bool is_max = (xc > xm) && (xc > xp), is_min = (xc < xm) && (xc < xp);
-            if ((is_max || is_min) && pe.window_ok(i, xc, is_max, false, 0.0, 2)) {
+            if ((is_max || is_min) && window_fast(i, xc, is_max, false, 0.0, 2)) {
                 if (is_max) {
                     if (1 + cntM <= pmax - 1) maxl[1 + cntM] = i;
                     ++cntM;
@@ -355,8 +369,20 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
             if (rc == FHMC_OK && part && nM == P) {
                 pe.P = nM;
                 pe.nmin = nm;
-                if (a.d.compare_raw || !pe.verify(maxl, minl, c)) {
-                    const double xM = __dsub_rn(pe.U(maxl[nM - 1]), c), xl = __dsub_rn(pe.U(last), c);
+                // re-test the detected interior extrema on the normalised values, as PointEval::verify()
+                bool differs = false;
+                if (!a.d.compare_raw) {
+                    double Nd;
+                    for (int k = 0; k < nM + nm && !differs; ++k) {
+                        const bool is_max = k < nM;
+                        const int idx = is_max ? maxl[k] : minl[k - nM];
+                        if (idx > 0 && idx < last)
+                            differs = !window_fast(idx, __dsub_rn(load_u(idx, Nd), c), is_max, true, c, 1);
+                    }
+                }
+                if (!differs) {
+                    double Nd;
+                    const double xM = __dsub_rn(load_u(maxl[nM - 1], Nd), c), xl = __dsub_rn(load_u(last, Nd), c);
                     if (!(__dsub_rn(xM, xl) < a.d.cutoff)) flags |= FHMC_ST_SAFE;
                     a.out.status[sp] = flags | FHMC_ST_FAST;
                     a.out.nphase[sp] = nM;
