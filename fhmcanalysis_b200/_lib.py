@@ -68,7 +68,7 @@ class SweepOut(ctypes.Structure):
 EXPORTS = [
     "fhmc_version", "fhmc_last_error", "fhmc_device_info", "fhmc_sweep_1d", "fhmc_lnpi_1d",
     "fhmc_phase_moments", "fhmc_axpy_rows", "fhmc_find_phase_eq_1d", "fhmc_reweight_2d",
-    "fhmc_reweight_2d_workspace",
+    "fhmc_reweight_2d_workspace", "fhmc_pack_bytes", "fhmc_pack_phase_major",
     "fhmc_bench_dfma", "fhmc_bench_exp",
 ]
 
@@ -100,6 +100,10 @@ def load():
     L.fhmc_lnpi_1d.argtypes = [ctypes.POINTER(HistDesc), vp, ctypes.POINTER(States), vp, vp, vp]
     L.fhmc_phase_moments.restype = ci
     L.fhmc_phase_moments.argtypes = [vp, ci, vp, ci, vp, ci, vp, vp, vp]
+    L.fhmc_pack_bytes.restype = cll
+    L.fhmc_pack_bytes.argtypes = [cll, ci, ci]
+    L.fhmc_pack_phase_major.restype = ci
+    L.fhmc_pack_phase_major.argtypes = [ctypes.POINTER(SweepOut), cll, ci, ci, vp, vp, vp]
     L.fhmc_axpy_rows.restype = ci
     L.fhmc_axpy_rows.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(cd), ci, cll, vp, vp]
     L.fhmc_find_phase_eq_1d.restype = ci

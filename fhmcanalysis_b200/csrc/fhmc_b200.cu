@@ -297,6 +297,45 @@ static int launch_fast_mu(const SweepArgs &args, int sm_count, int smem_optin, c
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Phase-major repack of the sweep records (see fhmc_pack_phase_major in the header).  Pointwise, HBM bound:
+// reads one record (<= 4+4+pmax*(8+8*nsel+8) B) and writes as much per state point, all stores coalesced.
+// ---------------------------------------------------------------------------------------------
+struct PackArgs {
+    fhmc_sweep_out out;
+    long long S;
+    int pmax, nsel;
+    unsigned char *packed;
+    int *max_nphase;
+};
+
+__global__ void __launch_bounds__(256) k_pack_phase_major(const __grid_constant__ PackArgs a)
+{
+    int2 *head = reinterpret_cast<int2 *>(a.packed);
+    unsigned char *base = a.packed + 8 * a.S;
+    const int rec = 16 + 8 * a.nsel;
+    int pm = 0;
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < a.S; s += (long long)gridDim.x * blockDim.x) {
+        const unsigned st = a.out.status[s];
+        const int P = a.out.nphase[s];
+        head[s] = make_int2((int)st, P);
+        const int Pe = ((st & FHMC_ST_CODE_MASK) == FHMC_OK) ? min(max(P, 0), a.pmax) : 0;
+        pm = max(pm, Pe);
+        for (int p = 0; p < a.pmax; ++p) {
+            double *r = reinterpret_cast<double *>(base + ((long long)p * a.S + s) * rec);
+            const bool live = p < Pe;
+            r[0] = live ? a.out.fe[s * a.pmax + p] : CUDART_NAN;
+            for (int q = 0; q < a.nsel; ++q) r[1 + q] = live ? a.out.avg[(s * a.pmax + p) * a.nsel + q] : CUDART_NAN;
+            const int2 b = live ? *reinterpret_cast<const int2 *>(a.out.bounds + (s * a.pmax + p) * 2) : make_int2(-1, -1);
+            *reinterpret_cast<int2 *>(r + 1 + a.nsel) = b;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pm = max(pm, __shfl_xor_sync(0xffffffffu, pm, o));
+    if ((threadIdx.x & 31) == 0 && pm > 0) atomicMax(a.max_nphase, pm);
+}
+
 #define FHMC_FAST_MIN_STATES 4096
 
 int choose_lanes(long long n_states, int bins, const DevInfo *di)
@@ -425,6 +464,32 @@ int fhmc_axpy_rows(const double *const *src, const double *w_host, int n_src, lo
     if (blocks > 148 * 16) blocks = 148 * 16;
     k_axpy_rows<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, count, out);
     return check_cuda(cudaGetLastError(), "k_axpy_rows launch");
+}
+
+long long fhmc_pack_bytes(long long n_states, int pmax, int n_sel)
+{
+    if (n_states < 0 || pmax < 1 || n_sel < 0) return -1;
+    return 8 * n_states + (long long)pmax * n_states * (16 + 8 * (long long)n_sel);
+}
+
+int fhmc_pack_phase_major(const fhmc_sweep_out *out, long long n_states, int pmax, int n_sel, void *packed, int *max_nphase,
+                          void *stream)
+{
+    if (!out || !out->status || !out->nphase || !out->fe || !out->bounds || (n_sel > 0 && !out->avg) || !packed || !max_nphase ||
+        n_states < 0 || pmax < 1 || n_sel < 0 || n_sel > FHMC_MAX_SEL) { set_error("bad arguments"); return 1; }
+    if ((uintptr_t)packed & 15) { set_error("packed buffer must be 16-byte aligned"); return 1; }
+    if (n_states == 0) return 0;
+    PackArgs a;
+    a.out = *out;
+    a.S = n_states;
+    a.pmax = pmax;
+    a.nsel = n_sel;
+    a.packed = static_cast<unsigned char *>(packed);
+    a.max_nphase = max_nphase;
+    long long blocks = (n_states + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_pack_phase_major<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    return check_cuda(cudaGetLastError(), "k_pack_phase_major launch");
 }
 
 long long fhmc_bench_dfma(int iters, double *sink, void *stream)

@@ -166,6 +166,21 @@ int fhmc_phase_moments(const double *lnpi, int n, const double *mom, int n_array
                        int n_phase, double *avg, double *lnsum, void *stream);
 
 /*
+ * Phase-major repack of sweep records for the trip to the host (new; no reference counterpart).  fhmc_sweep_out keeps
+ * pmax slots per state point; most state points have one or two phases, so most of fe/avg/bounds is padding that need
+ * not cross PCIe.  After this call the fields of phase p of ALL state points are contiguous:
+ *   packed (bytes, S = n_states, R = 16 + 8*n_sel):
+ *     { u32 status; i32 nphase; }[S]  |  for p in 0..pmax-1: { f64 fe; f64 avg[n_sel]; i32 bounds[2]; }[S]
+ *   slots p >= nphase[s] (or every slot when the status code is not FHMC_OK) hold NaN / -1.
+ *   max_nphase: device int the caller zeroes; raised to max_s nphase[s] -> the first 8*S + max_nphase*R*S bytes are
+ *   all that needs to be copied.
+ * packed must be 16-byte aligned and hold fhmc_pack_bytes(n_states, pmax, n_sel) = 8*S + pmax*R*S bytes.
+ */
+long long fhmc_pack_bytes(long long n_states, int pmax, int n_sel);
+int fhmc_pack_phase_major(const fhmc_sweep_out *out, long long n_states, int pmax, int n_sel, void *packed,
+                          int *max_nphase, void *stream);
+
+/*
  * Pointwise Taylor update of a stack of arrays (moment extrapolation, GH:1027-1034 / 1162-1171,
  * and histogram.mix, GH:244-252):  out[a][i] = sum_t w[t] * src[t][a][i],  t < n_src.
  */

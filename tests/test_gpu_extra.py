@@ -187,3 +187,35 @@ def test_fast_taylor_kernel_agrees_with_generic(golden, golden_meta):
         a = dh.sweep(mu, b1, pmax=4, lanes=1).host()
         b = dh.sweep(mu, b1, pmax=4, lanes=-1).host()
         _agree(a, b, ("sw", order, moments))
+
+
+def test_compact_host_sweep_matches_plain_host_sweep():
+    """sweep_host_compact (phase-major repack, only live phase blocks cross PCIe) returns what sweep_host returns."""
+    from fhmcanalysis_b200 import engine, synth
+    n = 301
+    lnpi = synth.two_peak_lnpi(n, noise=1e-3, scale=0.3)
+    N = np.arange(n, dtype=np.float64)
+    dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=5, sel=["N", N * N])
+    for S, chunk in ((5000, 2048), (4097, 1 << 18), (1, 1 << 18)):
+        mu = np.linspace(-0.12, 0.10, S)
+        a = dh.sweep_host(mu, pmax=4, chunk=chunk)
+        c = dh.sweep_host_compact(mu, pmax=4, chunk=chunk)
+        st = a["status"].numpy().view(np.uint32)
+        assert np.array_equal(c["status"].numpy().view(np.uint32), st)
+        P = a["nphase"].numpy()
+        assert np.array_equal(c["nphase"].numpy(), P) and c["max_nphase"] == P.max()
+        fe_a, fe_c = a["fe"].numpy(), c["fe"].numpy()
+        av_a, av_c = a["avg"].numpy(), c["avg"].numpy()
+        b_a, b_c = a["bounds"].numpy(), c["bounds"].numpy()
+        assert fe_c.shape == fe_a.shape and av_c.shape == av_a.shape and b_c.shape == b_a.shape
+        for p in range(4):
+            live = ((st & 0xFF) == 0) & (P > p)
+            assert np.array_equal(fe_c[live, p], fe_a[live, p])
+            assert np.array_equal(av_c[live, p], av_a[live, p])
+            assert np.array_equal(b_c[live, p], b_a[live, p])
+            assert np.all(np.isnan(fe_c[~live, p])) and np.all(b_c[~live, p] == -1)
+        assert c["d2h_bytes"] <= 8 * S + 4 * S * (16 + 16)
+    # reuse of the result buffers: a later call with fewer phases must not leave stale phase blocks behind
+    mu2 = np.full(5000, -3.0)            # far from coexistence: one phase everywhere
+    c2 = dh.sweep_host_compact(mu2, pmax=4, chunk=2048, out=dh.sweep_host_compact(np.linspace(-0.12, 0.10, 5000), pmax=4, chunk=2048))
+    assert c2["max_nphase"] == 1 and np.all(np.isnan(c2["fe"].numpy()[:, 1:]))
