@@ -51,15 +51,21 @@ struct FastLayout {
     static constexpr int DOFF = ROWS;
 };
 
-template <int NSEL, bool SEL0N, int NC, int NT, bool REC = false>
-__global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constant__ SweepArgs a)
+// what the per-state-point walk needs to know about the CTA's packed copy
+struct FastCtx {
+    uint32_t s_pk, s_slope;   // shared-memory addresses: packed rows, hull edge slopes (NC == 0)
+    double *s_tab;            // 2^(j/64) table, followed by the deferred-fallback queue of the sweep kernel
+    const double *g_hidx;     // hull vertex bin indices (global)
+    int H;                    // hull vertices
+};
+
+// Build the CTA's packed copy (all threads of the CTA; ends with a barrier).
+template <int NSEL, bool SEL0N, int NC, int NT, bool REC>
+__device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned char *smem_raw)
 {
-    static_assert(!REC || NC == 0, "the exp recurrence only exists for pure mu sweeps");
     using LY = FastLayout<NSEL, SEL0N, NC, NT, REC>;
-    constexpr int NX = LY::NX, PK = LY::PK, XOFF = LY::XOFF;
-    constexpr bool TAYLOR = (NC > 0) || (NT > 1);
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int n = a.d.n, last = n - 1, pmax = a.d.pmax, npad = a.d.n_pad;
+    constexpr int PK = LY::PK, XOFF = LY::XOFF;
+    const int n = a.d.n, npad = a.d.n_pad;
     double *pk = reinterpret_cast<double *>(smem_raw);
     double *stage = pk + (size_t)npad * PK;
     uint64_t *bar = reinterpret_cast<uint64_t *>(stage + npad);
@@ -81,14 +87,14 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
             }
             mbar_wait(bar, parity);
             parity ^= 1u;
-            for (int i = threadIdx.x; i < n; i += FHMC_CTA) pk[(size_t)i * PK + slot] = stage[i];
+            for (int i = threadIdx.x; i < n; i += blockDim.x) pk[(size_t)i * PK + slot] = stage[i];
             __syncthreads();
         }
         if (REC)   // G_i = exp(lnPI_i - lnPI_{i-4}): e_i = e_{i-4} * exp(4 s dN) * G_i along each of the four bin chains
-            for (int i = threadIdx.x; i < n; i += FHMC_CTA)
+            for (int i = threadIdx.x; i < n; i += blockDim.x)
                 pk[(size_t)i * PK + LY::DOFF] = (i >= 4) ? exp(pk[(size_t)i * PK] - pk[(size_t)(i - 4) * PK]) : 1.0;
         if (LY::RAW & 1)
-            for (int i = threadIdx.x; i < n; i += FHMC_CTA) pk[(size_t)i * PK + LY::RAW] = 0.0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) pk[(size_t)i * PK + LY::RAW] = 0.0;
         if (NC == 0) {  // the one-row staging buffer is free now: keep the hull edge slopes in it for the binary search
             if (threadIdx.x == 0) {
                 mbar_expect_tx(bar, (uint32_t)npad * 8u);
@@ -98,43 +104,29 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
         }
         __syncthreads();
     }
-    const uint32_t s_slope = smem_u32(stage);
-    const uint32_t s_pk = smem_u32(pk);
-    PointEval<1, TAYLOR> pe(a, a.blob, threadIdx.x & 31, s_tab);   // rare paths (window test, repair) read HBM/L2
-    const uint32_t tab = pe.tab;
-    const double *g_slope = a.blob + (size_t)a.d.hull_row * npad, *g_hidx = g_slope + npad;
-    const int H = a.d.hull_len;
-    const ExpRegs ec = load_exp_regs();   // reduction / polynomial constants pinned in registers for the hot loop
+    FastCtx cx;
+    cx.s_slope = smem_u32(stage);
+    cx.s_pk = smem_u32(pk);
+    cx.s_tab = s_tab;
+    cx.g_hidx = a.blob + (size_t)a.d.hull_row * npad + npad;
+    cx.H = a.d.hull_len;
+    return cx;
+}
 
-    // Irregular state points are not re-run on the spot (one such lane would stall its whole warp for a full generic
-    // evaluation): they are queued in shared memory and drained by all threads of the CTA, one queued point per thread.
-    // The queue is inspected (one CTA barrier) only every fourth tile.
-    long long *queue = reinterpret_cast<long long *>(s_tab + 64);
-    int *q_count = reinterpret_cast<int *>(queue + FHMC_FAST_QUEUE);
-    if (threadIdx.x == 0) *q_count = 0;
-    __syncthreads();
-    auto drain = [&]() {
-        const int cnt = *q_count;
-        for (int k = threadIdx.x; k < cnt; k += FHMC_CTA) {
-            const long long qs = queue[k];
-            const double qm = a.st.mu1[(qs / a.st.mu1_div) % a.st.n_mu1];
-            const double qb = (TAYLOR && a.st.beta) ? a.st.beta[(qs / a.st.beta_div) % a.st.n_beta] : a.d.beta_ref;
-            const double qd = (TAYLOR && a.st.dmu) ? a.st.dmu[(qs / a.st.dmu_div) % a.st.n_dmu] : a.d.dmu_ref;
-            run_generic_point<TAYLOR>(a, s_tab, threadIdx.x & 31, qm, qb, qd, qs);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) *q_count = 0;
-        __syncthreads();
-    };
-    int tile_no = 0;
-
-    const long long S = a.st.n_states;
-    for (long long base = (long long)blockIdx.x * FHMC_CTA; base < S; base += (long long)gridDim.x * FHMC_CTA) {
-      const long long sp = base + threadIdx.x;
-      if (sp < S) {
-        const double mu1 = a.st.mu1[(sp / a.st.mu1_div) % a.st.n_mu1];
-        const double beta = (TAYLOR && a.st.beta) ? a.st.beta[(sp / a.st.beta_div) % a.st.n_beta] : a.d.beta_ref;
-        const double dmu = (TAYLOR && a.st.dmu) ? a.st.dmu[(sp / a.st.dmu_div) % a.st.n_dmu] : a.d.dmu_ref;
+// One state point, walked by the calling thread; fe/avg/bounds/extrema/status go to record `sp`.  Returns false when the
+// state point is not a plain case and must be re-run by the generic evaluator (nothing final has been written then).
+template <int NSEL, bool SEL0N, int NC, int NT, bool REC>
+__device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx, PointEval<1, (NC > 0) || (NT > 1)> &pe,
+                                           const ExpRegs &ec, long long sp, double mu1, double beta, double dmu)
+{
+    using LY = FastLayout<NSEL, SEL0N, NC, NT, REC>;
+    constexpr int NX = LY::NX, PK = LY::PK, XOFF = LY::XOFF;
+    constexpr bool TAYLOR = (NC > 0) || (NT > 1);
+    const int n = a.d.n, last = n - 1, pmax = a.d.pmax;
+    const uint32_t s_pk = cx.s_pk, s_slope = cx.s_slope, tab = pe.tab;
+    const double *g_hidx = cx.g_hidx;
+    const int H = cx.H;
+    (void)TAYLOR; (void)XOFF; (void)s_slope; (void)g_hidx; (void)H;
         pe.setup(mu1, beta, dmu);
         const double s = pe.s;
         double xi[NC > 0 ? NC : 1], ts[NT];
@@ -210,6 +202,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
         int *bl = a.out.bounds + sp * pmax * 2;
         int cntM = 0, cntm = 0, P = 0;
         bool bad = false;
+        unsigned rescue = 0;
         double Sacc = 0.0, Stot = 0.0, A[NSEL > 0 ? NSEL : 1];
 #pragma unroll
         for (int q = 0; q < NSEL; ++q) A[q] = 0.0;
@@ -234,6 +227,8 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
                 a.out.fe[sp * pmax + P] = -(add_shift(Mq, log(Sacc)) - u0);
 #pragma unroll
                 for (int q = 0; q < NSEL; ++q) a.out.avg[(sp * pmax + P) * NSEL + q] = A[q] / Sacc;
+            } else if (P < pmax) {
+                rescue |= 1u << P;   // phase too unlikely for the common shift: re-integrated about its own maximum below
             } else {
                 bad = true;
             }
@@ -382,6 +377,31 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
                 }
                 if (!differs) {
                     double Nd;
+                    // phases whose weight underflowed next to the global maximum (far from coexistence): integrate them
+                    // about their own maximum, as PointEval::partition_sum_probe() does (status bit RESCUED)
+                    for (int p = 0; rescue != 0 && p < nM; ++p) {
+                        if (!((rescue >> p) & 1u)) continue;
+                        const int left = bl[2 * p], right = bl[2 * p + 1];
+                        double ml = -CUDART_INF;
+                        for (int j = left; j < right; ++j) ml = fmax(ml, load_u(j, Nd));
+                        const int Mp = shift_for_max(ml);
+                        double Sp = 0.0, Ap[NSEL > 0 ? NSEL : 1];
+#pragma unroll
+                        for (int q = 0; q < NSEL; ++q) Ap[q] = 0.0;
+                        for (int j = left; j < right; ++j) {
+                            Bin b;
+                            load_bin(j, b);
+                            const double e = exp_scaled_r(b.u, Mp, tab, ec);
+                            Sp += e;
+                            if (SEL0N) Ap[0] = fma(e, b.N, Ap[0]);
+#pragma unroll
+                            for (int q = 0; q < NX; ++q) Ap[q + (SEL0N ? 1 : 0)] = fma(e, b.x[q], Ap[q + (SEL0N ? 1 : 0)]);
+                        }
+                        a.out.fe[sp * pmax + p] = -(add_shift(Mp, log(Sp)) - u0);
+#pragma unroll
+                        for (int q = 0; q < NSEL; ++q) a.out.avg[(sp * pmax + p) * NSEL + q] = Ap[q] / Sp;
+                        flags |= FHMC_ST_RESCUED;
+                    }
                     const double xM = __dsub_rn(load_u(maxl[nM - 1], Nd), c), xl = __dsub_rn(load_u(last, Nd), c);
                     if (!(__dsub_rn(xM, xl) < a.d.cutoff)) flags |= FHMC_ST_SAFE;
                     a.out.status[sp] = flags | FHMC_ST_FAST;
@@ -392,7 +412,51 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
                 }
             }
         }
-        if (!done) queue[atomicAdd(q_count, 1)] = sp;  // anything unusual: defer to the generic evaluator
+        return done;
+}
+
+template <int NSEL, bool SEL0N, int NC, int NT, bool REC = false>
+__global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constant__ SweepArgs a)
+{
+    static_assert(!REC || NC == 0, "the exp recurrence only exists for pure mu sweeps");
+    constexpr bool TAYLOR = (NC > 0) || (NT > 1);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const FastCtx cx = fast_prepare<NSEL, SEL0N, NC, NT, REC>(a, smem_raw);
+    double *s_tab = cx.s_tab;
+    PointEval<1, TAYLOR> pe(a, a.blob, threadIdx.x & 31, s_tab);   // rare paths (repair) read HBM/L2
+    const ExpRegs ec = load_exp_regs();   // reduction / polynomial constants pinned in registers for the hot loop
+
+    // Irregular state points are not re-run on the spot (one such lane would stall its whole warp for a full generic
+    // evaluation): they are queued in shared memory and drained by all threads of the CTA, one queued point per thread.
+    // The queue is inspected (one CTA barrier) only every fourth tile.
+    long long *queue = reinterpret_cast<long long *>(s_tab + 64);
+    int *q_count = reinterpret_cast<int *>(queue + FHMC_FAST_QUEUE);
+    if (threadIdx.x == 0) *q_count = 0;
+    __syncthreads();
+    auto drain = [&]() {
+        const int cnt = *q_count;
+        for (int k = threadIdx.x; k < cnt; k += FHMC_CTA) {
+            const long long qs = queue[k];
+            const double qm = a.st.mu1[(qs / a.st.mu1_div) % a.st.n_mu1];
+            const double qb = (TAYLOR && a.st.beta) ? a.st.beta[(qs / a.st.beta_div) % a.st.n_beta] : a.d.beta_ref;
+            const double qd = (TAYLOR && a.st.dmu) ? a.st.dmu[(qs / a.st.dmu_div) % a.st.n_dmu] : a.d.dmu_ref;
+            run_generic_point<TAYLOR>(a, s_tab, threadIdx.x & 31, qm, qb, qd, qs);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *q_count = 0;
+        __syncthreads();
+    };
+    int tile_no = 0;
+
+    const long long S = a.st.n_states;
+    for (long long base = (long long)blockIdx.x * FHMC_CTA; base < S; base += (long long)gridDim.x * FHMC_CTA) {
+      const long long sp = base + threadIdx.x;
+      if (sp < S) {
+        const double mu1 = a.st.mu1[(sp / a.st.mu1_div) % a.st.n_mu1];
+        const double beta = (TAYLOR && a.st.beta) ? a.st.beta[(sp / a.st.beta_div) % a.st.n_beta] : a.d.beta_ref;
+        const double dmu = (TAYLOR && a.st.dmu) ? a.st.dmu[(sp / a.st.dmu_div) % a.st.n_dmu] : a.d.dmu_ref;
+        if (!fast_point<NSEL, SEL0N, NC, NT, REC>(a, cx, pe, ec, sp, mu1, beta, dmu))
+            queue[atomicAdd(q_count, 1)] = sp;  // anything unusual: defer to the generic evaluator
       }
       if ((++tile_no & 3) == 0) {
           __syncthreads();

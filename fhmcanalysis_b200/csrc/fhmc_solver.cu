@@ -10,17 +10,11 @@
 // full fused state-point pass of fhmc_point.cuh (reweight + Taylor + phase split + thermo).
 #include <stdlib.h>
 
-#include "fhmc_point.cuh"
+#include "fhmc_solver.cuh"
 
 namespace fhmc {
 
-struct SolveArgs {
-    SweepArgs sw;
-    double lnz_tol, mu_step;
-    int max_iter;
-    double *mu_coex, *dfe;
-    int *iters;
-};
+#define FHMC_SOLVE_FAST_MIN (1LL << 40)   // never chosen automatically, see below
 
 template <int G, bool TAYLOR, int CTA>
 __global__ void __launch_bounds__(CTA) k_find_phase_eq(const __grid_constant__ SolveArgs sa)
@@ -34,8 +28,6 @@ __global__ void __launch_bounds__(CTA) k_find_phase_eq(const __grid_constant__ S
     const int grp = threadIdx.x / G;
     const long long T = a.st.n_states;
     const long long ntiles = (T + GPC - 1) / GPC;
-    const int pmax = a.d.pmax, nsel = a.d.n_sel;
-    const int min_width = a.d.min_width > 0 ? a.d.min_width : 2 * a.d.smooth;  // ntot/gc_hist.pyx:652, n1/gc_hist.pyx:1479
     PointEval<G, TAYLOR> pe(a, sm, threadIdx.x & 31, s_tab);
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -47,102 +39,19 @@ __global__ void __launch_bounds__(CTA) k_find_phase_eq(const __grid_constant__ S
         beta = st.beta ? st.beta[(rec / st.beta_div) % st.n_beta] : a.d.beta_ref;
         dmu = st.dmu ? st.dmu[(rec / st.dmu_div) % st.n_dmu] : a.d.dmu_ref;
 
-        bool have_lo = false, have_hi = false, converged = false, located = false, have_glo = false, have_ghi = false;
-        double lo = 0.0, hi = 0.0, mu_good = mu, d = 0.0, glo = 0.0, ghi = 0.0, step = sa.mu_step;
         const double n_mid = 0.5 * (sm[a.d.n_pad] + sm[a.d.n_pad + a.d.n - 1]);
-        unsigned status = 0;
-        int code = FHMC_E_NO_COEX, it = 0, nevals = 0;
-        for (it = 0; it < sa.max_iter; ++it) {
-            pe.setup(mu, beta, dmu);
-            status = pe.run(rec);
-            ++nevals;
+        solve_one(sa, rec, mu, beta, n_mid, pe.g == 0, [&](double m, int &P_now) {
+            pe.setup(m, beta, dmu);
+            const unsigned st_ = pe.run(rec);
             if (G > 1) __syncwarp(pe.member);
-            // pair selection of gc_hist.pyx:2614-2630 (every lane, uniform)
-            bool ok = false;
-            double slope = 0.0;
-            if ((status & FHMC_ST_CODE_MASK) == FHMC_OK) {
-                const double *fe = a.out.fe + rec * pmax;
-                const int *bl = a.out.bounds + rec * pmax * 2;
-                double best = 1.7976931348623157e308;
-                int bi = -1, bj = -1;
-                for (int i = 0; i < pe.P; ++i) {
-                    if (bl[2 * i + 1] - bl[2 * i] < min_width) continue;
-                    for (int j = i + 1; j < pe.P; ++j) {
-                        if (bl[2 * j + 1] - bl[2 * j] < min_width) continue;
-                        const double dd = fe[i] - fe[j];
-                        if (dd * dd < best) { best = dd * dd; bi = i; bj = j; d = dd; }
-                    }
-                }
-                if (bi >= 0) {
-                    ok = true;
-                    const double *av = a.out.avg + rec * pmax * nsel;
-                    slope = beta * (av[bj * nsel] - av[bi * nsel]);
-                }
-            }
-            if (!ok) {
-                if ((status & FHMC_ST_CODE_MASK) != FHMC_OK) { code = (int)(status & FHMC_ST_CODE_MASK); break; }
-                if (located) {
-                    mu = 0.5 * (mu + mu_good);  // stepped out of the two-phase window: come back half way
-                    continue;
-                }
-                // ---- locate the two-phase window: <N>_total(mu) is monotone, the window is where it crosses the
-                // middle of the N range.  Expand geometrically from the guess until bracketed, then bisect.
-                const double *fe = a.out.fe + rec * pmax;
-                const double *av = a.out.avg + rec * pmax * nsel;
-                double fmin_ = fe[0];
-                for (int p = 1; p < pe.P; ++p) fmin_ = fmin(fmin_, fe[p]);
-                double wsum = 0.0, nsum = 0.0;
-                for (int p = 0; p < pe.P; ++p) {
-                    const double wgt = exp(-(fe[p] - fmin_));
-                    wsum += wgt;
-                    nsum += wgt * av[p * nsel];
-                }
-                const double g = nsum / wsum - n_mid;
-                if (g < 0.0) { glo = mu; have_glo = true; } else { ghi = mu; have_ghi = true; }
-                if (have_glo && have_ghi) {
-                    if (fabs(ghi - glo) <= 1e-13 * fmax(1.0, fmax(fabs(glo), fabs(ghi)))) { code = FHMC_E_NO_COEX; break; }
-                    mu = 0.5 * (glo + ghi);
-                } else {
-                    mu += (g < 0.0) ? step : -step;
-                    step *= 2.0;
-                }
-                continue;
-            }
-            located = true;
-            mu_good = mu;
-            if (fabs(d) <= sa.lnz_tol) { converged = true; code = FHMC_OK; break; }
-            const bool below = (slope >= 0.0) ? (d < 0.0) : (d > 0.0);
-            if (below) { lo = mu; have_lo = true; } else { hi = mu; have_hi = true; }
-            double mu_n = mu;
-            if (slope != 0.0) {
-                double dm = -d / slope;
-                const double cap = 16.0 * sa.mu_step;  // Newton steps are trusted further than the blind search step
-                if (dm > cap) dm = cap;
-                if (dm < -cap) dm = -cap;
-                mu_n = mu + dm;
-            } else {
-                mu_n = mu + (below ? sa.mu_step : -sa.mu_step);
-            }
-            if (have_lo && have_hi) {
-                const double l = fmin(lo, hi), h = fmax(lo, hi);
-                if (!(mu_n > l && mu_n < h)) mu_n = 0.5 * (lo + hi);
-                if (mu_n == mu || h - l <= 4.0 * 2.220446049250313e-16 * fmax(fabs(l), fabs(h))) {
-                    converged = true;  // bracket exhausted at fp64 resolution
-                    code = FHMC_OK;
-                    break;
-                }
-            }
-            mu = mu_n;
-        }
-        if (!converged && code == FHMC_E_NO_COEX && it >= sa.max_iter) code = FHMC_E_NO_COEX + 1;  // iteration cap
-        if (pe.g == 0) {
-            sa.mu_coex[rec] = mu_good;
-            sa.dfe[rec] = d;
-            sa.iters[rec] = nevals;
-            if (code != FHMC_OK) a.out.status[rec] = (a.out.status[rec] & ~FHMC_ST_CODE_MASK) | (unsigned)code;
-        }
+            P_now = pe.P;
+            return st_;
+        });
     }
 }
+
+// thread-per-solve kernels (fhmc_solver_fast.cu)
+int launch_solver_fast(const SolveArgs &sa, int sm_count, int smem_optin, cudaStream_t stream);
 
 struct DevCaps {
     int sm_count, smem_optin;
@@ -228,8 +137,17 @@ extern "C" int fhmc_find_phase_eq_1d(const fhmc_hist_desc *desc, const double *b
     const long long T = states->n_states;
     cudaStream_t s = (cudaStream_t)stream;
     // a solve is ~10 dependent state-point passes: prefer wide groups unless there are very many solves
-    const char *force = getenv("FHMC_SOLVER_LANES");  // tuning/debug override
+    const char *force = getenv("FHMC_SOLVER_LANES");  // tuning/test override: 1/4/32 lanes per solve, 1000 = thread-per-solve walk
     const int forced = force ? atoi(force) : 0;
+    // Measured on B200 (scripts/probe_solver_scale.py, config-4 histogram, 10 rows x 2001 bins): the thread-per-solve
+    // walk needs ~9x fewer instructions per evaluation, but its packed rows leave room for one 256-thread CTA per SM
+    // (8 warps), every warp waits for its slowest lane's evaluation count, and one irregular evaluation stalls 31
+    // others: 7.8 / 9.1 / 79 / 87 ms against 4.6 / 10 / 30 / 88 ms of the warp-per-solve kernel at 1e4 / 3e4 / 1e5 / 3e5
+    // solves.  It is therefore only reachable through the override (tests keep it honest).
+    if ((forced == 0 && T >= FHMC_SOLVE_FAST_MIN) || forced == 1000) {
+        const int rc = launch_solver_fast(sa, caps.sm_count, caps.smem_optin, s);
+        if (rc >= 0) return rc;
+    }
     if (forced == 1) return taylor ? launch_solver<1, true>(sa, smem, caps, s) : launch_solver<1, false>(sa, smem, caps, s);
     if (forced == 4) return taylor ? launch_solver<4, true>(sa, smem, caps, s) : launch_solver<4, false>(sa, smem, caps, s);
     if (forced == 32 || T * 32 <= (long long)caps.sm_count * 2048 * 4)

@@ -219,3 +219,38 @@ def test_compact_host_sweep_matches_plain_host_sweep():
     mu2 = np.full(5000, -3.0)            # far from coexistence: one phase everywhere
     c2 = dh.sweep_host_compact(mu2, pmax=4, chunk=2048, out=dh.sweep_host_compact(np.linspace(-0.12, 0.10, 5000), pmax=4, chunk=2048))
     assert c2["max_nphase"] == 1 and np.all(np.isnan(c2["fe"].numpy()[:, 1:]))
+
+
+def test_thread_per_solve_kernel_matches_group_per_solve(monkeypatch):
+    """K4: the one-solve-per-thread kernel (one-pass walk) and the warp-per-solve kernel run the same iteration on
+    evaluations that agree to rounding: same mu_coex, same integers, same evaluation counts."""
+    from fhmcanalysis_b200 import synth
+    from fhmcanalysis_b200.moments.histogram.one_dim.ntot.gc_hist import histogram
+    h = histogram.from_arrays(synth.two_peak_lnpi(801, scale=0.8), synth.one_comp_moments(801, max_order=3), 1.0, [0.0], 10)
+    betas = 1.0 / np.linspace(0.92, 1.05, 700)
+    for order, moments in ((2, ("N", "N2", "U")), (1, ("N",))):
+        dh = h.device_histogram(beta=betas, order=order, moments=moments)
+        monkeypatch.setenv("FHMC_SOLVER_LANES", "32")
+        a = dh.find_phase_eq(np.zeros_like(betas), beta=betas, lnz_tol=1e-10, pmax=4).host()
+        monkeypatch.setenv("FHMC_SOLVER_LANES", "1000")
+        b = dh.find_phase_eq(np.zeros_like(betas), beta=betas, lnz_tol=1e-10, pmax=4).host()
+        monkeypatch.delenv("FHMC_SOLVER_LANES")
+        assert np.array_equal(a["code"], b["code"]) and (a["code"] == 0).mean() > 0.9
+        ok = a["code"] == 0
+        assert np.allclose(a["mu_coex"][ok], b["mu_coex"][ok], rtol=0, atol=1e-9)
+        assert np.array_equal(a["nphase"][ok], b["nphase"][ok]) and np.array_equal(a["bounds"][ok], b["bounds"][ok])
+        assert np.allclose(a["fe"][ok, :2], b["fe"][ok, :2], rtol=1e-9, atol=1e-9)
+        assert (b["status"][ok] & 0x1000).mean() > 0.9          # the final records come from the one-pass walk
+    # pure mu solves (no extrapolation): the shift comes from the hull rows
+    N = np.arange(801.0)
+    from fhmcanalysis_b200 import engine
+    dh = engine.DeviceHistogram(synth.two_peak_lnpi(801, scale=0.8), N, 1.0, 0.0, smooth=10, sel=["N"])
+    dh.ensure_hull()
+    g = np.linspace(-0.05, 0.05, 300)
+    monkeypatch.setenv("FHMC_SOLVER_LANES", "32")
+    a = dh.find_phase_eq(g).host()
+    monkeypatch.setenv("FHMC_SOLVER_LANES", "1000")
+    b = dh.find_phase_eq(g).host()
+    monkeypatch.delenv("FHMC_SOLVER_LANES")
+    assert np.all(a["code"] == 0) and np.all(b["code"] == 0)
+    assert np.allclose(a["mu_coex"], b["mu_coex"], rtol=0, atol=1e-10) and np.ptp(b["mu_coex"]) < 1e-9
