@@ -283,6 +283,10 @@ static int launch_sweep_t(bool taylor, const SweepArgs &args, size_t smem, const
 // one-pass mu-sweep kernel (fhmc_fast.cuh, NC = 0): one thread per state point
 static int launch_fast_mu(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream)
 {
+    if (args.d.mu_recurrence >= 2) {
+        const int rc = launch_fast_mu_prod(args, sm_count, smem_optin, stream);   // fhmc_fast_prod.cu
+        if (rc >= 0) return rc;
+    }
     if (args.d.mu_recurrence) {
         const int rc = launch_fast_mu_rec(args, sm_count, smem_optin, stream);   // fhmc_fast_rec.cu
         if (rc >= 0) return rc;

@@ -40,15 +40,18 @@ __device__ __noinline__ void run_generic_point(const SweepArgs &a, const double 
     pe.run(sp);
 }
 
-template <int NSEL, bool SEL0N, int NC, int NT, bool REC = false>
+template <int NSEL, bool SEL0N, int NC, int NT, int REC = 0>
 struct FastLayout {
     static constexpr int NX = NSEL - (SEL0N ? 1 : 0);   // quantities that need their own rows
     static constexpr int NCR = NC > 0 ? NC - 1 : 0;     // coefficient rows (term 0 re-uses the N row)
     static constexpr int ROWS = 2 + NCR + NX * NT;      // slots copied from blob rows
-    static constexpr int RAW = ROWS + (REC ? 1 : 0);    // + the 4-bin ratio exp(lnPI_i - lnPI_{i-4}) of the recurrence
+    static constexpr int RAW = ROWS + (REC == 1 ? 1 : 0);   // + the 4-bin ratio exp(lnPI_i - lnPI_{i-4}) of the recurrence
     static constexpr int PK = RAW + (RAW & 1);          // doubles per packed bin (even -> 16-byte aligned)
     static constexpr int XOFF = 2 + NCR;
     static constexpr int DOFF = ROWS;
+    // REC == 2 (product form): per 4-bin block {key(Dmin), key(Dmax) | pad | P x4 | P*X_q x4 ...} doubles
+    static constexpr int BW = 2 + 4 * (1 + NSEL);
+    static constexpr int SEGB = 32;                     // blocks per anchor segment (128 bins)
 };
 
 // what the per-state-point walk needs to know about the CTA's packed copy
@@ -57,10 +60,26 @@ struct FastCtx {
     double *s_tab;            // 2^(j/64) table, followed by the deferred-fallback queue of the sweep kernel
     const double *g_hidx;     // hull vertex bin indices (global)
     int H;                    // hull vertices
+    uint32_t s_prod, s_anch;  // REC == 2: per-block product rows, per-segment anchors (max lnPI of the segment)
+    double lmax;              // REC == 2: max |lnPI_i| (rounding margin of the extremum prefilter)
 };
 
+// order-preserving int32 key of the upper word of a double: key(a) < key(b) implies a < b
+__device__ __forceinline__ int hi_key(double x)
+{
+    const int h = __double2hiint(x);
+    return h ^ ((h >> 31) & 0x7fffffff);
+}
+
+// bytes of the packed rows + staging row + barrier + exp table + fallback queue (what every variant needs)
+template <int PK>
+__host__ __device__ constexpr size_t fast_base_bytes(int n_pad)
+{
+    return (((size_t)n_pad * 8 * (PK + 1) + 16 + 512 + FHMC_FAST_QUEUE * 8 + 64) + 15) & ~(size_t)15;
+}
+
 // Build the CTA's packed copy (all threads of the CTA; ends with a barrier).
-template <int NSEL, bool SEL0N, int NC, int NT, bool REC>
+template <int NSEL, bool SEL0N, int NC, int NT, int REC>
 __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned char *smem_raw)
 {
     using LY = FastLayout<NSEL, SEL0N, NC, NT, REC>;
@@ -90,7 +109,7 @@ __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned cha
             for (int i = threadIdx.x; i < n; i += blockDim.x) pk[(size_t)i * PK + slot] = stage[i];
             __syncthreads();
         }
-        if (REC)   // G_i = exp(lnPI_i - lnPI_{i-4}): e_i = e_{i-4} * exp(4 s dN) * G_i along each of the four bin chains
+        if (REC == 1)   // G_i = exp(lnPI_i - lnPI_{i-4}): e_i = e_{i-4} * exp(4 s dN) * G_i along each of the four bin chains
             for (int i = threadIdx.x; i < n; i += blockDim.x)
                 pk[(size_t)i * PK + LY::DOFF] = (i >= 4) ? exp(pk[(size_t)i * PK] - pk[(size_t)(i - 4) * PK]) : 1.0;
         if (LY::RAW & 1)
@@ -105,6 +124,58 @@ __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned cha
         __syncthreads();
     }
     FastCtx cx;
+    cx.s_prod = cx.s_anch = 0;
+    cx.lmax = 0.0;
+    if (REC == 2) {
+        // Product form: bins 1+4b .. 4+4b make block b (nb full blocks, bin 4+4b+... <= last - 0), SEGB blocks share the
+        // anchor A_g = max lnPI over the segment.  P_i = exp(lnPI_i - A_g) <= 1 and P_i * X_q(i) are tabulated, so that
+        // sum_i exp(lnPI_i + s N_i - shift) X_i over a block is a Horner polynomial in exp(s dN) times one running factor.
+        // D_j = lnPI_j - lnPI_{j-1}: a strict extremum of lnPI + s N inside the block needs -s dN within [Dmin, Dmax] of
+        // the five differences that touch the block; only the order-preserving keys of their upper words are kept.
+        const int nb = (n - 2) / 4;
+        const int nseg = (nb + LY::SEGB - 1) / LY::SEGB;
+        double *prod = reinterpret_cast<double *>(smem_raw + fast_base_bytes<PK>(npad));
+        double *anch = prod + (size_t)nb * LY::BW;
+        unsigned long long *s_lmax = reinterpret_cast<unsigned long long *>(anch + nseg);
+        if (threadIdx.x == 0) *s_lmax = 0ull;
+        __syncthreads();
+        double lm = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) lm = fmax(lm, fabs(pk[(size_t)i * PK]));
+        atomicMax(s_lmax, (unsigned long long)__double_as_longlong(lm));
+        for (int g = threadIdx.x; g < nseg; g += blockDim.x) {
+            const int i0 = 1 + 4 * LY::SEGB * g, i1 = min(1 + 4 * LY::SEGB * (g + 1), 1 + 4 * nb);
+            double m = -CUDART_INF;
+            for (int i = i0; i < i1; ++i) m = fmax(m, pk[(size_t)i * PK]);
+            anch[g] = m;
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+            const int i = 1 + 4 * b;
+            const double A = anch[b / LY::SEGB];
+            double dmin = CUDART_INF, dmax = -CUDART_INF;
+            for (int j = i; j <= i + 4; ++j) {
+                const double D = pk[(size_t)j * PK] - pk[(size_t)(j - 1) * PK];
+                dmin = fmin(dmin, D);
+                dmax = fmax(dmax, D);
+            }
+            double *pb = prod + (size_t)b * LY::BW;
+            int *kb = reinterpret_cast<int *>(pb);
+            kb[0] = hi_key(dmin);
+            kb[1] = hi_key(dmax);
+            pb[1] = 0.0;
+            for (int k = 0; k < 4; ++k) {
+                const double *row = pk + (size_t)(i + k) * PK;
+                const double P = exp(row[0] - A);
+                pb[2 + k] = P;
+                if (SEL0N) pb[6 + k] = P * row[1];
+                for (int q = 0; q < LY::NX; ++q) pb[2 + 4 * (1 + q + (SEL0N ? 1 : 0)) + k] = P * row[XOFF + q];
+            }
+        }
+        __syncthreads();
+        cx.s_prod = smem_u32(prod);
+        cx.s_anch = smem_u32(anch);
+        cx.lmax = __longlong_as_double((long long)*s_lmax);
+    }
     cx.s_slope = smem_u32(stage);
     cx.s_pk = smem_u32(pk);
     cx.s_tab = s_tab;
@@ -115,7 +186,7 @@ __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned cha
 
 // One state point, walked by the calling thread; fe/avg/bounds/extrema/status go to record `sp`.  Returns false when the
 // state point is not a plain case and must be re-run by the generic evaluator (nothing final has been written then).
-template <int NSEL, bool SEL0N, int NC, int NT, bool REC>
+template <int NSEL, bool SEL0N, int NC, int NT, int REC>
 __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx, PointEval<1, (NC > 0) || (NT > 1)> &pe,
                                            const ExpRegs &ec, long long sp, double mu1, double beta, double dmu)
 {
@@ -166,7 +237,7 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
                 for (int t = 1; t < NT; ++t) x = fma(ts[t], lds_f64(addr + 8u * (q * NT + t)), x);
                 b.x[q] = x;
             }
-            if (REC) b.g = lds_f64(s_pk + (uint32_t)i * (uint32_t)(PK * 8) + 8u * LY::DOFF);
+            if (REC == 1) b.g = lds_f64(s_pk + (uint32_t)i * (uint32_t)(PK * 8) + 8u * LY::DOFF);
         };
 
         // ---- shift -------------------------------------------------------------------------------------
@@ -253,8 +324,7 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
             return true;
         };
         // exact strict 1-neighbour test + window test of bin i (values xm, xc, xp), then its contribution
-        auto slow_bin = [&](int i, double xm, const Bin &c, double xp) {
-            const double xc = c.u;
+        auto test_bin = [&](int i, double xm, double xc, double xp) {
             const bool is_max = (xc > xm) && (xc > xp), is_min = (xc < xm) && (xc < xp);
             if ((is_max || is_min) && window_fast(i, xc, is_max, false, 0.0, 2)) {
                 if (is_max) {
@@ -266,6 +336,9 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
                     flush();  // a minimum bin opens the phase to its right (GH:498-520)
                 }
             }
+        };
+        auto slow_bin = [&](int i, double xm, const Bin &c, double xp) {
+            test_bin(i, xm, c.u, xp);
             return accumulate(c);
         };
         // exp recurrence (REC): four chains, one per bin position in the block; e_i = (e_{i-4} * r4) * G_i.  Chains are
@@ -273,10 +346,13 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
         // bounds the accumulated rounding at ~3e-15 relative.
         double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0, r4 = 1.0;
         int since_anchor = 16;
+        double r1 = 1.0;
         if (REC) {
-            const double t4 = 4.0 * s * (lds_f64(s_pk + (uint32_t)(PK * 8) + 8u) - lds_f64(s_pk + 8u));   // 4 s dN
+            const double sdn = s * (lds_f64(s_pk + (uint32_t)(PK * 8) + 8u) - lds_f64(s_pk + 8u));   // s dN
+            const double t4 = 4.0 * sdn;
             if (!(fabs(t4) < 200.0)) bad = true;   // extreme tilt: leave it to the generic evaluator
             r4 = exp(t4);
+            if (REC == 2) r1 = exp(sdn);
         }
 
         if (n >= 3 && !bad) {
@@ -286,6 +362,114 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
             double xm = u0;
             double dc = __dsub_rn(c.u, xm);  // sign(dc) is the exact order of (xm, xc)
             int i = 1;
+            if constexpr (REC == 2) {
+                // ---- product form -------------------------------------------------------------------------------
+                // A block's sums are Horner polynomials in r1 = exp(s dN) over the tabulated P_i (* X_i), scaled by the
+                // running factor t = exp(A_g + s N_i - shift) of the block's first bin: 4 fp64 ops per block and summed
+                // quantity, + 1 for t.  u itself is only formed in blocks that may hold an extremum: a block skips the
+                // exact tests when every difference D_j + s dN that touches it is further from zero than the rounding
+                // of fl(u_j - u_{j-1}) can reach (keys: upper words, conservative).
+                const double sdn = s * (lds_f64(s_pk + (uint32_t)(PK * 8) + 8u) - lds_f64(s_pk + 8u));
+                const double Na = fmax(fabs(lds_f64(s_pk + 8u)), fabs(lds_f64(s_pk + (uint32_t)last * (uint32_t)(PK * 8) + 8u)));
+                const double margin = 1.8e-15 * (cx.lmax + fabs(s) * Na) + 1e-300;   // 8 * 2^-52 * (|lnPI| + |s N|)
+                const int k_hi = hi_key(-sdn + margin), k_lo = hi_key(-sdn - margin);
+                const bool chain_ok = fabs(sdn) < 4.5;   // exp(|s dN| * 128 bins) must stay finite
+                const int nb = (n - 2) / 4;
+                const double r2 = r1 * r1, r8 = r4 * r4;
+                constexpr uint32_t BWB = (uint32_t)(LY::BW * 8);
+                // sums of one block from the tabulated products: Horner in r1, split in two halves (depth 2)
+                auto fast_block = [&](uint32_t pb, double tb) {
+                    double p0, p1, p2, p3;
+                    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(p0), "=d"(p1) : "r"(pb + 16u));
+                    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(p2), "=d"(p3) : "r"(pb + 32u));
+                    Sacc = fma(fma(fma(p3, r1, p2), r2, fma(p1, r1, p0)), tb, Sacc);
+#pragma unroll
+                    for (int q = 0; q < NSEL; ++q) {
+                        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(p0), "=d"(p1) : "r"(pb + 48u + 32u * q));
+                        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(p2), "=d"(p3) : "r"(pb + 64u + 32u * q));
+                        A[q] = fma(fma(fma(p3, r1, p2), r2, fma(p1, r1, p0)), tb, A[q]);
+                    }
+                };
+                // exact tests on u, bin by bin (a confirmed minimum flushes the sums before its own term is added); the
+                // terms themselves still come from the tabulated products: e_{i+k} = P_{i+k} t r1^k
+                auto careful_block = [&](uint32_t pb, int ib, double tb) {
+                    double Nd, uu[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) uu[k] = load_u(ib - 1 + k, Nd);
+                    double tk = tb;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        test_bin(ib + k, uu[k], uu[k + 1], uu[k + 2]);
+                        Sacc = fma(lds_f64(pb + 16u + 8u * k), tk, Sacc);
+#pragma unroll
+                        for (int q = 0; q < NSEL; ++q) A[q] = fma(lds_f64(pb + 48u + 32u * q + 8u * k), tk, A[q]);
+                        tk *= r1;
+                    }
+                };
+                auto flagged = [&](uint32_t pb) {   // an extremum may sit in the block at pb
+                    int ka, kb;
+                    asm("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(ka), "=r"(kb) : "r"(pb));
+                    return !((ka > k_hi) | (kb < k_lo));
+                };
+                uint32_t pb = cx.s_prod;
+                int b = 0;
+                for (int g = 0; b < nb; ++g) {
+                    const int bend = min(nb, b + LY::SEGB);
+                    // the tabulated P_i of this segment are relative to A_g: t = exp(A_g + s N_i - shift) at its first bin
+                    double Ni;
+                    const double lA = lds_f64(cx.s_anch + 8u * (uint32_t)g);
+                    asm("ld.shared.f64 %0, [%1];" : "=d"(Ni) : "r"(s_pk + (uint32_t)i * (uint32_t)(PK * 8) + 8u));
+                    double t = exp_scaled_r(__dadd_rn(lA, __dmul_rn(s, Ni)), Mq, tab, ec);
+                    if (!(t > 2.3e-308) || !chain_ok) {
+                        // clamped (underflowed) or unusable factor: the segment takes one true exp per bin instead
+                        for (; b < bend; ++b, i += 4, pb += BWB) {
+                            if (flagged(pb)) {
+                                double Nd;
+                                Bin c0, b1, b2, b3;
+                                const double um = load_u(i - 1, Nd);
+                                load_bin(i, c0);
+                                load_bin(i + 1, b1);
+                                load_bin(i + 2, b2);
+                                load_bin(i + 3, b3);
+                                const double u4 = load_u(i + 4, Nd);
+                                slow_bin(i, um, c0, b1.u);
+                                slow_bin(i + 1, c0.u, b1, b2.u);
+                                slow_bin(i + 2, b1.u, b2, b3.u);
+                                slow_bin(i + 3, b2.u, b3, u4);
+                            } else {
+                                Bin c0;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    load_bin(i + k, c0);
+                                    accumulate(c0);
+                                }
+                            }
+                        }
+                        continue;
+                    }
+                    for (; b + 1 < bend; b += 2, i += 8, pb += 2u * BWB) {   // two blocks per iteration
+                        const bool fa = flagged(pb), fb = flagged(pb + BWB);
+                        const double t2 = t * r4;
+                        if (fa | fb) {
+                            if (fa) careful_block(pb, i, t); else fast_block(pb, t);
+                            if (fb) careful_block(pb + BWB, i + 4, t2); else fast_block(pb + BWB, t2);
+                        } else {
+                            fast_block(pb, t);
+                            fast_block(pb + BWB, t2);
+                        }
+                        t *= r8;
+                    }
+                    if (b < bend) {
+                        if (flagged(pb)) careful_block(pb, i, t); else fast_block(pb, t);
+                        ++b;
+                        i += 4;
+                        pb += BWB;
+                    }
+                }
+                double Nd;
+                xm = load_u(i - 1, Nd);
+                load_bin(i, c);
+            } else {
 #pragma unroll 2
             for (; i + 3 < last; i += 4) {   // bins i..i+3 are interior, i+4 <= last exists
                 Bin b1, b2, b3, b4;
@@ -322,6 +506,7 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
                 xm = b3.u;
                 c = b4;
                 dc = d4;
+            }
             }
             for (; i < last; ++i) {
                 Bin nx;
@@ -415,10 +600,10 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
         return done;
 }
 
-template <int NSEL, bool SEL0N, int NC, int NT, bool REC = false>
+template <int NSEL, bool SEL0N, int NC, int NT, int REC = 0>
 __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constant__ SweepArgs a)
 {
-    static_assert(!REC || NC == 0, "the exp recurrence only exists for pure mu sweeps");
+    static_assert(!REC || (NC == 0 && NT == 1), "the exp recurrence only exists for pure mu sweeps");
     constexpr bool TAYLOR = (NC > 0) || (NT > 1);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const FastCtx cx = fast_prepare<NSEL, SEL0N, NC, NT, REC>(a, smem_raw);
@@ -468,10 +653,16 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
 }
 
 // shared memory the fast kernel needs for this histogram
-template <int NSEL, bool SEL0N, int NC, int NT, bool REC = false>
+template <int NSEL, bool SEL0N, int NC, int NT, int REC = 0>
 static size_t fast_smem_bytes(int n_pad)
 {
-    return (size_t)n_pad * 8 * (FastLayout<NSEL, SEL0N, NC, NT, REC>::PK + 1) + 16 + 512 + FHMC_FAST_QUEUE * 8 + 64;
+    using LY = FastLayout<NSEL, SEL0N, NC, NT, REC>;
+    size_t b = fast_base_bytes<LY::PK>(n_pad);
+    if (REC == 2) {
+        const size_t nb = (size_t)(n_pad / 4 + 1);
+        b += nb * LY::BW * 8 + (nb / LY::SEGB + 2) * 8 + 16;
+    }
+    return b;
 }
 
 }  // namespace fhmc
@@ -482,7 +673,7 @@ static size_t fast_smem_bytes(int n_pad)
 namespace fhmc {
 
 // returns 0 ok, 1 error, -1 "does not fit / not applicable" (caller falls back to the generic kernel)
-template <int NSEL, bool SEL0N, int NC, int NT, bool REC = false>
+template <int NSEL, bool SEL0N, int NC, int NT, int REC = 0>
 static int launch_fast(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream)
 {
     const size_t smem = fast_smem_bytes<NSEL, SEL0N, NC, NT, REC>(args.d.n_pad);
@@ -503,5 +694,7 @@ static int launch_fast(const SweepArgs &args, int sm_count, int smem_optin, cuda
 int launch_fast_taylor(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream);
 // pure mu sweeps with the exp recurrence (fhmc_fast_rec.cu)
 int launch_fast_mu_rec(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream);
+// pure mu sweeps, product form of the recurrence (fhmc_fast_prod.cu)
+int launch_fast_mu_prod(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream);
 
 }  // namespace fhmc

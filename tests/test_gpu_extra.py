@@ -80,18 +80,19 @@ def test_reweight_2d_vs_oracle(oracle, n1, n2, nprop):
 
 
 def test_fast_and_generic_kernels_agree():
-    """The one-pass mu-sweep kernel (with and without the exp recurrence) and the generic two-pass kernel must give
-    identical integers and fp64 to 1e-10."""
+    """The one-pass mu-sweep kernel (product form, chain recurrence, true exps) and the generic two-pass kernel must
+    give identical integers and fp64 to 1e-10."""
     from fhmcanalysis_b200 import engine, synth
     for n, smooth, noise in ((1001, 10, 1e-3), (573, 3, 5e-2), (2001, 30, 0.0)):
         lnpi = synth.two_peak_lnpi(n, noise=noise, scale=n / 1001.0)
         N = np.arange(n, dtype=float)
-        for rec in (True, False):
+        for rec in (2, 1, 0):   # product form, multiplicative chains, one true exp per bin
             dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=smooth, sel=["N", N * N])
             dh.use_recurrence = rec
             dh.ensure_hull()
-            assert dh.desc.mu_recurrence == int(rec)
-            mus = np.linspace(-0.05, 0.05, 5000)
+            assert dh.desc.mu_recurrence == rec
+            # mostly the coexistence region, plus strong tilts (product form: anchors underflow / chain switched off)
+            mus = np.concatenate([np.linspace(-0.05, 0.05, 4600), np.linspace(-6.0, 6.0, 400)])
             a = dh.sweep_auto(mus, pmax=4, lanes=1).host()      # one-pass fast kernel
             if n == 1001:
                 assert np.mean((a["status"] & 0x1000) != 0) > 0.99   # really produced by the fast kernel
