@@ -52,6 +52,9 @@ struct FastLayout {
     // REC == 2 (product form): per 4-bin block {key(Dmin), key(Dmax) | pad | P x4 | P*X_q x4 ...} doubles
     static constexpr int BW = 2 + 4 * (1 + NSEL);
     static constexpr int SEGB = 32;                     // blocks per anchor segment (128 bins)
+    static constexpr int QN = FHMC_FAST_QUEUE;          // deferred-fallback queue entries
+    static constexpr int QTILES = 4;                    // tiles between two looks at the queue
+    // (three CTAs per SM with a 512-entry queue and an 80-register cap measured 10 % slower for REC == 2)
 };
 
 // what the per-state-point walk needs to know about the CTA's packed copy
@@ -72,10 +75,10 @@ __device__ __forceinline__ int hi_key(double x)
 }
 
 // bytes of the packed rows + staging row + barrier + exp table + fallback queue (what every variant needs)
-template <int PK>
+template <int PK, int QN = FHMC_FAST_QUEUE>
 __host__ __device__ constexpr size_t fast_base_bytes(int n_pad)
 {
-    return (((size_t)n_pad * 8 * (PK + 1) + 16 + 512 + FHMC_FAST_QUEUE * 8 + 64) + 15) & ~(size_t)15;
+    return (((size_t)n_pad * 8 * (PK + 1) + 16 + 512 + QN * 8 + 64) + 15) & ~(size_t)15;
 }
 
 // Build the CTA's packed copy (all threads of the CTA; ends with a barrier).
@@ -130,11 +133,11 @@ __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned cha
         // Product form: bins 1+4b .. 4+4b make block b (nb full blocks, bin 4+4b+... <= last - 0), SEGB blocks share the
         // anchor A_g = max lnPI over the segment.  P_i = exp(lnPI_i - A_g) <= 1 and P_i * X_q(i) are tabulated, so that
         // sum_i exp(lnPI_i + s N_i - shift) X_i over a block is a Horner polynomial in exp(s dN) times one running factor.
-        // D_j = lnPI_j - lnPI_{j-1}: a strict extremum of lnPI + s N inside the block needs -s dN within [Dmin, Dmax] of
-        // the five differences that touch the block; only the order-preserving keys of their upper words are kept.
+        // Each block also carries the range of tilts -s dN for which one of its bins can be a windowed extremum; only the
+        // order-preserving keys of the upper words of that range are kept.
         const int nb = (n - 2) / 4;
         const int nseg = (nb + LY::SEGB - 1) / LY::SEGB;
-        double *prod = reinterpret_cast<double *>(smem_raw + fast_base_bytes<PK>(npad));
+        double *prod = reinterpret_cast<double *>(smem_raw + fast_base_bytes<PK, LY::QN>(npad));
         double *anch = prod + (size_t)nb * LY::BW;
         unsigned long long *s_lmax = reinterpret_cast<unsigned long long *>(anch + nseg);
         if (threadIdx.x == 0) *s_lmax = 0ull;
@@ -149,14 +152,33 @@ __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned cha
             anch[g] = m;
         }
         __syncthreads();
+        const double lmax_all = __longlong_as_double((long long)*s_lmax);
+        const double dN0 = pk[PK + 1] - pk[1];
+        const double slack = 4.0 * (1.8e-15 * (lmax_all + 4.5 * fmax(fabs(pk[1]), fabs(pk[(size_t)(n - 1) * PK + 1])) / dN0) + 1e-300)
+                             + 1e-12 * fabs(dN0);
         for (int b = threadIdx.x; b < nb; b += blockDim.x) {
             const int i = 1 + 4 * b;
             const double A = anch[b / LY::SEGB];
+            // For which tilts a = -s dN can a bin of this block be a windowed extremum?  u_j - u_k = lnPI_j - lnPI_k - a (j-k),
+            // so bin j is a strict maximum over +-w iff max_d SR_d < a < min_d SL_d with the chord slopes
+            // SL_d = (lnPI_j - lnPI_jl)/(j - jl), SR_d = (lnPI_jr - lnPI_j)/(jr - j) (jl, jr clipped like argrelextrema's
+            // 'clip' mode), and a strict minimum iff max_d SL_d < a < min_d SR_d.  The block keeps the hull [dmin, dmax] of
+            // its non-empty intervals (widened by `slack`, the largest rounding margin a chained state point can have).
             double dmin = CUDART_INF, dmax = -CUDART_INF;
-            for (int j = i; j <= i + 4; ++j) {
-                const double D = pk[(size_t)j * PK] - pk[(size_t)(j - 1) * PK];
-                dmin = fmin(dmin, D);
-                dmax = fmax(dmax, D);
+            for (int j = i; j < i + 4; ++j) {
+                const double lj = pk[(size_t)j * PK];
+                double maxSL = -CUDART_INF, minSL = CUDART_INF, maxSR = -CUDART_INF, minSR = CUDART_INF;
+                for (int d = 1; d <= a.d.smooth; ++d) {
+                    const int jl = max(j - d, 0), jr = min(j + d, n - 1);
+                    const double SL = (lj - pk[(size_t)jl * PK]) / (double)(j - jl);
+                    const double SR = (pk[(size_t)jr * PK] - lj) / (double)(jr - j);
+                    maxSL = fmax(maxSL, SL);
+                    minSL = fmin(minSL, SL);
+                    maxSR = fmax(maxSR, SR);
+                    minSR = fmin(minSR, SR);
+                }
+                if (maxSR <= minSL + slack) { dmin = fmin(dmin, maxSR); dmax = fmax(dmax, minSL); }   // maximum possible
+                if (maxSL <= minSR + slack) { dmin = fmin(dmin, maxSL); dmax = fmax(dmax, minSR); }   // minimum possible
             }
             double *pb = prod + (size_t)b * LY::BW;
             int *kb = reinterpret_cast<int *>(pb);
@@ -311,8 +333,19 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
         };
         // remaining shifts d0..smooth of the argrelextrema test, on the packed shared-memory rows (the generic
         // evaluator's window_ok()/verify() would read the blob through global memory here)
+        // `robust` (REC == 2): every comparison behind an accepted extremum was decided by more than vmargin, the most
+        // that rounding fl(u - c) can move two values against each other -- the re-test on the normalised values
+        // below then cannot differ and is skipped.
+        bool robust = (REC == 2);
+        double vmargin = 0.0;
+        if (REC == 2) {
+            const double Na = fmax(fabs(lds_f64(s_pk + 8u)), fabs(lds_f64(s_pk + (uint32_t)last * (uint32_t)(PK * 8) + 8u)));
+            vmargin = 1.8e-15 * (cx.lmax + fabs(s) * Na) + 1e-14;   // >= 2^-51 (|u| + |c|) for every bin
+        }
         auto window_fast = [&](int i, double xc, bool is_max, bool use_c, double cc, int d0) {
             double Nd;
+            const double xg = is_max ? xc - vmargin : xc + vmargin;
+            bool rb = true;
             for (int d = d0; d <= pe.w; ++d) {
                 const int jl = (i - d < 0) ? 0 : i - d;
                 const int jr = (i + d > last) ? last : i + d;
@@ -320,13 +353,16 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
                 if (use_c) { xl = __dsub_rn(xl, cc); xr = __dsub_rn(xr, cc); }
                 const bool ok = is_max ? (xc > xl && xc > xr) : (xc < xl && xc < xr);
                 if (!ok) return false;
+                if (REC == 2) rb &= is_max ? (xg > xl && xg > xr) : (xg < xl && xg < xr);
             }
+            if (REC == 2 && !use_c) robust &= rb;
             return true;
         };
         // exact strict 1-neighbour test + window test of bin i (values xm, xc, xp), then its contribution
         auto test_bin = [&](int i, double xm, double xc, double xp) {
             const bool is_max = (xc > xm) && (xc > xp), is_min = (xc < xm) && (xc < xp);
             if ((is_max || is_min) && window_fast(i, xc, is_max, false, 0.0, 2)) {
+                if (REC == 2) robust &= is_max ? (xc - vmargin > xm && xc - vmargin > xp) : (xc + vmargin < xm && xc + vmargin < xp);
                 if (is_max) {
                     if (1 + cntM <= pmax - 1) maxl[1 + cntM] = i;
                     ++cntM;
@@ -372,8 +408,9 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
                 const double sdn = s * (lds_f64(s_pk + (uint32_t)(PK * 8) + 8u) - lds_f64(s_pk + 8u));
                 const double Na = fmax(fabs(lds_f64(s_pk + 8u)), fabs(lds_f64(s_pk + (uint32_t)last * (uint32_t)(PK * 8) + 8u)));
                 const double margin = 1.8e-15 * (cx.lmax + fabs(s) * Na) + 1e-300;   // 8 * 2^-52 * (|lnPI| + |s N|)
-                const int k_hi = hi_key(-sdn + margin), k_lo = hi_key(-sdn - margin);
                 const bool chain_ok = fabs(sdn) < 4.5;   // exp(|s dN| * 128 bins) must stay finite
+                // (the tabulated ranges assume |s dN| < 4.5 in their rounding slack: beyond it every block is examined)
+                const int k_hi = chain_ok ? hi_key(-sdn + margin) : 0x7fffffff, k_lo = chain_ok ? hi_key(-sdn - margin) : (int)0x80000000;
                 const int nb = (n - 2) / 4;
                 const double r2 = r1 * r1, r8 = r4 * r4;
                 constexpr uint32_t BWB = (uint32_t)(LY::BW * 8);
@@ -447,8 +484,14 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
                         }
                         continue;
                     }
-                    for (; b + 1 < bend; b += 2, i += 8, pb += 2u * BWB) {   // two blocks per iteration
-                        const bool fa = flagged(pb), fb = flagged(pb + BWB);
+                    // two blocks per iteration; the range keys of the next two are fetched while these are summed
+                    int ka0, kb0, ka1, kb1;
+                    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(ka0), "=r"(kb0) : "r"(pb));
+                    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(ka1), "=r"(kb1) : "r"(pb + BWB));
+                    for (; b + 1 < bend; b += 2, i += 8, pb += 2u * BWB) {
+                        const bool fa = !((ka0 > k_hi) | (kb0 < k_lo)), fb = !((ka1 > k_hi) | (kb1 < k_lo));
+                        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(ka0), "=r"(kb0) : "r"(pb + 2u * BWB));
+                        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(ka1), "=r"(kb1) : "r"(pb + 3u * BWB));
                         const double t2 = t * r4;
                         if (fa | fb) {
                             if (fa) careful_block(pb, i, t); else fast_block(pb, t);
@@ -536,6 +579,7 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
                 // scan on fl(u - c) here; only genuine ties go to the generic evaluator.
                 double vM = -CUDART_INF, vm = CUDART_INF, Nd;
                 int cM = 0, cm = 0, pM = 0, pm = 0;
+                robust = false;   // nothing was decided by the walk: keep the re-test of whatever repair() lists
                 for (int j = 0; j < n; ++j) {
                     const double v = __dsub_rn(load_u(j, Nd), c);
                     if (v > vM) { vM = v; cM = 1; pM = j; } else if (v == vM) ++cM;
@@ -551,7 +595,7 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
                 pe.nmin = nm;
                 // re-test the detected interior extrema on the normalised values, as PointEval::verify()
                 bool differs = false;
-                if (!a.d.compare_raw) {
+                if (!a.d.compare_raw && !robust) {
                     double Nd;
                     for (int k = 0; k < nM + nm && !differs; ++k) {
                         const bool is_max = k < nM;
@@ -613,9 +657,10 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
 
     // Irregular state points are not re-run on the spot (one such lane would stall its whole warp for a full generic
     // evaluation): they are queued in shared memory and drained by all threads of the CTA, one queued point per thread.
-    // The queue is inspected (one CTA barrier) only every fourth tile.
+    // The queue is inspected (one CTA barrier) only every QTILES-th tile.
+    using LY = FastLayout<NSEL, SEL0N, NC, NT, REC>;
     long long *queue = reinterpret_cast<long long *>(s_tab + 64);
-    int *q_count = reinterpret_cast<int *>(queue + FHMC_FAST_QUEUE);
+    int *q_count = reinterpret_cast<int *>(queue + LY::QN);
     if (threadIdx.x == 0) *q_count = 0;
     __syncthreads();
     auto drain = [&]() {
@@ -643,9 +688,9 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
         if (!fast_point<NSEL, SEL0N, NC, NT, REC>(a, cx, pe, ec, sp, mu1, beta, dmu))
             queue[atomicAdd(q_count, 1)] = sp;  // anything unusual: defer to the generic evaluator
       }
-      if ((++tile_no & 3) == 0) {
+      if ((++tile_no % LY::QTILES) == 0) {
           __syncthreads();
-          if (*q_count > FHMC_FAST_QUEUE - 4 * FHMC_CTA) drain();   // uniform across the CTA (read after the barrier)
+          if (*q_count > LY::QN - LY::QTILES * FHMC_CTA) drain();   // uniform across the CTA (read after the barrier)
       }
     }
     __syncthreads();
@@ -657,10 +702,10 @@ template <int NSEL, bool SEL0N, int NC, int NT, int REC = 0>
 static size_t fast_smem_bytes(int n_pad)
 {
     using LY = FastLayout<NSEL, SEL0N, NC, NT, REC>;
-    size_t b = fast_base_bytes<LY::PK>(n_pad);
+    size_t b = fast_base_bytes<LY::PK, LY::QN>(n_pad);
     if (REC == 2) {
         const size_t nb = (size_t)(n_pad / 4 + 1);
-        b += nb * LY::BW * 8 + (nb / LY::SEGB + 2) * 8 + 16;
+        b += (nb + 3) * LY::BW * 8 + (nb / LY::SEGB + 2) * 8 + 16;   // (+3 blocks: the key prefetch reads ahead)
     }
     return b;
 }
