@@ -8,6 +8,7 @@ _MODULES = [
     "moments.histogram.one_dim.ntot.gc_hist", "moments.histogram.one_dim.ntot.gc_binary",
     "moments.histogram.one_dim.ntot.collect", "moments.histogram.one_dim.n1", "moments.histogram.one_dim.n1.gc_hist",
     "moments.histogram.two_dim", "moments.histogram.two_dim.joint_hist",
+    "moments.histogram.two_dim.h_ntot", "moments.histogram.two_dim.h_ntot.pore_hist",
 ]
 for _m in _MODULES:
     try:

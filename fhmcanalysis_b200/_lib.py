@@ -69,6 +69,7 @@ EXPORTS = [
     "fhmc_version", "fhmc_last_error", "fhmc_device_info", "fhmc_sweep_1d", "fhmc_lnpi_1d",
     "fhmc_phase_moments", "fhmc_axpy_rows", "fhmc_find_phase_eq_1d", "fhmc_reweight_2d",
     "fhmc_reweight_2d_workspace", "fhmc_pack_bytes", "fhmc_pack_phase_major",
+    "fhmc_masked_lse_2d", "fhmc_masked_lse_2d_workspace",
     "fhmc_bench_dfma", "fhmc_bench_exp",
 ]
 
@@ -113,6 +114,10 @@ def load():
     L.fhmc_reweight_2d_workspace.restype = ctypes.c_size_t
     L.fhmc_reweight_2d_workspace.argtypes = [ci, ci, ci, cll]
     L.fhmc_reweight_2d.argtypes = [vp, vp, ci, ci, vp, vp, vp, ci, vp, vp, cll, vp, vp, ctypes.c_size_t, vp]
+    L.fhmc_masked_lse_2d_workspace.restype = ctypes.c_size_t
+    L.fhmc_masked_lse_2d_workspace.argtypes = [ci, ci, ci]
+    L.fhmc_masked_lse_2d.restype = ci
+    L.fhmc_masked_lse_2d.argtypes = [vp, vp, vp, ci, ci, vp, ci, vp, vp, ci, vp, vp, ctypes.c_size_t, vp]
     L.fhmc_bench_dfma.restype = cll
     L.fhmc_bench_dfma.argtypes = [ci, vp, vp]
     L.fhmc_bench_exp.restype = cll

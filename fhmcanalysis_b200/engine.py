@@ -654,6 +654,69 @@ def reweight_2d(lnpi, bounds, op1, op2, a1, a2, props=None, device=None, return_
     return out if return_device else out.cpu().numpy()
 
 
+MASKED_2D_MAXPROP = 8
+
+
+def masked_lse_2d(lnpi, mask=None, edge=None, props=None, shifted=False, device=None, peak_cap=64):
+    """One-shot ragged / masked log-sum-exp of a surface lnPI[n1, n2] with averages of property matrices
+    (pore_hist.normalize / pore_hist.thermo, two_dim/h_ntot/pore_hist.pyx:57-80, 154-184).
+
+    mask  [n1, n2] bool (True = bin belongs to the region) or None;  edge [n1] = last valid column per row or None;
+    props [n_prop, n1, n2] or None (any n_prop: processed eight matrices per launch).
+    Returns dict(lnsum, max, avg[n_prop], peak_idx = (rows, cols) of the selected bins equal to the maximum,
+    shifted = lnPI - lnsum when ``shifted``)."""
+    L = _lib.load()
+    t = torch()
+    dev = require_cuda(device)
+    lnpi_t = t.from_numpy(np.ascontiguousarray(lnpi, dtype=np.float64)).to(dev)
+    if lnpi_t.dim() != 2:
+        raise ValueError("lnpi must be two-dimensional")
+    n1, n2 = lnpi_t.shape
+    mask_t = None
+    if mask is not None:
+        mk = np.ascontiguousarray(mask).astype(np.uint8)
+        if mk.shape != (n1, n2):
+            raise ValueError("mask must have the shape of ln(PI)")
+        mask_t = t.from_numpy(mk).to(dev)
+    edge_t = None
+    if edge is not None:
+        ed = np.ascontiguousarray(edge, dtype=np.int32)
+        if ed.shape != (n1,):
+            raise ValueError("edge must hold one column index per row")
+        edge_t = t.from_numpy(ed).to(dev)
+    pr = None if props is None or len(props) == 0 else np.ascontiguousarray(props, dtype=np.float64)
+    n_prop = 0 if pr is None else pr.shape[0]
+    if pr is not None and pr.shape[1:] != (n1, n2):
+        raise ValueError("props must be [n_prop, n1, n2]")
+    avg = np.empty(n_prop, dtype=np.float64)
+    shifted_t = t.empty_like(lnpi_t) if shifted else None
+    res = None
+    with t.cuda.device(dev):
+        for q0 in range(0, max(n_prop, 1), MASKED_2D_MAXPROP):
+            nq = min(MASKED_2D_MAXPROP, n_prop - q0) if n_prop else 0
+            p_t = t.from_numpy(pr[q0:q0 + nq]).to(dev) if nq else None
+            out = t.empty(2 + MASKED_2D_MAXPROP, dtype=t.float64, device=dev)
+            peak = t.empty(1 + peak_cap, dtype=t.int64, device=dev)
+            ws_bytes = L.fhmc_masked_lse_2d_workspace(n1, n2, nq)
+            ws = t.empty(max(ws_bytes // 8, 2), dtype=t.float64, device=dev)
+            rc = L.fhmc_masked_lse_2d(_ptr(lnpi_t), _ptr(mask_t), _ptr(edge_t), n1, n2, _ptr(p_t), nq, _ptr(out), _ptr(peak),
+                                      peak_cap, _ptr(shifted_t) if (shifted and q0 == 0) else None, _ptr(ws), ws_bytes,
+                                      _stream_ptr(dev))
+            _lib.check(rc, "fhmc_masked_lse_2d")
+            oh = out.cpu().numpy()
+            avg[q0:q0 + nq] = oh[2:2 + nq]
+            if res is None:
+                pk = peak.cpu().numpy()
+                if pk[0] > peak_cap:   # more ties with the maximum than the buffer holds: ask again with room for all
+                    return masked_lse_2d(lnpi, mask, edge, props, shifted, device, peak_cap=int(pk[0]))
+                flat = np.sort(pk[1:1 + pk[0]])
+                res = {"lnsum": float(oh[0]), "max": float(oh[1]), "peak_idx": (flat // n2, flat % n2)}
+    res["avg"] = avg
+    if shifted:
+        res["shifted"] = shifted_t.cpu().numpy()
+    return res
+
+
 def measure_peaks(device=None, iters=20000):
     """Register-resident fp64 micro-benchmarks: returns dict(dfma_per_s, exp_per_s) measured with CUDA events."""
     L = _lib.load()

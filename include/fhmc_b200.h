@@ -214,6 +214,19 @@ int fhmc_reweight_2d(const double *lnpi, const int *bounds, int n1, int n2, cons
                      const double *a2, long long n_states, double *out, double *workspace,
                      size_t workspace_bytes, void *stream);
 
+/*
+ * Ragged / masked 2-D log-sum-exp with averages, one surface per call (HBM-bound streaming reduction):
+ *   pore_hist.normalize (two_dim/h_ntot/pore_hist.pyx:57-80, 147-152): edge[i] = last valid column of row i, mask NULL,
+ *       lnpi_shifted (nullable) receives lnPI - ln sum exp lnPI;
+ *   pore_hist.thermo(mask) (pore_hist.pyx:154-184): mask[n1][n2] (1 = bin belongs to the phase), props [n_prop][n1][n2].
+ * out[0] = ln sum_sel exp lnPI, out[1] = max_sel lnPI, out[2+q] = <prop_q>;  peak[0] = number of selected bins equal to
+ * the maximum, peak[1..peak_cap] their flat indices (unordered; np.where(lp == np.max(lp)), PH:182).  n_prop <= 8.
+ */
+size_t fhmc_masked_lse_2d_workspace(int n1, int n2, int n_prop);
+int fhmc_masked_lse_2d(const double *lnpi, const unsigned char *mask, const int *edge, int n1, int n2,
+                       const double *props, int n_prop, double *out, long long *peak, int peak_cap,
+                       double *lnpi_shifted, double *workspace, size_t workspace_bytes, void *stream);
+
 /* Roofline micro-benchmarks (register-resident): return ops executed; time with CUDA events. */
 long long fhmc_bench_dfma(int iters, double *sink, void *stream);
 long long fhmc_bench_exp(int iters, double *sink, void *stream);

@@ -34,6 +34,7 @@ SOURCES = {
     "gc_binary": "moments/histogram/one_dim/ntot/gc_binary.pyx",
     "joint_hist": "moments/histogram/two_dim/joint_hist.pyx",
     "gc_hist_n1": "moments/histogram/one_dim/n1/gc_hist.pyx",      # N_1 order parameter
+    "pore_hist": "moments/histogram/two_dim/h_ntot/pore_hist.pyx",  # 2-D normalise / masked averages
 }
 
 # (module, regex, replacement, expected count or None) -- porting edits only.

@@ -14,8 +14,10 @@ Parity status: pinned -- see tests/test_oracle_golden.py (reference unit-test kn
 golden vectors generated from the compiled reference by tests/golden/make_golden.py).
 """
 import ctypes
+import math
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -284,3 +286,39 @@ def reweight_2d(lnpi, bounds, op1, op2, b_dmu1, b_dmu2, props=None):
     lib().fo_reweight_2d(_d(lnpi), _i(b), n1, n2, _d(o1), _d(o2), float(b_dmu1), float(b_dmu2),
                          _d(props) if props.shape[0] else None, props.shape[0], _d(out))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# pore_hist (moments/histogram/two_dim/h_ntot/pore_hist.pyx) -- SURVEY 8(f) row 3
+# ----------------------------------------------------------------------------------------------
+def _spec_exp(a, b):
+    """ln(exp(a) + exp(b)) as pore_hist.pyx:35-53: max(a, b) + log(1 + exp(-|a - b|))."""
+    return max(a, b) + math.log(1.0 + math.exp(-abs(a - b)))
+
+
+def pore_normalize(lnpi, edge):
+    """pore_hist._cy_normalize (pore_hist.pyx:57-80): sequential specExp fold, row-major over j <= edge[i], starting
+    from -DBL_MAX; returns data - lnNormPI.  Pinned on the compiled reference (tests/golden/pore_vectors.npz)."""
+    lnpi = np.asarray(lnpi, dtype=np.float64)
+    acc = -sys.float_info.max
+    for i in range(lnpi.shape[0]):
+        for j in range(0, int(edge[i]) + 1):
+            acc = _spec_exp(acc, float(lnpi[i, j]))
+    return lnpi - acc
+
+
+def pore_thermo(lnpi, mask, props):
+    """pore_hist.thermo (pore_hist.pyx:154-184) with ``lp[not mask]`` read as ``lp[~mask]`` (the reference raises on any
+    mask of more than one element -- PARITY UNPINNED for this function).
+    Returns ({name: average}, peak_idx)."""
+    lp = np.array(lnpi, dtype=np.float64, copy=True)
+    mask = np.asarray(mask, dtype=bool)
+    with np.errstate(all="ignore"):
+        lp -= np.max(lp)                       # PH:169
+        lp[~mask] = -np.inf                    # PH:170
+        lp -= np.log(np.sum(np.exp(lp)))       # PH:171
+        lp[~mask] = -np.inf                    # PH:172
+        prob = np.exp(lp)                      # PH:174
+        sum_prob = np.sum(prob)                # PH:175
+        ave = {p: np.sum(prob * np.where(mask, props[p], 0.0)) / sum_prob for p in props}   # PH:178-179 (0 * x outside the mask)
+    return ave, np.where(lp == np.max(lp))     # PH:182
