@@ -5,12 +5,29 @@
 // multiply-adds per block and summed quantity instead of an exp per bin, re-anchored with a true exp every 128 bins and
 // after every block that runs the exact extremum tests ("strength reduction ... re-anchored every k bins
 // is allowed").  Used when the caller set fhmc_hist_desc.mu_recurrence = 2.
-#include "fhmc_fast.cuh"
+#include "fhmc_prod.cuh"
 
 namespace fhmc {
 
+// two state points per thread (fhmc_prod.cuh): halves the shared-memory traffic per state point
+static int launch_fast_mu_prod2(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream)
+{
+    const bool s0n = args.d.n_sel > 0 && args.d.sel_row[0] == 1;
+    switch (args.d.n_sel) {
+    case 0: return launch_prod2<0, false>(args, sm_count, smem_optin, stream);
+    case 1: return s0n ? launch_prod2<1, true>(args, sm_count, smem_optin, stream) : launch_prod2<1, false>(args, sm_count, smem_optin, stream);
+    case 2: return s0n ? launch_prod2<2, true>(args, sm_count, smem_optin, stream) : launch_prod2<2, false>(args, sm_count, smem_optin, stream);
+    default: return -1;   // three or four summed quantities: the table registers of two points do not fit; one point per thread
+    }
+}
+
 int launch_fast_mu_prod(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream)
 {
+    // enough state points for two resident CTAs per SM at two points per thread (else the one-point form fills the GPU better)
+    if (args.d.mu_recurrence >= 3 && args.st.n_states >= (long long)sm_count * 4 * FHMC_CTA) {
+        const int rc = launch_fast_mu_prod2(args, sm_count, smem_optin, stream);
+        if (rc >= 0) return rc;
+    }
     const bool s0n = args.d.n_sel > 0 && args.d.sel_row[0] == 1;
     switch (args.d.n_sel) {
     case 0: return launch_fast<0, false, 0, 1, 2>(args, sm_count, smem_optin, stream);

@@ -207,9 +207,10 @@ class DeviceHistogram(object):
             rows.extend(np.ascontiguousarray(r, dtype=np.float64) for r in terms)
         hull_row, hull_len = 0, 0          # the hull rows are added lazily (ensure_hull) by large mu sweeps only
         self._hull_possible = not coef
-        # exp strength reduction of large pure-mu sweeps, fixed before the first one: 2 = product form (Horner blocks,
-        # fhmc_fast_prod.cu), 1 = four multiplicative chains (fhmc_fast_rec.cu), 0/False = one true exp per bin
-        self.use_recurrence = int(os.environ.get("FHMC_MU_RECURRENCE", "2"))
+        # exp strength reduction of large pure-mu sweeps, fixed before the first one: 3 = product form (Horner blocks,
+        # fhmc_fast_prod.cu) with two state points per thread where the sweep is large enough, 2 = product form, one
+        # point per thread, 1 = four multiplicative chains (fhmc_fast_rec.cu), 0/False = one true exp per bin
+        self.use_recurrence = int(os.environ.get("FHMC_MU_RECURRENCE", "3"))
         blob = np.zeros((len(rows), n_pad), dtype=np.float64)
         for i, r in enumerate(rows):
             if r.shape != (n,):
@@ -256,7 +257,7 @@ class DeviceHistogram(object):
         Nrow, lrow = self.blob_host[1, :self.n], self.blob_host[0, :self.n]
         dN = np.diff(Nrow)
         if self.n > 8 and np.all(dN == dN[0]) and dN[0] > 0 and np.max(np.abs(lrow[4:] - lrow[:-4])) < 300.0 and self.use_recurrence:
-            self.desc.mu_recurrence = 2 if int(self.use_recurrence) >= 2 else 1
+            self.desc.mu_recurrence = min(3, max(1, int(self.use_recurrence)))
         self.blob_host = np.ascontiguousarray(np.vstack([self.blob_host, extra]))
         self.n_rows += 2
         self.desc.n_rows = self.n_rows

@@ -32,7 +32,7 @@ def main():
     n = 1001
     lnpi = synth.two_peak_lnpi(n)
     N = np.arange(n, dtype=float)
-    variants = [int(v) for v in (sys.argv[1:] or ["2", "1", "0"])]
+    variants = [int(v) for v in (sys.argv[1:] or ["3", "2", "1", "0"])]
     for rec in variants:
         dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=10, sel=["N", N * N])
         dh.use_recurrence = rec

@@ -86,13 +86,15 @@ def test_fast_and_generic_kernels_agree():
     for n, smooth, noise in ((1001, 10, 1e-3), (573, 3, 5e-2), (2001, 30, 0.0)):
         lnpi = synth.two_peak_lnpi(n, noise=noise, scale=n / 1001.0)
         N = np.arange(n, dtype=float)
-        for rec in (2, 1, 0):   # product form, multiplicative chains, one true exp per bin
+        for rec in (3, 2, 1, 0):   # product form (two points / one point per thread), multiplicative chains, true exps
             dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=smooth, sel=["N", N * N])
             dh.use_recurrence = rec
             dh.ensure_hull()
             assert dh.desc.mu_recurrence == rec
             # mostly the coexistence region, plus strong tilts (product form: anchors underflow / chain switched off)
             mus = np.concatenate([np.linspace(-0.05, 0.05, 4600), np.linspace(-6.0, 6.0, 400)])
+            if rec == 3:   # the two-point kernel only runs from 4 * 256 state points per SM on
+                mus = np.concatenate([np.linspace(-0.05, 0.05, 158000), np.linspace(-6.0, 6.0, 4001)])
             a = dh.sweep_auto(mus, pmax=4, lanes=1).host()      # one-pass fast kernel
             if n == 1001:
                 assert np.mean((a["status"] & 0x1000) != 0) > 0.99   # really produced by the fast kernel
