@@ -258,7 +258,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     h2d = mu_host.numel() * 8 + dh.h2d_bytes
 
     def e2e_step():
-        # public host-buffer entry point: chunked, double-buffered H2D(mu) -> kernel -> repack -> D2H(results) pipeline
+        # public host-buffer entry point (one C-ABI call): chunked, double-buffered H2D(mu) -> kernel -> repack -> D2H(results)
         host_out["r"] = dh.sweep_host_compact(mu_host, pmax=PMAX, lanes=args.lanes, out=host_out["r"])
 
     for _ in range(2):
@@ -276,7 +276,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * S / (float(e2e_ms.item()) * 1e-3)
     d2h = int(host_out["r"]["d2h_bytes"])
-    e2e_launches = 2 * ((S + (1 << 17) - 1) >> 17)      # sweep + repack kernel per chunk
+    e2e_launches = 2 * ((S + (1 << 18) - 1) >> 18)      # sweep + repack kernel per chunk
     clocks = sampler.stop()
 
     # ---- the one collective of the path: final gather of packed results (not in `value`) ----------
@@ -351,7 +351,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             "config": {"workload": "config2: synthetic 1-comp N_tot lnPI, N_max=1000 (1001 bins), smooth=10, 10^6-point mu sweep per GPU with thermo "
                                    "(<N>, <N^2>, per-phase lnZ, phase split, is_safe)",
                        "state_points_per_gpu": S, "bins": N_BINS, "smooth": SMOOTH, "pmax": PMAX, "moments": list(moments),
-                       "lanes_per_point": args.lanes or "auto", "e2e_outputs": list(E2E_FIELDS), "e2e_path": "sweep_host_compact: per 2^17-point chunk H2D(mu) -> k_sweep_fast -> k_pack_phase_major -> D2H of the live phase blocks", "e2e_gpu_launches_per_step": e2e_launches, "l2": "flushed (256 MiB memset) before every timed step",
+                       "lanes_per_point": args.lanes or "auto", "e2e_outputs": list(E2E_FIELDS), "e2e_path": "fhmc_sweep_host_compact (C ABI, host buffers): per 2^18-point chunk H2D(mu) -> sweep kernel -> k_pack_phase_major -> D2H of the live phase blocks, two streams", "e2e_gpu_launches_per_step": e2e_launches, "l2": "flushed (256 MiB memset) before every timed step",
                        "parallelism": "dp%d over state points, no data-path collective" % world,
                        "final_gather_ms": gather_ms, "ok_fraction": ok_frac, "fast_kernel_fraction": fast_frac, "wall_s_timed_region": wall},
             "clocks": clocks,

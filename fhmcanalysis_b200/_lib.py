@@ -69,7 +69,7 @@ EXPORTS = [
     "fhmc_version", "fhmc_last_error", "fhmc_device_info", "fhmc_sweep_1d", "fhmc_lnpi_1d",
     "fhmc_phase_moments", "fhmc_axpy_rows", "fhmc_find_phase_eq_1d", "fhmc_reweight_2d",
     "fhmc_reweight_2d_workspace", "fhmc_pack_bytes", "fhmc_pack_phase_major",
-    "fhmc_masked_lse_2d", "fhmc_masked_lse_2d_workspace",
+    "fhmc_masked_lse_2d", "fhmc_masked_lse_2d_workspace", "fhmc_sweep_host_workspace", "fhmc_sweep_host_compact",
     "fhmc_bench_dfma", "fhmc_bench_exp",
 ]
 
@@ -118,6 +118,11 @@ def load():
     L.fhmc_masked_lse_2d_workspace.argtypes = [ci, ci, ci]
     L.fhmc_masked_lse_2d.restype = ci
     L.fhmc_masked_lse_2d.argtypes = [vp, vp, vp, ci, ci, vp, ci, vp, vp, ci, vp, vp, ctypes.c_size_t, vp]
+    L.fhmc_sweep_host_workspace.restype = ctypes.c_size_t
+    L.fhmc_sweep_host_workspace.argtypes = [cll, ci, ci]
+    L.fhmc_sweep_host_compact.restype = ci
+    L.fhmc_sweep_host_compact.argtypes = [ctypes.POINTER(HistDesc), vp, vp, cll, ci, cll, vp, ctypes.c_size_t, vp, vp, ci,
+                                          ctypes.POINTER(ci), ctypes.POINTER(cll), vp]
     L.fhmc_bench_dfma.restype = cll
     L.fhmc_bench_dfma.argtypes = [ci, vp, vp]
     L.fhmc_bench_exp.restype = cll

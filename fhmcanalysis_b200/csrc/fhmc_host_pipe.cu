@@ -1,0 +1,165 @@
+// fhmc_host_pipe.cu -- the host-buffer entry point of the mu sweep (new; the reference's seam for this is a Python loop of
+// reweight()/thermo() calls on host arrays, GH:268-289, 451-554, README.md:60-85).
+//
+// fhmc_sweep_host_compact: pinned host mu[S] in, pinned host results out, everything in between pipelined on two private
+// streams in chunks: H2D(mu chunk) -> fhmc_sweep_1d -> fhmc_pack_phase_major -> D2H of the chunk's head and of the phase
+// blocks that exist.  The number of live phase blocks of a chunk is only known after its kernels ran; waiting for it
+// before queueing copies would idle the copy engine, so copies are queued at once for `guess` blocks (what the previous
+// chunk needed) and a chunk that needed more is topped up when its flag is read, two chunks later, just before its device
+// buffers are reused.  Driving this loop from C costs a few microseconds per chunk, which is what allows 2^16-point
+// chunks (short pipeline fill) without becoming launch-bound.
+#include "fhmc_common.cuh"
+
+namespace fhmc {
+
+struct HostPipe {
+    cudaStream_t st[2];
+    cudaEvent_t ev[2], ready;
+    int device;
+    bool ok;
+};
+
+static HostPipe *host_pipe()
+{
+    static HostPipe pipes[16];
+    static bool made[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    HostPipe &p = pipes[dev];
+    if (!made[dev]) {
+        p.device = dev;
+        p.ok = cudaStreamCreateWithFlags(&p.st[0], cudaStreamNonBlocking) == cudaSuccess &&
+               cudaStreamCreateWithFlags(&p.st[1], cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&p.ev[0], cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&p.ev[1], cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&p.ready, cudaEventDisableTiming) == cudaSuccess;
+        made[dev] = true;
+    }
+    return p.ok ? &p : nullptr;
+}
+
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// device scratch of ONE of the two buffer sets
+struct PipeBuf {
+    double *mu;
+    fhmc_sweep_out out;
+    unsigned char *packed;
+    int *flag;
+    size_t bytes;
+};
+
+static PipeBuf carve(unsigned char *base, long long c, int pmax, int nsel)
+{
+    PipeBuf b;
+    size_t off = 0;
+    auto take = [&](size_t nbytes) { unsigned char *p = base ? base + off : nullptr; off += al256(nbytes); return p; };
+    b.mu = reinterpret_cast<double *>(take(8 * c));
+    b.out.status = reinterpret_cast<unsigned *>(take(4 * c));
+    b.out.nphase = reinterpret_cast<int *>(take(4 * c));
+    b.out.nmin = reinterpret_cast<int *>(take(4 * c));
+    b.out.lnnorm = reinterpret_cast<double *>(take(8 * c));
+    b.out.fe = reinterpret_cast<double *>(take(8 * c * pmax));
+    b.out.avg = reinterpret_cast<double *>(take(8 * c * pmax * (nsel > 0 ? nsel : 1)));
+    b.out.bounds = reinterpret_cast<int *>(take(8 * c * pmax));
+    b.out.max_idx = reinterpret_cast<int *>(take(4 * c * pmax));
+    b.out.min_idx = reinterpret_cast<int *>(take(4 * c * (pmax + 1)));
+    b.packed = take((size_t)fhmc_pack_bytes(c, pmax, nsel));
+    b.flag = reinterpret_cast<int *>(take(16));
+    b.bytes = off;
+    return b;
+}
+
+}  // namespace fhmc
+
+using namespace fhmc;
+
+extern "C" size_t fhmc_sweep_host_workspace(long long chunk, int pmax, int n_sel)
+{
+    if (chunk < 1 || pmax < 1 || n_sel < 0 || n_sel > FHMC_MAX_SEL) return 0;
+    return 2 * carve(nullptr, chunk, pmax, n_sel).bytes;
+}
+
+extern "C" int fhmc_sweep_host_compact(const fhmc_hist_desc *desc, const double *blob, const double *mu_host, long long n_states,
+                                       int lanes_per_point, long long chunk, void *workspace, size_t workspace_bytes,
+                                       void *out_host, int *flags_host, int guess_nphase, int *max_nphase_out,
+                                       long long *d2h_bytes_out, void *stream)
+{
+    if (!desc || !blob || !mu_host || !workspace || !out_host || !flags_host || n_states < 0 || chunk < 1) { set_error("bad arguments"); return 1; }
+    const int pmax = desc->pmax, nsel = desc->n_sel;
+    const size_t need = fhmc_sweep_host_workspace(chunk, pmax, nsel);
+    if (need == 0 || workspace_bytes < need) { set_error("workspace too small: need %zu bytes", need); return 1; }
+    if ((uintptr_t)workspace & 255) { set_error("workspace must be 256-byte aligned"); return 1; }
+    HostPipe *hp = host_pipe();
+    if (!hp) { set_error("could not create the pipeline streams"); return 1; }
+    if (max_nphase_out) *max_nphase_out = 0;
+    if (d2h_bytes_out) *d2h_bytes_out = 0;
+    if (n_states == 0) return 0;
+    PipeBuf buf[2];
+    buf[0] = carve(static_cast<unsigned char *>(workspace), chunk, pmax, nsel);
+    buf[1] = carve(static_cast<unsigned char *>(workspace) + buf[0].bytes, chunk, pmax, nsel);
+    const long long S = n_states, rec = 16 + 8 * (long long)nsel;
+    const long long n_chunks = (S + chunk - 1) / chunk;
+    unsigned char *oh = static_cast<unsigned char *>(out_host);
+    int guess = guess_nphase < 1 ? 1 : (guess_nphase > pmax ? pmax : guess_nphase);
+    int top = 0;
+    long long moved = 0;
+    // whatever the caller queued on `stream` (the blob upload) comes first
+    if (check_cuda(cudaEventRecord(hp->ready, (cudaStream_t)stream), "cudaEventRecord")) return 1;
+    for (int b = 0; b < 2; ++b)
+        if (check_cuda(cudaStreamWaitEvent(hp->st[b], hp->ready, 0), "cudaStreamWaitEvent")) return 1;
+
+    // blocks [from, upto] of chunk k: block 0 = head {status, nphase}[m], block 1+p = phase p records
+    auto copies = [&](long long k, int from, int upto) -> int {
+        const long long lo = k * chunk, m = (lo + chunk <= S ? chunk : S - lo);
+        const PipeBuf &B = buf[k & 1];
+        for (int j = from; j <= upto; ++j) {
+            const unsigned char *src = (j == 0) ? B.packed : B.packed + 8 * m + (long long)(j - 1) * m * rec;
+            unsigned char *dst = (j == 0) ? oh + 8 * lo : oh + 8 * S + ((long long)(j - 1) * S + lo) * rec;
+            const size_t nb = (size_t)((j == 0) ? 8 * m : m * rec);
+            if (check_cuda(cudaMemcpyAsync(dst, src, nb, cudaMemcpyDeviceToHost, hp->st[k & 1]), "cudaMemcpyAsync D2H")) return 1;
+            moved += (long long)nb;
+        }
+        return 0;
+    };
+    int sent[2] = {0, 0};   // phase blocks already queued for the chunk that owns buffer set b
+    auto settle = [&](long long k) -> int {
+        if (check_cuda(cudaEventSynchronize(hp->ev[k & 1]), "cudaEventSynchronize")) return 1;
+        int live = flags_host[k];
+        live = live < 1 ? 1 : (live > pmax ? pmax : live);
+        if (live > top) top = live;
+        if (live > guess) guess = live;
+        if (live > sent[k & 1]) {
+            if (copies(k, 1 + sent[k & 1], live)) return 1;
+            sent[k & 1] = live;
+        }
+        return 0;
+    };
+    fhmc_hist_desc d = *desc;
+    for (long long k = 0; k < n_chunks; ++k) {
+        const int b = (int)(k & 1);
+        if (k >= 2 && settle(k - 2)) return 1;   // same stream and buffers as chunk k: finish it before they are reused
+        const long long lo = k * chunk, m = (lo + chunk <= S ? chunk : S - lo);
+        cudaStream_t s = hp->st[b];
+        if (check_cuda(cudaMemcpyAsync(buf[b].mu, mu_host + lo, (size_t)(8 * m), cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D")) return 1;
+        fhmc_states st;
+        st.n_states = m;
+        st.mu1 = buf[b].mu; st.n_mu1 = m; st.mu1_div = 1;
+        st.beta = nullptr; st.n_beta = 1; st.beta_div = 1;
+        st.dmu = nullptr; st.n_dmu = 1; st.dmu_div = 1;
+        if (fhmc_sweep_1d(&d, blob, &st, &buf[b].out, lanes_per_point, s)) return 1;
+        if (check_cuda(cudaMemsetAsync(buf[b].flag, 0, 4, s), "cudaMemsetAsync")) return 1;
+        if (fhmc_pack_phase_major(&buf[b].out, m, pmax, nsel, buf[b].packed, buf[b].flag, s)) return 1;
+        if (check_cuda(cudaMemcpyAsync(&flags_host[k], buf[b].flag, 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync flag")) return 1;
+        if (check_cuda(cudaEventRecord(hp->ev[b], s), "cudaEventRecord")) return 1;
+        if (copies(k, 0, guess)) return 1;
+        sent[b] = guess;
+    }
+    for (long long k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; ++k)
+        if (settle(k)) return 1;
+    for (int b = 0; b < 2; ++b)
+        if (check_cuda(cudaStreamSynchronize(hp->st[b]), "cudaStreamSynchronize")) return 1;
+    if (max_nphase_out) *max_nphase_out = top;
+    if (d2h_bytes_out) *d2h_bytes_out = moved;
+    return 0;
+}

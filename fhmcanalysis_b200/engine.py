@@ -396,8 +396,76 @@ class DeviceHistogram(object):
         cur.synchronize()
         return out
 
-    def sweep_host_compact(self, mu1, pmax=4, lanes=0, chunk=1 << 17, out=None):
-        """As ``sweep_host`` for the result set {status, nphase, fe, avg, bounds}, but only the phase slots that exist
+    def sweep_host_compact(self, mu1, pmax=4, lanes=0, chunk=1 << 18, out=None):
+        """Host buffers in, host buffers out: result set {status, nphase, fe, avg, bounds} of a mu sweep, with only the phase
+        slots that exist crossing PCIe.  One call of ``fhmc_sweep_host_compact`` (csrc/fhmc_host_pipe.cu), which pipelines
+        H2D(mu) -> sweep -> phase-major repack -> D2H in chunks on two private streams.  The returned CPU tensors are
+        [S, pmax, ...] VIEWS of one pinned phase-major buffer; slots p >= nphase[s] hold NaN / -1.  ``out`` = a previous
+        result to reuse (its pinned buffers are recycled)."""
+        t = torch()
+        L = _lib.load()
+        dev = self.device
+        mu_h = mu1 if isinstance(mu1, t.Tensor) else t.from_numpy(np.ascontiguousarray(mu1, dtype=np.float64))
+        if not mu_h.is_pinned():
+            mu_h = mu_h.pin_memory()
+        S = mu_h.numel()
+        nsel = self.n_sel
+        rec = 16 + 8 * nsel
+        chunk = int(min(chunk, max(S, 1)))
+        if S >= self.FAST_PATH_MIN_STATES and lanes in (0, 1):
+            self.ensure_hull()
+        n_chunks = (S + chunk - 1) // chunk
+        if not hasattr(self, "_hpipe") or self._hpipe["key"] != (chunk, pmax):
+            ws_bytes = int(L.fhmc_sweep_host_workspace(chunk, pmax, nsel))
+            self._hpipe = {"key": (chunk, pmax), "ws": t.empty(ws_bytes + 256, dtype=t.uint8, device=dev), "ws_bytes": ws_bytes}
+        hpipe = self._hpipe
+        ws_ptr = (hpipe["ws"].data_ptr() + 255) & ~255
+        if out is None or out.get("_key") != (S, pmax, nsel, chunk):
+            out = self._host_result_views(S, pmax, nsel, chunk)
+            out["_flags"] = t.zeros(n_chunks, dtype=t.int32).pin_memory()
+        d = self._desc(pmax)
+        if not hasattr(self, "_blob_pin"):
+            self._blob_pin = t.from_numpy(self.blob_host).pin_memory()
+        cur = t.cuda.current_stream(dev)
+        blob_d = t.empty_like(self.blob)
+        blob_d.copy_(self._blob_pin, non_blocking=True)     # the histogram travels with every call (it is host data too)
+        top, moved = ctypes.c_int(0), ctypes.c_longlong(0)
+        with t.cuda.device(dev):
+            rc = L.fhmc_sweep_host_compact(ctypes.byref(d), _ptr(blob_d), ctypes.c_void_p(mu_h.data_ptr()), S, int(lanes), chunk,
+                                           ctypes.c_void_p(ws_ptr), hpipe["ws_bytes"], ctypes.c_void_p(out["_buf"].data_ptr()),
+                                           ctypes.c_void_p(out["_flags"].data_ptr()), int(out.get("max_nphase", 1)),
+                                           ctypes.byref(top), ctypes.byref(moved), ctypes.c_void_p(cur.cuda_stream))
+        _lib.check(rc, "fhmc_sweep_host_compact")
+        top = int(top.value)
+        # phase blocks that no chunk of this call filled: NaN / -1, like the empty slots inside a block
+        for p in range(top, max(top, out["_prev_top"])):
+            out["fe"][:, p].fill_(float("nan"))
+            if nsel:
+                out["avg"][:, p].fill_(float("nan"))
+            out["bounds"][:, p].fill_(-1)
+        out["_prev_top"] = top
+        out["max_nphase"] = top
+        out["d2h_bytes"] = int(moved.value) + 4 * n_chunks       # + the per-chunk phase counts
+        return out
+
+    def _host_result_views(self, S, pmax, nsel, chunk):
+        """One pinned phase-major buffer (layout of fhmc_pack_phase_major for S state points) and [S, pmax, ...] views of it."""
+        t = torch()
+        rec = 16 + 8 * nsel
+        buf = t.empty(8 * S + pmax * rec * S, dtype=t.uint8).pin_memory()
+        out = {"_key": (S, pmax, nsel, chunk), "_buf": buf, "_prev_top": pmax}   # every phase block starts out stale
+        head = buf[:8 * S].view(t.int32)
+        out["status"] = t.as_strided(head, (S,), (2,))
+        out["nphase"] = t.as_strided(head, (S,), (2,), head.storage_offset() + 1)
+        body64, body32 = buf[8 * S:].view(t.float64), buf[8 * S:].view(t.int32)
+        out["fe"] = t.as_strided(body64, (S, pmax), (rec // 8, S * rec // 8))
+        out["avg"] = t.as_strided(body64, (S, pmax, nsel), (rec // 8, S * rec // 8, 1), body64.storage_offset() + 1) if nsel else None
+        out["bounds"] = t.as_strided(body32, (S, pmax, 2), (rec // 4, S * rec // 4, 1), body32.storage_offset() + 2 + 2 * nsel)
+        return out
+
+    def sweep_host_compact_py(self, mu1, pmax=4, lanes=0, chunk=1 << 17, out=None):
+        """The same pipeline driven from Python (kept for comparison, scripts/probe_e2e.py): ~0.1 ms of host time per chunk.
+        As ``sweep_host`` for the result set {status, nphase, fe, avg, bounds}, but only the phase slots that exist
         cross PCIe: each chunk's records are repacked phase-major on the device (``fhmc_pack_phase_major``) and phase
         blocks p >= max_s nphase[s] of the chunk are not copied.  The returned CPU tensors are [S, pmax, ...] VIEWS of
         one pinned phase-major buffer; slots p >= nphase[s] hold NaN / -1.  ``out`` = a previous result to reuse."""

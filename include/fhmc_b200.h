@@ -184,6 +184,23 @@ int fhmc_pack_phase_major(const fhmc_sweep_out *out, long long n_states, int pma
                           int *max_nphase, void *stream);
 
 /*
+ * Host-buffer mu sweep (new; replaces the user's Python loop of reweight()/thermo()/is_safe() calls on host arrays,
+ * GH:268-289, 451-596, README.md:60-85).  mu_host[n_states] and out_host are PINNED host memory; everything in between is
+ * pipelined on two private streams in chunks of `chunk` state points: H2D(mu) -> fhmc_sweep_1d -> fhmc_pack_phase_major
+ * -> D2H of the head and of the phase blocks that exist.  Returns when the results are in out_host, laid out as
+ * fhmc_pack_phase_major describes for S = n_states (phase blocks >= *max_nphase_out are not written).
+ *   desc->pmax, desc->n_sel size the records; workspace: device, 256-byte aligned, fhmc_sweep_host_workspace() bytes
+ *   flags_host: pinned, one int per chunk (receives max nphase of the chunk)
+ *   guess_nphase: phase blocks to copy speculatively per chunk (a chunk that needs more is topped up later)
+ *   stream: work already queued there (e.g. the blob upload) is waited for before the first chunk starts
+ */
+size_t fhmc_sweep_host_workspace(long long chunk, int pmax, int n_sel);
+int fhmc_sweep_host_compact(const fhmc_hist_desc *desc, const double *blob, const double *mu_host, long long n_states,
+                            int lanes_per_point, long long chunk, void *workspace, size_t workspace_bytes,
+                            void *out_host, int *flags_host, int guess_nphase, int *max_nphase_out,
+                            long long *d2h_bytes_out, void *stream);
+
+/*
  * Pointwise Taylor update of a stack of arrays (moment extrapolation, GH:1027-1034 / 1162-1171,
  * and histogram.mix, GH:244-252):  out[a][i] = sum_t w[t] * src[t][a][i],  t < n_src.
  */

@@ -30,12 +30,15 @@ def wall(fn, reps=20, warm=3):
     return (time.perf_counter() - t0) / reps * 1e3
 
 
-for chunk in (1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20):
-    st = {"o": None}
+for chunk in (1 << 15, 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20):
+    st = {"o": None, "p": None}
 
     def f():
         st["o"] = dh.sweep_host_compact(mu, pmax=4, chunk=chunk, out=st["o"])
-    print(json.dumps({"chunk": chunk, "compact_ms": wall(f), "d2h_bytes": st["o"]["d2h_bytes"]}), flush=True)
+
+    def fpy():
+        st["p"] = dh.sweep_host_compact_py(mu, pmax=4, chunk=chunk, out=st["p"])
+    print(json.dumps({"chunk": chunk, "compact_c_ms": wall(f), "compact_py_ms": wall(fpy), "d2h_bytes": st["o"]["d2h_bytes"]}), flush=True)
 # pieces
 dev = torch.device("cuda:0")
 buf_d = torch.empty(72000000, dtype=torch.uint8, device=dev)
