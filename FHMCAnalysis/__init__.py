@@ -9,6 +9,7 @@ _MODULES = [
     "moments.histogram.one_dim.ntot.collect", "moments.histogram.one_dim.n1", "moments.histogram.one_dim.n1.gc_hist",
     "moments.histogram.two_dim", "moments.histogram.two_dim.joint_hist",
     "moments.histogram.two_dim.h_ntot", "moments.histogram.two_dim.h_ntot.pore_hist",
+    "moments.win_patch", "moments.win_patch.fhmc_patch",
 ]
 for _m in _MODULES:
     try:

@@ -70,6 +70,7 @@ EXPORTS = [
     "fhmc_phase_moments", "fhmc_axpy_rows", "fhmc_find_phase_eq_1d", "fhmc_reweight_2d",
     "fhmc_reweight_2d_workspace", "fhmc_pack_bytes", "fhmc_pack_phase_major",
     "fhmc_masked_lse_2d", "fhmc_masked_lse_2d_workspace", "fhmc_sweep_host_workspace", "fhmc_sweep_host_compact",
+    "fhmc_patch_shifts",
     "fhmc_bench_dfma", "fhmc_bench_exp",
 ]
 
@@ -123,6 +124,8 @@ def load():
     L.fhmc_sweep_host_compact.restype = ci
     L.fhmc_sweep_host_compact.argtypes = [ctypes.POINTER(HistDesc), vp, vp, cll, ci, cll, vp, ctypes.c_size_t, vp, vp, ci,
                                           ctypes.POINTER(ci), ctypes.POINTER(cll), vp]
+    L.fhmc_patch_shifts.restype = ci
+    L.fhmc_patch_shifts.argtypes = [vp, vp, vp, ci, vp, vp, vp]
     L.fhmc_bench_dfma.restype = cll
     L.fhmc_bench_dfma.argtypes = [ci, vp, vp]
     L.fhmc_bench_exp.restype = cll

@@ -1,0 +1,48 @@
+// fhmc_patch.cu -- batched window-patching shift solve.
+//
+// Reference: moments/win_patch/fhmc_patch.pyx:640-709 (identical copies in chkpt_patch.pyx:638 and feasst_patch.pyx:384):
+// patch_window_pair() minimises window_patch_error(x) = sum_i ((a_i + x) - b_i)^2 over the overlap of two windows with
+// scipy.optimize.fmin and returns (x*, error(x*) / len).  The objective is a parabola in x: x* = mean(b - a) in closed form
+// and error(x*) = sum (a_i + x* - b_i)^2.  One warp per window pair: coalesced 8-byte loads of both slices, shuffle
+// reductions, two passes (mean first, squared residuals about it second) so that the error does not lose digits to
+// cancellation.  HBM-bound: 2 * 8 bytes per overlapping bin, read twice (second pass from L2).
+#include "fhmc_common.cuh"
+
+namespace fhmc {
+
+__global__ void __launch_bounds__(256) k_patch_shifts(const double *__restrict__ a, const double *__restrict__ b,
+                                                      const long long *__restrict__ offsets, int n_pairs,
+                                                      double *__restrict__ shift, double *__restrict__ err2)
+{
+    const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= n_pairs) return;
+    const long long lo = offsets[w], hi = offsets[w + 1], len = hi - lo;
+    double s = 0.0;
+    for (long long i = lo + lane; i < hi; i += 32) s += b[i] - a[i];
+    s = group_sum<32>(s, 0xffffffffu);
+    const double x = (len > 0) ? s / (double)len : CUDART_NAN;
+    double e = 0.0;
+    for (long long i = lo + lane; i < hi; i += 32) {
+        const double r = (a[i] + x) - b[i];   // evaluated as window_patch_error does (fhmc_patch.pyx:663)
+        e = fma(r, r, e);
+    }
+    e = group_sum<32>(e, 0xffffffffu);
+    if (lane == 0) {
+        shift[w] = x;
+        err2[w] = (len > 0) ? e / (double)len : CUDART_NAN;
+    }
+}
+
+}  // namespace fhmc
+
+using namespace fhmc;
+
+extern "C" int fhmc_patch_shifts(const double *a, const double *b, const long long *offsets, int n_pairs, double *shift,
+                                 double *err2, void *stream)
+{
+    if (!a || !b || !offsets || !shift || !err2 || n_pairs < 0) { set_error("bad arguments"); return 1; }
+    if (n_pairs == 0) return 0;
+    const int warps_per_cta = 8;
+    k_patch_shifts<<<(n_pairs + warps_per_cta - 1) / warps_per_cta, 32 * warps_per_cta, 0, (cudaStream_t)stream>>>(a, b, offsets, n_pairs, shift, err2);
+    return check_cuda(cudaGetLastError(), "k_patch_shifts launch");
+}

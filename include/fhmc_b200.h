@@ -247,6 +247,14 @@ int fhmc_masked_lse_2d(const double *lnpi, const unsigned char *mask, const int 
                        const double *props, int n_prop, double *out, long long *peak, int peak_cap,
                        double *lnpi_shifted, double *workspace, size_t workspace_bytes, void *stream);
 
+/*
+ * Window patching shift solve, batched (moments/win_patch/fhmc_patch.pyx:640-709): pair w owns a[offsets[w]:offsets[w+1]]
+ * (the upper window's overlap slice) and b[...] (the lower window's); shift[w] = argmin_x sum ((a_i + x) - b_i)^2 =
+ * mean(b - a) (the reference finds it with scipy.optimize.fmin), err2[w] = sum ((a_i + shift) - b_i)^2 / len.
+ */
+int fhmc_patch_shifts(const double *a, const double *b, const long long *offsets, int n_pairs, double *shift,
+                      double *err2, void *stream);
+
 /* Roofline micro-benchmarks (register-resident): return ops executed; time with CUDA events. */
 long long fhmc_bench_dfma(int iters, double *sink, void *stream);
 long long fhmc_bench_exp(int iters, double *sink, void *stream);

@@ -322,3 +322,29 @@ def pore_thermo(lnpi, mask, props):
         sum_prob = np.sum(prob)                # PH:175
         ave = {p: np.sum(prob * np.where(mask, props[p], 0.0)) / sum_prob for p in props}   # PH:178-179 (0 * x outside the mask)
     return ave, np.where(lp == np.max(lp))     # PH:182
+
+
+# ----------------------------------------------------------------------------------------------
+# window patching shift solve (moments/win_patch/fhmc_patch.pyx:640-709) -- SURVEY 8(f) row 4
+# ----------------------------------------------------------------------------------------------
+def window_patch_error(x, this_lnpi, other_lnpi):
+    """fhmc_patch.pyx:640-664: total square error of (this + x) against other, accumulated in index order."""
+    e2 = 0.0
+    for i in range(len(this_lnpi)):
+        e2 += ((this_lnpi[i] + x) - other_lnpi[i]) ** 2
+    return e2
+
+
+def patch_window_pair_slices(data_slice1, data_slice2, ftol=0.000001):
+    """The optimisation of patch_window_pair (fhmc_patch.pyx:699-709) on already aligned overlap slices: Nelder-Mead from
+    the first-point guess, (x*, error(x*) / len).  The cdef function cannot be called from Python and the module needs the
+    simulation's file formats to build windows, so this is a restatement with the same scipy.optimize.fmin call
+    (PARITY UNPINNED on the reference's own objects; the minimiser of a parabola is also known in closed form)."""
+    from scipy.optimize import fmin
+    a = np.asarray(data_slice1, dtype=np.float64)
+    b = np.asarray(data_slice2, dtype=np.float64)
+    guess = b[0] - a[0]
+    full_out = fmin(window_patch_error, guess, ftol=ftol, args=(a, b), maxiter=10000, maxfun=10000, full_output=True, disp=False)
+    if full_out[4] != 0:
+        raise Exception("Error, unable to mimize")
+    return float(full_out[0][0]), float(full_out[1]) / len(a)
