@@ -39,9 +39,9 @@ MU_LO, MU_HI = -0.03, 0.03
 PMAX = 4
 METRIC = "reweighted state points/sec (lnPI+thermo) at N_max=1000"
 UNIT = "state points/s"
-# warp instructions per state point of k_sweep_fast<2,1,0,1,2> on this workload (ncu --set full, profiles/r01b_prod_sweep_ncu_summary.txt)
-FP64_INSTR_PER_POINT = 4318
-INSTR_PER_POINT = 10402
+# warp instructions per state point of k_sweep_prod2<2,1> on this workload (ncu --set full, profiles/r01b_prod2_sweep_ncu_summary.txt)
+FP64_INSTR_PER_POINT = 4362
+INSTR_PER_POINT = 9671
 E2E_FIELDS = ("status", "nphase", "bounds", "fe", "avg")   # what the e2e arm copies back to the host every step
 
 
@@ -367,8 +367,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                          # the algorithmic count.  What the kernel really executes, from the committed ncu capture:
                          "executed": {"fp64_pipe_instr_per_state_point": FP64_INSTR_PER_POINT, "instr_per_state_point": INSTR_PER_POINT,
                                       "fp64_pipe_frac_of_dfma_peak": S * FP64_INSTR_PER_POINT / (np.mean(kern_ms) * 1e-3) / peaks["dfma_per_s"],
-                                      "limiter": "shared-memory pipe (broadcast LDS.128 of the product tables), then fp64 issue",
-                                      "source": "profiles/r01b_prod_sweep_ncu_summary.txt"},
+                                      "limiter": "fp64 issue at 50 % pipe utilisation with 4 warps per scheduler (128 registers, 85 KB shared memory per CTA); shared-memory pipe 45 %",
+                                      "source": "profiles/r01b_prod2_sweep_ncu_summary.txt"},
                          "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (np.mean(kern_ms) * 1e-3) / 1e9,
                                  "peak_gbs": hbm_peak, "frac": (algo_bytes / (np.mean(kern_ms) * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
                                  "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else "absent"}},
