@@ -112,6 +112,37 @@ def test_fast_and_generic_kernels_agree():
             assert np.allclose(a["lnnorm"], b["lnnorm"], rtol=1e-13, atol=1e-13)
 
 
+@pytest.mark.parametrize("nsel,sel0n", [(0, False), (1, True), (1, False), (2, False), (3, True), (4, False)])
+def test_product_form_for_every_selection_shape(nsel, sel0n):
+    """Every instantiation of the product-form kernels (0..4 summed quantities, first one N or not; one and two state points
+    per thread) against the generic kernel: the tabulated P*X rows of quantities other than N, N-spacing other than 1 and a
+    non-zero first bin are all exercised."""
+    from fhmcanalysis_b200 import engine, synth
+    n = 801
+    rng = np.random.default_rng(100 * nsel + sel0n)
+    lnpi = synth.two_peak_lnpi(n, noise=2e-3, scale=n / 1001.0)
+    N = 3.0 + 0.5 * np.arange(n)                              # uniform spacing 0.5, first bin at 3
+    extra = [N * N, -2.0 * N - 0.002 * N * N + rng.normal(size=n), np.sin(N / 40.0), 1.0 / (1.0 + N)]
+    sel = (["N"] if sel0n else []) + extra[:nsel - (1 if sel0n else 0)]
+    for rec, S in ((3, 170000), (2, 6000)):
+        dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=7, sel=sel)
+        dh.use_recurrence = rec
+        dh.ensure_hull()
+        assert dh.desc.mu_recurrence == rec
+        mus = np.concatenate([np.linspace(-0.12, 0.12, S - 500), np.linspace(-9.0, 9.0, 500)])
+        a = dh.sweep_auto(mus, pmax=4, lanes=1).host()
+        b = dh.sweep_auto(mus, pmax=a["fe"].shape[1], lanes=-1).host()
+        assert np.mean((a["status"] & 0x1000) != 0) > 0.9
+        for k in ("code", "nphase", "nmin", "safe"):
+            assert np.array_equal(a[k], b[k]), (rec, k)
+        ok = a["code"] == 0
+        mask = (np.arange(a["fe"].shape[1])[None, :] < a["nphase"][:, None]) & ok[:, None]
+        assert np.array_equal(a["bounds"][mask], b["bounds"][mask])
+        assert np.allclose(a["fe"][mask], b["fe"][mask], rtol=1e-10, atol=1e-10)
+        if nsel:
+            assert np.allclose(a["avg"][mask], b["avg"][mask], rtol=1e-10, atol=1e-12)
+
+
 def test_sharded_sweep_single_process(golden, golden_meta):
     """parallel.sweep_sharded without an initialised process group == plain sweep."""
     from fhmcanalysis_b200 import engine, parallel
