@@ -690,8 +690,10 @@ def axpy_rows(arrays, weights, device=None):
     return out.cpu().numpy().reshape(shape)
 
 
-def reweight_2d(lnpi, bounds, op1, op2, a1, a2, props=None, device=None, return_device=False):
-    """K5: 2-D joint histogram reweight for S state points; returns [S][3+n_prop] (lnZ, <op1>, <op2>, <prop>...)."""
+def reweight_2d(lnpi, bounds, op1, op2, a1, a2, props=None, device=None, return_device=False, product=None):
+    """K5: 2-D joint histogram reweight for S state points; returns [S][3+n_prop] (lnZ, <op1>, <op2>, <prop>...).
+    product: use the product-form kernel (uniformly spaced op2, |a2| * span(op2) < 300); None = decide from host copies
+    of op2 / a2 when they are host arrays, else the exp-per-bin kernel."""
     L = _lib.load()
     t = torch()
     dev = require_cuda(device)
@@ -714,12 +716,23 @@ def reweight_2d(lnpi, bounds, op1, op2, a1, a2, props=None, device=None, return_
         p_t = dv(props, np.float64)
         n_prop = p_t.shape[0]
     out = t.empty((S, 3 + n_prop), dtype=t.float64, device=dev)
-    ws_bytes = L.fhmc_reweight_2d_workspace(n1, n2, n_prop, S)
+    if product is None:
+        product = False
+        if not isinstance(op2, t.Tensor) and not isinstance(a2, t.Tensor) and n2 >= 8 and S >= 64:
+            o2h, a2h = np.asarray(op2, dtype=np.float64), np.atleast_1d(np.asarray(a2, dtype=np.float64))
+            d2 = np.diff(o2h)
+            product = bool(np.all(d2 == d2[0]) and d2[0] > 0 and np.max(np.abs(a2h)) * (o2h[-1] - o2h[0]) < 300.0)
+    ws_bytes = L.fhmc_reweight_2d_prod_workspace(n1, n2, n_prop, S) if product else 0
+    if product and ws_bytes == 0:
+        product = False
+    if not product:
+        ws_bytes = L.fhmc_reweight_2d_workspace(n1, n2, n_prop, S)
     ws = t.empty(max(ws_bytes // 8, 1), dtype=t.float64, device=dev)
+    fn = L.fhmc_reweight_2d_prod if product else L.fhmc_reweight_2d
     with t.cuda.device(dev):
-        rc = L.fhmc_reweight_2d(_ptr(lnpi_t), _ptr(b_t), n1, n2, _ptr(o1), _ptr(o2), _ptr(p_t), n_prop, _ptr(a1_t),
-                                _ptr(a2_t), S, _ptr(out), _ptr(ws), ws_bytes, _stream_ptr(dev))
-    _lib.check(rc, "fhmc_reweight_2d")
+        rc = fn(_ptr(lnpi_t), _ptr(b_t), n1, n2, _ptr(o1), _ptr(o2), _ptr(p_t), n_prop, _ptr(a1_t),
+                _ptr(a2_t), S, _ptr(out), _ptr(ws), ws_bytes, _stream_ptr(dev))
+    _lib.check(rc, "fhmc_reweight_2d_prod" if product else "fhmc_reweight_2d")
     return out if return_device else out.cpu().numpy()
 
 

@@ -235,6 +235,18 @@ int fhmc_reweight_2d(const double *lnpi, const int *bounds, int n1, int n2, cons
                      size_t workspace_bytes, void *stream);
 
 /*
+ * K5 in product form: same outputs as fhmc_reweight_2d.  The caller promises that op2 is uniformly spaced and that
+ * max_s |a2[s]| * (op2[n2-1] - op2[0]) < 300; then exp(lnPI_ij + a2 op2_j) factorises into a tabulated exp(lnPI_ij - A) and
+ * a geometric sequence along the row, the sums of a 4-bin block become Horner polynomials in exp(a2 d2) and a true exp
+ * is only evaluated once per 128-bin row segment.  workspace additionally holds the tables (built by the call).
+ */
+size_t fhmc_reweight_2d_prod_workspace(int n1, int n2, int n_prop, long long n_states);
+int fhmc_reweight_2d_prod(const double *lnpi, const int *bounds, int n1, int n2, const double *op1,
+                          const double *op2, const double *props, int n_prop, const double *a1,
+                          const double *a2, long long n_states, double *out, double *workspace,
+                          size_t workspace_bytes, void *stream);
+
+/*
  * Ragged / masked 2-D log-sum-exp with averages, one surface per call (HBM-bound streaming reduction):
  *   pore_hist.normalize (two_dim/h_ntot/pore_hist.pyx:57-80, 147-152): edge[i] = last valid column of row i, mask NULL,
  *       lnpi_shifted (nullable) receives lnPI - ln sum exp lnPI;

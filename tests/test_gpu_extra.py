@@ -69,10 +69,21 @@ def test_reweight_2d_vs_oracle(oracle, n1, n2, nprop):
     props = rng.random((nprop, n1, n2)) if nprop else None
     S = 300
     a1, a2 = rng.uniform(-0.05, 0.05, S), rng.uniform(-0.05, 0.05, S)
-    out = engine.reweight_2d(lnpi, bounds, op1, op2, a1, a2, props)
-    for s in range(0, S, 37):
-        ref = oracle.reweight_2d(lnpi, bounds, op1, op2, a1[s], a2[s], props)
-        assert np.allclose(out[s], ref, rtol=1e-10, atol=0)
+    for product in (False, True):   # exp-per-bin kernel and product-form kernel
+        out = engine.reweight_2d(lnpi, bounds, op1, op2, a1, a2, props, product=product)
+        for s in range(0, S, 37):
+            ref = oracle.reweight_2d(lnpi, bounds, op1, op2, a1[s], a2[s], props)
+            assert np.allclose(out[s], ref, rtol=1e-10, atol=0), (product, s)
+    # an odd number of state points, stronger tilts, op2 starting away from zero with spacing 0.5, -inf holes inside the support
+    lnpi2 = lnpi.copy()
+    lnpi2[n1 // 3, bounds[n1 // 3, 0] + 2] = -np.inf
+    op2b = 7.0 + 0.5 * np.arange(n2)
+    a1b, a2b = rng.uniform(-0.3, 0.3, 77), rng.uniform(-0.5, 0.5, 77)
+    outp = engine.reweight_2d(lnpi2, bounds, op1, op2b, a1b, a2b, props, product=True)
+    oute = engine.reweight_2d(lnpi2, bounds, op1, op2b, a1b, a2b, props, product=False)
+    assert np.allclose(outp, oute, rtol=1e-10, atol=0)
+    ref = oracle.reweight_2d(lnpi2, bounds, op1, op2b, a1b[5], a2b[5], props)
+    assert np.allclose(outp[5], ref, rtol=1e-10, atol=0)
     # linearity property at full batch: <op1> is non-decreasing in a1 at fixed a2
     a1s = np.linspace(-0.05, 0.05, 257)
     o = engine.reweight_2d(lnpi, bounds, op1, op2, a1s, np.zeros_like(a1s))
@@ -103,7 +114,8 @@ def test_fast_and_generic_kernels_agree():
                 assert np.array_equal(a[k], b[k]), (n, k)
             ok = a["code"] == 0                                   # records of raised state points carry no thermo
             for k in ("bounds", "max_idx", "min_idx"):
-                pm = np.arange(a[k].shape[1])[None, :] < (a["nphase"] + (1 if k == "min_idx" else 0))[:, None]
+                # entries beyond the list lengths (nphase maxima / bounds, nmin minima) are never written
+                pm = np.arange(a[k].shape[1])[None, :] < (a["nmin"] if k == "min_idx" else a["nphase"])[:, None]
                 m2 = (pm & ok[:, None]) if a[k].ndim == 2 else (pm & ok[:, None])[:, :, None].repeat(2, 2)
                 assert np.array_equal(a[k][m2], b[k][m2]), (n, k)
             mask = (np.arange(a["fe"].shape[1])[None, :] < a["nphase"][:, None]) & ok[:, None]
@@ -188,7 +200,7 @@ def _agree(a, b, tag):
     ok = a["code"] == 0
     P = a["nphase"]
     for k in ("max_idx", "min_idx"):
-        pm = np.arange(a[k].shape[1])[None, :] < (P + (1 if k == "min_idx" else 0))[:, None]
+        pm = np.arange(a[k].shape[1])[None, :] < (a["nmin"] if k == "min_idx" else P)[:, None]   # written entries only
         assert np.array_equal(a[k][pm & ok[:, None]], b[k][pm & ok[:, None]]), (tag, k)
     mask = (np.arange(a["fe"].shape[1])[None, :] < P[:, None]) & ok[:, None]
     assert np.allclose(a["fe"][mask], b["fe"][mask], rtol=1e-10, atol=1e-11), tag
