@@ -155,6 +155,25 @@ def test_product_form_for_every_selection_shape(nsel, sel0n):
             assert np.allclose(a["avg"][mask], b["avg"][mask], rtol=1e-10, atol=1e-12)
 
 
+@pytest.mark.parametrize("n", [9, 10, 11, 12, 130, 131, 257])
+def test_product_form_small_and_odd_histograms(n):
+    """Few bins (a single partial segment, every tail length n mod 4) and segment-boundary sizes through both product-form
+    kernels, against the generic kernel; smooth = 1 makes nearly every block hold an extremum."""
+    from fhmcanalysis_b200 import engine
+    rng = np.random.default_rng(n)
+    lnpi = np.cumsum(rng.normal(0.0, 0.6, size=n))
+    N = np.arange(n, dtype=float)
+    for rec, S in ((3, 152001), (2, 5003)):
+        dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=1, sel=["N", N * N])
+        dh.use_recurrence = rec
+        dh.ensure_hull()
+        assert dh.desc.mu_recurrence == rec
+        mus = np.linspace(-1.5, 1.5, S)
+        a = dh.sweep_auto(mus, pmax=8, lanes=1).host()
+        b = dh.sweep_auto(mus, pmax=a["fe"].shape[1], lanes=-1).host()
+        _agree(a, b, (n, rec))
+
+
 def test_sharded_sweep_single_process(golden, golden_meta):
     """parallel.sweep_sharded without an initialised process group == plain sweep."""
     from fhmcanalysis_b200 import engine, parallel
