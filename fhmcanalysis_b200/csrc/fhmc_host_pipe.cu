@@ -6,8 +6,9 @@
 // blocks that exist.  The number of live phase blocks of a chunk is only known after its kernels ran; waiting for it
 // before queueing copies would idle the copy engine, so copies are queued at once for `guess` blocks (what the previous
 // chunk needed) and a chunk that needed more is topped up when its flag is read, two chunks later, just before its device
-// buffers are reused.  Driving this loop from C costs a few microseconds per chunk, which is what allows 2^16-point
-// chunks (short pipeline fill) without becoming launch-bound.
+// buffers are reused.  Driving this loop from C costs a few microseconds per chunk.  Measured on a B200 (10^6 state
+// points, 72 B of results each): 1.72 ms at 2^18-point chunks against 1.26 ms for the D2H alone; smaller chunks are slower
+// (a 2^16-point chunk holds fewer tiles than the GPU has resident CTAs), and a short-first-chunk schedule gains nothing.
 #include "fhmc_common.cuh"
 
 namespace fhmc {
