@@ -17,16 +17,32 @@ __global__ void __launch_bounds__(256) k_patch_shifts(const double *__restrict__
     const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (w >= n_pairs) return;
     const long long lo = offsets[w], hi = offsets[w + 1], len = hi - lo;
-    double s = 0.0;
-    for (long long i = lo + lane; i < hi; i += 32) s += b[i] - a[i];
-    s = group_sum<32>(s, 0xffffffffu);
+    double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    long long i = lo + lane;
+    for (; i + 96 < hi; i += 128) {   // eight independent loads in flight per lane
+        s += b[i] - a[i];
+        s1 += b[i + 32] - a[i + 32];
+        s2 += b[i + 64] - a[i + 64];
+        s3 += b[i + 96] - a[i + 96];
+    }
+    for (; i < hi; i += 32) s += b[i] - a[i];
+    s = group_sum<32>((s + s1) + (s2 + s3), 0xffffffffu);
     const double x = (len > 0) ? s / (double)len : CUDART_NAN;
-    double e = 0.0;
-    for (long long i = lo + lane; i < hi; i += 32) {
-        const double r = (a[i] + x) - b[i];   // evaluated as window_patch_error does (fhmc_patch.pyx:663)
+    double e = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+    i = lo + lane;
+    for (; i + 96 < hi; i += 128) {
+        const double r0 = (a[i] + x) - b[i], r1 = (a[i + 32] + x) - b[i + 32];   // as window_patch_error (fhmc_patch.pyx:663)
+        const double r2 = (a[i + 64] + x) - b[i + 64], r3 = (a[i + 96] + x) - b[i + 96];
+        e = fma(r0, r0, e);
+        e1 = fma(r1, r1, e1);
+        e2 = fma(r2, r2, e2);
+        e3 = fma(r3, r3, e3);
+    }
+    for (; i < hi; i += 32) {
+        const double r = (a[i] + x) - b[i];
         e = fma(r, r, e);
     }
-    e = group_sum<32>(e, 0xffffffffu);
+    e = group_sum<32>((e + e1) + (e2 + e3), 0xffffffffu);
     if (lane == 0) {
         shift[w] = x;
         err2[w] = (len > 0) ? e / (double)len : CUDART_NAN;

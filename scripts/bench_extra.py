@@ -152,6 +152,45 @@ def main():
         r = engine.SweepResult(S_, 4, dh1.n_sel, dev)
         ms = timed(lambda: dh1.sweep(None, states=st, out=r, pmax=4), reps=5, warm=2)
         out.append({"config": "config-2 histogram, %d state points (auto lanes)" % S_, "ms": ms, "value": S_ / (ms * 1e-3), "unit": "state points/s"})
+    # ---- HBM-bound streaming kernels, device-resident, through the C ABI -------------------
+    import ctypes
+    from fhmcanalysis_b200 import _lib
+    L = _lib.load()
+    sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    for n1m, n2m, nprop in ((512, 512, 2), (4096, 4096, 2)):
+        rng = np.random.default_rng(3)
+        lp = torch.from_numpy(rng.normal(size=(n1m, n2m))).to(dev)
+        pr = torch.from_numpy(rng.normal(size=(nprop, n1m, n2m))).to(dev)
+        mk = torch.ones((n1m, n2m), dtype=torch.uint8, device=dev)
+        o_t = torch.empty(2 + 8, dtype=torch.float64, device=dev)
+        pk = torch.empty(65, dtype=torch.int64, device=dev)
+        wsb = int(L.fhmc_masked_lse_2d_workspace(n1m, n2m, nprop))
+        ws_t = torch.empty(wsb // 8 + 2, dtype=torch.float64, device=dev)
+
+        def m2d():
+            _lib.check(L.fhmc_masked_lse_2d(lp.data_ptr(), mk.data_ptr(), None, n1m, n2m, pr.data_ptr(), nprop, o_t.data_ptr(), pk.data_ptr(), 64,
+                                            None, ws_t.data_ptr(), wsb, sp), "fhmc_masked_lse_2d")
+        msm = timed(m2d, reps=10, warm=3)
+        bytes_m = 8.0 * n1m * n2m * (2 + nprop) + 2.0 * n1m * n2m
+        out.append({"config": "8f-3 pore_hist.thermo(mask): fhmc_masked_lse_2d %dx%d, %d property matrices" % (n1m, n2m, nprop), "ms": msm,
+                    "roofline": {"bound": "hbm", "algorithmic_bytes": bytes_m, "achieved_gbs": bytes_m / (msm * 1e-3) / 1e9, "peak_gbs": hbm,
+                                 "frac": (bytes_m / (msm * 1e-3) / 1e9 / hbm) if hbm else None,
+                                 "note": "4 launches; the 512x512 case is launch-latency bound (2 MiB per matrix)"}})
+    for W, ln in ((10000, 1000), (200, 400)):
+        a_t = torch.randn(W * ln, dtype=torch.float64, device=dev)
+        b_t = a_t + 3.0
+        off = torch.arange(0, (W + 1) * ln, ln, dtype=torch.int64, device=dev)
+        sh = torch.empty((2, W), dtype=torch.float64, device=dev)
+
+        def pshift():
+            _lib.check(L.fhmc_patch_shifts(a_t.data_ptr(), b_t.data_ptr(), off.data_ptr(), W, sh[0].data_ptr(), sh[1].data_ptr(), sp), "fhmc_patch_shifts")
+        msp = timed(pshift, reps=10, warm=3)
+        bytes_p = 16.0 * W * ln
+        out.append({"config": "8f-4 window patching: fhmc_patch_shifts, %d window pairs x %d overlapping bins" % (W, ln), "ms": msp,
+                    "value": W / (msp * 1e-3), "unit": "window pairs/s",
+                    "roofline": {"bound": "hbm", "algorithmic_bytes": bytes_p, "achieved_gbs": bytes_p / (msp * 1e-3) / 1e9, "peak_gbs": hbm,
+                                 "frac": (bytes_p / (msp * 1e-3) / 1e9 / hbm) if hbm else None,
+                                 "note": "second pass over the same slices comes from L2"}})
     for o in out:
         print(json.dumps(o))
 
