@@ -186,7 +186,8 @@ def run_gpu_arm(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner (NCCL_DEBUG=VERSION) off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     # CPU baseline first, on rank 0 at N=1 only (bounded sample), before the GPU is busy
