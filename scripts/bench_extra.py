@@ -152,6 +152,32 @@ def main():
         r = engine.SweepResult(S_, 4, dh1.n_sel, dev)
         ms = timed(lambda: dh1.sweep(None, states=st, out=r, pmax=4), reps=5, warm=2)
         out.append({"config": "config-2 histogram, %d state points (auto lanes)" % S_, "ms": ms, "value": S_ / (ms * 1e-3), "unit": "state points/s"})
+    # ---- isopleth.make_grid_multi over a (mu1, dmu2) grid (reference: ~105 ms per grid cell at N = 201,
+    #      SURVEY 8(c) [probed]) -------------------------------------------------------------------------------------------
+    try:
+        import io as _io
+        from contextlib import redirect_stdout
+        from fhmcanalysis_b200.moments.histogram.one_dim.ntot import gc_binary as gcB
+        n_iso = 1001
+        mom_iso = synth.two_comp_moments(n_iso)
+        hs = []
+        for k, d2 in enumerate((-0.2, 0.5, 1.2)):
+            ln_k = synth.two_peak_lnpi(n_iso, noise=1e-3, scale=1.0, seed=100 + k) + 0.0004 * k * np.arange(n_iso)
+            hs.append(histogram.from_arrays(ln_k, mom_iso, 1.0, [-3.0, -3.0 + d2], 5, volume=512.0))
+        iso = gcB.isopleth(hs, 1.0, 1)
+        with redirect_stdout(_io.StringIO()):
+            iso.make_grid_multi([-3.02, -2.98], [0.0, 1.0], [0.0005, 0.0125], 2.5)      # warm-up (builds device histograms)
+            t0 = time.perf_counter()
+            Z, (X, Y) = iso.make_grid_multi([-3.02, -2.98], [0.0, 1.0], [0.0005, 0.0125], 2.5)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        out.append({"config": "isopleth.make_grid_multi, 3 two-species histograms (N_max=1000), order 1, %d x %d grid" % Z.shape,
+                    "grid_cells": int(Z.size), "ms": dt * 1e3, "value": Z.size / dt, "unit": "grid cells/s",
+                    "filled_fraction": float(np.mean(Z != 0)),
+                    "note": "wall clock of the whole drop-in call (host orchestration + batched kernels + results to host)"})
+    except Exception as e:  # secondary number
+        out.append({"config": "isopleth.make_grid_multi", "error": repr(e)})
+
     # ---- HBM-bound streaming kernels, device-resident, through the C ABI -------------------
     import ctypes
     from fhmcanalysis_b200 import _lib
