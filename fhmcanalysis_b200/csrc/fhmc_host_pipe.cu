@@ -1,22 +1,28 @@
 // fhmc_host_pipe.cu -- the host-buffer entry point of the mu sweep (new; the reference's seam for this is a Python loop of
 // reweight()/thermo() calls on host arrays, GH:268-289, 451-554, README.md:60-85).
 //
-// fhmc_sweep_host_compact: pinned host mu[S] in, pinned host results out, everything in between pipelined on two private
-// streams in chunks: H2D(mu chunk) -> fhmc_sweep_1d -> fhmc_pack_phase_major -> D2H of the chunk's head and of the phase
-// blocks that exist.  The number of live phase blocks of a chunk is only known after its kernels ran; waiting for it
+// fhmc_sweep_host_compact: pinned host mu[S] in, pinned host results out, everything in between pipelined in chunks on
+// three private streams (upload, compute, download): H2D(mu chunk) -> fhmc_sweep_1d -> fhmc_pack_phase_major -> D2H of the
+// chunk's head and of the phase blocks that exist.  The number of live phase blocks of a chunk is only known after its kernels ran; waiting for it
 // before queueing copies would idle the copy engine, so copies are queued at once for `guess` blocks (what the previous
 // chunk needed) and a chunk that needed more is topped up when its flag is read, two chunks later, just before its device
-// buffers are reused.  Driving this loop from C costs a few microseconds per chunk.  Measured on a B200 (10^6 state
-// points, 72 B of results each): 1.72 ms at 2^18-point chunks against 1.26 ms for the D2H alone; smaller chunks are slower
-// (a 2^16-point chunk holds fewer tiles than the GPU has resident CTAs), and a short-first-chunk schedule gains nothing.
+// buffers are reused.  Measured on a B200 (10^6 state points, 72 B of results each, FHMC_PIPE_TRACE=1 prints the device
+// timeline): 1.70 ms at 2^17-point chunks; the download stream is busy from the end of the first chunk's kernels on, at
+// ~50 GB/s (57 GB/s for one large copy), so what is left over the 1.26 ms D2H floor is the pipeline fill (~0.2 ms) and the
+// gaps between the 3 copies per chunk.  Chunks below 2^16 points are slower: they hold fewer tiles than the GPU has CTAs.
+#include <cstdio>
+#include <cstdlib>
+
 #include "fhmc_common.cuh"
 
 namespace fhmc {
 
+// One stream per engine: all kernels of all chunks on `comp` (a chunk's repack must not queue behind the NEXT chunk's
+// persistent sweep CTAs, which is what happened when whole chunks alternated between two streams), mu uploads on `up`,
+// result copies on `down`.
 struct HostPipe {
-    cudaStream_t st[2];
-    cudaEvent_t ev[2], ready;
-    int device;
+    cudaStream_t comp, up, down;
+    cudaEvent_t ready, h2d[2], done[2], flag[2], freed[2];
     bool ok;
 };
 
@@ -28,12 +34,16 @@ static HostPipe *host_pipe()
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
     HostPipe &p = pipes[dev];
     if (!made[dev]) {
-        p.device = dev;
-        p.ok = cudaStreamCreateWithFlags(&p.st[0], cudaStreamNonBlocking) == cudaSuccess &&
-               cudaStreamCreateWithFlags(&p.st[1], cudaStreamNonBlocking) == cudaSuccess &&
-               cudaEventCreateWithFlags(&p.ev[0], cudaEventDisableTiming) == cudaSuccess &&
-               cudaEventCreateWithFlags(&p.ev[1], cudaEventDisableTiming) == cudaSuccess &&
-               cudaEventCreateWithFlags(&p.ready, cudaEventDisableTiming) == cudaSuccess;
+        bool ok = cudaStreamCreateWithFlags(&p.comp, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&p.up, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&p.down, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&p.ready, cudaEventDisableTiming) == cudaSuccess;
+        for (int b = 0; b < 2 && ok; ++b)
+            ok = cudaEventCreateWithFlags(&p.h2d[b], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p.done[b], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p.flag[b], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p.freed[b], cudaEventDisableTiming) == cudaSuccess;
+        p.ok = ok;
         made[dev] = true;
     }
     return p.ok ? &p : nullptr;
@@ -107,8 +117,7 @@ extern "C" int fhmc_sweep_host_compact(const fhmc_hist_desc *desc, const double 
     long long moved = 0;
     // whatever the caller queued on `stream` (the blob upload) comes first
     if (check_cuda(cudaEventRecord(hp->ready, (cudaStream_t)stream), "cudaEventRecord")) return 1;
-    for (int b = 0; b < 2; ++b)
-        if (check_cuda(cudaStreamWaitEvent(hp->st[b], hp->ready, 0), "cudaStreamWaitEvent")) return 1;
+    if (check_cuda(cudaStreamWaitEvent(hp->comp, hp->ready, 0), "cudaStreamWaitEvent")) return 1;
 
     // blocks [from, upto] of chunk k: block 0 = head {status, nphase}[m], block 1+p = phase p records
     auto copies = [&](long long k, int from, int upto) -> int {
@@ -118,48 +127,61 @@ extern "C" int fhmc_sweep_host_compact(const fhmc_hist_desc *desc, const double 
             const unsigned char *src = (j == 0) ? B.packed : B.packed + 8 * m + (long long)(j - 1) * m * rec;
             unsigned char *dst = (j == 0) ? oh + 8 * lo : oh + 8 * S + ((long long)(j - 1) * S + lo) * rec;
             const size_t nb = (size_t)((j == 0) ? 8 * m : m * rec);
-            if (check_cuda(cudaMemcpyAsync(dst, src, nb, cudaMemcpyDeviceToHost, hp->st[k & 1]), "cudaMemcpyAsync D2H")) return 1;
+            if (check_cuda(cudaMemcpyAsync(dst, src, nb, cudaMemcpyDeviceToHost, hp->down), "cudaMemcpyAsync D2H")) return 1;
             moved += (long long)nb;
         }
         return 0;
     };
     int sent[2] = {0, 0};   // phase blocks already queued for the chunk that owns buffer set b
+    // chunk k's live phase count is known once its flag arrived: top its copies up if the guess was short
     auto settle = [&](long long k) -> int {
-        if (check_cuda(cudaEventSynchronize(hp->ev[k & 1]), "cudaEventSynchronize")) return 1;
+        const int b = (int)(k & 1);
+        if (check_cuda(cudaEventSynchronize(hp->flag[b]), "cudaEventSynchronize")) return 1;
         int live = flags_host[k];
         live = live < 1 ? 1 : (live > pmax ? pmax : live);
         if (live > top) top = live;
         if (live > guess) guess = live;
-        if (live > sent[k & 1]) {
-            if (copies(k, 1 + sent[k & 1], live)) return 1;
-            sent[k & 1] = live;
+        if (live > sent[b]) {   // rare (first call, or a chunk with more phases than the last): re-mark the buffer set
+            if (copies(k, 1 + sent[b], live)) return 1;
+            sent[b] = live;
+            return check_cuda(cudaEventRecord(hp->freed[b], hp->down), "cudaEventRecord");
         }
         return 0;
     };
     fhmc_hist_desc d = *desc;
     for (long long k = 0; k < n_chunks; ++k) {
         const int b = (int)(k & 1);
-        if (k >= 2 && settle(k - 2)) return 1;   // same stream and buffers as chunk k: finish it before they are reused
         const long long lo = k * chunk, m = (lo + chunk <= S ? chunk : S - lo);
-        cudaStream_t s = hp->st[b];
-        if (check_cuda(cudaMemcpyAsync(buf[b].mu, mu_host + lo, (size_t)(8 * m), cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D")) return 1;
+        if (k >= 2) {
+            if (settle(k - 2)) return 1;
+            // the kernels of chunk k overwrite what chunk k - 2 left in buffer set b: wait for its copies
+            if (check_cuda(cudaStreamWaitEvent(hp->comp, hp->freed[b], 0), "cudaStreamWaitEvent")) return 1;
+            // its mu buffer is free once the sweep of chunk k - 2 has run
+            if (check_cuda(cudaStreamWaitEvent(hp->up, hp->done[b], 0), "cudaStreamWaitEvent")) return 1;
+        }
+        if (check_cuda(cudaMemcpyAsync(buf[b].mu, mu_host + lo, (size_t)(8 * m), cudaMemcpyHostToDevice, hp->up), "cudaMemcpyAsync H2D")) return 1;
+        if (check_cuda(cudaEventRecord(hp->h2d[b], hp->up), "cudaEventRecord")) return 1;
+        if (check_cuda(cudaStreamWaitEvent(hp->comp, hp->h2d[b], 0), "cudaStreamWaitEvent")) return 1;
         fhmc_states st;
         st.n_states = m;
         st.mu1 = buf[b].mu; st.n_mu1 = m; st.mu1_div = 1;
         st.beta = nullptr; st.n_beta = 1; st.beta_div = 1;
         st.dmu = nullptr; st.n_dmu = 1; st.dmu_div = 1;
-        if (fhmc_sweep_1d(&d, blob, &st, &buf[b].out, lanes_per_point, s)) return 1;
-        if (check_cuda(cudaMemsetAsync(buf[b].flag, 0, 4, s), "cudaMemsetAsync")) return 1;
-        if (fhmc_pack_phase_major(&buf[b].out, m, pmax, nsel, buf[b].packed, buf[b].flag, s)) return 1;
-        if (check_cuda(cudaMemcpyAsync(&flags_host[k], buf[b].flag, 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync flag")) return 1;
-        if (check_cuda(cudaEventRecord(hp->ev[b], s), "cudaEventRecord")) return 1;
+        if (fhmc_sweep_1d(&d, blob, &st, &buf[b].out, lanes_per_point, hp->comp)) return 1;
+        if (check_cuda(cudaMemsetAsync(buf[b].flag, 0, 4, hp->comp), "cudaMemsetAsync")) return 1;
+        if (fhmc_pack_phase_major(&buf[b].out, m, pmax, nsel, buf[b].packed, buf[b].flag, hp->comp)) return 1;
+        if (check_cuda(cudaEventRecord(hp->done[b], hp->comp), "cudaEventRecord")) return 1;
+        if (check_cuda(cudaStreamWaitEvent(hp->down, hp->done[b], 0), "cudaStreamWaitEvent")) return 1;
+        if (check_cuda(cudaMemcpyAsync(&flags_host[k], buf[b].flag, 4, cudaMemcpyDeviceToHost, hp->down), "cudaMemcpyAsync flag")) return 1;
+        if (check_cuda(cudaEventRecord(hp->flag[b], hp->down), "cudaEventRecord")) return 1;
         if (copies(k, 0, guess)) return 1;
         sent[b] = guess;
+        if (check_cuda(cudaEventRecord(hp->freed[b], hp->down), "cudaEventRecord")) return 1;   // buffer set b free again
     }
     for (long long k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; ++k)
         if (settle(k)) return 1;
-    for (int b = 0; b < 2; ++b)
-        if (check_cuda(cudaStreamSynchronize(hp->st[b]), "cudaStreamSynchronize")) return 1;
+    if (check_cuda(cudaStreamSynchronize(hp->down), "cudaStreamSynchronize")) return 1;
+    if (check_cuda(cudaStreamSynchronize(hp->comp), "cudaStreamSynchronize")) return 1;
     if (max_nphase_out) *max_nphase_out = top;
     if (d2h_bytes_out) *d2h_bytes_out = moved;
     return 0;

@@ -396,10 +396,10 @@ class DeviceHistogram(object):
         cur.synchronize()
         return out
 
-    def sweep_host_compact(self, mu1, pmax=4, lanes=0, chunk=1 << 18, out=None):
+    def sweep_host_compact(self, mu1, pmax=4, lanes=0, chunk=1 << 17, out=None):
         """Host buffers in, host buffers out: result set {status, nphase, fe, avg, bounds} of a mu sweep, with only the phase
         slots that exist crossing PCIe.  One call of ``fhmc_sweep_host_compact`` (csrc/fhmc_host_pipe.cu), which pipelines
-        H2D(mu) -> sweep -> phase-major repack -> D2H in chunks on two private streams.  The returned CPU tensors are
+        H2D(mu) -> sweep -> phase-major repack -> D2H in chunks on three private streams (upload, compute, download).  The returned CPU tensors are
         [S, pmax, ...] VIEWS of one pinned phase-major buffer; slots p >= nphase[s] hold NaN / -1.  ``out`` = a previous
         result to reuse (its pinned buffers are recycled)."""
         t = torch()

@@ -186,7 +186,7 @@ int fhmc_pack_phase_major(const fhmc_sweep_out *out, long long n_states, int pma
 /*
  * Host-buffer mu sweep (new; replaces the user's Python loop of reweight()/thermo()/is_safe() calls on host arrays,
  * GH:268-289, 451-596, README.md:60-85).  mu_host[n_states] and out_host are PINNED host memory; everything in between is
- * pipelined on two private streams in chunks of `chunk` state points: H2D(mu) -> fhmc_sweep_1d -> fhmc_pack_phase_major
+ * pipelined on three private streams (upload, compute, download) in chunks of `chunk` state points: H2D(mu) -> fhmc_sweep_1d -> fhmc_pack_phase_major
  * -> D2H of the head and of the phase blocks that exist.  Returns when the results are in out_host, laid out as
  * fhmc_pack_phase_major describes for S = n_states (phase blocks >= *max_nphase_out are not written).
  *   desc->pmax, desc->n_sel size the records; workspace: device, 256-byte aligned, fhmc_sweep_host_workspace() bytes
