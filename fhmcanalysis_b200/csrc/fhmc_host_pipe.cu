@@ -123,12 +123,18 @@ extern "C" int fhmc_sweep_host_compact(const fhmc_hist_desc *desc, const double 
     auto copies = [&](long long k, int from, int upto) -> int {
         const long long lo = k * chunk, m = (lo + chunk <= S ? chunk : S - lo);
         const PipeBuf &B = buf[k & 1];
-        for (int j = from; j <= upto; ++j) {
-            const unsigned char *src = (j == 0) ? B.packed : B.packed + 8 * m + (long long)(j - 1) * m * rec;
-            unsigned char *dst = (j == 0) ? oh + 8 * lo : oh + 8 * S + ((long long)(j - 1) * S + lo) * rec;
-            const size_t nb = (size_t)((j == 0) ? 8 * m : m * rec);
-            if (check_cuda(cudaMemcpyAsync(dst, src, nb, cudaMemcpyDeviceToHost, hp->down), "cudaMemcpyAsync D2H")) return 1;
-            moved += (long long)nb;
+        if (from == 0) {
+            if (check_cuda(cudaMemcpyAsync(oh + 8 * lo, B.packed, (size_t)(8 * m), cudaMemcpyDeviceToHost, hp->down), "cudaMemcpyAsync D2H")) return 1;
+            moved += 8 * m;
+            from = 1;
+        }
+        if (upto >= from) {   // phase blocks from..upto in ONE strided copy: rows of m records, S records apart on the host
+            const int np = upto - from + 1;
+            const unsigned char *src = B.packed + 8 * m + (long long)(from - 1) * m * rec;
+            unsigned char *dst = oh + 8 * S + ((long long)(from - 1) * S + lo) * rec;
+            if (check_cuda(cudaMemcpy2DAsync(dst, (size_t)(S * rec), src, (size_t)(m * rec), (size_t)(m * rec), (size_t)np,
+                                             cudaMemcpyDeviceToHost, hp->down), "cudaMemcpy2DAsync D2H")) return 1;
+            moved += (long long)np * m * rec;
         }
         return 0;
     };
