@@ -29,13 +29,27 @@ struct ProdWalk {
         double u, N, x[NX > 0 ? NX : 1];
     };
     // one state point in flight
+    // (kept small on purpose: two of these plus one block of table entries must fit the 128-register budget of two CTAs
+    // per SM without the hot loop re-deriving exp(s dN)^2 every iteration -- u_0 and the decision margin are recomputed
+    // where the rare paths need them, the three flags share a word)
     struct PS {
-        double s, u0, Sacc, Stot, A[NA], t, r1, r4, vmargin;
+        double s, Sacc, Stot, A[NA], t, r1, r4;
         long long sp;
         int Mq, k_hi, k_lo, cntM, cntm, P;
-        unsigned rescue;
-        bool bad, robust, chain_ok;
+        unsigned rescue, fl;
     };
+    static constexpr unsigned F_BAD = 1u, F_ROBUST = 2u, F_CHAIN = 4u;
+    __device__ __forceinline__ double u0(const PS &p) const
+    {
+        double Nd;
+        return load_u(p, 0, Nd);
+    }
+    // more than rounding of fl(u - c) can move two values against each other: >= 2^-51 (|u| + |c|) for every bin
+    __device__ __forceinline__ double vmargin(const PS &p) const
+    {
+        const double Na = fmax(fabs(lds_f64(s_pk + 8u)), fabs(lds_f64(s_pk + (uint32_t)last * (uint32_t)(PK * 8) + 8u)));
+        return 1.8e-15 * (cx.lmax + fabs(p.s) * Na) + 1e-300 + 1e-14;
+    }
 
     const SweepArgs &a;
     const FastCtx &cx;
@@ -78,13 +92,13 @@ struct ProdWalk {
     __device__ __forceinline__ void flush(PS &p) const
     {
         if (p.P < pmax && p.Sacc >= 1e-280) {
-            a.out.fe[p.sp * pmax + p.P] = -(add_shift(p.Mq, log(p.Sacc)) - p.u0);
+            a.out.fe[p.sp * pmax + p.P] = -(add_shift(p.Mq, log(p.Sacc)) - u0(p));
 #pragma unroll
             for (int q = 0; q < NSEL; ++q) a.out.avg[(p.sp * pmax + p.P) * NSEL + q] = p.A[q] / p.Sacc;
         } else if (p.P < pmax) {
             p.rescue |= 1u << p.P;   // phase too unlikely for the common shift: re-integrated about its own maximum in finish()
         } else {
-            p.bad = true;
+            p.fl |= F_BAD;
         }
         p.Stot += p.Sacc;
         p.Sacc = 0.0;
@@ -96,7 +110,8 @@ struct ProdWalk {
     __device__ __forceinline__ bool window(PS &p, int i, double xc, bool is_max, bool use_c, double cc, int d0, bool track) const
     {
         double Nd;
-        const double xg = is_max ? xc - p.vmargin : xc + p.vmargin;
+        const double vm = vmargin(p);
+        const double xg = is_max ? xc - vm : xc + vm;
         bool rb = true;
         for (int d = d0; d <= pe.w; ++d) {
             const int jl = (i - d < 0) ? 0 : i - d;
@@ -107,7 +122,7 @@ struct ProdWalk {
             if (!ok) return false;
             rb &= is_max ? (xg > xl && xg > xr) : (xg < xl && xg < xr);
         }
-        if (track) p.robust &= rb;
+        if (track && !rb) p.fl &= ~F_ROBUST;
         return true;
     }
     // exact strict 1-neighbour test + window test of bin i (values xm, xc, xp); bookkeeping of a confirmed extremum
@@ -115,7 +130,8 @@ struct ProdWalk {
     {
         const bool is_max = (xc > xm) && (xc > xp), is_min = (xc < xm) && (xc < xp);
         if ((is_max || is_min) && window(p, i, xc, is_max, false, 0.0, 2, true)) {
-            p.robust &= is_max ? (xc - p.vmargin > xm && xc - p.vmargin > xp) : (xc + p.vmargin < xm && xc + p.vmargin < xp);
+            const double vm = vmargin(p);
+            if (!(is_max ? (xc - vm > xm && xc - vm > xp) : (xc + vm < xm && xc + vm < xp))) p.fl &= ~F_ROBUST;
             if (is_max) {
                 if (1 + p.cntM <= pmax - 1) maxl(p)[1 + p.cntM] = i;
                 ++p.cntM;
@@ -196,7 +212,7 @@ struct ProdWalk {
         const double lA = lds_f64(cx.s_anch + 8u * (uint32_t)g);
         asm("ld.shared.f64 %0, [%1];" : "=d"(Ni) : "r"(s_pk + (uint32_t)i * (uint32_t)(PK * 8) + 8u));
         p.t = exp_scaled(__dadd_rn(lA, __dmul_rn(p.s, Ni)), p.Mq, tab);
-        return (p.t > 2.3e-308) && p.chain_ok;
+        return (p.t > 2.3e-308) && (p.fl & F_CHAIN);
     }
     // blocks [b, bend) of one segment for one point (usable: chained products; else true exps)
     __device__ __forceinline__ void segment_single(PS &p, bool usable, int b, int bend, int i, uint32_t pb) const
@@ -229,8 +245,7 @@ struct ProdWalk {
         p.sp = sp;
         p.cntM = p.cntm = p.P = 0;
         p.rescue = 0;
-        p.bad = (n < 3);
-        p.robust = true;
+        p.fl = F_ROBUST | (n < 3 ? F_BAD : 0u);
         p.Sacc = p.Stot = 0.0;
         p.t = 0.0;
 #pragma unroll
@@ -245,19 +260,18 @@ struct ProdWalk {
         double Nm;
         p.Mq = shift_for_max(load_u(p, (int)cx.g_hidx[lo], Nm));
         const double sdn = p.s * (lds_f64(s_pk + (uint32_t)(PK * 8) + 8u) - lds_f64(s_pk + 8u));   // s dN
-        if (!(fabs(4.0 * sdn) < 200.0)) p.bad = true;   // extreme tilt: leave it to the generic evaluator
+        if (!(fabs(4.0 * sdn) < 200.0)) p.fl |= F_BAD;   // extreme tilt: leave it to the generic evaluator
         p.r1 = exp(sdn);
         p.r4 = exp(4.0 * sdn);
         const double Na = fmax(fabs(lds_f64(s_pk + 8u)), fabs(lds_f64(s_pk + (uint32_t)last * (uint32_t)(PK * 8) + 8u)));
         const double margin = 1.8e-15 * (cx.lmax + fabs(p.s) * Na) + 1e-300;   // 8 * 2^-52 * (|lnPI| + |s N|)
-        p.vmargin = margin + 1e-14;                                              // >= 2^-51 (|u| + |c|) for every bin
-        p.chain_ok = fabs(sdn) < 4.5;   // exp(|s dN| * 128 bins) must stay finite; beyond it every block is examined
-        p.k_hi = p.chain_ok ? hi_key(-sdn + margin) : 0x7fffffff;
-        p.k_lo = p.chain_ok ? hi_key(-sdn - margin) : (int)0x80000000;
+        const bool chain_ok = fabs(sdn) < 4.5;   // exp(|s dN| * 128 bins) must stay finite; beyond it every block is examined
+        if (chain_ok) p.fl |= F_CHAIN;
+        p.k_hi = chain_ok ? hi_key(-sdn + margin) : 0x7fffffff;
+        p.k_lo = chain_ok ? hi_key(-sdn - margin) : (int)0x80000000;
         Bin b0;
         load_bin(p, 0, b0);
-        p.u0 = b0.u;
-        if (!p.bad) accumulate(p, b0);
+        if (!(p.fl & F_BAD)) accumulate(p, b0);
     }
 
     // ---- the walk over the full blocks (bins 1 .. 4 nb) -------------------------------------------------------
@@ -277,7 +291,7 @@ struct ProdWalk {
     __device__ __forceinline__ void walk2(PS &p0, PS &p1) const
     {
         const int nb = (n - 2) / 4;
-        const double r2a = p0.r1 * p0.r1, r2b = p1.r1 * p1.r1;
+        const double r2a = p0.r1 * p0.r1, r2b = p1.r1 * p1.r1;   // (pinning these in registers costs a spill in the loop: measured slower)
         uint32_t pb = cx.s_prod;
         int b = 0, i = 1;
         for (int g = 0; b < nb; ++g) {
@@ -315,7 +329,7 @@ struct ProdWalk {
     // Returns false when the state point is not a plain case and must be re-run by the generic evaluator.
     __device__ __forceinline__ bool finish(PS &p) const
     {
-        if (p.bad) return false;
+        if (p.fl & F_BAD) return false;
         pe.s = p.s;
         {
             int i = 1 + 4 * ((n - 2) / 4);
@@ -334,7 +348,7 @@ struct ProdWalk {
             accumulate(p, c);
             flush(p);
         }
-        if (p.bad || a.d.complete) return false;
+        if ((p.fl & F_BAD) || a.d.complete) return false;
         int *const ml = maxl(p), *const mn = minl(p), *const bb = bl(p);
         const long long sp = p.sp;
         int nM = 0, nm = 0;
@@ -347,7 +361,7 @@ struct ProdWalk {
             // NORMALISED array (GH:382-386).  One light scan on fl(u - c); only genuine ties go to the generic evaluator.
             double vM = -CUDART_INF, vm = CUDART_INF, Nd;
             int cM = 0, cm = 0, pM = 0, pm = 0;
-            p.robust = false;   // nothing was decided by the walk: keep the re-test of whatever repair() lists
+            p.fl &= ~F_ROBUST;   // nothing was decided by the walk: keep the re-test of whatever repair() lists
             for (int j = 0; j < n; ++j) {
                 const double v = __dsub_rn(load_u(p, j, Nd), c);
                 if (v > vM) { vM = v; cM = 1; pM = j; } else if (v == vM) ++cM;
@@ -363,7 +377,7 @@ struct ProdWalk {
         pe.nmin = nm;
         // re-test the detected interior extrema on the normalised values, as PointEval::verify() -- unless every
         // comparison behind them was decided by more than rounding can move (p.robust)
-        if (!a.d.compare_raw && !p.robust) {
+        if (!a.d.compare_raw && !(p.fl & F_ROBUST)) {
             double Nd;
             for (int k = 0; k < nM + nm; ++k) {
                 const bool is_max = k < nM;
@@ -393,7 +407,7 @@ struct ProdWalk {
 #pragma unroll
                 for (int q = 0; q < NX; ++q) Ap[q + (SEL0N ? 1 : 0)] = fma(e, b.x[q], Ap[q + (SEL0N ? 1 : 0)]);
             }
-            a.out.fe[sp * pmax + ph] = -(add_shift(Mp, log(Sp)) - p.u0);
+            a.out.fe[sp * pmax + ph] = -(add_shift(Mp, log(Sp)) - u0(p));
 #pragma unroll
             for (int q = 0; q < NSEL; ++q) a.out.avg[(sp * pmax + ph) * NSEL + q] = Ap[q] / Sp;
             flags |= FHMC_ST_RESCUED;
@@ -445,16 +459,16 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_prod2(const __grid_consta
             bool ok0, ok1 = true;
             if (sp1 < S) {
                 w.init(p1, sp1, a.st.mu1[(sp1 / a.st.mu1_div) % a.st.n_mu1]);
-                if (!p0.bad && !p1.bad) {
+                if (!((p0.fl | p1.fl) & W::F_BAD)) {
                     w.walk2(p0, p1);
                 } else {
-                    if (!p0.bad) w.walk1(p0);
-                    if (!p1.bad) w.walk1(p1);
+                    if (!(p0.fl & W::F_BAD)) w.walk1(p0);
+                    if (!(p1.fl & W::F_BAD)) w.walk1(p1);
                 }
                 ok0 = w.finish(p0);
                 ok1 = w.finish(p1);
             } else {
-                if (!p0.bad) w.walk1(p0);
+                if (!(p0.fl & W::F_BAD)) w.walk1(p0);
                 ok0 = w.finish(p0);
             }
             if (!ok0) queue[atomicAdd(q_count, 1)] = sp0;   // anything unusual: defer to the generic evaluator
