@@ -352,7 +352,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             "config": {"workload": "config2: synthetic 1-comp N_tot lnPI, N_max=1000 (1001 bins), smooth=10, 10^6-point mu sweep per GPU with thermo "
                                    "(<N>, <N^2>, per-phase lnZ, phase split, is_safe)",
                        "state_points_per_gpu": S, "bins": N_BINS, "smooth": SMOOTH, "pmax": PMAX, "moments": list(moments),
-                       "lanes_per_point": args.lanes or "auto", "e2e_outputs": list(E2E_FIELDS), "e2e_path": "fhmc_sweep_host_compact (C ABI, host buffers): per 2^17-point chunk H2D(mu) -> sweep kernel -> k_pack_phase_major -> D2H of the live phase blocks; upload, compute and download streams", "e2e_gpu_launches_per_step": e2e_launches, "l2": "flushed (256 MiB memset) before every timed step",
+                       "lanes_per_point": args.lanes or "auto", "e2e_outputs": list(E2E_FIELDS), "e2e_path": "fhmc_sweep_host_compact (C ABI, host buffers): per 2^17-point chunk H2D(mu) -> sweep kernel -> k_pack_phase_soa16 (status i16, nphase u8, bounds i16; fe/avg f64) -> D2H of the live phase blocks; upload, compute and download streams", "e2e_gpu_launches_per_step": e2e_launches, "l2": "flushed (256 MiB memset) before every timed step",
                        "parallelism": "dp%d over state points, no data-path collective" % world,
                        "final_gather_ms": gather_ms, "ok_fraction": ok_frac, "fast_kernel_fraction": fast_frac, "wall_s_timed_region": wall},
             "clocks": clocks,

@@ -70,6 +70,7 @@ EXPORTS = [
     "fhmc_phase_moments", "fhmc_axpy_rows", "fhmc_find_phase_eq_1d", "fhmc_reweight_2d",
     "fhmc_reweight_2d_workspace", "fhmc_pack_bytes", "fhmc_pack_phase_major",
     "fhmc_masked_lse_2d", "fhmc_masked_lse_2d_workspace", "fhmc_sweep_host_workspace", "fhmc_sweep_host_compact",
+    "fhmc_sweep_host_compact16", "fhmc_pack_soa16_bytes", "fhmc_pack_phase_soa16",
     "fhmc_patch_shifts", "fhmc_reweight_2d_prod", "fhmc_reweight_2d_prod_workspace",
     "fhmc_bench_dfma", "fhmc_bench_exp",
 ]
@@ -128,6 +129,12 @@ def load():
     L.fhmc_reweight_2d_prod_workspace.restype = ctypes.c_size_t
     L.fhmc_reweight_2d_prod_workspace.argtypes = [ci, ci, ci, cll]
     L.fhmc_reweight_2d_prod.argtypes = [vp, vp, ci, ci, vp, vp, vp, ci, vp, vp, cll, vp, vp, ctypes.c_size_t, vp]
+    L.fhmc_sweep_host_compact16.restype = ci
+    L.fhmc_sweep_host_compact16.argtypes = L.fhmc_sweep_host_compact.argtypes
+    L.fhmc_pack_soa16_bytes.restype = cll
+    L.fhmc_pack_soa16_bytes.argtypes = [cll, ci, ci]
+    L.fhmc_pack_phase_soa16.restype = ci
+    L.fhmc_pack_phase_soa16.argtypes = [ctypes.POINTER(SweepOut), cll, ci, ci, vp, vp, vp]
     L.fhmc_patch_shifts.restype = ci
     L.fhmc_patch_shifts.argtypes = [vp, vp, vp, ci, vp, vp, vp]
     L.fhmc_bench_dfma.restype = cll

@@ -340,6 +340,36 @@ __global__ void __launch_bounds__(256) k_pack_phase_major(const __grid_constant_
     if ((threadIdx.x & 31) == 0 && pm > 0) atomicMax(a.max_nphase, pm);
 }
 
+// Narrow variant of the repack (fhmc_pack_phase_soa16): 4-byte head {u16 status, u8 nphase, u8 0}, then per phase the fp64
+// fields {fe, avg[nsel]}[S] and, in a separate array, the bounds as int16 pairs -- 4 + P (8 + 8 nsel + 4) bytes per state
+// point instead of 8 + P (16 + 8 nsel).
+__global__ void __launch_bounds__(256) k_pack_phase_soa16(const __grid_constant__ PackArgs a)
+{
+    uchar4 *head = reinterpret_cast<uchar4 *>(a.packed);
+    const int nf = 1 + a.nsel;
+    double *F = reinterpret_cast<double *>(a.packed + ((4 * a.S + 15) & ~15ll));
+    short2 *B = reinterpret_cast<short2 *>(reinterpret_cast<unsigned char *>(F) + (long long)a.pmax * a.S * nf * 8);
+    int pm = 0;
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < a.S; s += (long long)gridDim.x * blockDim.x) {
+        const unsigned st = a.out.status[s];
+        const int P = a.out.nphase[s];
+        head[s] = make_uchar4((unsigned char)(st & 0xFFu), (unsigned char)((st >> 8) & 0xFFu), (unsigned char)min(max(P, 0), 255), 0);
+        const int Pe = ((st & FHMC_ST_CODE_MASK) == FHMC_OK) ? min(max(P, 0), a.pmax) : 0;
+        pm = max(pm, Pe);
+        for (int p = 0; p < a.pmax; ++p) {
+            double *r = F + ((long long)p * a.S + s) * nf;
+            const bool live = p < Pe;
+            r[0] = live ? a.out.fe[s * a.pmax + p] : CUDART_NAN;
+            for (int q = 0; q < a.nsel; ++q) r[1 + q] = live ? a.out.avg[(s * a.pmax + p) * a.nsel + q] : CUDART_NAN;
+            const int2 b = live ? *reinterpret_cast<const int2 *>(a.out.bounds + (s * a.pmax + p) * 2) : make_int2(-1, -1);
+            B[(long long)p * a.S + s] = make_short2((short)b.x, (short)b.y);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pm = max(pm, __shfl_xor_sync(0xffffffffu, pm, o));
+    if ((threadIdx.x & 31) == 0 && pm > 0) atomicMax(a.max_nphase, pm);
+}
+
 #define FHMC_FAST_MIN_STATES 4096
 
 int choose_lanes(long long n_states, int bins, const DevInfo *di)
@@ -494,6 +524,32 @@ int fhmc_pack_phase_major(const fhmc_sweep_out *out, long long n_states, int pma
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_pack_phase_major<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
     return check_cuda(cudaGetLastError(), "k_pack_phase_major launch");
+}
+
+long long fhmc_pack_soa16_bytes(long long n_states, int pmax, int n_sel)
+{
+    if (n_states < 0 || pmax < 1 || n_sel < 0) return -1;
+    return ((4 * n_states + 15) & ~15ll) + (long long)pmax * n_states * (8 * (1 + (long long)n_sel) + 4);
+}
+
+int fhmc_pack_phase_soa16(const fhmc_sweep_out *out, long long n_states, int pmax, int n_sel, void *packed, int *max_nphase,
+                          void *stream)
+{
+    if (!out || !out->status || !out->nphase || !out->fe || !out->bounds || (n_sel > 0 && !out->avg) || !packed || !max_nphase ||
+        n_states < 0 || pmax < 1 || n_sel < 0 || n_sel > FHMC_MAX_SEL) { set_error("bad arguments"); return 1; }
+    if ((uintptr_t)packed & 15) { set_error("packed buffer must be 16-byte aligned"); return 1; }
+    if (n_states == 0) return 0;
+    PackArgs a;
+    a.out = *out;
+    a.S = n_states;
+    a.pmax = pmax;
+    a.nsel = n_sel;
+    a.packed = static_cast<unsigned char *>(packed);
+    a.max_nphase = max_nphase;
+    long long blocks = (n_states + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_pack_phase_soa16<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    return check_cuda(cudaGetLastError(), "k_pack_phase_soa16 launch");
 }
 
 long long fhmc_bench_dfma(int iters, double *sink, void *stream)

@@ -75,7 +75,7 @@ static PipeBuf carve(unsigned char *base, long long c, int pmax, int nsel)
     b.out.bounds = reinterpret_cast<int *>(take(8 * c * pmax));
     b.out.max_idx = reinterpret_cast<int *>(take(4 * c * pmax));
     b.out.min_idx = reinterpret_cast<int *>(take(4 * c * (pmax + 1)));
-    b.packed = take((size_t)fhmc_pack_bytes(c, pmax, nsel));
+    b.packed = take((size_t)fhmc_pack_bytes(c, pmax, nsel));   // (>= fhmc_pack_soa16_bytes)
     b.flag = reinterpret_cast<int *>(take(16));
     b.bytes = off;
     return b;
@@ -91,10 +91,10 @@ extern "C" size_t fhmc_sweep_host_workspace(long long chunk, int pmax, int n_sel
     return 2 * carve(nullptr, chunk, pmax, n_sel).bytes;
 }
 
-extern "C" int fhmc_sweep_host_compact(const fhmc_hist_desc *desc, const double *blob, const double *mu_host, long long n_states,
-                                       int lanes_per_point, long long chunk, void *workspace, size_t workspace_bytes,
-                                       void *out_host, int *flags_host, int guess_nphase, int *max_nphase_out,
-                                       long long *d2h_bytes_out, void *stream)
+static int sweep_host_impl(const fhmc_hist_desc *desc, const double *blob, const double *mu_host, long long n_states,
+                           int lanes_per_point, long long chunk, void *workspace, size_t workspace_bytes,
+                           void *out_host, int *flags_host, int guess_nphase, int *max_nphase_out,
+                           long long *d2h_bytes_out, void *stream, bool narrow)
 {
     if (!desc || !blob || !mu_host || !workspace || !out_host || !flags_host || n_states < 0 || chunk < 1) { set_error("bad arguments"); return 1; }
     const int pmax = desc->pmax, nsel = desc->n_sel;
@@ -119,23 +119,36 @@ extern "C" int fhmc_sweep_host_compact(const fhmc_hist_desc *desc, const double 
     if (check_cuda(cudaEventRecord(hp->ready, (cudaStream_t)stream), "cudaEventRecord")) return 1;
     if (check_cuda(cudaStreamWaitEvent(hp->comp, hp->ready, 0), "cudaStreamWaitEvent")) return 1;
 
-    // blocks [from, upto] of chunk k: block 0 = head {status, nphase}[m], block 1+p = phase p records
+    // blocks [from, upto] of chunk k: block 0 = head, block 1+p = phase p.  The live phase blocks leave in ONE strided copy
+    // per array: rows of m records on the device, S records apart on the host.
+    const long long nf8 = 8 * (1 + (long long)nsel);
     auto copies = [&](long long k, int from, int upto) -> int {
         const long long lo = k * chunk, m = (lo + chunk <= S ? chunk : S - lo);
         const PipeBuf &B = buf[k & 1];
+        const long long hb = narrow ? 4 : 8;   // head bytes per state point
         if (from == 0) {
-            if (check_cuda(cudaMemcpyAsync(oh + 8 * lo, B.packed, (size_t)(8 * m), cudaMemcpyDeviceToHost, hp->down), "cudaMemcpyAsync D2H")) return 1;
-            moved += 8 * m;
+            if (check_cuda(cudaMemcpyAsync(oh + hb * lo, B.packed, (size_t)(hb * m), cudaMemcpyDeviceToHost, hp->down), "cudaMemcpyAsync D2H")) return 1;
+            moved += hb * m;
             from = 1;
         }
-        if (upto >= from) {   // phase blocks from..upto in ONE strided copy: rows of m records, S records apart on the host
-            const int np = upto - from + 1;
+        if (upto < from) return 0;
+        const int np = upto - from + 1;
+        if (!narrow) {
             const unsigned char *src = B.packed + 8 * m + (long long)(from - 1) * m * rec;
             unsigned char *dst = oh + 8 * S + ((long long)(from - 1) * S + lo) * rec;
             if (check_cuda(cudaMemcpy2DAsync(dst, (size_t)(S * rec), src, (size_t)(m * rec), (size_t)(m * rec), (size_t)np,
                                              cudaMemcpyDeviceToHost, hp->down), "cudaMemcpy2DAsync D2H")) return 1;
             moved += (long long)np * m * rec;
+            return 0;
         }
+        // narrow layout: fp64 fields and int16 bounds are separate arrays (fhmc_pack_phase_soa16)
+        const unsigned char *Fd = B.packed + ((4 * m + 15) & ~15ll), *Bd = Fd + (long long)pmax * m * nf8;
+        unsigned char *Fh = oh + ((4 * S + 15) & ~15ll), *Bh = Fh + (long long)pmax * S * nf8;
+        if (check_cuda(cudaMemcpy2DAsync(Fh + ((long long)(from - 1) * S + lo) * nf8, (size_t)(S * nf8), Fd + (long long)(from - 1) * m * nf8,
+                                         (size_t)(m * nf8), (size_t)(m * nf8), (size_t)np, cudaMemcpyDeviceToHost, hp->down), "cudaMemcpy2DAsync D2H")) return 1;
+        if (check_cuda(cudaMemcpy2DAsync(Bh + ((long long)(from - 1) * S + lo) * 4, (size_t)(S * 4), Bd + (long long)(from - 1) * m * 4,
+                                         (size_t)(m * 4), (size_t)(m * 4), (size_t)np, cudaMemcpyDeviceToHost, hp->down), "cudaMemcpy2DAsync D2H")) return 1;
+        moved += (long long)np * m * (nf8 + 4);
         return 0;
     };
     int sent[2] = {0, 0};   // phase blocks already queued for the chunk that owns buffer set b
@@ -175,7 +188,8 @@ extern "C" int fhmc_sweep_host_compact(const fhmc_hist_desc *desc, const double 
         st.dmu = nullptr; st.n_dmu = 1; st.dmu_div = 1;
         if (fhmc_sweep_1d(&d, blob, &st, &buf[b].out, lanes_per_point, hp->comp)) return 1;
         if (check_cuda(cudaMemsetAsync(buf[b].flag, 0, 4, hp->comp), "cudaMemsetAsync")) return 1;
-        if (fhmc_pack_phase_major(&buf[b].out, m, pmax, nsel, buf[b].packed, buf[b].flag, hp->comp)) return 1;
+        if (narrow ? fhmc_pack_phase_soa16(&buf[b].out, m, pmax, nsel, buf[b].packed, buf[b].flag, hp->comp)
+                   : fhmc_pack_phase_major(&buf[b].out, m, pmax, nsel, buf[b].packed, buf[b].flag, hp->comp)) return 1;
         if (check_cuda(cudaEventRecord(hp->done[b], hp->comp), "cudaEventRecord")) return 1;
         if (check_cuda(cudaStreamWaitEvent(hp->down, hp->done[b], 0), "cudaStreamWaitEvent")) return 1;
         if (check_cuda(cudaMemcpyAsync(&flags_host[k], buf[b].flag, 4, cudaMemcpyDeviceToHost, hp->down), "cudaMemcpyAsync flag")) return 1;
@@ -191,4 +205,24 @@ extern "C" int fhmc_sweep_host_compact(const fhmc_hist_desc *desc, const double 
     if (max_nphase_out) *max_nphase_out = top;
     if (d2h_bytes_out) *d2h_bytes_out = moved;
     return 0;
+}
+
+extern "C" int fhmc_sweep_host_compact(const fhmc_hist_desc *desc, const double *blob, const double *mu_host, long long n_states,
+                                       int lanes_per_point, long long chunk, void *workspace, size_t workspace_bytes,
+                                       void *out_host, int *flags_host, int guess_nphase, int *max_nphase_out,
+                                       long long *d2h_bytes_out, void *stream)
+{
+    return sweep_host_impl(desc, blob, mu_host, n_states, lanes_per_point, chunk, workspace, workspace_bytes, out_host, flags_host,
+                           guess_nphase, max_nphase_out, d2h_bytes_out, stream, false);
+}
+
+// Same pipeline with the narrow records of fhmc_pack_phase_soa16 (desc->n must be <= 32767: bounds travel as int16).
+extern "C" int fhmc_sweep_host_compact16(const fhmc_hist_desc *desc, const double *blob, const double *mu_host, long long n_states,
+                                         int lanes_per_point, long long chunk, void *workspace, size_t workspace_bytes,
+                                         void *out_host, int *flags_host, int guess_nphase, int *max_nphase_out,
+                                         long long *d2h_bytes_out, void *stream)
+{
+    if (desc && desc->n > 32767) { set_error("histogram too long for int16 bounds: use fhmc_sweep_host_compact"); return 1; }
+    return sweep_host_impl(desc, blob, mu_host, n_states, lanes_per_point, chunk, workspace, workspace_bytes, out_host, flags_host,
+                           guess_nphase, max_nphase_out, d2h_bytes_out, stream, true);
 }

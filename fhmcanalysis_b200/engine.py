@@ -396,15 +396,18 @@ class DeviceHistogram(object):
         cur.synchronize()
         return out
 
-    def sweep_host_compact(self, mu1, pmax=4, lanes=0, chunk=1 << 17, out=None):
+    def sweep_host_compact(self, mu1, pmax=4, lanes=0, chunk=1 << 17, out=None, narrow=None):
         """Host buffers in, host buffers out: result set {status, nphase, fe, avg, bounds} of a mu sweep, with only the phase
         slots that exist crossing PCIe.  One call of ``fhmc_sweep_host_compact`` (csrc/fhmc_host_pipe.cu), which pipelines
         H2D(mu) -> sweep -> phase-major repack -> D2H in chunks on three private streams (upload, compute, download).  The returned CPU tensors are
         [S, pmax, ...] VIEWS of one pinned phase-major buffer; slots p >= nphase[s] hold NaN / -1.  ``out`` = a previous
-        result to reuse (its pinned buffers are recycled)."""
+        result to reuse (its pinned buffers are recycled).  ``narrow`` (default: whenever the bin indices fit int16) sends
+        the records of ``fhmc_pack_phase_soa16``: status as int16, nphase as uint8, bounds as int16 -- 60 instead of 72
+        bytes per two-phase state point with two averaged quantities; fe / avg stay fp64."""
         t = torch()
         L = _lib.load()
         dev = self.device
+        narrow = (self.n <= 32767) if narrow is None else bool(narrow)
         mu_h = mu1 if isinstance(mu1, t.Tensor) else t.from_numpy(np.ascontiguousarray(mu1, dtype=np.float64))
         if not mu_h.is_pinned():
             mu_h = mu_h.pin_memory()
@@ -420,8 +423,8 @@ class DeviceHistogram(object):
             self._hpipe = {"key": (chunk, pmax), "ws": t.empty(ws_bytes + 256, dtype=t.uint8, device=dev), "ws_bytes": ws_bytes}
         hpipe = self._hpipe
         ws_ptr = (hpipe["ws"].data_ptr() + 255) & ~255
-        if out is None or out.get("_key") != (S, pmax, nsel, chunk):
-            out = self._host_result_views(S, pmax, nsel, chunk)
+        if out is None or out.get("_key") != (S, pmax, nsel, chunk, narrow):
+            out = self._host_result_views(S, pmax, nsel, chunk, narrow)
             out["_flags"] = t.zeros(n_chunks, dtype=t.int32).pin_memory()
         d = self._desc(pmax)
         if not hasattr(self, "_blob_pin"):
@@ -431,7 +434,8 @@ class DeviceHistogram(object):
         blob_d.copy_(self._blob_pin, non_blocking=True)     # the histogram travels with every call (it is host data too)
         top, moved = ctypes.c_int(0), ctypes.c_longlong(0)
         with t.cuda.device(dev):
-            rc = L.fhmc_sweep_host_compact(ctypes.byref(d), _ptr(blob_d), ctypes.c_void_p(mu_h.data_ptr()), S, int(lanes), chunk,
+            fn = L.fhmc_sweep_host_compact16 if narrow else L.fhmc_sweep_host_compact
+            rc = fn(ctypes.byref(d), _ptr(blob_d), ctypes.c_void_p(mu_h.data_ptr()), S, int(lanes), chunk,
                                            ctypes.c_void_p(ws_ptr), hpipe["ws_bytes"], ctypes.c_void_p(out["_buf"].data_ptr()),
                                            ctypes.c_void_p(out["_flags"].data_ptr()), int(out.get("max_nphase", 1)),
                                            ctypes.byref(top), ctypes.byref(moved), ctypes.c_void_p(cur.cuda_stream))
@@ -448,12 +452,27 @@ class DeviceHistogram(object):
         out["d2h_bytes"] = int(moved.value) + 4 * n_chunks       # + the per-chunk phase counts
         return out
 
-    def _host_result_views(self, S, pmax, nsel, chunk):
-        """One pinned phase-major buffer (layout of fhmc_pack_phase_major for S state points) and [S, pmax, ...] views of it."""
+    def _host_result_views(self, S, pmax, nsel, chunk, narrow=False):
+        """One pinned phase-major buffer (layout of fhmc_pack_phase_major, or of fhmc_pack_phase_soa16 when ``narrow``, for
+        S state points) and [S, pmax, ...] views of it."""
         t = torch()
+        if narrow:
+            L = _lib.load()
+            nf = 1 + nsel
+            buf = t.empty(int(L.fhmc_pack_soa16_bytes(S, pmax, nsel)), dtype=t.uint8).pin_memory()
+            out = {"_key": (S, pmax, nsel, chunk, True), "_buf": buf, "_prev_top": pmax}
+            out["status"] = t.as_strided(buf[:4 * S].view(t.int16), (S,), (2,))
+            out["nphase"] = t.as_strided(buf[:4 * S], (S,), (4,), buf.storage_offset() + 2)
+            f0 = (4 * S + 15) & ~15
+            F = buf[f0:f0 + pmax * S * nf * 8].view(t.float64)
+            B = buf[f0 + pmax * S * nf * 8:f0 + pmax * S * nf * 8 + pmax * S * 4].view(t.int16)
+            out["fe"] = t.as_strided(F, (S, pmax), (nf, S * nf), F.storage_offset())
+            out["avg"] = t.as_strided(F, (S, pmax, nsel), (nf, S * nf, 1), F.storage_offset() + 1) if nsel else None
+            out["bounds"] = t.as_strided(B, (S, pmax, 2), (2, 2 * S, 1), B.storage_offset())
+            return out
         rec = 16 + 8 * nsel
         buf = t.empty(8 * S + pmax * rec * S, dtype=t.uint8).pin_memory()
-        out = {"_key": (S, pmax, nsel, chunk), "_buf": buf, "_prev_top": pmax}   # every phase block starts out stale
+        out = {"_key": (S, pmax, nsel, chunk, False), "_buf": buf, "_prev_top": pmax}   # every phase block starts out stale
         head = buf[:8 * S].view(t.int32)
         out["status"] = t.as_strided(head, (S,), (2,))
         out["nphase"] = t.as_strided(head, (S,), (2,), head.storage_offset() + 1)

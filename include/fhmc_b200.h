@@ -184,6 +184,16 @@ int fhmc_pack_phase_major(const fhmc_sweep_out *out, long long n_states, int pma
                           int *max_nphase, void *stream);
 
 /*
+ * Narrow variant of the repack: 4 + P (8 + 8 n_sel + 4) bytes per state point with P live phases.
+ *   packed: { u16 status (FHMC_ST_* fit 13 bits); u8 nphase; u8 0 }[S], padded to 16 bytes  |
+ *           for p in 0..pmax-1: { f64 fe; f64 avg[n_sel]; }[S]  |  for p in 0..pmax-1: { i16 bounds[2]; }[S]
+ * (bin indices must fit int16: n <= 32767).  Slots p >= nphase[s] hold NaN / -1 as in fhmc_pack_phase_major.
+ */
+long long fhmc_pack_soa16_bytes(long long n_states, int pmax, int n_sel);
+int fhmc_pack_phase_soa16(const fhmc_sweep_out *out, long long n_states, int pmax, int n_sel, void *packed,
+                          int *max_nphase, void *stream);
+
+/*
  * Host-buffer mu sweep (new; replaces the user's Python loop of reweight()/thermo()/is_safe() calls on host arrays,
  * GH:268-289, 451-596, README.md:60-85).  mu_host[n_states] and out_host are PINNED host memory; everything in between is
  * pipelined on three private streams (upload, compute, download) in chunks of `chunk` state points: H2D(mu) -> fhmc_sweep_1d -> fhmc_pack_phase_major
@@ -199,6 +209,11 @@ int fhmc_sweep_host_compact(const fhmc_hist_desc *desc, const double *blob, cons
                             int lanes_per_point, long long chunk, void *workspace, size_t workspace_bytes,
                             void *out_host, int *flags_host, int guess_nphase, int *max_nphase_out,
                             long long *d2h_bytes_out, void *stream);
+/* the same with the records of fhmc_pack_phase_soa16 in out_host (fhmc_pack_soa16_bytes(n_states, ...) bytes) */
+int fhmc_sweep_host_compact16(const fhmc_hist_desc *desc, const double *blob, const double *mu_host, long long n_states,
+                              int lanes_per_point, long long chunk, void *workspace, size_t workspace_bytes,
+                              void *out_host, int *flags_host, int guess_nphase, int *max_nphase_out,
+                              long long *d2h_bytes_out, void *stream);
 
 /*
  * Pointwise Taylor update of a stack of arrays (moment extrapolation, GH:1027-1034 / 1162-1171,

@@ -254,6 +254,16 @@ def test_fast_taylor_kernel_agrees_with_generic(golden, golden_meta):
         _agree(a, b, ("sw", order, moments))
 
 
+def torch_int16():
+    import torch
+    return torch.int16
+
+
+def torch_int32():
+    import torch
+    return torch.int32
+
+
 def test_compact_host_sweep_matches_plain_host_sweep():
     """sweep_host_compact (phase-major repack, only live phase blocks cross PCIe) returns what sweep_host returns."""
     from fhmcanalysis_b200 import engine, synth
@@ -261,12 +271,13 @@ def test_compact_host_sweep_matches_plain_host_sweep():
     lnpi = synth.two_peak_lnpi(n, noise=1e-3, scale=0.3)
     N = np.arange(n, dtype=np.float64)
     dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=5, sel=["N", N * N])
-    for S, chunk in ((5000, 2048), (4097, 1 << 18), (1, 1 << 18)):
+    for S, chunk, narrow in ((5000, 2048, True), (5000, 2048, False), (4097, 1 << 18, None), (1, 1 << 18, True)):
         mu = np.linspace(-0.12, 0.10, S)
         a = dh.sweep_host(mu, pmax=4, chunk=chunk)
-        c = dh.sweep_host_compact(mu, pmax=4, chunk=chunk)
+        c = dh.sweep_host_compact(mu, pmax=4, chunk=chunk, narrow=narrow)
         st = a["status"].numpy().view(np.uint32)
-        assert np.array_equal(c["status"].numpy().view(np.uint32), st)
+        assert c["status"].dtype == (torch_int32() if narrow is False else torch_int16())   # narrow records by default
+        assert np.array_equal(c["status"].numpy().astype(np.int64), st.astype(np.int64))
         P = a["nphase"].numpy()
         assert np.array_equal(c["nphase"].numpy(), P) and c["max_nphase"] == P.max()
         fe_a, fe_c = a["fe"].numpy(), c["fe"].numpy()
@@ -279,7 +290,9 @@ def test_compact_host_sweep_matches_plain_host_sweep():
             assert np.array_equal(av_c[live, p], av_a[live, p])
             assert np.array_equal(b_c[live, p], b_a[live, p])
             assert np.all(np.isnan(fe_c[~live, p])) and np.all(b_c[~live, p] == -1)
-        assert c["d2h_bytes"] <= 8 * S + 4 * S * (16 + 16)
+        assert c["d2h_bytes"] <= 8 * S + 4 * S * (16 + 16) + 64
+        if narrow is not False and S == 5000:
+            assert c["d2h_bytes"] <= 4 * S + c["max_nphase"] * S * 28 + 64
     # reuse of the result buffers: a later call with fewer phases must not leave stale phase blocks behind
     mu2 = np.full(5000, -3.0)            # far from coexistence: one phase everywhere
     c2 = dh.sweep_host_compact(mu2, pmax=4, chunk=2048, out=dh.sweep_host_compact(np.linspace(-0.12, 0.10, 5000), pmax=4, chunk=2048))
