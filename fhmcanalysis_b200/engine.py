@@ -208,7 +208,7 @@ class DeviceHistogram(object):
         hull_row, hull_len = 0, 0          # the hull rows are added lazily (ensure_hull) by large mu sweeps only
         self._hull_possible = not coef
         # exp strength reduction of large pure-mu sweeps, fixed before the first one: 3 = product form (Horner blocks,
-        # fhmc_fast_prod.cu) with two state points per thread where the sweep is large enough, 2 = product form, one
+        # fhmc_fast_prod.cu) with two state points per thread where the sweep is large enough (> 512 points per SM), 2 = product form, one
         # point per thread, 1 = four multiplicative chains (fhmc_fast_rec.cu), 0/False = one true exp per bin
         self.use_recurrence = int(os.environ.get("FHMC_MU_RECURRENCE", "3"))
         blob = np.zeros((len(rows), n_pad), dtype=np.float64)

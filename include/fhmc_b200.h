@@ -102,7 +102,7 @@ typedef struct fhmc_hist_desc {
      * (e_i = e_{i-4} * exp(4 s dN) * exp(lnPI_i - lnPI_{i-4})), re-anchored with a true exp every 64 bins (value 1).
      * Value 2: product form -- exp(lnPI_i - A_seg) tabulated per CTA, the sums of a 4-bin block are Horner polynomials in
      * exp(s dN), re-anchored every 128 bins (fhmc_fast_prod.cu).  Value 3: as 2 with two state points per thread when the
-     * sweep has at least 4*256 state points per SM (fhmc_prod.cuh).                                                   */
+     * sweep has more than 2*256 state points per SM (fhmc_prod.cuh).                                                   */
     int mu_recurrence;
     /* fhmc_find_phase_eq_1d only: minimum width (bins) of a phase that counts in the coexistence objective.
      * 0 = 2*smooth (ntot/gc_hist.pyx:652); n1/gc_hist.pyx:1479 passes smooth itself.                                  */
