@@ -26,6 +26,8 @@ CASES = [   # (key, path below example/ntot, T, dMu2 or None, smooth)
     ("ig_T1.00_m1.10", "binary_ideal_gas/T_1.00/dMu2_-1.10", 1.00, -1.10, 5),
     ("ig_T1.00_0.00", "binary_ideal_gas/T_1.00/dMu2_0.00", 1.00, 0.00, 5),
     ("ig_T1.00_2.94", "binary_ideal_gas/T_1.00/dMu2_2.94", 1.00, 2.94, 5),
+    ("ig_T1.00_1.10", "binary_ideal_gas/T_1.00/dMu2_1.10", 1.00, 1.10, 5),
+    ("ig_T1.00_m2.94", "binary_ideal_gas/T_1.00/dMu2_-2.94", 1.00, -2.94, 5),
     ("ig_T1.20_1.10", "binary_ideal_gas/T_1.20/dMu2_1.10", 1.20, 1.10, 5),
     ("ig_T1.20_m2.94", "binary_ideal_gas/T_1.20/dMu2_-2.94", 1.20, -2.94, 5),
     ("sw_T1.10", "square_well/T_1.10", 1.10, None, 10),
@@ -83,12 +85,27 @@ def main():
                     hn = h.temp_dmu_extrap(tb, np.array([dmu2 + 0.05]), order, 10.0, True, True, True, False)
             out["%s/extrap%d" % (key, order)] = np.array(hn.data["ln(PI)"], dtype=np.float64)
         meta[key]["extrap"] = {"beta": tb, "dmu": None if dmu2 is None else [dmu2 + 0.05]}
+    # ---- isopleth.make_grid_multi over the five T* = 1.00 ideal-gas composites (gc_binary.pyx:173-290) ----------------
+    iso_keys = ["ig_T1.00_m2.94", "ig_T1.00_m1.10", "ig_T1.00_0.00", "ig_T1.00_1.10", "ig_T1.00_2.94"]
+    hs = []
+    for k in iso_keys:
+        rel = [c[1] for c in CASES if c[0] == k][0]
+        hs.append(H(os.path.join(REF, "example/ntot", rel, "composite.nc"), 1.0, meta[k]["mu_ref"], 5))
+    meta["iso"] = {"keys": iso_keys, "beta_ref": 1.0, "order": 1, "mu1_bounds": [-4.5, -3.0], "dmu2_bounds": [-2.5, 2.5],
+                   "delta": [0.25, 0.5], "m": 2.5}
+    with redirect_stdout(io.StringIO()):
+        iso = ns.gc_binary.isopleth(hs, 1.0, 1)
+        Z, (X, Y) = iso.make_grid_multi([-4.5, -3.0], [-2.5, 2.5], [0.25, 0.5], 2.5)
+    out["iso/x1"], out["iso/density"], out["iso/fe"] = np.array(Z), np.array(iso.data["density"]), np.array(iso.data["F.E./kT"])
+    out["iso/X"], out["iso/Y"] = np.array(X), np.array(Y)
     np.savez_compressed(os.path.join(HERE, "examples_vectors.npz"), **out)
     with open(os.path.join(HERE, "examples_vectors.json"), "w") as f:
         json.dump(meta, f, indent=1, sort_keys=True)
     print("wrote %d arrays, %.0f KB" % (len(out), os.path.getsize(os.path.join(HERE, "examples_vectors.npz")) / 1024.0))
     for k, v in meta.items():
-        print(k, v["status"], [round(m, 4) for m in v["mus"]])
+        if "status" in v:
+            print(k, v["status"], [round(m, 4) for m in v["mus"]])
+    print("iso filled fraction", float(np.mean(out["iso/x1"] != 0)))
 
 
 if __name__ == "__main__":

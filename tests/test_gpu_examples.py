@@ -10,7 +10,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
-KEYS = ["ig_T1.00_m1.10", "ig_T1.00_0.00", "ig_T1.00_2.94", "ig_T1.20_1.10", "ig_T1.20_m2.94", "sw_T1.10"]
+KEYS = ["ig_T1.00_m1.10", "ig_T1.00_0.00", "ig_T1.00_2.94", "ig_T1.00_1.10", "ig_T1.00_m2.94", "ig_T1.20_1.10", "ig_T1.20_m2.94",
+        "sw_T1.10"]
 
 
 @pytest.fixture(scope="module")
@@ -61,3 +62,24 @@ def test_example_composite_sweep_and_extrapolation(ex, key):
             hn = h.temp_extrap(m["extrap"]["beta"], order, 10.0, True, True, True)
         ref = g["%s/extrap%d" % (key, order)]
         assert np.max(np.abs(hn.data["ln(PI)"] - ref)) <= 1e-9 * max(1.0, np.max(np.abs(ref)))
+
+
+def test_isopleth_over_the_ideal_gas_composites(ex):
+    """isopleth.make_grid_multi (gc_binary.pyx:173-290) over the five T* = 1.00 binary ideal-gas composites of the reference's
+    examples: same cells filled, same x1 / density / F.E. grids as the compiled reference."""
+    import FHMCAnalysis.moments.histogram.one_dim.ntot.gc_hist as oneDH
+    import FHMCAnalysis.moments.histogram.one_dim.ntot.gc_binary as gcB
+    g, meta = ex
+    mi = meta["iso"]
+    hists = []
+    for k in mi["keys"]:
+        m = meta[k]
+        hists.append(oneDH.histogram.from_arrays(g[k + "/lnpi"], g[k + "/mom"], m["beta_ref"], m["mu_ref"], m["smooth"], volume=m["volume"]))
+    iso = gcB.isopleth(hists, mi["beta_ref"], mi["order"])
+    Z, (X, Y) = iso.make_grid_multi(mi["mu1_bounds"], mi["dmu2_bounds"], mi["delta"], mi["m"])
+    assert np.allclose(X, g["iso/X"]) and np.allclose(Y, g["iso/Y"])
+    assert np.array_equal(Z == 0, g["iso/x1"] == 0)
+    assert np.mean(Z != 0) > 0.5
+    assert np.allclose(Z, g["iso/x1"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(iso.data["density"], g["iso/density"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(iso.data["F.E./kT"], g["iso/fe"], rtol=1e-9, atol=1e-12)
