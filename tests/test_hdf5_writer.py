@@ -107,3 +107,31 @@ def test_results_roundtrip(tmp_path):
     assert attrs["beta"] == 1.25 and attrs["producer"] == "fhmcanalysis_b200"
     for k in ("status", "code", "safe", "fe", "bounds"):
         assert np.array_equal(back[k], host[k]) and back[k].dtype == host[k].dtype, k
+
+
+def test_every_example_composite_reads_and_round_trips(tmp_path):
+    """All twelve composites under the reference's example/ directory (written by netCDF4 / libhdf5) through the built-in
+    reader, then through write_composite and the reader again: identical arrays and attributes.  (Needs /root/reference;
+    the GPU box skips it -- the vectors recorded from these files travel in tests/golden/examples_vectors.npz.)"""
+    import glob
+    from fhmcanalysis_b200.io.hdf5_min import Dataset, write_composite
+    files = sorted(glob.glob("/root/reference/example/ntot/*/*/composite.nc") + glob.glob("/root/reference/example/ntot/*/*/*/composite.nc"))
+    if not files:
+        pytest.skip("/root/reference not present on this machine")
+    assert len(files) == 12
+    for k, f in enumerate(files):
+        d = Dataset(f)
+        lnpi = np.array(d.variables["ln(PI)"][:], dtype=np.float64)
+        ntot = np.array(d.variables["N_{tot}"][:])
+        mom = np.array(d.variables["N_{i}^{j}*N_{k}^{m}*U^{p}"][:], dtype=np.float64)
+        nspec, max_order = int(d.nspec), int(d.max_order)
+        assert ntot.dtype == np.int64 and np.array_equal(ntot, np.arange(len(lnpi)))
+        assert mom.shape == (nspec, max_order + 1, nspec, max_order + 1, max_order + 1, len(lnpi))
+        assert np.all(mom[0, 0, 0, 0, 0] == 1.0) and np.all(np.isfinite(lnpi)) and float(d.volume) > 0
+        out = str(tmp_path / ("c%d.nc" % k))
+        write_composite(out, lnpi, ntot, mom, float(d.volume), nspec, max_order, history=str(getattr(d, "history", "")))
+        e = Dataset(out)
+        assert np.array_equal(np.array(e.variables["ln(PI)"][:]), lnpi)
+        assert np.array_equal(np.array(e.variables["N_{tot}"][:]), ntot)
+        assert np.array_equal(np.array(e.variables["N_{i}^{j}*N_{k}^{m}*U^{p}"][:]), mom)
+        assert float(e.volume) == float(d.volume) and int(e.nspec) == nspec and int(e.max_order) == max_order
