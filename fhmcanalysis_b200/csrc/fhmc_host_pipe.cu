@@ -1,15 +1,18 @@
 // fhmc_host_pipe.cu -- the host-buffer entry point of the mu sweep (new; the reference's seam for this is a Python loop of
 // reweight()/thermo() calls on host arrays, GH:268-289, 451-554, README.md:60-85).
 //
-// fhmc_sweep_host_compact: pinned host mu[S] in, pinned host results out, everything in between pipelined in chunks on
-// three private streams (upload, compute, download): H2D(mu chunk) -> fhmc_sweep_1d -> fhmc_pack_phase_major -> D2H of the
-// chunk's head and of the phase blocks that exist.  The number of live phase blocks of a chunk is only known after its kernels ran; waiting for it
-// before queueing copies would idle the copy engine, so copies are queued at once for `guess` blocks (what the previous
-// chunk needed) and a chunk that needed more is topped up when its flag is read, two chunks later, just before its device
-// buffers are reused.  Measured on a B200 (10^6 state points, 72 B of results each, FHMC_PIPE_TRACE=1 prints the device
-// timeline): 1.70 ms at 2^17-point chunks; the download stream is busy from the end of the first chunk's kernels on, at
-// ~50 GB/s (57 GB/s for one large copy), so what is left over the 1.26 ms D2H floor is the pipeline fill (~0.2 ms) and the
-// gaps between the 3 copies per chunk.  Chunks below 2^16 points are slower: they hold fewer tiles than the GPU has CTAs.
+// fhmc_sweep_host_compact / fhmc_sweep_host_compact16: pinned host mu[S] in, pinned host results out, everything in between
+// pipelined in chunks on three private streams (upload, compute, download): H2D(mu chunk) -> fhmc_sweep_1d -> repack
+// (fhmc_pack_phase_major, or the narrow records of fhmc_pack_phase_soa16) -> D2H of the chunk's head and of the phase blocks
+// that exist.  The number of live phase blocks of a chunk is only known after its kernels ran; waiting for it before
+// queueing copies would idle the copy engine, so copies are queued at once for `guess` blocks (what the previous chunk
+// needed) and a chunk that needed more is topped up when its flag is read, two chunks later, just before its device
+// buffers are reused.
+// Measured on a B200 (10^6 state points, 2^17-point chunks; FHMC_PIPE_TRACE=1 prints the device timeline): 1.44 ms with the
+// 60-byte narrow records, 1.61-1.66 ms with the 72-byte ones.  The download stream is busy from the end of the first
+// chunk's kernels on at ~50 GB/s (57 GB/s for one large copy); what is left over the D2H floor is the pipeline fill
+// (~0.17 ms).  Tried without gain: a short first chunk, two download streams, driving the loop from Python (host time is
+// not the limit).  Chunks below 2^16 points are slower: they hold fewer tiles than the GPU has resident CTAs.
 #include <cstdio>
 #include <cstdlib>
 
