@@ -40,6 +40,17 @@ __device__ __noinline__ void run_generic_point(const SweepArgs &a, const double 
     pe.run(sp);
 }
 
+// the same with all 32 lanes of the calling warp on ONE state point (queue drain: a queued point evaluated by a single lane
+// kept the rest of its CTA waiting at the barrier for ~1 ms -- 29 % of the Taylor grid's kernel time)
+template <bool TAYLOR>
+__device__ __noinline__ void run_generic_point_warp(const SweepArgs &a, const double *s_tab, int lane, double mu1, double beta,
+                                                    double dmu, long long sp)
+{
+    PointEval<32, TAYLOR> pe(a, a.blob, lane, s_tab);
+    pe.setup(mu1, beta, dmu);
+    pe.run(sp);
+}
+
 template <int NSEL, bool SEL0N, int NC, int NT, int REC = 0>
 struct FastLayout {
     static constexpr int NX = NSEL - (SEL0N ? 1 : 0);   // quantities that need their own rows
@@ -656,7 +667,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
     const ExpRegs ec = load_exp_regs();   // reduction / polynomial constants pinned in registers for the hot loop
 
     // Irregular state points are not re-run on the spot (one such lane would stall its whole warp for a full generic
-    // evaluation): they are queued in shared memory and drained by all threads of the CTA, one queued point per thread.
+    // evaluation): they are queued in shared memory and drained by all warps of the CTA, one queued point per warp.
     // The queue is inspected (one CTA barrier) only every QTILES-th tile.
     using LY = FastLayout<NSEL, SEL0N, NC, NT, REC>;
     long long *queue = reinterpret_cast<long long *>(s_tab + 64);
@@ -665,12 +676,12 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_fast(const __grid_constan
     __syncthreads();
     auto drain = [&]() {
         const int cnt = *q_count;
-        for (int k = threadIdx.x; k < cnt; k += FHMC_CTA) {
+        for (int k = threadIdx.x >> 5; k < cnt; k += FHMC_CTA / 32) {   // one queued state point per WARP
             const long long qs = queue[k];
             const double qm = a.st.mu1[(qs / a.st.mu1_div) % a.st.n_mu1];
             const double qb = (TAYLOR && a.st.beta) ? a.st.beta[(qs / a.st.beta_div) % a.st.n_beta] : a.d.beta_ref;
             const double qd = (TAYLOR && a.st.dmu) ? a.st.dmu[(qs / a.st.dmu_div) % a.st.n_dmu] : a.d.dmu_ref;
-            run_generic_point<TAYLOR>(a, s_tab, threadIdx.x & 31, qm, qb, qd, qs);
+            run_generic_point_warp<TAYLOR>(a, s_tab, threadIdx.x & 31, qm, qb, qd, qs);
         }
         __syncthreads();
         if (threadIdx.x == 0) *q_count = 0;

@@ -441,9 +441,9 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_prod2(const __grid_consta
     __syncthreads();
     auto drain = [&]() {
         const int cnt = *q_count;
-        for (int k = threadIdx.x; k < cnt; k += FHMC_CTA) {
+        for (int k = threadIdx.x >> 5; k < cnt; k += FHMC_CTA / 32) {   // one queued state point per warp, as in k_sweep_fast
             const long long qs = queue[k];
-            run_generic_point<false>(a, s_tab, threadIdx.x & 31, a.st.mu1[(qs / a.st.mu1_div) % a.st.n_mu1], a.d.beta_ref, a.d.dmu_ref, qs);
+            run_generic_point_warp<false>(a, s_tab, threadIdx.x & 31, a.st.mu1[(qs / a.st.mu1_div) % a.st.n_mu1], a.d.beta_ref, a.d.dmu_ref, qs);
         }
         __syncthreads();
         if (threadIdx.x == 0) *q_count = 0;
