@@ -185,22 +185,20 @@ class isopleth(object):
                                         cutoff=self.meta["cutoff"], sel=[rows["n1"], rows["n2"]])
             r = dh.sweep_auto(mu1_v, pmax=pmax).host()
             vol = href.data["volume"]
-            for jx in range(len(mu1_v)):
-                if not (edge_ok[left, jx] and edge_ok[right, jx]):
-                    continue
-                if r["code"][jx] != 0 or not r["safe"][jx]:
-                    continue
-                P = int(r["nphase"][jx])
-                p = int(np.argmin(r["fe"][jx, :P]))
-                n1, n2 = r["avg"][jx, p, 0], r["avg"][jx, p, 1]
-                try:
-                    with np.errstate(divide="raise", invalid="raise"):
-                        x1 = n1 / (n1 + n2)
-                except FloatingPointError:
-                    continue
-                self.data["Z"][i, jx] = x1
-                self.data["density"][i, jx] = (n1 + n2) / vol
-                self.data["F.E./kT"][i, jx] = r["fe"][jx, p]
+            # the whole row of cells at once: most stable phase = lowest F.E./kT among the nphase[jx] phases (GB:83-107);
+            # cells whose x1 would divide by zero / be invalid stay 0 like the reference's FloatingPointError branch
+            ok = edge_ok[left] & edge_ok[right] & (r["code"] == 0) & r["safe"].astype(bool)
+            nph = np.maximum(r["nphase"].astype(np.int64), 1)
+            fe = np.where(np.arange(r["fe"].shape[1])[None, :] < nph[:, None], r["fe"], np.inf)
+            p = np.argmin(fe, axis=1)
+            jj = np.arange(len(mu1_v))
+            n1, n2 = r["avg"][jj, p, 0], r["avg"][jj, p, 1]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                x1 = n1 / (n1 + n2)
+            ok &= np.isfinite(x1) & ((n1 + n2) != 0.0)
+            self.data["Z"][i, ok] = x1[ok]
+            self.data["density"][i, ok] = (n1[ok] + n2[ok]) / vol
+            self.data["F.E./kT"][i, ok] = r["fe"][jj, p][ok]
         return self.data["Z"], (self.data["X"], self.data["Y"])
 
     # ------------------------------------------------------------------------------------------
