@@ -124,7 +124,7 @@ def run_reference_arm(args, rank, world):
                        "state_points_per_step": per_core * last["cores"]},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -186,8 +186,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner (NCCL_DEBUG=VERSION) off stdout: ONE JSON line
+        guard_stdout()   # NCCL's version banner and any other library chatter on descriptor 1 go to stderr
         dist.init_process_group("nccl", device_id=dev)
 
     # CPU baseline first, on rank 0 at N=1 only (bounded sample), before the GPU is busy
@@ -376,10 +375,31 @@ def run_gpu_arm(args, rank, world, local_rank):
         }
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line of this run, on the process's ORIGINAL stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def guard_stdout():
+    """stdout must carry exactly one JSON line, but libraries write to file descriptor 1 behind Python's back (NCCL prints
+    its version banner there whenever NCCL_DEBUG is VERSION or higher).  Keep a private handle on the original stdout for
+    emit() and point descriptor 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
 
 
 def main():
