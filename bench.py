@@ -419,6 +419,7 @@ def main():
     if args.cpu_baseline_worker:
         print(json.dumps(cpu_arm(12000)))
         return 0
+    guard_stdout()   # from here on only emit() reaches the caller's stdout
     if args.impl == "reference":
         return run_reference_arm(args, rank, world)
     return run_gpu_arm(args, rank, world, local_rank)
