@@ -75,6 +75,7 @@ struct FastCtx {
     const double *g_hidx;     // hull vertex bin indices (global)
     int H;                    // hull vertices
     uint32_t s_prod, s_anch;  // REC == 2: per-block product rows, per-segment anchors (max lnPI of the segment)
+    uint32_t s_rng;           // REC == 2: per-segment spread (max - min finite lnPI): exp(lnPI_i - A_g) must not underflow
     double lmax;              // REC == 2: max |lnPI_i| (rounding margin of the extremum prefilter)
 };
 
@@ -138,7 +139,7 @@ __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned cha
         __syncthreads();
     }
     FastCtx cx;
-    cx.s_prod = cx.s_anch = 0;
+    cx.s_prod = cx.s_anch = cx.s_rng = 0;
     cx.lmax = 0.0;
     if (REC == 2) {
         // Product form: bins 1+4b .. 4+4b make block b (nb full blocks, bin 4+4b+... <= last - 0), SEGB blocks share the
@@ -151,6 +152,7 @@ __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned cha
         double *prod = reinterpret_cast<double *>(smem_raw + fast_base_bytes<PK, LY::QN>(npad));
         double *anch = prod + (size_t)nb * LY::BW;
         unsigned long long *s_lmax = reinterpret_cast<unsigned long long *>(anch + nseg);
+        double *rngp = reinterpret_cast<double *>(s_lmax + 1);
         if (threadIdx.x == 0) *s_lmax = 0ull;
         __syncthreads();
         double lm = 0.0;
@@ -158,9 +160,14 @@ __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned cha
         atomicMax(s_lmax, (unsigned long long)__double_as_longlong(lm));
         for (int g = threadIdx.x; g < nseg; g += blockDim.x) {
             const int i0 = 1 + 4 * LY::SEGB * g, i1 = min(1 + 4 * LY::SEGB * (g + 1), 1 + 4 * nb);
-            double m = -CUDART_INF;
-            for (int i = i0; i < i1; ++i) m = fmax(m, pk[(size_t)i * PK]);
+            double m = -CUDART_INF, lo = CUDART_INF;
+            for (int i = i0; i < i1; ++i) {
+                const double v = pk[(size_t)i * PK];
+                m = fmax(m, v);
+                if (v > -CUDART_INF) lo = fmin(lo, v);
+            }
             anch[g] = m;
+            rngp[g] = (lo < CUDART_INF) ? m - lo : 0.0;
         }
         __syncthreads();
         const double lmax_all = __longlong_as_double((long long)*s_lmax);
@@ -207,6 +214,7 @@ __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned cha
         __syncthreads();
         cx.s_prod = smem_u32(prod);
         cx.s_anch = smem_u32(anch);
+        cx.s_rng = smem_u32(rngp);
         cx.lmax = __longlong_as_double((long long)*s_lmax);
     }
     cx.s_slope = smem_u32(stage);
@@ -331,9 +339,9 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
                 a.out.fe[sp * pmax + P] = -(add_shift(Mq, log(Sacc)) - u0);
 #pragma unroll
                 for (int q = 0; q < NSEL; ++q) a.out.avg[(sp * pmax + P) * NSEL + q] = A[q] / Sacc;
-            } else if (P < pmax) {
+            } else if (P < pmax && P < 32) {
                 rescue |= 1u << P;   // phase too unlikely for the common shift: re-integrated about its own maximum below
-            } else {
+            } else {   // (also: a negligible phase beyond the 32 the rescue mask can name -- left to the generic evaluator)
                 bad = true;
             }
             Stot += Sacc;
@@ -468,7 +476,10 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
                     const double lA = lds_f64(cx.s_anch + 8u * (uint32_t)g);
                     asm("ld.shared.f64 %0, [%1];" : "=d"(Ni) : "r"(s_pk + (uint32_t)i * (uint32_t)(PK * 8) + 8u));
                     double t = exp_scaled_r(__dadd_rn(lA, __dmul_rn(s, Ni)), Mq, tab, ec);
-                    if (!(t > 2.3e-308) || !chain_ok) {
+                    // exp_scaled_r() clamps an underflowing result to [2^-1022, 2^-1020): anything that small is not usable.
+                    // P_i = exp(lnPI_i - A_g) and t r^k must both stay normal numbers wherever their product matters: the
+                    // spread of the segment plus the growth of t over its 128 bins has to fit the fp64 exponent range
+                    if (!(t > 1e-300) || !chain_ok || !(lds_f64(cx.s_rng + 8u * (uint32_t)g) + 128.0 * fabs(sdn) < 600.0)) {
                         // clamped (underflowed) or unusable factor: the segment takes one true exp per bin instead
                         for (; b < bend; ++b, i += 4, pb += BWB) {
                             if (flagged(pb)) {
@@ -716,7 +727,7 @@ static size_t fast_smem_bytes(int n_pad)
     size_t b = fast_base_bytes<LY::PK, LY::QN>(n_pad);
     if (REC == 2) {
         const size_t nb = (size_t)(n_pad / 4 + 1);
-        b += (nb + 3) * LY::BW * 8 + (nb / LY::SEGB + 2) * 8 + 16;   // (+3 blocks: the key prefetch reads ahead)
+        b += (nb + 3) * LY::BW * 8 + 2 * (nb / LY::SEGB + 2) * 8 + 16;   // (+3 blocks: the key prefetch reads ahead)
     }
     return b;
 }
