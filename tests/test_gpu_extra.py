@@ -174,6 +174,36 @@ def test_product_form_small_and_odd_histograms(n):
         _agree(a, b, (n, rec))
 
 
+@pytest.mark.parametrize("case", ["steep_large_tilt", "many_negligible_phases"])
+def test_product_form_exponent_range_cases(case):
+    """Cases scripts/soak_prod_parity.py found: (i) a steep ln(PI) (hundreds of units per 128-bin segment) under tilts of
+    several units per bin -- exp(lnPI_i - A_seg) or the running factor leave the fp64 exponent range, and an anchor that
+    underflowed comes back clamped, not zero; (ii) smooth = 1 on a random walk -- more than 32 phases, some of them
+    negligible (rescued about their own maximum).  Both product-form kernels against the generic evaluator."""
+    from fhmcanalysis_b200 import engine
+    rng = np.random.default_rng(7)
+    if case == "steep_large_tilt":
+        n, smooth, span = 1578, 9, 8.0
+        x = np.arange(n, dtype=float)
+        lnpi = -1.45 * x + 40.0 * np.sin(x / 57.0) + 1e-3 * rng.normal(size=n)
+        N = 0.5 * x
+    else:
+        n, smooth, span = 700, 1, 2.0
+        lnpi = np.cumsum(rng.normal(0.0, 0.9, size=n))
+        N = 2.0 + np.arange(n, dtype=float)
+    for rec, S in ((3, 155000), (2, 6000)):
+        dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=smooth, sel=["N", N * N])
+        dh.use_recurrence = rec
+        dh.ensure_hull()
+        assert dh.desc.mu_recurrence == rec
+        mus = rng.uniform(-span, span, size=S)
+        a = dh.sweep_auto(mus, pmax=8, lanes=1).host()
+        b = dh.sweep_auto(mus, pmax=a["fe"].shape[1], lanes=-1).host()
+        if case == "many_negligible_phases":
+            assert a["nphase"].max() > 32 and np.any(b["status"] & 0x800)     # phases beyond the rescue mask, rescued ones
+        _agree(a, b, (case, rec))
+
+
 def test_sharded_sweep_single_process(golden, golden_meta):
     """parallel.sweep_sharded without an initialised process group == plain sweep."""
     from fhmcanalysis_b200 import engine, parallel
