@@ -75,7 +75,7 @@ struct FastCtx {
     const double *g_hidx;     // hull vertex bin indices (global)
     int H;                    // hull vertices
     uint32_t s_prod, s_anch;  // REC == 2: per-block product rows, per-segment anchors (max lnPI of the segment)
-    uint32_t s_rng;           // REC == 2: per-segment spread (max - min finite lnPI): exp(lnPI_i - A_g) must not underflow
+    double sdn_lim;           // REC == 2: largest |s dN| for which every segment can be walked in product form (see fast_prepare)
     double lmax;              // REC == 2: max |lnPI_i| (rounding margin of the extremum prefilter)
 };
 
@@ -139,7 +139,8 @@ __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned cha
         __syncthreads();
     }
     FastCtx cx;
-    cx.s_prod = cx.s_anch = cx.s_rng = 0;
+    cx.s_prod = cx.s_anch = 0;
+    cx.sdn_lim = 0.0;
     cx.lmax = 0.0;
     if (REC == 2) {
         // Product form: bins 1+4b .. 4+4b make block b (nb full blocks, bin 4+4b+... <= last - 0), SEGB blocks share the
@@ -152,8 +153,8 @@ __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned cha
         double *prod = reinterpret_cast<double *>(smem_raw + fast_base_bytes<PK, LY::QN>(npad));
         double *anch = prod + (size_t)nb * LY::BW;
         unsigned long long *s_lmax = reinterpret_cast<unsigned long long *>(anch + nseg);
-        double *rngp = reinterpret_cast<double *>(s_lmax + 1);
-        if (threadIdx.x == 0) *s_lmax = 0ull;
+        unsigned long long *s_rmax = s_lmax + 1;   // largest lnPI spread (max - min finite value) of a segment
+        if (threadIdx.x == 0) { *s_lmax = 0ull; *s_rmax = 0ull; }
         __syncthreads();
         double lm = 0.0;
         for (int i = threadIdx.x; i < n; i += blockDim.x) lm = fmax(lm, fabs(pk[(size_t)i * PK]));
@@ -167,7 +168,7 @@ __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned cha
                 if (v > -CUDART_INF) lo = fmin(lo, v);
             }
             anch[g] = m;
-            rngp[g] = (lo < CUDART_INF) ? m - lo : 0.0;
+            if (lo < CUDART_INF) atomicMax(s_rmax, (unsigned long long)__double_as_longlong(m - lo));
         }
         __syncthreads();
         const double lmax_all = __longlong_as_double((long long)*s_lmax);
@@ -214,7 +215,10 @@ __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned cha
         __syncthreads();
         cx.s_prod = smem_u32(prod);
         cx.s_anch = smem_u32(anch);
-        cx.s_rng = smem_u32(rngp);
+        // P_i = exp(lnPI_i - A_g) and the running factor t r^k must both stay normal numbers wherever their product
+        // matters: the lnPI spread of a segment plus the growth of t over its 128 bins has to fit the fp64 exponent
+        // range, and exp(|s dN| * 128) itself must stay finite (4.5).  State points beyond the limit take true exps.
+        cx.sdn_lim = fmin(4.5, (600.0 - __longlong_as_double((long long)*s_rmax)) / 128.0);
         cx.lmax = __longlong_as_double((long long)*s_lmax);
     }
     cx.s_slope = smem_u32(stage);
@@ -427,7 +431,7 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
                 const double sdn = s * (lds_f64(s_pk + (uint32_t)(PK * 8) + 8u) - lds_f64(s_pk + 8u));
                 const double Na = fmax(fabs(lds_f64(s_pk + 8u)), fabs(lds_f64(s_pk + (uint32_t)last * (uint32_t)(PK * 8) + 8u)));
                 const double margin = 1.8e-15 * (cx.lmax + fabs(s) * Na) + 1e-300;   // 8 * 2^-52 * (|lnPI| + |s N|)
-                const bool chain_ok = fabs(sdn) < 4.5;   // exp(|s dN| * 128 bins) must stay finite
+                const bool chain_ok = fabs(sdn) < cx.sdn_lim;   // product form usable for this tilt (fast_prepare)
                 // (the tabulated ranges assume |s dN| < 4.5 in their rounding slack: beyond it every block is examined)
                 const int k_hi = chain_ok ? hi_key(-sdn + margin) : 0x7fffffff, k_lo = chain_ok ? hi_key(-sdn - margin) : (int)0x80000000;
                 const int nb = (n - 2) / 4;
@@ -477,9 +481,7 @@ __device__ __forceinline__ bool fast_point(const SweepArgs &a, const FastCtx &cx
                     asm("ld.shared.f64 %0, [%1];" : "=d"(Ni) : "r"(s_pk + (uint32_t)i * (uint32_t)(PK * 8) + 8u));
                     double t = exp_scaled_r(__dadd_rn(lA, __dmul_rn(s, Ni)), Mq, tab, ec);
                     // exp_scaled_r() clamps an underflowing result to [2^-1022, 2^-1020): anything that small is not usable.
-                    // P_i = exp(lnPI_i - A_g) and t r^k must both stay normal numbers wherever their product matters: the
-                    // spread of the segment plus the growth of t over its 128 bins has to fit the fp64 exponent range
-                    if (!(t > 1e-300) || !chain_ok || !(lds_f64(cx.s_rng + 8u * (uint32_t)g) + 128.0 * fabs(sdn) < 600.0)) {
+                    if (!(t > 1e-300) || !chain_ok) {
                         // clamped (underflowed) or unusable factor: the segment takes one true exp per bin instead
                         for (; b < bend; ++b, i += 4, pb += BWB) {
                             if (flagged(pb)) {
@@ -727,7 +729,7 @@ static size_t fast_smem_bytes(int n_pad)
     size_t b = fast_base_bytes<LY::PK, LY::QN>(n_pad);
     if (REC == 2) {
         const size_t nb = (size_t)(n_pad / 4 + 1);
-        b += (nb + 3) * LY::BW * 8 + 2 * (nb / LY::SEGB + 2) * 8 + 16;   // (+3 blocks: the key prefetch reads ahead)
+        b += (nb + 3) * LY::BW * 8 + (nb / LY::SEGB + 2) * 8 + 32;   // (+3 blocks: the key prefetch reads ahead)
     }
     return b;
 }

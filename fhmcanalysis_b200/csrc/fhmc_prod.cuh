@@ -37,7 +37,6 @@ struct ProdWalk {
         long long sp;
         int Mq, k_hi, k_lo, cntM, cntm, P;
         unsigned rescue, fl;
-        float room;   // 600 - 128 |s dN|: the largest lnPI spread of a segment whose tabulated products stay normal numbers
     };
     static constexpr unsigned F_BAD = 1u, F_ROBUST = 2u, F_CHAIN = 4u;
     __device__ __forceinline__ double u0(const PS &p) const
@@ -214,8 +213,7 @@ struct ProdWalk {
         asm("ld.shared.f64 %0, [%1];" : "=d"(Ni) : "r"(s_pk + (uint32_t)i * (uint32_t)(PK * 8) + 8u));
         p.t = exp_scaled(__dadd_rn(lA, __dmul_rn(p.s, Ni)), p.Mq, tab);
         // exp_scaled() clamps an underflowing result to [2^-1022, 2^-1020): anything that small is not a usable factor.
-        // (P_i = exp(lnPI_i - A_g) and t r^k must both stay normal numbers wherever their product matters)
-        return (p.t > 1e-300) && (p.fl & F_CHAIN) && (lds_f64(cx.s_rng + 8u * (uint32_t)g) < (double)p.room);
+        return (p.t > 1e-300) && (p.fl & F_CHAIN);
     }
     // blocks [b, bend) of one segment for one point (usable: chained products; else true exps)
     __device__ __forceinline__ void segment_single(PS &p, bool usable, int b, int bend, int i, uint32_t pb) const
@@ -268,9 +266,8 @@ struct ProdWalk {
         p.r4 = exp(4.0 * sdn);
         const double Na = fmax(fabs(lds_f64(s_pk + 8u)), fabs(lds_f64(s_pk + (uint32_t)last * (uint32_t)(PK * 8) + 8u)));
         const double margin = 1.8e-15 * (cx.lmax + fabs(p.s) * Na) + 1e-300;   // 8 * 2^-52 * (|lnPI| + |s N|)
-        const bool chain_ok = fabs(sdn) < 4.5;   // exp(|s dN| * 128 bins) must stay finite; beyond it every block is examined
+        const bool chain_ok = fabs(sdn) < cx.sdn_lim;   // product form usable for this tilt (fast_prepare); else every block is examined
         if (chain_ok) p.fl |= F_CHAIN;
-        p.room = (float)(599.0 - 128.0 * fabs(sdn));   // (rounded to float: one unit of slack)
         p.k_hi = chain_ok ? hi_key(-sdn + margin) : 0x7fffffff;
         p.k_lo = chain_ok ? hi_key(-sdn - margin) : (int)0x80000000;
         Bin b0;

@@ -195,11 +195,12 @@ def test_full_size_properties():
     idx = np.arange(S)
     assert np.all(h["bounds"][:, 0, 0] == 0) and np.all(h["bounds"][idx, P - 1, 1] == n)
     mask = np.arange(4)[None, :] < P[:, None]
-    lse = np.log(np.sum(np.where(mask, np.exp(-(h["fe"] - h["fe"][:, :1])), 0.0), axis=1)) - h["fe"][:, 0]
+    # (slots p >= nphase are never written: mask them BEFORE they reach exp)
+    w = np.where(mask, np.exp(-np.where(mask, h["fe"] - h["fe"][:, :1], 0.0)), 0.0)
+    lse = np.log(np.sum(w, axis=1)) - h["fe"][:, 0]
     u0 = lnpi[0]  # N_0 = 0: reweighting leaves bin 0 unchanged
     assert np.max(np.abs(lse - (h["lnnorm"] - u0))) < 1e-9
-    ntot = np.sum(np.where(mask, h["avg"][:, :, 0] * np.exp(-(h["fe"] - h["fe"][:, :1])), 0.0), axis=1) / \
-        np.sum(np.where(mask, np.exp(-(h["fe"] - h["fe"][:, :1])), 0.0), axis=1)
+    ntot = np.sum(np.where(mask, h["avg"][:, :, 0], 0.0) * w, axis=1) / np.sum(w, axis=1)
     assert np.all(np.diff(ntot) > -1e-9)
     sub = slice(0, S, 97)
     h4 = dh.sweep(mu[sub].contiguous(), pmax=4, lanes=4).host()
