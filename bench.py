@@ -40,8 +40,8 @@ PMAX = 4
 METRIC = "reweighted state points/sec (lnPI+thermo) at N_max=1000"
 UNIT = "state points/s"
 # warp instructions per state point of k_sweep_prod2<2,1> on this workload (ncu --set full, profiles/r01b_prod2_sweep_ncu_summary.txt)
-FP64_INSTR_PER_POINT = 4362
-INSTR_PER_POINT = 9671
+FP64_INSTR_PER_POINT = 4355
+INSTR_PER_POINT = 9653
 E2E_FIELDS = ("status", "nphase", "bounds", "fe", "avg")   # what the e2e arm copies back to the host every step
 
 
