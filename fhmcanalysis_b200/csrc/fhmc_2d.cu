@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(FHMC_2D_CTA) k_rw2d_partial(const __grid_const
     const double *g_lnpi = a.lnpi + (size_t)r0 * n2;
     bool tma_ok = (((uintptr_t)g_lnpi | chunk_bytes) & 15) == 0;
     for (int q = 0; q < NPROP; ++q) tma_ok = tma_ok && ((((uintptr_t)(a.props + ((size_t)q * a.n1 + r0) * n2)) & 15) == 0);
+    // the property chunks land rows * n2 doubles apart in shared memory: bulk copies need 16-byte aligned destinations too
+    if (NPROP > 0) tma_ok = tma_ok && ((((size_t)a.rows * n2 * 8) & 15) == 0);
     if (tma_ok) {
         if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();

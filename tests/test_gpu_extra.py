@@ -59,7 +59,7 @@ def test_joint_hist_container_and_reweight(golden, golden_meta, oracle):
         assert np.allclose(out[s], ref, rtol=1e-12, atol=0)
 
 
-@pytest.mark.parametrize("n1,n2,nprop", [(64, 48, 0), (129, 77, 1), (512, 512, 2)])
+@pytest.mark.parametrize("n1,n2,nprop", [(64, 48, 0), (129, 77, 1), (129, 77, 2), (512, 512, 2)])   # (129, 77, 2): odd rows * n2 with two staged property chunks
 def test_reweight_2d_vs_oracle(oracle, n1, n2, nprop):
     """BASELINE config 5 generator (two anisotropic Gaussians, triangular -inf region) at three sizes."""
     from fhmcanalysis_b200 import engine, synth
