@@ -23,8 +23,10 @@ Timed numbers
 import argparse
 import json
 import os
+import hashlib
 import subprocess
 import sys
+import tempfile
 import time
 
 import numpy as np
@@ -42,6 +44,7 @@ UNIT = "state points/s"
 # warp instructions per state point of k_sweep_prod2<2,1> on this workload (ncu --set full, profiles/r01b_prod2_sweep_ncu_summary.txt)
 FP64_INSTR_PER_POINT = 4355
 INSTR_PER_POINT = 9653
+PROFILE_SOURCE = "profiles/r01b_prod2_sweep_ncu_summary.txt"
 E2E_FIELDS = ("status", "nphase", "bounds", "fe", "avg")   # what the e2e arm copies back to the host every step
 
 
@@ -55,33 +58,68 @@ def workload_arrays():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own implementation on host cores (bounded sample)
 # ------------------------------------------------------------------------------------------------
+def sample_indices(total):
+    """Indices into the 10^6-point mu grid of the workload that the CPU leg evaluates: every stride-th point, so that the
+    very same doubles are state points of the GPU arm's timed sweep (parity in the same run)."""
+    stride = max(S_PER_GPU // max(int(total), 1), 1)
+    return np.arange(0, S_PER_GPU, stride)[:total]
+
+
 def _cpu_chunk(args):
-    kind, mus = args
+    kind, idx, matched = args
     lnpi, mom = workload_arrays()
+    mus = np.linspace(MU_LO, MU_HI, S_PER_GPU)[idx]
+    m = len(mus)
+    rec = {"nphase": np.zeros(m, np.int32), "safe": np.zeros(m, np.int8), "bounds": np.full((m, PMAX, 2), -1, np.int32),
+           "max_idx": np.full((m, PMAX), -1, np.int32), "min_idx": np.full((m, PMAX + 1), -1, np.int32),
+           "fe": np.full((m, PMAX), np.nan), "avg": np.full((m, PMAX, 2), np.nan)}
     t0 = time.perf_counter()
     if kind == "reference":
         from oracle import ref
         import copy
         base = ref.make_histogram(lnpi, mom, 1.0, [0.0], SMOOTH)
-        acc = 0.0
-        for mu in mus:
+        for k, mu in enumerate(mus):
             h = copy.deepcopy(base)
             h.reweight(float(mu))
-            h.thermo()
-            acc += h.is_safe() + h.data["thermo"][0]["F.E./kT"]
+            h.thermo(props=not matched)
+            rec["safe"][k] = h.is_safe()
+            th = h.data["thermo"]
+            P = min(len(th), PMAX)
+            rec["nphase"][k] = len(th)
+            M, mn = h.data["ln(PI)_maxima_idx"], h.data["ln(PI)_minima_idx"]
+            rec["max_idx"][k, :min(len(M), PMAX)] = M[:PMAX]
+            rec["min_idx"][k, :min(len(mn), PMAX + 1)] = mn[:PMAX + 1]
+            for p in range(P):
+                rec["bounds"][k, p] = th[p]["bound_idx"]
+                rec["fe"][k, p] = th[p]["F.E./kT"]
+                if not matched:
+                    rec["avg"][k, p, 0] = th[p]["mom"][0, 1, 0, 0, 0]
+                    rec["avg"][k, p, 1] = th[p]["mom"][0, 2, 0, 0, 0]
+                else:   # <N>, <N^2> the way thermo() forms them (GH:530-541), for these two arrays only
+                    l, r = th[p]["bound_idx"]
+                    prob = np.exp(h.data["ln(PI)"][l:r])
+                    sp = np.sum(prob)
+                    rec["avg"][k, p, 0] = np.sum(prob * h.data["mom"][0, 1, 0, 0, 0, l:r]) / sp
+                    rec["avg"][k, p, 1] = np.sum(prob * h.data["mom"][0, 2, 0, 0, 0, l:r]) / sp
     else:
         from oracle import fhmc_oracle as fo
         i = np.arange(N_BINS, dtype=float)
         sel = np.stack([i, i * i])
-        acc = 0.0
-        for mu in mus:
+        for k, mu in enumerate(mus):
             r = fo.state_point(lnpi, np.arange(N_BINS), 1.0, 0.0, float(mu), SMOOTH, sel=sel, pmax=PMAX)
-            acc += r["fe"][0]
-    return len(mus), time.perf_counter() - t0, acc
+            P = min(r["nphase"], PMAX)
+            rec["nphase"][k], rec["safe"][k] = r["nphase"], r["safe"]
+            rec["max_idx"][k, :P] = r["max_idx"][:P]
+            rec["min_idx"][k, :min(len(r["min_idx"]), PMAX + 1)] = r["min_idx"][:PMAX + 1]
+            rec["bounds"][k, :P] = np.asarray(r["bounds"]).reshape(-1, 2)[:P]
+            rec["fe"][k, :P] = r["fe"][:P]
+            rec["avg"][k, :P] = r["avg"][:P, :2]
+    return len(mus), time.perf_counter() - t0, idx, rec
 
 
-def cpu_arm(sample_per_core, cores=None):
-    """Time the CPU reference on `cores` processes; returns dict(value, cores, kind, sample)."""
+def cpu_arm(sample_per_core, cores=None, matched=False, keep=None):
+    """Time the CPU reference on `cores` processes; returns dict(value, cores, kind, sample).  keep: path of an .npz that
+    receives the sample's outputs (indices into the 10^6-point grid + records) for the GPU arm's parity check."""
     import multiprocessing as mp
     from oracle import ref
     kind = "reference" if ref.available() else "port"
@@ -90,18 +128,26 @@ def cpu_arm(sample_per_core, cores=None):
         fhmc_oracle.build()
     cores = cores or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
     total = sample_per_core * cores
-    mus = np.linspace(MU_LO, MU_HI, total)
-    chunks = [(kind, mus[c::cores]) for c in range(cores)]
+    idx = sample_indices(total)
+    chunks = [(kind, idx[c::cores], matched) for c in range(cores)]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_chunk, [(kind, mus[:2])] * cores)  # warm-up: imports, page-in
+        pool.map(_cpu_chunk, [(kind, idx[:2], matched)] * cores)  # warm-up: imports, page-in
         t0 = time.perf_counter()
         res = pool.map(_cpu_chunk, chunks)
         wall = time.perf_counter() - t0
     n = sum(r[0] for r in res)
+    if keep:
+        order = np.argsort(np.concatenate([r[2] for r in res]))
+        out = {"idx": np.concatenate([r[2] for r in res])[order]}
+        for k in res[0][3]:
+            out[k] = np.concatenate([r[3][k] for r in res])[order]
+        np.savez(keep, **out)
+    work = ("deepcopy->reweight->thermo(props=False)->is_safe + the two moment averages the GPU arm forms (matched work)" if matched
+            else "deepcopy->reweight->thermo->is_safe (thermo averages all 27 moment arrays; the GPU arm averages 2: ~1.6x more CPU work per point)")
     return {"value": n / wall, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": "%d of the 10^6 state points of the workload (every %d-th), %s driven as deepcopy->reweight->thermo->is_safe, "
-                      "%d processes, %.1f s wall" % (n, max(S_PER_GPU // n, 1), "compiled reference (oracle/_ref)" if kind == "reference" else "C port (oracle/fhmc_oracle.c)", cores, wall),
+            "sample": "%d of the 10^6 state points of the workload (every %d-th), %s driven as %s, "
+                      "%d processes, %.1f s wall" % (n, max(S_PER_GPU // n, 1), "compiled reference (oracle/_ref)" if kind == "reference" else "C port (oracle/fhmc_oracle.c)", work, cores, wall),
             "wall_s": wall}
 
 
@@ -117,15 +163,50 @@ def run_reference_arm(args, rank, world):
         if k >= min(warm, 1):
             vals.append(last["value"])
     v = float(np.mean(vals))
+    matched = cpu_arm(max(per_core // 3, 1), matched=True)   # same per-point work as the GPU arm (two moment averages)
     line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": 1e3 * per_core * last["cores"] / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "gpu_launches": 0,
             "config": {"workload": "config2: synthetic 1-comp N_tot lnPI, N_max=1000, smooth=10, mu sweep in [-0.03,0.03]; bounded sample",
                        "state_points_per_step": per_core * last["cores"]},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+            "matched_work": {"value": matched["value"], "unit": UNIT, "sample": matched["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
     return 0
+
+
+def parity_block(cpu_npz, gpu, tag, rtol=1e-10):
+    """Compare GPU records (dict of arrays indexed by state point: nphase, safe, bounds, fe, avg [, max_idx, min_idx]) with
+    the CPU leg's outputs at the same state points.  Integers must be identical, F.E./kT and the averages agree to rtol."""
+    z = np.load(cpu_npz)
+    idx = z["idx"]
+    idx = idx[idx < len(gpu["nphase"])]
+    m = len(idx)
+    ref = {k: z[k][:m] for k in z.files if k != "idx"}
+    P = ref["nphase"]
+    bad = int(np.sum(gpu["nphase"][idx] != P)) + int(np.sum(gpu["safe"][idx].astype(bool) != ref["safe"].astype(bool)))
+    live = np.arange(PMAX)[None, :] < np.minimum(P, PMAX)[:, None]
+    bad += int(np.sum((gpu["bounds"][idx].astype(np.int64) != ref["bounds"])[live]))
+    if "max_idx" in gpu:
+        bad += int(np.sum((gpu["max_idx"][idx] != ref["max_idx"])[live]))
+        live_m = np.arange(PMAX + 1)[None, :] < (ref["min_idx"] >= 0).sum(axis=1)[:, None]
+        bad += int(np.sum((gpu["min_idx"][idx] != ref["min_idx"])[live_m]))
+    rel = 0.0
+    with np.errstate(all="ignore"):
+        for a, b in ((gpu["fe"][idx], ref["fe"]), (gpu["avg"][idx][..., 0], ref["avg"][..., 0]), (gpu["avg"][idx][..., 1], ref["avg"][..., 1])):
+            d = np.abs(a - b)[live] / np.abs(b[live])
+            if d.size:
+                rel = max(rel, float(np.nanmax(d)))
+            bad += int(np.sum(np.isnan(a[live])))
+    return {"checked": tag, "n": int(m), "int_mismatches": int(bad), "max_rel": rel, "rtol": rtol, "ok": bool(bad == 0 and rel <= rtol)}
+
+
+def sha16(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()[:16]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -178,7 +259,7 @@ class ClockSampler(object):
 def run_gpu_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from fhmcanalysis_b200 import engine
+    from fhmcanalysis_b200 import _lib, engine
     from fhmcanalysis_b200.moments.histogram.one_dim.ntot.gc_hist import histogram
 
     if not torch.cuda.is_available():
@@ -193,9 +274,11 @@ def run_gpu_arm(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-worker"], capture_output=True, text=True,
-                                 timeout=600)
+            keep_path = os.path.join(tempfile.mkdtemp(prefix="fhmc_bench_"), "cpu_sample.npz")
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-worker", "--keep", keep_path],
+                                 capture_output=True, text=True, timeout=600)
             cpu = json.loads(out.stdout.strip().splitlines()[-1])
+            cpu["keep"] = keep_path
         except Exception as e:  # keep the GPU measurement even if the CPU leg breaks
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": "cpu baseline failed: %r" % (e,)}
 
@@ -242,6 +325,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         ev[k][1].record()
     barrier()
     wall = time.perf_counter() - t_wall0
+    timed_kernel = _lib.last_kernel()
     kern_ms = [a.elapsed_time(b) for a, b in ev]
     t_ms = torch.tensor([float(np.sum(kern_ms))], dtype=torch.float64, device=dev)
     if world > 1:
@@ -296,9 +380,24 @@ def run_gpu_arm(args, rank, world, local_rank):
         gather_ms = float(gt.item())
 
     # sanity: the timed kernel really produced results
-    h_status = out.status.cpu().numpy().view(np.uint32)
+    hrec = out.host()
+    h_status = hrec["status"]
     ok_frac = float(np.mean((h_status & 0xFF) == 0))
     fast_frac = float(np.mean((h_status & 0x1000) != 0))
+
+    # ---- parity in the same run: the records the TIMED kernel left behind (and the e2e arm's host records) against the
+    #      outputs of the cpu_baseline leg at the same state points -------------------------
+    parity = None
+    if rank == 0 and cpu is not None and cpu.get("keep") and os.path.exists(cpu["keep"]):
+        try:
+            parity = parity_block(cpu["keep"], hrec, "records of the timed kernel (%s) vs cpu_baseline outputs (%s), same mu" % (timed_kernel, cpu["kind"]))
+            e2e_rec = {"nphase": host_out["r"]["nphase"].numpy().astype(np.int32),
+                       "safe": (host_out["r"]["status"].numpy().astype(np.int64) & 0x100) != 0,
+                       "bounds": host_out["r"]["bounds"].numpy(), "fe": host_out["r"]["fe"].numpy(), "avg": host_out["r"]["avg"].numpy()}
+            pe = parity_block(cpu["keep"], e2e_rec, "e2e host records")
+            parity["e2e"] = {k: pe[k] for k in ("n", "int_mismatches", "max_rel", "ok")}
+        except Exception as e:
+            parity = {"checked": False, "error": repr(e)}
 
     # ---- second half of the BASELINE metric: coexistence points/s (config 4: 10^4 temperatures, N_max = 2000, smooth 10,
     #      order-2 beta extrapolation, one batched find_phase_eq launch, guesses = mu_ref for every temperature) ----------
@@ -357,21 +456,24 @@ def run_gpu_arm(args, rank, world, local_rank):
             "clocks": clocks,
             "coexistence": coex,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "roofline": {"bound": "fp64_exp", "achieved": exps / 1e9, "peak": peaks["exp_per_s"] / 1e9, "unit": "Gexp/s",
-                         "frac": exps / peaks["exp_per_s"], "traffic": traffic,
-                         "peak_source": "exp_nonpos micro-benchmark measured in this process (no fp64-exp figure in MEASURED_PEAKS.json)",
-                         "dfma_peak_gops": peaks["dfma_per_s"] / 1e9,
-                         "algorithmic_exp_per_state_point": N_BINS,
-                         # frac can exceed 1: the product-form kernel (fhmc_fast_prod.cu) replaces most exps by fused
-                         # multiply-adds over tabulated products, which SURVEY 8(d) allows while the fraction stays on
-                         # the algorithmic count.  What the kernel really executes, from the committed ncu capture:
-                         "executed": {"fp64_pipe_instr_per_state_point": FP64_INSTR_PER_POINT, "instr_per_state_point": INSTR_PER_POINT,
-                                      "fp64_pipe_frac_of_dfma_peak": S * FP64_INSTR_PER_POINT / (np.mean(kern_ms) * 1e-3) / peaks["dfma_per_s"],
-                                      "limiter": "fp64 issue at 50 % pipe utilisation with 4 warps per scheduler (128 registers, 85 KB shared memory per CTA); shared-memory pipe 45 %",
-                                      "source": "profiles/r01b_prod2_sweep_ncu_summary.txt"},
+            # Roofline of the dominant kernel: fp64 ISSUE.  frac = fp64-pipe instructions the kernel EXECUTES per second (count per
+            # state point from the committed ncu capture of this build x measured state points/s) / the DFMA issue peak measured
+            # in this process.  The algorithmic count of SURVEY 8(d) (1001 exp per state point against the measured exp-issue
+            # peak) is kept beside it as algorithmic_frac: it exceeds 1 because the product form replaces most exps by FMAs.
+            "roofline": {"bound": "fp64_issue", "kernel": timed_kernel,
+                         "achieved": S * FP64_INSTR_PER_POINT / (np.mean(kern_ms) * 1e-3) / 1e9, "peak": peaks["dfma_per_s"] / 1e9,
+                         "unit": "G fp64-pipe instr/s (per lane)",
+                         "frac": S * FP64_INSTR_PER_POINT / (np.mean(kern_ms) * 1e-3) / peaks["dfma_per_s"], "traffic": traffic,
+                         "peak_source": "k_bench_dfma, register-resident DFMA chains, measured in this process (no fp64 figure in MEASURED_PEAKS.json)",
+                         "fp64_pipe_instr_per_state_point": FP64_INSTR_PER_POINT, "instr_per_state_point": INSTR_PER_POINT,
+                         "instr_count_source": PROFILE_SOURCE,
+                         "algorithmic_frac": exps / peaks["exp_per_s"], "algorithmic_exp_per_state_point": N_BINS,
+                         "algorithmic_achieved_gexp_s": exps / 1e9, "exp_peak_gexp_s": peaks["exp_per_s"] / 1e9,
                          "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (np.mean(kern_ms) * 1e-3) / 1e9,
                                  "peak_gbs": hbm_peak, "frac": (algo_bytes / (np.mean(kern_ms) * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
                                  "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else "absent"}},
+            "parity": parity,
+            "inputs_sha256_16": {"lnpi": sha16(lnpi), "mom": sha16(mom), "mu_rank0": sha16(mu_host.numpy())},
         }
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -412,12 +514,13 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="lanes per state point (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--keep", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.cpu_baseline_worker:
-        print(json.dumps(cpu_arm(12000)))
+        print(json.dumps(cpu_arm(12000, keep=args.keep)))
         return 0
     guard_stdout()   # from here on only emit() reaches the caller's stdout
     if args.impl == "reference":

@@ -66,7 +66,7 @@ class SweepOut(ctypes.Structure):
 
 
 EXPORTS = [
-    "fhmc_version", "fhmc_last_error", "fhmc_device_info", "fhmc_sweep_1d", "fhmc_lnpi_1d",
+    "fhmc_version", "fhmc_last_error", "fhmc_last_kernel", "fhmc_device_info", "fhmc_sweep_1d", "fhmc_lnpi_1d",
     "fhmc_phase_moments", "fhmc_axpy_rows", "fhmc_find_phase_eq_1d", "fhmc_reweight_2d",
     "fhmc_reweight_2d_workspace", "fhmc_pack_bytes", "fhmc_pack_phase_major",
     "fhmc_masked_lse_2d", "fhmc_masked_lse_2d_workspace", "fhmc_sweep_host_workspace", "fhmc_sweep_host_compact",
@@ -95,6 +95,7 @@ def load():
     vp, ci, cd, cll = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_longlong
     L.fhmc_version.restype = ci
     L.fhmc_last_error.restype = ctypes.c_char_p
+    L.fhmc_last_kernel.restype = ctypes.c_char_p
     L.fhmc_device_info.restype = ci
     L.fhmc_device_info.argtypes = [ctypes.POINTER(ci), ctypes.POINTER(ci)]
     L.fhmc_sweep_1d.restype = ci
@@ -148,3 +149,8 @@ def load():
 def check(rc, what):
     if rc != 0:
         raise RuntimeError("%s failed: %s" % (what, load().fhmc_last_error().decode("utf-8", "replace")))
+
+
+def last_kernel():
+    """Name of the sweep / solver kernel this thread launched last (diagnostic, fhmc_last_kernel)."""
+    return load().fhmc_last_kernel().decode("ascii", "replace")

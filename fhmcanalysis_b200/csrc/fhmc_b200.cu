@@ -25,6 +25,9 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+static thread_local const char *g_last_kernel = "";
+void note_kernel(const char *name) { g_last_kernel = name; }
+
 int check_cuda(cudaError_t e, const char *what)
 {
     if (e == cudaSuccess) return 0;
@@ -255,6 +258,7 @@ static int launch_sweep_cta(const SweepArgs &args, size_t smem, const DevInfo *d
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, CTA, smem, stream>>>(args);
+    note_kernel(G == 32 ? "k_sweep_1d<32>" : (G == 4 ? "k_sweep_1d<4>" : "k_sweep_1d<1>"));
     return check_cuda(cudaGetLastError(), "k_sweep_1d launch");
 }
 
@@ -395,6 +399,8 @@ extern "C" {
 int fhmc_version(void) { return FHMC_ABI_VERSION; }
 
 const char *fhmc_last_error(void) { return g_err; }
+
+const char *fhmc_last_kernel(void) { return g_last_kernel; }
 
 int fhmc_device_info(int *sm_count, int *max_smem_optin)
 {

@@ -15,6 +15,7 @@ namespace fhmc {
 // ---------------------------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);
+void note_kernel(const char *name);   // diagnostic: name of the sweep / solver kernel this thread launched last (fhmc_last_kernel)
 
 // ---------------------------------------------------------------------------------------------
 // fp64 exp for the max-shifted sums:   exp_scaled(u, Mq) = exp(u - Mq*ln2),  u - Mq*ln2 <~ 0.

@@ -756,6 +756,7 @@ static int launch_fast(const SweepArgs &args, int sm_count, int smem_optin, cuda
     long long grid = (long long)sm_count * occ;
     if (grid > ntiles) grid = ntiles;
     kern<<<(unsigned)grid, FHMC_CTA, smem, stream>>>(args);
+    note_kernel(REC == 2 ? "k_sweep_fast<prod>" : (REC == 1 ? "k_sweep_fast<rec>" : (NC > 0 || NT > 1 ? "k_sweep_fast<taylor>" : "k_sweep_fast")));
     return check_cuda(cudaGetLastError(), "k_sweep_fast launch");
 }
 

@@ -13,8 +13,10 @@
 // chunk's kernels on at ~50 GB/s (57 GB/s for one large copy); what is left over the D2H floor is the pipeline fill
 // (~0.17 ms).  Tried without gain: a short first chunk, two download streams, driving the loop from Python (host time is
 // not the limit).  Chunks below 2^16 points are slower: they hold fewer tiles than the GPU has resident CTAs.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "fhmc_common.cuh"
 
@@ -155,6 +157,7 @@ static int sweep_host_impl(const fhmc_hist_desc *desc, const double *blob, const
         return 0;
     };
     int sent[2] = {0, 0};   // phase blocks already queued for the chunk that owns buffer set b
+    std::vector<int> sent_final((size_t)n_chunks, 0);   // phase blocks chunk k has in out_host when the call returns
     // chunk k's live phase count is known once its flag arrived: top its copies up if the guess was short
     auto settle = [&](long long k) -> int {
         const int b = (int)(k & 1);
@@ -166,8 +169,10 @@ static int sweep_host_impl(const fhmc_hist_desc *desc, const double *blob, const
         if (live > sent[b]) {   // rare (first call, or a chunk with more phases than the last): re-mark the buffer set
             if (copies(k, 1 + sent[b], live)) return 1;
             sent[b] = live;
+            sent_final[(size_t)k] = live;
             return check_cuda(cudaEventRecord(hp->freed[b], hp->down), "cudaEventRecord");
         }
+        sent_final[(size_t)k] = sent[b];
         return 0;
     };
     fhmc_hist_desc d = *desc;
@@ -205,6 +210,29 @@ static int sweep_host_impl(const fhmc_hist_desc *desc, const double *blob, const
         if (settle(k)) return 1;
     if (check_cuda(cudaStreamSynchronize(hp->down), "cudaStreamSynchronize")) return 1;
     if (check_cuda(cudaStreamSynchronize(hp->comp), "cudaStreamSynchronize")) return 1;
+    // A chunk copied max(guess at queue time, its own live count) phase blocks; `top` is the maximum over ALL chunks.  Blocks
+    // [sent_final[k], top) of chunk k never crossed PCIe (no state point of the chunk has such a phase): give them the NaN / -1
+    // the repack kernel writes into empty slots, so that every block below *max_nphase_out is defined for every state point.
+    for (long long k = 0; k < n_chunks; ++k) {
+        const long long lo = k * chunk, m = (lo + chunk <= S ? chunk : S - lo);
+        for (int p = sent_final[(size_t)k]; p < top; ++p) {
+            if (!narrow) {
+                unsigned char *r = oh + 8 * S + ((long long)p * S + lo) * rec;
+                for (long long j = 0; j < m; ++j, r += rec) {
+                    double *f = reinterpret_cast<double *>(r);
+                    for (int q = 0; q <= nsel; ++q) f[q] = NAN;
+                    int *bi = reinterpret_cast<int *>(f + 1 + nsel);
+                    bi[0] = bi[1] = -1;
+                }
+            } else {
+                unsigned char *Fh = oh + ((4 * S + 15) & ~15ll), *Bh = Fh + (long long)pmax * S * nf8;
+                double *f = reinterpret_cast<double *>(Fh + ((long long)p * S + lo) * nf8);
+                for (long long j = 0; j < m * (1 + nsel); ++j) f[j] = NAN;
+                short *bi = reinterpret_cast<short *>(Bh + ((long long)p * S + lo) * 4);
+                for (long long j = 0; j < 2 * m; ++j) bi[j] = -1;
+            }
+        }
+    }
     if (max_nphase_out) *max_nphase_out = top;
     if (d2h_bytes_out) *d2h_bytes_out = moved;
     return 0;

@@ -498,6 +498,7 @@ static int launch_prod2(const SweepArgs &args, int sm_count, int smem_optin, cud
     long long grid = (long long)sm_count * occ;
     if (grid > ntiles) grid = ntiles;
     kern<<<(unsigned)grid, FHMC_CTA, smem, stream>>>(args);
+    note_kernel("k_sweep_prod2");
     return check_cuda(cudaGetLastError(), "k_sweep_prod2 launch");
 }
 

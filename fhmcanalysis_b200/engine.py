@@ -482,136 +482,6 @@ class DeviceHistogram(object):
         out["bounds"] = t.as_strided(body32, (S, pmax, 2), (rec // 4, S * rec // 4, 1), body32.storage_offset() + 2 + 2 * nsel)
         return out
 
-    def sweep_host_compact_py(self, mu1, pmax=4, lanes=0, chunk=1 << 17, out=None):
-        """The same pipeline driven from Python (kept for comparison, scripts/probe_e2e.py): ~0.1 ms of host time per chunk.
-        As ``sweep_host`` for the result set {status, nphase, fe, avg, bounds}, but only the phase slots that exist
-        cross PCIe: each chunk's records are repacked phase-major on the device (``fhmc_pack_phase_major``) and phase
-        blocks p >= max_s nphase[s] of the chunk are not copied.  The returned CPU tensors are [S, pmax, ...] VIEWS of
-        one pinned phase-major buffer; slots p >= nphase[s] hold NaN / -1.  ``out`` = a previous result to reuse."""
-        t = torch()
-        L = _lib.load()
-        dev = self.device
-        mu_h = mu1 if isinstance(mu1, t.Tensor) else t.from_numpy(np.ascontiguousarray(mu1, dtype=np.float64))
-        if not mu_h.is_pinned():
-            mu_h = mu_h.pin_memory()
-        S = mu_h.numel()
-        nsel = self.n_sel
-        rec = 16 + 8 * nsel                       # bytes of one {fe, avg[nsel], bounds[2]} record
-        chunk = int(min(chunk, max(S, 1)))
-        if S >= self.FAST_PATH_MIN_STATES and lanes in (0, 1):
-            self.ensure_hull()
-        spans = [(lo, min(S, lo + chunk)) for lo in range(0, S, chunk)]
-        if not hasattr(self, "_cpipe") or self._cpipe["key"] != (chunk, pmax):
-            self._cpipe = {"key": (chunk, pmax), "streams": [t.cuda.Stream(dev), t.cuda.Stream(dev)],
-                           "mu": [t.empty(chunk, dtype=t.float64, device=dev) for _ in range(2)],
-                           "res": [SweepResult(chunk, pmax, nsel, dev) for _ in range(2)],
-                           "packed": [t.empty(int(L.fhmc_pack_bytes(chunk, pmax, nsel)), dtype=t.uint8, device=dev) for _ in range(2)],
-                           "flag_d": [t.zeros(1, dtype=t.int32, device=dev) for _ in range(2)],
-                           "flag_h": [t.zeros(1, dtype=t.int32).pin_memory() for _ in range(2)], "views": {}}
-        cp = self._cpipe
-        streams, mu_d, res, packed_d, flag_d, flag_h = (cp[k] for k in ("streams", "mu", "res", "packed", "flag_d", "flag_h"))
-        if out is None or out.get("_key") != (S, pmax, nsel, chunk):
-            buf = t.empty(8 * S + pmax * rec * S, dtype=t.uint8).pin_memory()
-            out = {"_key": (S, pmax, nsel, chunk), "_buf": buf, "_prev_top": pmax}   # every phase block starts out stale
-            head = buf[:8 * S].view(t.int32)
-            out["status"] = t.as_strided(head, (S,), (2,))
-            out["nphase"] = t.as_strided(head, (S,), (2,), head.storage_offset() + 1)
-            body64, body32 = buf[8 * S:].view(t.float64), buf[8 * S:].view(t.int32)
-            out["fe"] = t.as_strided(body64, (S, pmax), (rec // 8, S * rec // 8))
-            out["avg"] = t.as_strided(body64, (S, pmax, nsel), (rec // 8, S * rec // 8, 1), body64.storage_offset() + 1) if nsel else None
-            out["bounds"] = t.as_strided(body32, (S, pmax, 2), (rec // 4, S * rec // 4, 1), body32.storage_offset() + 2 + 2 * nsel)
-            # byte ranges of every chunk: head + one block per phase, contiguous on both sides
-            out["_dst"] = [[buf[8 * lo:8 * hi]] + [buf[8 * S + (p * S + lo) * rec:8 * S + (p * S + hi) * rec] for p in range(pmax)]
-                           for lo, hi in spans]
-        for m in set(hi - lo for lo, hi in spans):
-            if m not in cp["views"]:
-                cp["views"][m] = [[pd[:8 * m]] + [pd[8 * m + p * m * rec:8 * m + (p + 1) * m * rec] for p in range(pmax)]
-                                  for pd in packed_d]
-        d = self._desc(pmax)
-        cur = t.cuda.current_stream(dev)
-        if not hasattr(self, "_blob_pin"):
-            self._blob_pin = t.from_numpy(self.blob_host).pin_memory()
-        blob_d = t.empty_like(self.blob)
-        blob_d.copy_(self._blob_pin, non_blocking=True)
-        ready = t.cuda.Event()
-        ready.record(cur)
-        for st_ in streams:
-            st_.wait_event(ready)
-        events = [None, None]
-        top = 0
-        moved = 0
-
-        def compute(k):
-            lo, hi = spans[k]
-            b = k & 1
-            with t.cuda.stream(streams[b]):
-                mu_d[b][:hi - lo].copy_(mu_h[lo:hi], non_blocking=True)
-                st = _lib.States()
-                st.n_states = hi - lo
-                st.mu1, st.n_mu1, st.mu1_div = _ptr(mu_d[b]), hi - lo, 1
-                st.beta, st.n_beta, st.beta_div = None, 1, 1
-                st.dmu, st.n_dmu, st.dmu_div = None, 1, 1
-                cs = res[b].c_struct()
-                sp = ctypes.c_void_p(streams[b].cuda_stream)
-                _lib.check(L.fhmc_sweep_1d(ctypes.byref(d), _ptr(blob_d), ctypes.byref(st), ctypes.byref(cs), int(lanes), sp),
-                           "fhmc_sweep_1d")
-                flag_d[b].zero_()
-                _lib.check(L.fhmc_pack_phase_major(ctypes.byref(cs), hi - lo, pmax, nsel, _ptr(packed_d[b]), _ptr(flag_d[b]), sp),
-                           "fhmc_pack_phase_major")
-                flag_h[b].copy_(flag_d[b], non_blocking=True)
-                events[b] = t.cuda.Event()
-                events[b].record(streams[b])
-
-        # The number of live phase blocks of a chunk is only known once its kernels have run.  Waiting for it before
-        # queueing the copies would idle the GPU, so the copies are queued at once for `guess` blocks (what the previous
-        # chunk / previous call needed) and a chunk that turns out to need more gets the rest when its flag is read --
-        # two chunks later, just before its device buffer is reused, by which time the wait is free.
-        guess = max(1, min(pmax, int(out.get("max_nphase", 1))))
-        sent = [0] * len(spans)
-
-        def copies(k, upto):
-            nonlocal moved
-            lo, hi = spans[k]
-            b = k & 1
-            src, dst = cp["views"][hi - lo][b], out["_dst"][k]
-            with t.cuda.stream(streams[b]):
-                for j in range(sent[k], 1 + upto):
-                    dst[j].copy_(src[j], non_blocking=True)
-                    moved += dst[j].numel()
-            sent[k] = max(sent[k], 1 + upto)
-
-        def settle(k):
-            nonlocal top, guess
-            events[k & 1].synchronize()
-            live = max(1, min(pmax, int(flag_h[k & 1].item())))
-            top = max(top, live)
-            guess = max(guess, live)
-            if 1 + live > sent[k]:
-                copies(k, live)
-
-        for k in range(len(spans)):
-            if k >= 2:
-                settle(k - 2)     # same stream and buffers as chunk k: finish it before they are reused
-            compute(k)
-            copies(k, guess)
-        for k in range(max(0, len(spans) - 2), len(spans)):
-            settle(k)
-        for st_ in streams:
-            cur.wait_stream(st_)
-        blob_d.record_stream(streams[0])
-        blob_d.record_stream(streams[1])
-        cur.synchronize()
-        # phase blocks that no chunk of this call filled: NaN / -1, like the empty slots inside a block
-        for p in range(top, max(top, out["_prev_top"])):
-            out["fe"][:, p].fill_(float("nan"))
-            if nsel:
-                out["avg"][:, p].fill_(float("nan"))
-            out["bounds"][:, p].fill_(-1)
-        out["_prev_top"] = top
-        out["max_nphase"] = top
-        out["d2h_bytes"] = moved + 4 * len(spans)       # + the per-chunk phase counts
-        return out
-
     def sweep_auto(self, mu1, beta=None, dmu=None, grid=False, pmax=4, **kw):
         """sweep() that grows pmax until no state point reports FHMC_E_CAPACITY (synchronises)."""
         while True:

@@ -447,7 +447,7 @@ class TaylorMixin(object):
         from fhmcanalysis_b200 import _lib as L
         ns = self.data["nspec"]
         if ns > 2:
-            raise Exception("batched Taylor extrapolation supports at most two species")
+            raise NotImplementedError("batched Taylor extrapolation supports at most two species")
         if order < 1 or order > 3 or (order == 3 and ns > 1):
             raise Exception("No implementation for this order of extrapolation")
         if self.data["max_order"] < order:

@@ -403,7 +403,17 @@ class histogram(TaylorMixin):
         extrap = (beta != self.data["curr_beta"]) or not np.all(new_dMu == curr_dMu)
         tmp_hist.normalize()
         min_width = tmp_hist.metadata["smooth"] * 2
-        if collect is not None:
+        coef, use_host_search = (), collect is not None
+        if extrap and not use_host_search:
+            if np.abs(self.metadata["beta_ref"] - self.data["curr_beta"]) > 1.0e-6:
+                raise Exception("Cannot extrapolate the same histogram class twice")
+            # (no edge assert here: the reference runs the whole search with override=True, GH:652, and applies the
+            # caller's `override` only to the final extrapolation at mu*, GH:660)
+            try:
+                coef = tmp_hist.taylor_rows(extrap_order)
+            except NotImplementedError:
+                use_host_search = True      # > 2 species: no coefficient-row form; the reference's simplex on device evaluations
+        if use_host_search:
             from scipy.optimize import fmin
             full_out = fmin(phase_eq_error, mu_guess, ftol=lnZ_tol,
                             args=(tmp_hist, beta, new_dMu, extrap_order, cutoff, True, min_width, collect),
@@ -412,20 +422,16 @@ class histogram(TaylorMixin):
                 raise Exception("Error, unable to locate phase coexistence : " + str(full_out))
             mu_star, err2 = float(full_out[0][0]), float(full_out[1])
         else:
-            coef = ()
-            if extrap:
-                if np.abs(self.metadata["beta_ref"] - self.data["curr_beta"]) > 1.0e-6:
-                    raise Exception("Cannot extrapolate the same histogram class twice")
-                if not override:
-                    lp = tmp_hist.data["ln(PI)"]
-                    assert np.max(lp) - cutoff > lp[len(lp) - 1], \
-                        "Error, histogram edge effect encountered in temperature extrapolation"
-                coef = tmp_hist.taylor_rows(extrap_order)
             dh = tmp_hist._device_hist(sel=["N"], coef=coef, cutoff=cutoff)
-            res = dh.find_phase_eq(np.array([float(mu_guess)]), beta=np.array([float(beta)]) if extrap else None,
-                                   dmu=np.array([float(new_dMu[0])]) if (extrap and len(new_dMu)) else None,
-                                   lnz_tol=min(float(lnZ_tol), 1e-10), pmax=8)
-            h = res.host()
+            pmax = 8
+            while True:   # a noisy ln(PI) can show more extrema than pmax at some intermediate mu: grow, like sweep_auto
+                res = dh.find_phase_eq(np.array([float(mu_guess)]), beta=np.array([float(beta)]) if extrap else None,
+                                       dmu=np.array([float(new_dMu[0])]) if (extrap and len(new_dMu)) else None,
+                                       lnz_tol=min(float(lnZ_tol), 1e-10), pmax=pmax)
+                h = res.host()
+                if int(h["code"][0]) != _lib.E_CAPACITY or pmax > len(tmp_hist.data["ln(PI)"]):
+                    break
+                pmax = min(pmax * 4, len(tmp_hist.data["ln(PI)"]) + 1)
             if int(h["code"][0]) != 0:
                 raise Exception("Error, unable to locate phase coexistence : " +
                                 _lib.STATUS_TEXT.get(int(h["code"][0]), "solver status %d" % int(h["code"][0])))

@@ -139,6 +139,9 @@ typedef struct fhmc_sweep_out {
 
 int fhmc_version(void);
 const char *fhmc_last_error(void);
+/* Diagnostic: name of the sweep / solver kernel the calling thread launched last ("k_sweep_prod2", "k_sweep_fast<prod>",
+ * "k_sweep_1d<32>", "k_solve_tab", ...): lets tests and bench.py state which kernel produced the records they check. */
+const char *fhmc_last_kernel(void);
 
 /* Device/SM query used by the host layer to size grids. */
 int fhmc_device_info(int *sm_count, int *max_smem_optin);

@@ -329,6 +329,31 @@ def test_compact_host_sweep_matches_plain_host_sweep():
     assert c2["max_nphase"] == 1 and np.all(np.isnan(c2["fe"].numpy()[:, 1:]))
 
 
+@pytest.mark.parametrize("narrow", [True, False])
+def test_compact_host_sweep_first_call_ascending_phase_count(narrow):
+    """First call on a FRESH result buffer (speculative copy guess = 1), ascending mu: the first two chunks are one-phase
+    everywhere, the last one is two-phase.  Phase block 1 of the early chunks never crosses PCIe and must still read
+    NaN / -1 (the header's contract: only blocks >= max_nphase are undefined)."""
+    from fhmcanalysis_b200 import engine, synth
+    n = 301
+    lnpi = synth.two_peak_lnpi(n, noise=1e-3, scale=0.3)
+    N = np.arange(n, dtype=np.float64)
+    dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=5, sel=["N", N * N])
+    mu = np.linspace(-3.0, 0.05, 5000)
+    a = dh.sweep_host(mu, pmax=4, chunk=2048)
+    P = a["nphase"].numpy()
+    assert P[:4096].max() == 1 and P[4096:].max() == 2
+    c = dh.sweep_host_compact(mu, pmax=4, chunk=2048, narrow=narrow)     # out=None: fresh pinned memory
+    assert c["max_nphase"] == 2 and np.array_equal(c["nphase"].numpy(), P)
+    fe_c, b_c, av_c = c["fe"].numpy(), c["bounds"].numpy(), c["avg"].numpy()
+    for p in range(2):
+        live = P > p
+        assert np.array_equal(fe_c[live, p], a["fe"].numpy()[live, p])
+        assert np.array_equal(b_c[live, p], a["bounds"].numpy()[live, p])
+        assert np.all(np.isnan(fe_c[~live, p])) and np.all(np.isnan(av_c[~live, p])) and np.all(b_c[~live, p] == -1)
+    assert np.all(np.isnan(fe_c[:, 2:])) and np.all(b_c[:, 2:] == -1)
+
+
 def test_thread_per_solve_kernel_matches_group_per_solve(monkeypatch):
     """K4: the one-solve-per-thread kernel (one-pass walk) and the warp-per-solve kernel run the same iteration on
     evaluations that agree to rounding: same mu_coex, same integers, same evaluation counts."""

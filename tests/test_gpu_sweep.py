@@ -206,3 +206,52 @@ def test_full_size_properties():
     h4 = dh.sweep(mu[sub].contiguous(), pmax=4, lanes=4).host()
     assert np.array_equal(h4["max_idx"][:, :1], h["max_idx"][sub, :1]) and np.array_equal(h4["nphase"], h["nphase"][sub])
     assert np.allclose(h4["fe"][:, 0], h["fe"][sub, 0], rtol=1e-12, atol=0)
+
+
+def test_headline_kernel_prod2_pinned_directly(oracle):
+    """The kernel bench.py times -- k_sweep_prod2<2,1>: BASELINE config 2 (N = 1001 bins, smooth 10, 10^6-point mu sweep in
+    [-0.03, 0.03], averaged quantities exactly (N, N^2) as bench.py builds them) -- checked DIRECTLY against the C oracle
+    (>= 2000 strided records) and against the compiled reference itself (>= 200 records: reweight -> thermo -> is_safe,
+    GH:71-78, 317-415, 498-596).  Integers bit-exact, F.E./kT and averages 1e-10 relative."""
+    import copy
+    import torch
+    from fhmcanalysis_b200 import _lib, synth
+    from fhmcanalysis_b200.moments.histogram.one_dim.ntot.gc_hist import histogram
+    from oracle import ref
+    n, smooth, S = 1001, 10, 1000000
+    lnpi, mom = synth.two_peak_lnpi(n), synth.one_comp_moments(n)
+    hist = histogram.from_arrays(lnpi, mom, 1.0, [0.0], smooth)
+    dh = hist.device_histogram(moments=("N", "N2"), device="cuda:0")      # bench.py:run_gpu_arm builds exactly this
+    mu = np.linspace(-0.03, 0.03, S)
+    res = dh.sweep(torch.from_numpy(mu).to("cuda:0"), pmax=4)
+    assert _lib.last_kernel() == "k_sweep_prod2" and dh.desc.mu_recurrence == 3 and dh.n_sel == 2
+    h = res.host()
+    assert np.mean((h["status"] & 0x1000) != 0) > 0.99          # records written by the product-form walk itself
+    Nf = np.arange(n, dtype=np.float64)
+    sel = np.stack([Nf, Nf * Nf])
+    idx = np.unique(np.concatenate([np.arange(0, S, 499), [S - 1]]))
+    assert len(idx) >= 2000
+    for k in idx:
+        assert h["status"][k] & 0x1000
+        r = oracle.state_point(lnpi, np.arange(n), 1.0, 0.0, mu[k], smooth, sel=sel)
+        _check_record(h, int(k), r, nsel=2)
+    assert ref.available(), "compiled reference (oracle/_ref) missing: run oracle/build_ref.py where /root/reference exists"
+    base = ref.make_histogram(lnpi, mom, 1.0, [0.0], smooth)
+    worst = 0.0
+    for k in idx[::9][:230]:
+        g = copy.deepcopy(base)
+        g.reweight(float(mu[k]))
+        g.thermo()
+        safe = g.is_safe()
+        th = g.data["thermo"]
+        P = len(th)
+        assert h["code"][k] == 0 and h["nphase"][k] == P and bool(h["safe"][k]) == bool(safe)
+        assert h["max_idx"][k, :P].tolist() == [int(v) for v in g.data["ln(PI)_maxima_idx"]]
+        assert h["min_idx"][k, :h["nmin"][k]].tolist() == [int(v) for v in g.data["ln(PI)_minima_idx"]]
+        for p in range(P):
+            assert tuple(h["bounds"][k, p]) == tuple(th[p]["bound_idx"])
+            got = np.array([h["fe"][k, p], h["avg"][k, p, 0], h["avg"][k, p, 1]])
+            want = np.array([th[p]["F.E./kT"], th[p]["mom"][0, 1, 0, 0, 0], th[p]["mom"][0, 2, 0, 0, 0]])
+            assert np.allclose(got, want, rtol=RTOL, atol=0)
+            worst = max(worst, float(np.max(np.abs(got - want) / np.abs(want))))
+    assert worst < RTOL
