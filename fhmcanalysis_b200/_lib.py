@@ -21,6 +21,8 @@ ST_GAP_FILL = 0x200
 ST_SLOW_PATH = 0x400
 ST_RESCUED = 0x800
 ST_FAST = 0x1000
+ST_JUMP = 0x2000
+ST_LEAN = 0x4000
 E_CAPACITY = 8
 E_NO_COEX = 100
 
@@ -72,7 +74,7 @@ EXPORTS = [
     "fhmc_masked_lse_2d", "fhmc_masked_lse_2d_workspace", "fhmc_sweep_host_workspace", "fhmc_sweep_host_compact",
     "fhmc_sweep_host_compact16", "fhmc_pack_soa16_bytes", "fhmc_pack_phase_soa16",
     "fhmc_patch_shifts", "fhmc_reweight_2d_prod", "fhmc_reweight_2d_prod_workspace",
-    "fhmc_bench_dfma", "fhmc_bench_exp",
+    "fhmc_bench_dfma", "fhmc_bench_exp", "fhmc_lean_stats",
 ]
 
 _lib = None
@@ -142,6 +144,8 @@ def load():
     L.fhmc_bench_dfma.argtypes = [ci, vp, vp]
     L.fhmc_bench_exp.restype = cll
     L.fhmc_bench_exp.argtypes = [ci, vp, vp]
+    L.fhmc_lean_stats.restype = ci
+    L.fhmc_lean_stats.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ci]
     _lib = L
     return L
 
@@ -154,3 +158,10 @@ def check(rc, what):
 def last_kernel():
     """Name of the sweep / solver kernel this thread launched last (diagnostic, fhmc_last_kernel)."""
     return load().fhmc_last_kernel().decode("ascii", "replace")
+
+
+def lean_stats(reset=False):
+    """Outcome counters of the lean evaluator (see fhmc_lean_stats in include/fhmc_b200.h) as a list of 8 ints."""
+    buf = (ctypes.c_ulonglong * 24)()     # (8 counters; 8 more cycle counters when built with -DFHMC_LEAN_PROFILE)
+    check(load().fhmc_lean_stats(buf, 1 if reset else 0), "fhmc_lean_stats")
+    return [int(x) for x in buf]

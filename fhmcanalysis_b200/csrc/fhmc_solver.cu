@@ -1,5 +1,7 @@
 // fhmc_solver.cu -- K4: batched find_phase_eq.
 //
+// This file: the C entry point and the general kernel (PointEval groups of 1/4/32 lanes per solve), which takes whatever
+// the default warp-per-solve kernel on the lean evaluator (fhmc_solver_lean.cu) has no instantiation for.
 // Reference: histogram.find_phase_eq (gc_hist.pyx:598-668) minimises, per temperature and one at a
 // time, phase_eq_error(mu) = min over pairs of phases at least 2*smooth bins wide of
 // (F.E._i - F.E._j)^2 (gc_hist.pyx:2570-2630) with scipy's Nelder-Mead.  Here every solve is an
@@ -13,8 +15,6 @@
 #include "fhmc_solver.cuh"
 
 namespace fhmc {
-
-#define FHMC_SOLVE_FAST_MIN (1LL << 40)   // never chosen automatically, see below
 
 template <int G, bool TAYLOR, int CTA>
 __global__ void __launch_bounds__(CTA) k_find_phase_eq(const __grid_constant__ SolveArgs sa)
@@ -40,18 +40,21 @@ __global__ void __launch_bounds__(CTA) k_find_phase_eq(const __grid_constant__ S
         dmu = st.dmu ? st.dmu[(rec / st.dmu_div) % st.n_dmu] : a.d.dmu_ref;
 
         const double n_mid = 0.5 * (sm[a.d.n_pad] + sm[a.d.n_pad + a.d.n - 1]);
-        solve_one(sa, rec, mu, beta, n_mid, pe.g == 0, [&](double m, int &P_now) {
+        solve_one(sa, rec, mu, beta, n_mid, pe.g == 0, [&](double m, int &P_now, EvalView &v) {
             pe.setup(m, beta, dmu);
             const unsigned st_ = pe.run(rec);
             if (G > 1) __syncwarp(pe.member);
             P_now = pe.P;
+            v.fe = a.out.fe + rec * a.d.pmax;
+            v.bl = a.out.bounds + rec * a.d.pmax * 2;
+            v.av = a.out.avg + rec * a.d.pmax * a.d.n_sel;
             return st_;
-        });
+        }, []() {});
     }
 }
 
-// thread-per-solve kernels (fhmc_solver_fast.cu)
-int launch_solver_fast(const SolveArgs &sa, int sm_count, int smem_optin, cudaStream_t stream);
+// warp-per-solve kernels on the lean evaluator (fhmc_solver_lean.cu): the default
+int launch_solver_lean(const SolveArgs &sa, int sm_count, int smem_optin, cudaStream_t stream);
 
 struct DevCaps {
     int sm_count, smem_optin;
@@ -137,17 +140,13 @@ extern "C" int fhmc_find_phase_eq_1d(const fhmc_hist_desc *desc, const double *b
     const long long T = states->n_states;
     cudaStream_t s = (cudaStream_t)stream;
     // a solve is ~10 dependent state-point passes: prefer wide groups unless there are very many solves
-    const char *force = getenv("FHMC_SOLVER_LANES");  // tuning/test override: 1/4/32 lanes per solve, 1000 = thread-per-solve walk
+    const char *force = getenv("FHMC_SOLVER_LANES");  // tuning/test override: 1/4/32 = the PointEval group kernel with that many lanes per solve
     const int forced = force ? atoi(force) : 0;
-    // Measured on B200 (scripts/probe_solver_scale.py, config-4 histogram, 10 rows x 2001 bins): the thread-per-solve
-    // walk needs ~9x fewer instructions per evaluation, but its packed rows leave room for one 256-thread CTA per SM
-    // (8 warps), every warp waits for its slowest lane's evaluation count, and one irregular evaluation stalls 31
-    // others: 7.8 / 9.1 / 79 / 87 ms against 4.6 / 10 / 30 / 88 ms of the warp-per-solve kernel at 1e4 / 3e4 / 1e5 / 3e5
-    // solves.  It is therefore only reachable through the override (tests keep it honest).
-    if ((forced == 0 && T >= FHMC_SOLVE_FAST_MIN) || forced == 1000) {
-        const int rc = launch_solver_fast(sa, caps.sm_count, caps.smem_optin, s);
+    if (forced == 0) {   // default: one warp per solve on the lean evaluator (fhmc_solver_lean.cu)
+        const int rc = launch_solver_lean(sa, caps.sm_count, caps.smem_optin, s);
         if (rc >= 0) return rc;
     }
+    note_kernel("k_find_phase_eq");
     if (forced == 1) return taylor ? launch_solver<1, true>(sa, smem, caps, s) : launch_solver<1, false>(sa, smem, caps, s);
     if (forced == 4) return taylor ? launch_solver<4, true>(sa, smem, caps, s) : launch_solver<4, false>(sa, smem, caps, s);
     if (forced == 32 || T * 32 <= (long long)caps.sm_count * 2048 * 4)

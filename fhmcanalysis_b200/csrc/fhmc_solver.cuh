@@ -13,14 +13,22 @@ struct SolveArgs {
 };
 
 
+// where the record of the evaluation just made can be read (the caller's arrays, or an evaluator's scratch)
+struct EvalView {
+    const double *fe;   // [P]
+    const int *bl;      // [P][2]
+    const double *av;   // [P][n_sel]
+};
+
 // One coexistence solve for record `rec`, executed by every lane of the group that owns it (uniform control flow).
-// eval(mu) runs one full state-point evaluation into record `rec` and returns (status word, number of phases).
-template <class Eval>
+// eval(mu, P, view) runs one full state-point evaluation and returns the status word, the number of phases and where its
+// F.E. / bounds / averages are; commit() makes sure the last evaluation's record is in record `rec` of the caller's arrays.
+template <class Eval, class Commit>
 __device__ __forceinline__ void solve_one(const SolveArgs &sa, long long rec, double mu, double beta, double n_mid, bool leader,
-                                          Eval &&eval)
+                                          Eval &&eval, Commit &&commit)
 {
     const SweepArgs &a = sa.sw;
-    const int pmax = a.d.pmax, nsel = a.d.n_sel;
+    const int nsel = a.d.n_sel;
     const int min_width = a.d.min_width > 0 ? a.d.min_width : 2 * a.d.smooth;  // ntot/gc_hist.pyx:652, n1/gc_hist.pyx:1479
     bool have_lo = false, have_hi = false, converged = false, located = false, have_glo = false, have_ghi = false;
     double lo = 0.0, hi = 0.0, mu_good = mu, d = 0.0, glo = 0.0, ghi = 0.0, step = sa.mu_step, d_lo = 0.0, d_hi = 0.0;
@@ -28,14 +36,15 @@ __device__ __forceinline__ void solve_one(const SolveArgs &sa, long long rec, do
     int code = FHMC_E_NO_COEX, it = 0, nevals = 0;
     for (it = 0; it < sa.max_iter; ++it) {
         int P_now = 0;
-        status = eval(mu, P_now);
+        EvalView v;
+        status = eval(mu, P_now, v);
         ++nevals;
         // pair selection of gc_hist.pyx:2614-2630 (every lane, uniform)
         bool ok = false;
         double slope = 0.0;
         if ((status & FHMC_ST_CODE_MASK) == FHMC_OK) {
-            const double *fe = a.out.fe + rec * pmax;
-            const int *bl = a.out.bounds + rec * pmax * 2;
+            const double *fe = v.fe;
+            const int *bl = v.bl;
             double best = 1.7976931348623157e308;
             int bi = -1, bj = -1;
             for (int i = 0; i < P_now; ++i) {
@@ -48,8 +57,7 @@ __device__ __forceinline__ void solve_one(const SolveArgs &sa, long long rec, do
             }
             if (bi >= 0) {
                 ok = true;
-                const double *av = a.out.avg + rec * pmax * nsel;
-                slope = beta * (av[bj * nsel] - av[bi * nsel]);
+                slope = beta * (v.av[bj * nsel] - v.av[bi * nsel]);
             }
         }
         if (!ok) {
@@ -60,8 +68,8 @@ __device__ __forceinline__ void solve_one(const SolveArgs &sa, long long rec, do
             }
             // ---- locate the two-phase window: <N>_total(mu) is monotone, the window is where it crosses the
             // middle of the N range.  Expand geometrically from the guess until bracketed, then bisect.
-            const double *fe = a.out.fe + rec * pmax;
-            const double *av = a.out.avg + rec * pmax * nsel;
+            const double *fe = v.fe;
+            const double *av = v.av;
             double fmin_ = fe[0];
             for (int p = 1; p < P_now; ++p) fmin_ = fmin(fmin_, fe[p]);
             double wsum = 0.0, nsum = 0.0;
@@ -100,7 +108,7 @@ __device__ __forceinline__ void solve_one(const SolveArgs &sa, long long rec, do
             const double l = fmin(lo, hi), h = fmax(lo, hi);
             if (!(mu_n > l && mu_n < h)) mu_n = 0.5 * (lo + hi);
             if (mu_n == mu || h - l <= 4.0 * 2.220446049250313e-16 * fmax(fabs(l), fabs(h))) {
-                converged = true;  // bracket exhausted at fp64 resolution
+                converged = true;  // bracket exhausted at fp64 resolution: d jumps across zero here (status bit JUMP below)
                 code = FHMC_OK;
                 break;
             }
@@ -112,15 +120,30 @@ __device__ __forceinline__ void solve_one(const SolveArgs &sa, long long rec, do
                 code = FHMC_OK;
                 break;
             }
+            // The same conclusion earlier: while the pair of phases persists d is smooth with d' = slope (exact, from the
+            // averages), so over a narrow bracket d can change by ~|slope| (h - l).  Residuals of opposite sign that are more
+            // than twice that apart cannot be joined by a smooth branch: the sign change is a jump (a phase boundary moved by
+            // a bin between l and h).  Newton lands on both sides of such a jump within two steps; without this test the
+            // bracket was then bisected to the last bit (15-20 evaluations that located nothing).
+            if (h - l <= 1e-6 * fmax(1.0, fmax(fabs(l), fabs(h))) && 2.0 * fabs(slope) * (h - l) < fabs(d_hi - d_lo) &&
+                fmin(fabs(d_lo), fabs(d_hi)) > sa.lnz_tol) {
+                converged = true;
+                code = FHMC_OK;
+                break;
+            }
         }
         mu = mu_n;
     }
     if (!converged && code == FHMC_E_NO_COEX && it >= sa.max_iter) code = FHMC_E_NO_COEX + 1;  // iteration cap
+    commit();
     if (leader) {
         sa.mu_coex[rec] = mu_good;
         sa.dfe[rec] = d;
         sa.iters[rec] = nevals;
         if (code != FHMC_OK) a.out.status[rec] = (a.out.status[rec] & ~FHMC_ST_CODE_MASK) | (unsigned)code;
+        // the search ended on a JUMP of the free-energy difference (a phase boundary moved by a bin, a phase appeared or
+        // vanished): mu_coex is the edge of the jump, |dfe| > lnz_tol.  Callers tell these from converged roots by this bit.
+        else if (!(fabs(d) <= sa.lnz_tol)) a.out.status[rec] |= FHMC_ST_JUMP;
     }
 }
 

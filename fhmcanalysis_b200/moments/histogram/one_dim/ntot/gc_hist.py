@@ -747,16 +747,23 @@ class histogram(TaylorMixin):
         return res if return_device else res.host()
 
     def find_phase_eq_batch(self, betas, mu_guess, dmu=None, order=1, lnZ_tol=1e-10, moments=("N", "N2", "U"), pmax=4,
-                            cutoff=10.0, max_iter=200, device=None, return_device=False):
+                            cutoff=10.0, max_iter=200, device=None, return_device=False, continuation=None):
         """One coexistence solve per temperature in ``betas`` (and optional ``dmu``), all concurrently (K4).
         ``mu_guess``: scalar or one guess per temperature.  Returns the thermo records at coexistence plus
-        'mu_coex', 'dfe' (signed residual F.E._i - F.E._j) and 'iters'."""
+        'mu_coex', 'dfe' (signed residual F.E._i - F.E._j), 'iters' and 'converged' (code 0 and |dfe| <= lnZ_tol; a solve
+        that ended on a jump of the free-energy difference has code 0, status bit ST_JUMP and converged False).
+        ``continuation``: see ``DeviceHistogram.find_phase_eq`` (default: automatic for one cold guess and many
+        temperatures -- a coarse subset is solved first and the other guesses are interpolated from its roots)."""
         betas = np.atleast_1d(np.asarray(betas, dtype=np.float64))
         moments = ["N"] + [m for m in moments if m != "N"]
         dh = self.device_histogram(betas, dmu, order, moments, cutoff, device)
         guess = np.broadcast_to(np.asarray(mu_guess, dtype=np.float64), betas.shape).copy()
-        res = dh.find_phase_eq(guess, beta=betas, dmu=dmu, lnz_tol=lnZ_tol, max_iter=max_iter, pmax=pmax)
-        return res if return_device else res.host()
+        res = dh.find_phase_eq(guess, beta=betas, dmu=dmu, lnz_tol=lnZ_tol, max_iter=max_iter, pmax=pmax, continuation=continuation)
+        if return_device:
+            return res
+        out = res.host()
+        out["converged"] = (out["code"] == 0) & ((out["status"] & _lib.ST_JUMP) == 0)
+        return out
 
 
 if __name__ == "__main__":

@@ -49,6 +49,8 @@ enum fhmc_monomial {
 #define FHMC_ST_SLOW_PATH   0x400u  /* extrema had to be re-evaluated on the normalised array     */
 #define FHMC_ST_RESCUED     0x800u  /* a phase with negligible weight was re-summed about its own max */
 #define FHMC_ST_FAST        0x1000u /* produced by the one-thread-per-point, one-exp-pass kernel (diagnostic)     */
+#define FHMC_ST_JUMP        0x2000u /* fhmc_find_phase_eq_1d: code 0 but |dfe| > lnz_tol -- the search ended on a jump of dF.E. */
+#define FHMC_ST_LEAN        0x4000u /* produced by the lean warp-per-point evaluator (diagnostic)                  */
 enum fhmc_status_code {
     FHMC_OK = 0,
     FHMC_E_TOO_SHORT = 1,       /* GH:326-327                                                    */
@@ -188,7 +190,7 @@ int fhmc_pack_phase_major(const fhmc_sweep_out *out, long long n_states, int pma
 
 /*
  * Narrow variant of the repack: 4 + P (8 + 8 n_sel + 4) bytes per state point with P live phases.
- *   packed: { u16 status (FHMC_ST_* fit 13 bits); u8 nphase; u8 0 }[S], padded to 16 bytes  |
+ *   packed: { u16 status (FHMC_ST_* fit 15 bits); u8 nphase; u8 0 }[S], padded to 16 bytes  |
  *           for p in 0..pmax-1: { f64 fe; f64 avg[n_sel]; }[S]  |  for p in 0..pmax-1: { i16 bounds[2]; }[S]
  * (bin indices must fit int16: n <= 32767).  Slots p >= nphase[s] hold NaN / -1 as in fhmc_pack_phase_major.
  */
@@ -228,10 +230,12 @@ int fhmc_axpy_rows(const double *const *src, const double *w_host, int n_src, lo
 /*
  * K4: batched find_phase_eq (GH:598-668 with the objective of GH:2570-2630).  One solve per
  * entry of `states` (mu1 there is the initial guess).  Root of the signed dF.E./kT between the
- * two phases the reference objective would select, by bracketing + bisection/secant, to
+ * two phases the reference objective would select, by bracketing + bisection/Newton, to
  * |dF.E.| <= lnz_tol.  Outputs: mu_coex[T], dfe[T] (signed residual), iters[T], status as above
- * (code FHMC_E_* or 100 = no two wide phases / no bracket).  The thermo at mu_coex is written
- * through `out` (same layout as fhmc_sweep_1d).
+ * (code FHMC_E_* or 100 = no two wide phases / no bracket).  A solve whose bracket closed on a JUMP of
+ * dF.E. (integer phase bounds moving with mu; no root exists at fp64 resolution) reports code 0 with
+ * FHMC_ST_JUMP set and the residual in dfe.  The thermo at mu_coex is written through `out` (same
+ * layout as fhmc_sweep_1d).
  */
 #define FHMC_E_NO_COEX 100
 int fhmc_find_phase_eq_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states,
@@ -284,6 +288,12 @@ int fhmc_masked_lse_2d(const double *lnpi, const unsigned char *mask, const int 
  */
 int fhmc_patch_shifts(const double *a, const double *b, const long long *offsets, int n_pairs, double *shift,
                       double *err2, void *stream);
+
+/* Diagnostic counters of the lean warp-per-point evaluator (K4), out24 = 24 values: [0] evaluations it finished, [1..7]
+ * evaluations handed to the general evaluator (too many candidates / repair needs the normalised array or the reference
+ * raises / phase count / underflowing phase / failed re-test on the normalised values / monotone ln(PI) with ties / monotone
+ * ln(PI) that is not one phase); [8..23] cycle counters, zero unless built with -DFHMC_LEAN_PROFILE.  Synchronises the device. */
+int fhmc_lean_stats(unsigned long long *out24, int reset);
 
 /* Roofline micro-benchmarks (register-resident): return ops executed; time with CUDA events. */
 long long fhmc_bench_dfma(int iters, double *sink, void *stream);

@@ -354,36 +354,39 @@ def test_compact_host_sweep_first_call_ascending_phase_count(narrow):
     assert np.all(np.isnan(fe_c[:, 2:])) and np.all(b_c[:, 2:] == -1)
 
 
-def test_thread_per_solve_kernel_matches_group_per_solve(monkeypatch):
-    """K4: the one-solve-per-thread kernel (one-pass walk) and the warp-per-solve kernel run the same iteration on
-    evaluations that agree to rounding: same mu_coex, same integers, same evaluation counts."""
-    from fhmcanalysis_b200 import synth
+def test_lean_solver_kernel_matches_group_kernel(monkeypatch):
+    """K4: the default warp-per-solve kernel on the lean evaluator (k_solve_lean) and the general PointEval group kernel run
+    the same iteration on bit-identical evaluations of u: same mu_coex, same integers, same evaluation counts."""
+    from fhmcanalysis_b200 import _lib, synth
     from fhmcanalysis_b200.moments.histogram.one_dim.ntot.gc_hist import histogram
     h = histogram.from_arrays(synth.two_peak_lnpi(801, scale=0.8), synth.one_comp_moments(801, max_order=3), 1.0, [0.0], 10)
     betas = 1.0 / np.linspace(0.92, 1.05, 700)
-    for order, moments in ((2, ("N", "N2", "U")), (1, ("N",))):
+    for order, moments in ((2, ("N", "N2", "U")), (1, ("N",)), (3, ("N", "N2", "U"))):
         dh = h.device_histogram(beta=betas, order=order, moments=moments)
         monkeypatch.setenv("FHMC_SOLVER_LANES", "32")
-        a = dh.find_phase_eq(np.zeros_like(betas), beta=betas, lnz_tol=1e-10, pmax=4).host()
-        monkeypatch.setenv("FHMC_SOLVER_LANES", "1000")
-        b = dh.find_phase_eq(np.zeros_like(betas), beta=betas, lnz_tol=1e-10, pmax=4).host()
+        a = dh.find_phase_eq(np.zeros_like(betas), beta=betas, lnz_tol=1e-10, pmax=4, continuation=False).host()
+        assert _lib.last_kernel() == "k_find_phase_eq"
         monkeypatch.delenv("FHMC_SOLVER_LANES")
+        b = dh.find_phase_eq(np.zeros_like(betas), beta=betas, lnz_tol=1e-10, pmax=4, continuation=False).host()
+        assert _lib.last_kernel() == "k_solve_lean"
         assert np.array_equal(a["code"], b["code"]) and (a["code"] == 0).mean() > 0.9
+        assert np.array_equal(a["status"] & 0x2000, b["status"] & 0x2000) and np.array_equal(a["iters"], b["iters"])
         ok = a["code"] == 0
-        assert np.allclose(a["mu_coex"][ok], b["mu_coex"][ok], rtol=0, atol=1e-9)
-        assert np.array_equal(a["nphase"][ok], b["nphase"][ok]) and np.array_equal(a["bounds"][ok], b["bounds"][ok])
-        assert np.allclose(a["fe"][ok, :2], b["fe"][ok, :2], rtol=1e-9, atol=1e-9)
-        assert (b["status"][ok] & 0x1000).mean() > 0.9          # the final records come from the one-pass walk
-    # pure mu solves (no extrapolation): the shift comes from the hull rows
+        assert np.allclose(a["mu_coex"][ok], b["mu_coex"][ok], rtol=0, atol=1e-13)
+        assert np.array_equal(a["nphase"][ok], b["nphase"][ok]) and np.array_equal(a["bounds"][ok][:, :2], b["bounds"][ok][:, :2])
+        assert np.array_equal(a["max_idx"][ok][:, :2], b["max_idx"][ok][:, :2])
+        assert np.allclose(a["fe"][ok, :2], b["fe"][ok, :2], rtol=1e-11, atol=1e-12)
+        assert np.allclose(a["avg"][ok, :2], b["avg"][ok, :2], rtol=1e-11, atol=0)
+        assert (b["status"][ok] & 0x4000).mean() > 0.9          # the final records come from the lean evaluator
+    # pure mu solves (no extrapolation)
     N = np.arange(801.0)
     from fhmcanalysis_b200 import engine
     dh = engine.DeviceHistogram(synth.two_peak_lnpi(801, scale=0.8), N, 1.0, 0.0, smooth=10, sel=["N"])
-    dh.ensure_hull()
     g = np.linspace(-0.05, 0.05, 300)
     monkeypatch.setenv("FHMC_SOLVER_LANES", "32")
     a = dh.find_phase_eq(g).host()
-    monkeypatch.setenv("FHMC_SOLVER_LANES", "1000")
-    b = dh.find_phase_eq(g).host()
     monkeypatch.delenv("FHMC_SOLVER_LANES")
+    b = dh.find_phase_eq(g).host()
+    assert _lib.last_kernel() == "k_solve_lean"
     assert np.all(a["code"] == 0) and np.all(b["code"] == 0)
-    assert np.allclose(a["mu_coex"], b["mu_coex"], rtol=0, atol=1e-10) and np.ptp(b["mu_coex"]) < 1e-9
+    assert np.allclose(a["mu_coex"], b["mu_coex"], rtol=0, atol=1e-12) and np.ptp(b["mu_coex"]) < 1e-9

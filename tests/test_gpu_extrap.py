@@ -92,3 +92,70 @@ def test_find_phase_eq_other_conditions(golden, golden_meta):
         assert abs(fe[0] - fe[1]) < 1e-8 and err < 1e-16
         assert np.allclose(fe, golden[key + "/fe"], rtol=0, atol=5e-2)      # the reference stops ~1e-4 away in mu
         assert h.data["curr_mu"][0] == meta["mu_ref"][0]                     # self untouched
+
+
+def _check_against_tight_oracle(oracle, lnpi, mom, betas, res, idx, smooth):
+    """mu_coex within 1e-10 of the tightened oracle (brentq on the signed dF.E. of the same pair) and the record
+    at mu_coex equal to the oracle's state point there: integers bit-exact, F.E. / averages 1e-10."""
+    n = len(lnpi)
+    A = oracle.taylor_coefficients(mom)
+    N = np.arange(n, dtype=float)
+    sel = np.stack([N, N * N, mom[0, 0, 0, 0, 1]])
+    dsel = np.stack([np.zeros(n), np.zeros(n), -(mom[0, 0, 0, 0, 2] - mom[0, 0, 0, 0, 1] ** 2)])   # d<U>(N)/d beta (1 species)
+    worst = 0.0
+    for k in idx:
+        xb = betas[k] - 1.0
+
+        def coef_fn(mu, xb=xb):
+            return np.stack([N, A["A_b"], A["A_bb"]]), np.array([xb * mu, xb, 0.5 * xb * xb])
+        mu = res["mu_coex"][k]
+        mu_t = None
+        for half in (1e-3, 1e-4, 1e-5, 1e-6):
+            try:
+                mu_t = oracle.find_phase_eq_tight(lnpi, N, 1.0, 0.0, smooth, mu - half, mu + half, coef_fn=coef_fn)
+                break
+            except (RuntimeError, ValueError):
+                continue
+        assert mu_t is not None, k
+        assert abs(mu - mu_t) <= 1e-10 * max(1.0, abs(mu_t)), (k, mu, mu_t)
+        worst = max(worst, abs(mu - mu_t))
+        coef, xi = coef_fn(mu)
+        r = oracle.state_point(lnpi, np.arange(n), 1.0, 0.0, mu, smooth, sel=sel + xb * dsel, coef=coef, xi=xi)
+        P = r["nphase"]
+        assert res["code"][k] == r["status"] == 0 and res["nphase"][k] == P
+        assert res["max_idx"][k, :P].tolist() == r["max_idx"].tolist()
+        assert res["min_idx"][k, :res["nmin"][k]].tolist() == r["min_idx"].tolist()
+        assert res["bounds"][k, :P].tolist() == r["bounds"].tolist()
+        assert bool(res["safe"][k]) == r["safe"]
+        assert np.allclose(res["fe"][k, :P], r["fe"], rtol=1e-10, atol=1e-12)
+        assert np.allclose(res["avg"][k, :P], r["avg"], rtol=1e-10, atol=0)
+    return worst
+
+
+def test_config4_coexistence_curve_at_size(oracle):
+    """BASELINE config 4 AT SIZE: N_max = 2000 (2001 bins), smooth 10, 10^4 temperatures, order-2 beta extrapolation, every
+    solve from the same cold guess (k_solve_lean).  >= 100 sampled solves against the tightened oracle; solves that ended on
+    a jump of dF.E. carry FHMC_ST_JUMP (not 'converged'); the staged-continuation mode lands on the same roots."""
+    from fhmcanalysis_b200 import _lib, synth
+    from fhmcanalysis_b200.moments.histogram.one_dim.ntot.gc_hist import histogram
+    n, T, smooth, tol = 2001, 10000, 10, 1e-10
+    lnpi, mom = synth.two_peak_lnpi(n, scale=2.0), synth.one_comp_moments(n, max_order=3)
+    h4 = histogram.from_arrays(lnpi, mom, 1.0, [0.0], smooth)
+    betas = 1.0 / np.linspace(0.90, 1.06, T)
+    cold = h4.find_phase_eq_batch(betas, 0.0, order=2, lnZ_tol=tol, continuation=False)
+    assert _lib.last_kernel() == "k_solve_lean"
+    conv = cold["converged"]
+    jump = (cold["code"] == 0) & ~conv
+    assert conv.mean() > 0.98 and np.all(np.abs(cold["dfe"][conv]) <= tol)
+    assert np.all(np.abs(cold["dfe"][jump]) > tol) and np.all((cold["status"][jump] & _lib.ST_JUMP) != 0)
+    assert np.mean((cold["status"][conv] & _lib.ST_LEAN) != 0) > 0.99      # final records written by the lean evaluator
+    idx = np.where(conv)[0][::83]
+    assert len(idx) >= 100
+    _check_against_tight_oracle(oracle, lnpi, mom, betas, cold, idx, smooth)
+    # staged continuation (coarse subset first, interpolated guesses): same roots, fewer evaluations
+    st = h4.find_phase_eq_batch(betas, 0.0, order=2, lnZ_tol=tol)           # automatic for one cold guess
+    both = conv & st["converged"]
+    assert both.mean() > 0.98 and st["iters"].mean() < 0.6 * cold["iters"].mean()
+    same = np.abs(st["mu_coex"][both] - cold["mu_coex"][both]) <= 1e-9
+    assert same.mean() > 0.995      # (a noisy ln(PI) near the critical temperature can hold more than one root)
+    _check_against_tight_oracle(oracle, lnpi, mom, betas, st, np.where(st["converged"])[0][::89], smooth)
