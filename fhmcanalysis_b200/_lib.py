@@ -62,6 +62,11 @@ class States(ctypes.Structure):
     ]
 
 
+class CompactOut(ctypes.Structure):
+    _fields_ = [("dst", ctypes.c_void_p * 8), ("n_dst", ctypes.c_int), ("n_total", ctypes.c_longlong), ("first", ctypes.c_longlong),
+                ("fill_dead", ctypes.c_int), ("max_nphase", ctypes.c_void_p)]
+
+
 class SweepOut(ctypes.Structure):
     _fields_ = [(k, ctypes.c_void_p) for k in
                 ("status", "nphase", "nmin", "lnnorm", "fe", "avg", "bounds", "max_idx", "min_idx")]
@@ -74,7 +79,7 @@ EXPORTS = [
     "fhmc_masked_lse_2d", "fhmc_masked_lse_2d_workspace", "fhmc_sweep_host_workspace", "fhmc_sweep_host_compact",
     "fhmc_sweep_host_compact16", "fhmc_pack_soa16_bytes", "fhmc_pack_phase_soa16",
     "fhmc_patch_shifts", "fhmc_reweight_2d_prod", "fhmc_reweight_2d_prod_workspace",
-    "fhmc_bench_dfma", "fhmc_bench_exp", "fhmc_lean_stats",
+    "fhmc_bench_dfma", "fhmc_bench_exp", "fhmc_lean_stats", "fhmc_sweep_1d_compact", "fhmc_sweep_compact_workspace",
 ]
 
 _lib = None
@@ -144,6 +149,11 @@ def load():
     L.fhmc_bench_dfma.argtypes = [ci, vp, vp]
     L.fhmc_bench_exp.restype = cll
     L.fhmc_bench_exp.argtypes = [ci, vp, vp]
+    L.fhmc_sweep_compact_workspace.restype = ctypes.c_size_t
+    L.fhmc_sweep_compact_workspace.argtypes = [ctypes.POINTER(HistDesc), cll]
+    L.fhmc_sweep_1d_compact.restype = ci
+    L.fhmc_sweep_1d_compact.argtypes = [ctypes.POINTER(HistDesc), vp, ctypes.POINTER(States), ctypes.POINTER(CompactOut), vp,
+                                        ctypes.c_size_t, vp]
     L.fhmc_lean_stats.restype = ci
     L.fhmc_lean_stats.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ci]
     _lib = L

@@ -316,6 +316,7 @@ struct PackArgs {
     int pmax, nsel;
     unsigned char *packed;
     int *max_nphase;
+    CompactArgs c;   // k_pack_phase_soa16: destinations (c.n_dst >= 1), layout size c.n_total, first record c.first
 };
 
 __global__ void __launch_bounds__(256) k_pack_phase_major(const __grid_constant__ PackArgs a)
@@ -349,30 +350,39 @@ __global__ void __launch_bounds__(256) k_pack_phase_major(const __grid_constant_
 // point instead of 8 + P (16 + 8 nsel).
 __global__ void __launch_bounds__(256) k_pack_phase_soa16(const __grid_constant__ PackArgs a)
 {
-    uchar4 *head = reinterpret_cast<uchar4 *>(a.packed);
     const int nf = 1 + a.nsel;
-    double *F = reinterpret_cast<double *>(a.packed + ((4 * a.S + 15) & ~15ll));
-    short2 *B = reinterpret_cast<short2 *>(reinterpret_cast<unsigned char *>(F) + (long long)a.pmax * a.S * nf * 8);
+    const long long NT = a.c.n_total;
     int pm = 0;
     for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < a.S; s += (long long)gridDim.x * blockDim.x) {
         const unsigned st = a.out.status[s];
         const int P = a.out.nphase[s];
-        head[s] = make_uchar4((unsigned char)(st & 0xFFu), (unsigned char)((st >> 8) & 0xFFu), (unsigned char)min(max(P, 0), 255), 0);
+        const uchar4 hd = make_uchar4((unsigned char)(st & 0xFFu), (unsigned char)((st >> 8) & 0xFFu), (unsigned char)min(max(P, 0), 255), 0);
         const int Pe = ((st & FHMC_ST_CODE_MASK) == FHMC_OK) ? min(max(P, 0), a.pmax) : 0;
         pm = max(pm, Pe);
-        for (int p = 0; p < a.pmax; ++p) {
-            double *r = F + ((long long)p * a.S + s) * nf;
-            const bool live = p < Pe;
-            r[0] = live ? a.out.fe[s * a.pmax + p] : CUDART_NAN;
-            for (int q = 0; q < a.nsel; ++q) r[1 + q] = live ? a.out.avg[(s * a.pmax + p) * a.nsel + q] : CUDART_NAN;
-            const int2 b = live ? *reinterpret_cast<const int2 *>(a.out.bounds + (s * a.pmax + p) * 2) : make_int2(-1, -1);
-            B[(long long)p * a.S + s] = make_short2((short)b.x, (short)b.y);
+        const long long g = a.c.first + s;
+        for (int d = 0; d < a.c.n_dst; ++d) {
+            unsigned char *base = a.c.dst[d];
+            reinterpret_cast<uchar4 *>(base)[g] = hd;
+            double *F = reinterpret_cast<double *>(base + ((4 * NT + 15) & ~15ll));
+            short2 *B = reinterpret_cast<short2 *>(reinterpret_cast<unsigned char *>(F) + (long long)a.pmax * NT * nf * 8);
+            const int pend = a.c.fill_dead ? a.pmax : Pe;
+            for (int p = 0; p < pend; ++p) {
+                double *r = F + ((long long)p * NT + g) * nf;
+                const bool live = p < Pe;
+                r[0] = live ? a.out.fe[s * a.pmax + p] : CUDART_NAN;
+                for (int q = 0; q < a.nsel; ++q) r[1 + q] = live ? a.out.avg[(s * a.pmax + p) * a.nsel + q] : CUDART_NAN;
+                const int2 b = live ? *reinterpret_cast<const int2 *>(a.out.bounds + (s * a.pmax + p) * 2) : make_int2(-1, -1);
+                B[(long long)p * NT + g] = make_short2((short)b.x, (short)b.y);
+            }
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) pm = max(pm, __shfl_xor_sync(0xffffffffu, pm, o));
-    if ((threadIdx.x & 31) == 0 && pm > 0) atomicMax(a.max_nphase, pm);
+    if ((threadIdx.x & 31) == 0 && pm > 0 && a.max_nphase) atomicMax(a.max_nphase, pm);
 }
+
+// compact-record instantiations of the headline kernel (fhmc_fast_prod_compact.cu)
+int launch_prod2_compact(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream, int *grid_out, bool dry);
 
 #define FHMC_FAST_MIN_STATES 4096
 
@@ -428,6 +438,7 @@ int fhmc_sweep_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_sta
     args.st = *states;
     args.out = *out;
     args.blob_global = 0;
+    memset(&args.c, 0, sizeof(args.c));
     if (smem > (size_t)di->smem_optin) {  // histogram larger than shared memory: read the rows through L1/L2
         args.blob_global = 1;
         smem = 16 + 512;
@@ -461,6 +472,104 @@ int fhmc_sweep_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_sta
     case 32: return launch_sweep_t<32>(taylor, args, smem, di, s);
     default: set_error("lanes_per_point must be 0, 1, 4 or 32"); return 1;
     }
+}
+
+// scratch records of a compact-record launch: one per warp that can be resident (fused path), or one per state point (general
+// path: plain sweep into the scratch, then the narrow repack)
+#define FHMC_COMPACT_SCRATCH_RECORDS 8192
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+static size_t carve_records(unsigned char *base, long long c, int pmax, int nsel, fhmc_sweep_out *o)
+{
+    size_t off = 0;
+    auto take = [&](size_t nbytes) { unsigned char *p = base ? base + off : nullptr; off += al256(nbytes); return p; };
+    fhmc_sweep_out t;
+    t.status = reinterpret_cast<unsigned *>(take(4 * c));
+    t.nphase = reinterpret_cast<int *>(take(4 * c));
+    t.nmin = reinterpret_cast<int *>(take(4 * c));
+    t.lnnorm = reinterpret_cast<double *>(take(8 * c));
+    t.fe = reinterpret_cast<double *>(take(8 * c * pmax));
+    t.avg = reinterpret_cast<double *>(take(8 * c * pmax * (nsel > 0 ? nsel : 1)));
+    t.bounds = reinterpret_cast<int *>(take(8 * c * pmax));
+    t.max_idx = reinterpret_cast<int *>(take(4 * c * pmax));
+    t.min_idx = reinterpret_cast<int *>(take(4 * c * (pmax + 1)));
+    if (o) *o = t;
+    return off;
+}
+
+size_t fhmc_sweep_compact_workspace(const fhmc_hist_desc *desc, long long n_states)
+{
+    if (!desc || n_states < 0 || desc->pmax < 1) return 0;
+    // the fused kernel needs FHMC_COMPACT_SCRATCH_RECORDS records; anything it does not cover needs a record per state point
+    const bool fused = desc->mu_recurrence >= 2 && desc->n_coef == 0 && desc->n_term <= 1 && !desc->complete && desc->n_sel <= 2 &&
+                       desc->pmax <= FHMC_COMPACT_PMAX && desc->n <= 32767;
+    const long long c = (fused && n_states > FHMC_COMPACT_SCRATCH_RECORDS) ? FHMC_COMPACT_SCRATCH_RECORDS
+                        : (n_states > FHMC_COMPACT_SCRATCH_RECORDS ? n_states : FHMC_COMPACT_SCRATCH_RECORDS);
+    return carve_records(nullptr, c, desc->pmax, desc->n_sel, nullptr);
+}
+
+int fhmc_sweep_1d_compact(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states, const fhmc_compact_out *cout,
+                          void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (validate_desc(desc) || validate_states(states)) return 1;
+    if (!blob || ((uintptr_t)blob & 15)) { set_error("blob must be a 16-byte aligned device pointer"); return 1; }
+    if (!cout || cout->n_dst < 1 || cout->n_dst > FHMC_COMPACT_DST || cout->n_total < 1 || cout->first < 0 ||
+        cout->first + states->n_states > cout->n_total) { set_error("bad compact-output description"); return 1; }
+    for (int d = 0; d < cout->n_dst; ++d)
+        if (!cout->dst[d] || ((uintptr_t)cout->dst[d] & 15)) { set_error("destination %d must be a 16-byte aligned device pointer", d); return 1; }
+    if (desc->n > 32767) { set_error("histogram too long for int16 bounds"); return 1; }
+    if (!workspace || ((uintptr_t)workspace & 255)) { set_error("workspace must be a 256-byte aligned device pointer"); return 1; }
+    if (states->n_states == 0) return 0;
+    const DevInfo *di = dev_info();
+    if (!di) { set_error("no CUDA device"); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    SweepArgs args;
+    args.d = *desc;
+    args.blob = blob;
+    args.st = *states;
+    args.blob_global = 0;
+    memset(&args.c, 0, sizeof(args.c));
+    for (int d = 0; d < cout->n_dst; ++d) args.c.dst[d] = static_cast<unsigned char *>(cout->dst[d]);
+    args.c.n_dst = cout->n_dst;
+    args.c.n_total = cout->n_total;
+    args.c.first = cout->first;
+    args.c.fill_dead = cout->fill_dead;
+    args.c.max_nphase = cout->max_nphase;
+    // fused path: the product-form kernel writes the records itself
+    if (states->n_states > (long long)di->sm_count * 2 * FHMC_CTA && !states->beta && !states->dmu) {
+        int grid = 0;
+        int rc = launch_prod2_compact(args, di->sm_count, di->smem_optin, s, &grid, true);
+        if (rc == 0) {
+            const long long need = (long long)grid * (FHMC_CTA / 32);
+            if (need <= FHMC_COMPACT_SCRATCH_RECORDS &&
+                carve_records(nullptr, FHMC_COMPACT_SCRATCH_RECORDS, desc->pmax, desc->n_sel, nullptr) <= workspace_bytes) {
+                carve_records(static_cast<unsigned char *>(workspace), FHMC_COMPACT_SCRATCH_RECORDS, desc->pmax, desc->n_sel, &args.out);
+                rc = launch_prod2_compact(args, di->sm_count, di->smem_optin, s, &grid, false);
+                if (rc >= 0) return rc;
+            }
+        } else if (rc == 1) {
+            return 1;
+        }
+    }
+    // general path: any kernel of fhmc_sweep_1d into scratch records, then the narrow repack to every destination
+    fhmc_sweep_out rec;
+    if (carve_records(nullptr, states->n_states, desc->pmax, desc->n_sel, nullptr) > workspace_bytes) {
+        set_error("workspace too small: need fhmc_sweep_compact_workspace() bytes");
+        return 1;
+    }
+    carve_records(static_cast<unsigned char *>(workspace), states->n_states, desc->pmax, desc->n_sel, &rec);
+    if (fhmc_sweep_1d(desc, blob, states, &rec, 0, stream)) return 1;
+    PackArgs a;
+    a.out = rec;
+    a.S = states->n_states;
+    a.pmax = desc->pmax;
+    a.nsel = desc->n_sel;
+    a.packed = nullptr;
+    a.max_nphase = cout->max_nphase;
+    a.c = args.c;
+    long long blocks = (a.S + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_pack_phase_soa16<<<(unsigned)blocks, 256, 0, s>>>(a);
+    return check_cuda(cudaGetLastError(), "k_pack_phase_soa16 launch");
 }
 
 int fhmc_lnpi_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states, const double *lnnorm,
@@ -526,6 +635,7 @@ int fhmc_pack_phase_major(const fhmc_sweep_out *out, long long n_states, int pma
     a.nsel = n_sel;
     a.packed = static_cast<unsigned char *>(packed);
     a.max_nphase = max_nphase;
+    memset(&a.c, 0, sizeof(a.c));
     long long blocks = (n_states + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_pack_phase_major<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
@@ -552,6 +662,12 @@ int fhmc_pack_phase_soa16(const fhmc_sweep_out *out, long long n_states, int pma
     a.nsel = n_sel;
     a.packed = static_cast<unsigned char *>(packed);
     a.max_nphase = max_nphase;
+    memset(&a.c, 0, sizeof(a.c));
+    a.c.dst[0] = a.packed;
+    a.c.n_dst = 1;
+    a.c.n_total = n_states;
+    a.c.first = 0;
+    a.c.fill_dead = 1;
     long long blocks = (n_states + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_pack_phase_soa16<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "fhmc_common.cuh"
@@ -63,6 +64,8 @@ struct PipeBuf {
     unsigned char *packed;
     int *flag;
     size_t bytes;
+    unsigned char *rec_base;   // the record arrays as one block (scratch of fhmc_sweep_1d_compact)
+    size_t rec_bytes;
 };
 
 static PipeBuf carve(unsigned char *base, long long c, int pmax, int nsel)
@@ -80,6 +83,8 @@ static PipeBuf carve(unsigned char *base, long long c, int pmax, int nsel)
     b.out.bounds = reinterpret_cast<int *>(take(8 * c * pmax));
     b.out.max_idx = reinterpret_cast<int *>(take(4 * c * pmax));
     b.out.min_idx = reinterpret_cast<int *>(take(4 * c * (pmax + 1)));
+    b.rec_base = reinterpret_cast<unsigned char *>(b.out.status);
+    b.rec_bytes = off - al256(8 * c);
     b.packed = take((size_t)fhmc_pack_bytes(c, pmax, nsel));   // (>= fhmc_pack_soa16_bytes)
     b.flag = reinterpret_cast<int *>(take(16));
     b.bytes = off;
@@ -194,10 +199,24 @@ static int sweep_host_impl(const fhmc_hist_desc *desc, const double *blob, const
         st.mu1 = buf[b].mu; st.n_mu1 = m; st.mu1_div = 1;
         st.beta = nullptr; st.n_beta = 1; st.beta_div = 1;
         st.dmu = nullptr; st.n_dmu = 1; st.dmu_div = 1;
-        if (fhmc_sweep_1d(&d, blob, &st, &buf[b].out, lanes_per_point, hp->comp)) return 1;
         if (check_cuda(cudaMemsetAsync(buf[b].flag, 0, 4, hp->comp), "cudaMemsetAsync")) return 1;
-        if (narrow ? fhmc_pack_phase_soa16(&buf[b].out, m, pmax, nsel, buf[b].packed, buf[b].flag, hp->comp)
-                   : fhmc_pack_phase_major(&buf[b].out, m, pmax, nsel, buf[b].packed, buf[b].flag, hp->comp)) return 1;
+        if (narrow && pmax <= 8 && lanes_per_point == 0) {
+            // the sweep kernel writes the narrow phase-major records itself (k_sweep_prod2<compact>; any other kernel + repack
+            // inside fhmc_sweep_1d_compact when the product form does not apply)
+            fhmc_compact_out co;
+            memset(&co, 0, sizeof(co));
+            co.dst[0] = buf[b].packed;
+            co.n_dst = 1;
+            co.n_total = m;
+            co.first = 0;
+            co.fill_dead = 1;
+            co.max_nphase = buf[b].flag;
+            if (fhmc_sweep_1d_compact(&d, blob, &st, &co, buf[b].rec_base, buf[b].rec_bytes, hp->comp)) return 1;
+        } else {
+            if (fhmc_sweep_1d(&d, blob, &st, &buf[b].out, lanes_per_point, hp->comp)) return 1;
+            if (narrow ? fhmc_pack_phase_soa16(&buf[b].out, m, pmax, nsel, buf[b].packed, buf[b].flag, hp->comp)
+                       : fhmc_pack_phase_major(&buf[b].out, m, pmax, nsel, buf[b].packed, buf[b].flag, hp->comp)) return 1;
+        }
         if (check_cuda(cudaEventRecord(hp->done[b], hp->comp), "cudaEventRecord")) return 1;
         if (check_cuda(cudaStreamWaitEvent(hp->down, hp->done[b], 0), "cudaStreamWaitEvent")) return 1;
         if (check_cuda(cudaMemcpyAsync(&flags_host[k], buf[b].flag, 4, cudaMemcpyDeviceToHost, hp->down), "cudaMemcpyAsync flag")) return 1;

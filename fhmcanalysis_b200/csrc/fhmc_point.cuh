@@ -19,12 +19,27 @@
 
 namespace fhmc {
 
+#define FHMC_COMPACT_PMAX 8   // phase slots per state point the compact-record kernels handle
+#define FHMC_COMPACT_DST 8    // destination buffers of one launch (this GPU's and, for a fused gather, its NVLink peers')
+
+// Compact-record output of the sweep kernels (fhmc_sweep_1d_compact): records leave the kernel in the phase-major narrow
+// form of fhmc_pack_phase_soa16, written straight to every destination buffer.
+struct CompactArgs {
+    unsigned char *dst[FHMC_COMPACT_DST];
+    int n_dst;
+    long long n_total;   // records a destination buffer is laid out for
+    long long first;     // record index of state point 0 of this launch
+    int fill_dead;       // write NaN / -1 into the phase slots >= nphase
+    int *max_nphase;     // device int raised (atomicMax) to the largest phase count; nullable
+};
+
 struct SweepArgs {
     fhmc_hist_desc d;
     const double *blob;
     fhmc_states st;
-    fhmc_sweep_out out;
+    fhmc_sweep_out out;   // compact-record launches: scratch records for the general evaluator, one per resident warp
     int blob_global;  // histogram too large for shared memory: rows are read from HBM/L2 (all lanes read the same bin)
+    CompactArgs c;
 };
 
 // Shared-memory prologue of the 1-D kernels: [blob | mbarrier(16 B) | 2^(j/64) table(512 B) | ...].  Returns the

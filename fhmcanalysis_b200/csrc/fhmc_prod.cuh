@@ -18,7 +18,10 @@
 
 namespace fhmc {
 
-template <int NSEL, bool SEL0N>
+// COMPACT: records leave in the phase-major narrow form of fhmc_pack_phase_soa16, written by the walk itself to every
+// destination of SweepArgs::c (this GPU's buffer and, for a gather fused into the sweep, the peers' buffers over NVLink):
+// no fhmc_sweep_out arrays, no repack kernel.  The extrema / bounds lists live in a per-thread local array meanwhile.
+template <int NSEL, bool SEL0N, bool COMPACT = false>
 struct ProdWalk {
     using LY = FastLayout<NSEL, SEL0N, 0, 1, 2>;
     static constexpr int NX = LY::NX, PK = LY::PK, XOFF = LY::XOFF;
@@ -37,7 +40,9 @@ struct ProdWalk {
         long long sp;
         int Mq, k_hi, k_lo, cntM, cntm, P;
         unsigned rescue, fl;
+        int *lst;   // COMPACT: this state point's lists {max_idx[PM], min_idx[PM + 1], bounds[2 PM]} (local memory)
     };
+    static constexpr int PM = FHMC_COMPACT_PMAX, LST = 4 * FHMC_COMPACT_PMAX + 1;
     static constexpr unsigned F_BAD = 1u, F_ROBUST = 2u, F_CHAIN = 4u;
     __device__ __forceinline__ double u0(const PS &p) const
     {
@@ -62,9 +67,40 @@ struct ProdWalk {
     {
     }
 
-    __device__ __forceinline__ int *maxl(const PS &p) const { return a.out.max_idx + p.sp * pmax; }
-    __device__ __forceinline__ int *minl(const PS &p) const { return a.out.min_idx + p.sp * (pmax + 1); }
-    __device__ __forceinline__ int *bl(const PS &p) const { return a.out.bounds + p.sp * pmax * 2; }
+    __device__ __forceinline__ int *maxl(const PS &p) const { return COMPACT ? p.lst : a.out.max_idx + p.sp * pmax; }
+    __device__ __forceinline__ int *minl(const PS &p) const { return COMPACT ? p.lst + PM : a.out.min_idx + p.sp * (pmax + 1); }
+    __device__ __forceinline__ int *bl(const PS &p) const { return COMPACT ? p.lst + 2 * PM + 1 : a.out.bounds + p.sp * pmax * 2; }
+
+    // ---- compact records: layout of fhmc_pack_phase_soa16 for c.n_total records, record c.first + sp ------------------------
+    __device__ __forceinline__ double *cF(int d, int ph, long long sp) const
+    {
+        unsigned char *base = a.c.dst[d] + ((4 * a.c.n_total + 15) & ~15ll);
+        return reinterpret_cast<double *>(base) + ((long long)ph * a.c.n_total + a.c.first + sp) * (1 + NSEL);
+    }
+    __device__ __forceinline__ short2 *cB(int d, int ph, long long sp) const
+    {
+        unsigned char *base = a.c.dst[d] + ((4 * a.c.n_total + 15) & ~15ll) + (long long)pmax * a.c.n_total * (1 + NSEL) * 8;
+        return reinterpret_cast<short2 *>(base) + (long long)ph * a.c.n_total + a.c.first + sp;
+    }
+    // F.E./kT and the averages of phase ph of state point sp
+    __device__ __forceinline__ void put_phase(long long sp, int ph, double fe, double S, const double *A) const
+    {
+        if (COMPACT) {
+            double v[NA];
+#pragma unroll
+            for (int q = 0; q < NSEL; ++q) v[q] = A[q] / S;
+            for (int d = 0; d < a.c.n_dst; ++d) {
+                double *f = cF(d, ph, sp);
+                f[0] = fe;
+#pragma unroll
+                for (int q = 0; q < NSEL; ++q) f[1 + q] = v[q];
+            }
+        } else {
+            a.out.fe[sp * pmax + ph] = fe;
+#pragma unroll
+            for (int q = 0; q < NSEL; ++q) a.out.avg[(sp * pmax + ph) * NSEL + q] = A[q] / S;
+        }
+    }
 
     // u_i = fl(lnPI_i + fl(s N_i)), bit-identical to GH:77
     __device__ __forceinline__ double load_u(const PS &p, int i, double &Ni) const
@@ -92,9 +128,7 @@ struct ProdWalk {
     __device__ __forceinline__ void flush(PS &p) const
     {
         if (p.P < pmax && p.Sacc >= 1e-280) {
-            a.out.fe[p.sp * pmax + p.P] = -(add_shift(p.Mq, log(p.Sacc)) - u0(p));
-#pragma unroll
-            for (int q = 0; q < NSEL; ++q) a.out.avg[(p.sp * pmax + p.P) * NSEL + q] = p.A[q] / p.Sacc;
+            put_phase(p.sp, p.P, -(add_shift(p.Mq, log(p.Sacc)) - u0(p)), p.Sacc, p.A);
         } else if (p.P < pmax && p.P < 32) {
             p.rescue |= 1u << p.P;   // phase too unlikely for the common shift: re-integrated about its own maximum in finish()
         } else {   // (also: a negligible phase beyond the 32 the rescue mask can name -- left to the generic evaluator)
@@ -408,27 +442,53 @@ struct ProdWalk {
 #pragma unroll
                 for (int q = 0; q < NX; ++q) Ap[q + (SEL0N ? 1 : 0)] = fma(e, b.x[q], Ap[q + (SEL0N ? 1 : 0)]);
             }
-            a.out.fe[sp * pmax + ph] = -(add_shift(Mp, log(Sp)) - u0(p));
-#pragma unroll
-            for (int q = 0; q < NSEL; ++q) a.out.avg[(sp * pmax + ph) * NSEL + q] = Ap[q] / Sp;
+            put_phase(sp, ph, -(add_shift(Mp, log(Sp)) - u0(p)), Sp, Ap);
             flags |= FHMC_ST_RESCUED;
         }
         const double xM = __dsub_rn(load_u(p, ml[nM - 1], Nd), c), xl = __dsub_rn(load_u(p, last, Nd), c);
         if (!(__dsub_rn(xM, xl) < a.d.cutoff)) flags |= FHMC_ST_SAFE;
-        a.out.status[sp] = flags | FHMC_ST_FAST;
-        a.out.nphase[sp] = nM;
-        a.out.nmin[sp] = nm;
-        a.out.lnnorm[sp] = c;
+        if (COMPACT) {
+            put_compact_tail(sp, flags | FHMC_ST_FAST, nM, bb);
+        } else {
+            a.out.status[sp] = flags | FHMC_ST_FAST;
+            a.out.nphase[sp] = nM;
+            a.out.nmin[sp] = nm;
+            a.out.lnnorm[sp] = c;
+        }
         return true;
+    }
+
+    // head + bounds (+ NaN / -1 in the phase slots that do not exist) of a compact record; fe / avg of the live phases are
+    // already in place (put_phase)
+    __device__ __forceinline__ void put_compact_tail(long long sp, unsigned status, int nM, const int *bb) const
+    {
+        put_compact_tail_fill(sp, status, nM, bb, a.c.fill_dead != 0);
+    }
+    __device__ __forceinline__ void put_compact_tail_fill(long long sp, unsigned status, int nM, const int *bb, bool fill) const
+    {
+        const int Pe = ((status & FHMC_ST_CODE_MASK) == FHMC_OK) ? min(max(nM, 0), pmax) : 0;
+        const uchar4 h = make_uchar4((unsigned char)(status & 0xFFu), (unsigned char)((status >> 8) & 0xFFu),
+                                     (unsigned char)min(max(nM, 0), 255), 0);
+        for (int d = 0; d < a.c.n_dst; ++d) {
+            reinterpret_cast<uchar4 *>(a.c.dst[d])[a.c.first + sp] = h;
+            for (int ph = 0; ph < Pe; ++ph) *cB(d, ph, sp) = make_short2((short)bb[2 * ph], (short)bb[2 * ph + 1]);
+            if (fill)
+                for (int ph = Pe; ph < pmax; ++ph) {
+                    double *f = cF(d, ph, sp);
+#pragma unroll
+                    for (int q = 0; q <= NSEL; ++q) f[q] = CUDART_NAN;
+                    *cB(d, ph, sp) = make_short2(-1, -1);
+                }
+        }
     }
 };
 
 // Two state points per thread: thread t of tile T owns state points T*512 + t and T*512 + 256 + t.
-template <int NSEL, bool SEL0N>
+template <int NSEL, bool SEL0N, bool COMPACT = false>
 __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_prod2(const __grid_constant__ SweepArgs a)
 {
     using LY = FastLayout<NSEL, SEL0N, 0, 1, 2>;
-    using W = ProdWalk<NSEL, SEL0N>;
+    using W = ProdWalk<NSEL, SEL0N, COMPACT>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const FastCtx cx = fast_prepare<NSEL, SEL0N, 0, 1, 2>(a, smem_raw);
     double *s_tab = cx.s_tab;
@@ -440,11 +500,33 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_prod2(const __grid_consta
     int *q_count = reinterpret_cast<int *>(queue + LY::QN);
     if (threadIdx.x == 0) *q_count = 0;
     __syncthreads();
+    int top = 0;   // COMPACT: largest phase count this thread has written
     auto drain = [&]() {
         const int cnt = *q_count;
         for (int k = threadIdx.x >> 5; k < cnt; k += FHMC_CTA / 32) {   // one queued state point per warp, as in k_sweep_fast
             const long long qs = queue[k];
-            run_generic_point_warp<false>(a, s_tab, threadIdx.x & 31, a.st.mu1[(qs / a.st.mu1_div) % a.st.n_mu1], a.d.beta_ref, a.d.dmu_ref, qs);
+            const double qm = a.st.mu1[(qs / a.st.mu1_div) % a.st.n_mu1];
+            if (!COMPACT) {
+                run_generic_point_warp<false>(a, s_tab, threadIdx.x & 31, qm, a.d.beta_ref, a.d.dmu_ref, qs);
+            } else {
+                // general evaluator into this warp's scratch record, then the compact record from it
+                const long long slot = (long long)blockIdx.x * (FHMC_CTA / 32) + (threadIdx.x >> 5);
+                run_generic_point_warp<false>(a, s_tab, threadIdx.x & 31, qm, a.d.beta_ref, a.d.dmu_ref, slot);
+                __syncwarp();
+                const unsigned st_ = a.out.status[slot];
+                const int nM = a.out.nphase[slot];
+                const int lane = threadIdx.x & 31;
+                const int Pe = ((st_ & FHMC_ST_CODE_MASK) == FHMC_OK) ? min(max(nM, 0), a.d.pmax) : 0;
+                if (lane < Pe)
+                    w.put_phase(qs, lane, a.out.fe[slot * a.d.pmax + lane], 1.0, a.out.avg + (slot * a.d.pmax + lane) * NSEL);
+                if (lane == 0) {
+                    // (a point that went through the walk first may have left fe / avg in slots the final record does not
+                    // have: always blank the dead slots of a re-evaluated point)
+                    w.put_compact_tail_fill(qs, st_, nM, a.out.bounds + slot * a.d.pmax * 2, true);
+                }
+                top = max(top, Pe);
+                __syncwarp();
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) *q_count = 0;
@@ -452,10 +534,13 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_prod2(const __grid_consta
     };
     int tile_no = 0;
     const long long S = a.st.n_states;
+    int lst0[COMPACT ? W::LST : 1], lst1[COMPACT ? W::LST : 1];
     for (long long base = (long long)blockIdx.x * (2 * FHMC_CTA); base < S; base += (long long)gridDim.x * (2 * FHMC_CTA)) {
         const long long sp0 = base + threadIdx.x, sp1 = sp0 + FHMC_CTA;
         if (sp0 < S) {
             typename W::PS p0, p1;
+            p0.lst = lst0;
+            p1.lst = lst1;
             w.init(p0, sp0, a.st.mu1[(sp0 / a.st.mu1_div) % a.st.n_mu1]);
             bool ok0, ok1 = true;
             if (sp1 < S) {
@@ -468,10 +553,12 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_prod2(const __grid_consta
                 }
                 ok0 = w.finish(p0);
                 ok1 = w.finish(p1);
+                if (COMPACT && ok1) top = max(top, p1.P);
             } else {
                 if (!(p0.fl & W::F_BAD)) w.walk1(p0);
                 ok0 = w.finish(p0);
             }
+            if (COMPACT && ok0) top = max(top, p0.P);
             if (!ok0) queue[atomicAdd(q_count, 1)] = sp0;   // anything unusual: defer to the generic evaluator
             if (!ok1) queue[atomicAdd(q_count, 1)] = sp1;
         }
@@ -482,23 +569,30 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_prod2(const __grid_consta
     }
     __syncthreads();
     drain();
+    if (COMPACT && a.c.max_nphase) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) top = max(top, __shfl_xor_sync(0xffffffffu, top, o));
+        if ((threadIdx.x & 31) == 0 && top > 0) atomicMax(a.c.max_nphase, top);
+    }
 }
 
-template <int NSEL, bool SEL0N>
-static int launch_prod2(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream)
+template <int NSEL, bool SEL0N, bool COMPACT = false>
+static int launch_prod2(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream, int *grid_out = nullptr, bool dry = false)
 {
     const size_t smem = fast_smem_bytes<NSEL, SEL0N, 0, 1, 2>(args.d.n_pad);
     if (smem > (size_t)smem_optin) return -1;
-    auto kern = k_sweep_prod2<NSEL, SEL0N>;
+    auto kern = k_sweep_prod2<NSEL, SEL0N, COMPACT>;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return 1;
     int occ = 0;
     if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FHMC_CTA, smem), "occupancy query")) return 1;
     if (occ < 1) return -1;
     const long long ntiles = (args.st.n_states + 2 * FHMC_CTA - 1) / (2 * FHMC_CTA);
     long long grid = (long long)sm_count * occ;
+    if (grid_out) *grid_out = (int)grid;   // (upper bound: what a scratch record per resident warp has to cover)
+    if (dry) return 0;
     if (grid > ntiles) grid = ntiles;
     kern<<<(unsigned)grid, FHMC_CTA, smem, stream>>>(args);
-    note_kernel("k_sweep_prod2");
+    note_kernel(COMPACT ? "k_sweep_prod2<compact>" : "k_sweep_prod2");
     return check_cuda(cudaGetLastError(), "k_sweep_prod2 launch");
 }
 

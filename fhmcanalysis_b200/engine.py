@@ -153,6 +153,23 @@ def load_results(fname):
     return out, dict(f.attrs)
 
 
+def soa16_views(buf, S, pmax, nsel):
+    """[S, ...] views of a uint8 tensor (host or device) laid out as fhmc_pack_phase_soa16 describes for S state points:
+    status (int16), nphase (uint8), fe [S, pmax], avg [S, pmax, nsel], bounds [S, pmax, 2] (int16); phase-major underneath."""
+    t = torch()
+    nf = 1 + nsel
+    out = {}
+    out["status"] = t.as_strided(buf[:4 * S].view(t.int16), (S,), (2,))
+    out["nphase"] = t.as_strided(buf[:4 * S], (S,), (4,), buf.storage_offset() + 2)
+    f0 = (4 * S + 15) & ~15
+    F = buf[f0:f0 + pmax * S * nf * 8].view(t.float64)
+    B = buf[f0 + pmax * S * nf * 8:f0 + pmax * S * nf * 8 + pmax * S * 4].view(t.int16)
+    out["fe"] = t.as_strided(F, (S, pmax), (nf, S * nf), F.storage_offset())
+    out["avg"] = t.as_strided(F, (S, pmax, nsel), (nf, S * nf, 1), F.storage_offset() + 1) if nsel else None
+    out["bounds"] = t.as_strided(B, (S, pmax, 2), (2, 2 * S, 1), B.storage_offset())
+    return out
+
+
 class DeviceHistogram(object):
     """One histogram resident in HBM as the row blob the kernels stage in shared memory.
 
@@ -333,6 +350,52 @@ class DeviceHistogram(object):
         out._states = st
         return out
 
+    def sweep_compact(self, mu1, pmax=4, dst=None, n_total=None, first=0, fill_dead=True, max_nphase=None, states=None):
+        """K1+K3+K2 with COMPACT records (fhmc_sweep_1d_compact): the state points leave the sweep kernel as phase-major narrow
+        records {status i16, nphase u8, fe/avg f64, bounds i16} at indices first .. first + S - 1 of every destination.
+
+        dst: None (a fresh device buffer for n_total records), a uint8 device tensor, or a list of raw device pointers
+        (ints) -- e.g. the buffers of this GPU's NVLink peers, for a sweep fused with its gather (parallel.py).
+        Returns dict(buf, status, nphase, fe, avg, bounds) of [n_total, ...] views of the first destination when it is a
+        tensor; asynchronous."""
+        t = torch()
+        L = _lib.load()
+        st = states if states is not None else self.make_states(mu1)
+        S = int(st.n_states)
+        if S >= self.FAST_PATH_MIN_STATES:
+            self.ensure_hull()
+        n_total = S + int(first) if n_total is None else int(n_total)
+        d = self._desc(pmax)
+        nbytes = int(L.fhmc_pack_soa16_bytes(n_total, pmax, self.n_sel))
+        buf = None
+        if dst is None:
+            buf = t.empty(nbytes, dtype=t.uint8, device=self.device)
+            ptrs = [buf.data_ptr()]
+        elif isinstance(dst, t.Tensor):
+            if dst.numel() < nbytes or dst.dtype != t.uint8:
+                raise ValueError("destination must be a uint8 tensor of >= %d bytes" % nbytes)
+            buf = dst
+            ptrs = [dst.data_ptr()]
+        else:
+            ptrs = [int(x) for x in dst]
+        co = _lib.CompactOut()
+        for k, ptr in enumerate(ptrs):
+            co.dst[k] = ptr
+        co.n_dst, co.n_total, co.first, co.fill_dead = len(ptrs), n_total, int(first), 1 if fill_dead else 0
+        co.max_nphase = max_nphase.data_ptr() if max_nphase is not None else None
+        ws_bytes = int(L.fhmc_sweep_compact_workspace(ctypes.byref(d), S))
+        if getattr(self, "_cws", None) is None or self._cws.numel() < ws_bytes + 256:
+            self._cws = t.empty(ws_bytes + 256, dtype=t.uint8, device=self.device)
+        ws_ptr = (self._cws.data_ptr() + 255) & ~255
+        with t.cuda.device(self.device):
+            rc = L.fhmc_sweep_1d_compact(ctypes.byref(d), _ptr(self.blob), ctypes.byref(st), ctypes.byref(co),
+                                         ctypes.c_void_p(ws_ptr), ws_bytes, _stream_ptr(self.device))
+        _lib.check(rc, "fhmc_sweep_1d_compact")
+        out = {"buf": buf, "_states": st, "n_total": n_total}
+        if buf is not None:
+            out.update(soa16_views(buf, n_total, pmax, self.n_sel))
+        return out
+
     def sweep_host(self, mu1, pmax=4, lanes=0, chunk=1 << 18, out=None, fields=None):
         """End-to-end mu sweep with HOST buffers (what `bench.py`'s e2e times): the state points are cut into chunks
         that alternate between two CUDA streams so that the pinned-host -> device copy of chunk k+1, the kernel of
@@ -461,14 +524,7 @@ class DeviceHistogram(object):
             nf = 1 + nsel
             buf = t.empty(int(L.fhmc_pack_soa16_bytes(S, pmax, nsel)), dtype=t.uint8).pin_memory()
             out = {"_key": (S, pmax, nsel, chunk, True), "_buf": buf, "_prev_top": pmax}
-            out["status"] = t.as_strided(buf[:4 * S].view(t.int16), (S,), (2,))
-            out["nphase"] = t.as_strided(buf[:4 * S], (S,), (4,), buf.storage_offset() + 2)
-            f0 = (4 * S + 15) & ~15
-            F = buf[f0:f0 + pmax * S * nf * 8].view(t.float64)
-            B = buf[f0 + pmax * S * nf * 8:f0 + pmax * S * nf * 8 + pmax * S * 4].view(t.int16)
-            out["fe"] = t.as_strided(F, (S, pmax), (nf, S * nf), F.storage_offset())
-            out["avg"] = t.as_strided(F, (S, pmax, nsel), (nf, S * nf, 1), F.storage_offset() + 1) if nsel else None
-            out["bounds"] = t.as_strided(B, (S, pmax, 2), (2, 2 * S, 1), B.storage_offset())
+            out.update(soa16_views(buf, S, pmax, nsel))
             return out
         rec = 16 + 8 * nsel
         buf = t.empty(8 * S + pmax * rec * S, dtype=t.uint8).pin_memory()

@@ -1,8 +1,21 @@
 """State-point sharding across the GPUs of one box (one process per GPU, torch.distributed).
 
-The path has no exchange step: state points are independent, so each rank takes a contiguous slice of the
-state-point range, runs the same kernels on it, and the only collective is the final gather of the packed result
-records (NCCL over NVLink on GPUs; gloo in the CPU tests of this host-side logic)."""
+The path has no exchange step: state points are independent, so each rank takes a contiguous slice of the state-point
+range, runs the same kernels on it, and the only communication is the final gather of the result records.  Two gathers:
+
+* ``sweep_sharded_compact`` (pure mu sweeps, the headline metric): the gather is FUSED INTO THE SWEEP KERNEL.  Every rank
+  allocates the gathered buffer in symmetric memory (torch.distributed._symmetric_memory: the buffers of all ranks are
+  mapped into each other's address space over NVLink / NVSwitch) and ``k_sweep_prod2<compact>`` writes each finished
+  record -- 60 bytes for a two-phase state point with two averaged quantities -- straight into block ``rank`` of EVERY
+  rank's buffer with plain stores while it is still walking the next state points.  No collective follows, only a barrier.
+  Where symmetric memory is not available the records are written locally and gathered with ONE NCCL
+  ``all_gather_into_tensor`` of the compact blocks (gloo in the CPU tests of this host-side logic).
+* ``sweep_sharded`` / ``find_phase_eq_sharded`` / ``reweight_2d_sharded`` / ``sweep_grid_sharded``: full records (or the
+  solver's / the 2-D kernel's outputs) gathered with padded ``all_gather_into_tensor`` calls, one per dtype.
+
+Layout of a gathered compact result: ``world`` blocks of ``fhmc_pack_soa16_bytes(smax, pmax, n_sel)`` bytes, block r = the
+narrow phase-major records of rank r's shard (``smax`` = largest shard).  ``ShardedRecords.host()`` concatenates them.
+"""
 import numpy as np
 
 
@@ -18,6 +31,13 @@ def shard_sizes(n_states, world):
     return [shard_bounds(n_states, world, r)[1] - shard_bounds(n_states, world, r)[0] for r in range(world)]
 
 
+def _world(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
 FLOAT_FIELDS = ("lnnorm", "fe", "avg")
 INT_FIELDS = ("status", "nphase", "nmin", "bounds", "max_idx", "min_idx")
 
@@ -26,8 +46,11 @@ def pack_records(rec):
     """dict of per-state-point tensors [S, ...] -> (float64 [S, F], int32 [S, I]) rows, one per state point."""
     import torch
     S = rec["lnnorm"].shape[0]
-    f = torch.cat([rec[k].reshape(S, -1) for k in FLOAT_FIELDS if rec.get(k) is not None], dim=1).contiguous()
-    i = torch.cat([rec[k].reshape(S, -1).to(torch.int32) for k in INT_FIELDS], dim=1).contiguous()
+
+    def rows(x):   # (S may be 0: an explicit width instead of -1)
+        return x.reshape(S, int(np.prod(x.shape[1:])))
+    f = torch.cat([rows(rec[k]) for k in FLOAT_FIELDS if rec.get(k) is not None], dim=1).contiguous()
+    i = torch.cat([rows(rec[k]).to(torch.int32) for k in INT_FIELDS], dim=1).contiguous()
     return f, i
 
 
@@ -48,47 +71,246 @@ def unpack_records(f, i, pmax, n_sel):
     return out
 
 
-def all_gather_records(f, i, n_states, group=None):
-    """Gather the per-rank packed rows into the full [n_states, ...] arrays on every rank (one all_gather per
-    dtype; shards are padded to the largest shard so all_gather_into_tensor can be used)."""
+def all_gather_rows(t, n_states, group=None):
+    """Gather per-rank row blocks [S_r, ...] into the full [n_states, ...] tensor on every rank (shards are padded to the
+    largest shard so that one all_gather_into_tensor does it; an EMPTY shard still joins the collective)."""
     import torch
     import torch.distributed as dist
-    world = dist.get_world_size(group)
+    world, _ = _world(group)
+    if world == 1:
+        return t
     sizes = shard_sizes(n_states, world)
-    smax = max(sizes)
-    outs = []
-    for t in (f, i):
-        pad = torch.zeros((smax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        pad[:t.shape[0]] = t
-        full = torch.empty((world * smax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(full, pad, group=group)
-        outs.append(torch.cat([full[r * smax:r * smax + sizes[r]] for r in range(world)], dim=0))
-    return outs[0], outs[1]
+    smax = max(max(sizes), 1)
+    pad = torch.zeros((smax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    full = torch.empty((world * smax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(full, pad, group=group)
+    return torch.cat([full[r * smax:r * smax + sizes[r]] for r in range(world)], dim=0)
+
+
+def all_gather_records(f, i, n_states, group=None):
+    return all_gather_rows(f, n_states, group), all_gather_rows(i, n_states, group)
+
+
+def _cut(x, lo, hi):
+    if x is None:
+        return None
+    x = np.asarray(x, dtype=np.float64)
+    return x if x.size == 1 else x[lo:hi]
 
 
 def sweep_sharded(make_device_hist, mu1, beta=None, dmu=None, pmax=4, lanes=0, gather=True, group=None):
-    """Run a flat state-point list sharded over the ranks of ``group`` (call from every rank).
+    """Run a flat state-point list sharded over the ranks of ``group`` (call from every rank); FULL records.
 
     make_device_hist: callable returning this rank's engine.DeviceHistogram (the blob is replicated by plain H2D).
     Returns the gathered dict of NumPy arrays on every rank (or this rank's shard when gather=False)."""
-    import torch.distributed as dist
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    mu1 = np.asarray(mu1, dtype=np.float64)
+    import torch
+    world, rank = _world(group)
+    mu1 = np.atleast_1d(np.asarray(mu1, dtype=np.float64))
     S = len(mu1)
     lo, hi = shard_bounds(S, world, rank)
-
-    def cut(x):
-        if x is None:
-            return None
-        x = np.asarray(x, dtype=np.float64)
-        return x if x.size == 1 else x[lo:hi]
-
     dh = make_device_hist()
-    res = dh.sweep(mu1[lo:hi], cut(beta), cut(dmu), pmax=pmax, lanes=lanes)
-    rec = {k: getattr(res, k) for k in FLOAT_FIELDS + INT_FIELDS}
-    f, i = pack_records(rec)
+    n_f, n_i = 1 + pmax + pmax * dh.n_sel, 3 + 2 * pmax + pmax + pmax + 1
+    if hi > lo:
+        res = dh.sweep(mu1[lo:hi], _cut(beta, lo, hi), _cut(dmu, lo, hi), pmax=pmax, lanes=lanes)
+        f, i = pack_records({k: getattr(res, k) for k in FLOAT_FIELDS + INT_FIELDS})
+    else:   # more ranks than state points: nothing to compute here, but the collective below needs every rank
+        f = torch.zeros((0, n_f), dtype=torch.float64, device=dh.device)
+        i = torch.zeros((0, n_i), dtype=torch.int32, device=dh.device)
     if gather and world > 1:
         f, i = all_gather_records(f, i, S, group)
     out = unpack_records(f, i, pmax, dh.n_sel)
     return {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+
+
+def sweep_grid_sharded(make_device_hist, mu1, betas, dmus, pmax=4, group=None):
+    """(beta x dmu) Taylor grid (temp_dmu_extrap_multi order: dmu fastest) at fixed mu1, the BETA rows sharded over the ranks
+    (BASELINE config 3).  Returns the gathered records as NumPy arrays of nb*nd state points on every rank."""
+    import torch
+    world, rank = _world(group)
+    betas = np.atleast_1d(np.asarray(betas, dtype=np.float64))
+    dmus = np.atleast_1d(np.asarray(dmus, dtype=np.float64))
+    nb, nd = len(betas), len(dmus)
+    lo, hi = shard_bounds(nb, world, rank)
+    dh = make_device_hist()
+    n_f, n_i = 1 + pmax + pmax * dh.n_sel, 3 + 2 * pmax + pmax + pmax + 1
+    if hi > lo:
+        res = dh.sweep(np.atleast_1d(mu1), betas[lo:hi], dmus, grid=True, pmax=pmax)
+        f, i = pack_records({k: getattr(res, k) for k in FLOAT_FIELDS + INT_FIELDS})
+    else:
+        f = torch.zeros((0, n_f), dtype=torch.float64, device=dh.device)
+        i = torch.zeros((0, n_i), dtype=torch.int32, device=dh.device)
+    if world > 1:
+        # shards are whole beta rows: gather row blocks of nd state points each
+        f = all_gather_rows(f.reshape(-1, nd, n_f), nb, group).reshape(-1, n_f)
+        i = all_gather_rows(i.reshape(-1, nd, n_i), nb, group).reshape(-1, n_i)
+    out = unpack_records(f, i, pmax, dh.n_sel)
+    return {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+
+
+def find_phase_eq_sharded(make_device_hist, mu_guess, betas, dmu=None, lnz_tol=1e-10, pmax=4, group=None, **kw):
+    """Batched coexistence solves (K4, BASELINE config 4) with the temperatures sharded over the ranks; every rank returns
+    the gathered dict: mu_coex, dfe, iters, status/code/converged, nphase, fe, avg, bounds."""
+    import torch
+    from . import _lib
+    world, rank = _world(group)
+    betas = np.atleast_1d(np.asarray(betas, dtype=np.float64))
+    T = len(betas)
+    lo, hi = shard_bounds(T, world, rank)
+    dh = make_device_hist()
+    g = np.broadcast_to(np.atleast_1d(np.asarray(mu_guess, dtype=np.float64)), betas.shape)
+    n_f, n_i = 2 + 1 + pmax + pmax * dh.n_sel, 1 + 3 + 2 * pmax + pmax + pmax + 1
+    if hi > lo:
+        res = dh.find_phase_eq(g[lo:hi].copy(), beta=betas[lo:hi], dmu=_cut(dmu, lo, hi), lnz_tol=lnz_tol, pmax=pmax, **kw)
+        f, i = pack_records({k: getattr(res, k) for k in FLOAT_FIELDS + INT_FIELDS})
+        f = torch.cat([res.extra["mu_coex"][:, None], res.extra["dfe"][:, None], f], dim=1).contiguous()
+        i = torch.cat([res.extra["iters"][:, None].to(torch.int32), i], dim=1).contiguous()
+    else:
+        f = torch.zeros((0, n_f), dtype=torch.float64, device=dh.device)
+        i = torch.zeros((0, n_i), dtype=torch.int32, device=dh.device)
+    f, i = all_gather_records(f, i, T, group)
+    out = unpack_records(f[:, 2:], i[:, 1:], max(pmax, 2), dh.n_sel)
+    out = {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+    out["mu_coex"], out["dfe"], out["iters"] = f[:, 0].cpu().numpy(), f[:, 1].cpu().numpy(), i[:, 0].cpu().numpy()
+    out["status"] = out["status"].view(np.uint32)
+    out["code"] = (out["status"] & _lib.ST_CODE_MASK).astype(np.int32)
+    out["converged"] = (out["code"] == 0) & ((out["status"] & _lib.ST_JUMP) == 0)
+    return out
+
+
+def reweight_2d_sharded(lnpi, bounds, op1, op2, a1, a2, props=None, device=None, group=None, product=None):
+    """K5 (BASELINE config 5): the (a1, a2) state points of a 2-D joint-histogram reweight sharded over the ranks, the
+    histogram replicated; returns the gathered [S, 3 + n_prop] array (lnZ, <op1>, <op2>, <prop>...) on every rank."""
+    import torch
+    from . import engine
+    world, rank = _world(group)
+    a1 = np.atleast_1d(np.asarray(a1, dtype=np.float64))
+    a2 = np.atleast_1d(np.asarray(a2, dtype=np.float64))
+    S = len(a1)
+    lo, hi = shard_bounds(S, world, rank)
+    n_prop = 0 if props is None else len(props)
+    dev = engine.require_cuda(device)
+    if hi > lo:
+        out = engine.reweight_2d(lnpi, bounds, op1, op2, a1[lo:hi], a2[lo:hi], props, device=dev, return_device=True, product=product)
+    else:
+        out = torch.zeros((0, 3 + n_prop), dtype=torch.float64, device=dev)
+    return all_gather_rows(out, S, group).cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# compact records, gather fused into the sweep kernel
+# ----------------------------------------------------------------------------------------------------------------------
+class ShardedRecords(object):
+    """Gathered compact records of a sharded mu sweep: ``buf`` = world blocks of narrow phase-major records (see module
+    docstring), on the device of this rank."""
+
+    def __init__(self, buf, n_states, world, pmax, n_sel, block_bytes, fused):
+        self.buf, self.n_states, self.world, self.pmax, self.n_sel = buf, int(n_states), int(world), int(pmax), int(n_sel)
+        self.block_bytes, self.fused = int(block_bytes), bool(fused)
+        self.sizes = shard_sizes(self.n_states, self.world)
+        self.smax = max(max(self.sizes), 1)
+
+    def views(self, rank):
+        """[smax, ...] views (status, nphase, fe, avg, bounds) of rank ``rank``'s block; rows >= sizes[rank] are padding."""
+        from .engine import soa16_views
+        return soa16_views(self.buf[rank * self.block_bytes:(rank + 1) * self.block_bytes], self.smax, self.pmax, self.n_sel)
+
+    def host(self):
+        """dict of NumPy arrays over all n_states state points: status (uint16), code, safe, nphase, fe, avg, bounds.
+        Phase slots p >= nphase[s] are not transported (the kernels only store what exists); they read NaN / -1 here."""
+        import torch
+        hb = self.buf.cpu() if self.buf.is_cuda else self.buf
+        parts = []
+        from .engine import soa16_views
+        for r in range(self.world):
+            v = soa16_views(hb[r * self.block_bytes:(r + 1) * self.block_bytes], self.smax, self.pmax, self.n_sel)
+            parts.append({k: (x[:self.sizes[r]] if x is not None else None) for k, x in v.items()})
+        out = {}
+        for k in parts[0]:
+            out[k] = None if parts[0][k] is None else torch.cat([p[k] for p in parts], dim=0).numpy()
+        out["status"] = out["status"].view(np.uint16)
+        out["code"] = (out["status"] & 0xFF).astype(np.int32)
+        out["safe"] = (out["status"] & 0x100) != 0
+        live = np.arange(self.pmax)[None, :] < np.where(out["code"] == 0, out["nphase"].astype(np.int64), 0)[:, None]
+        out["fe"] = np.where(live, out["fe"], np.nan)
+        if out["avg"] is not None:
+            out["avg"] = np.where(live[:, :, None], out["avg"], np.nan)
+        out["bounds"] = np.where(live[:, :, None], out["bounds"], -1).astype(np.int16)
+        return out
+
+
+class CompactGather(object):
+    """Reusable state of sweep_sharded_compact for one (n_states, pmax, n_sel): the gathered buffer (symmetric memory when
+    the NVLink-fused path is available) and, for that path, the peers' block pointers."""
+
+    def __init__(self, dh, n_states, pmax=4, group=None, fused=None):
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        self.world, self.rank = _world(group)
+        self.group, self.pmax, self.n_sel, self.n_states = group, int(pmax), dh.n_sel, int(n_states)
+        self.sizes = shard_sizes(self.n_states, self.world)
+        self.smax = max(max(self.sizes), 1)
+        L = _lib.load()
+        self.block_bytes = (int(L.fhmc_pack_soa16_bytes(self.smax, self.pmax, self.n_sel)) + 255) & ~255
+        self.fused, self.handle, self.why = False, None, ""
+        nbytes = self.world * self.block_bytes
+        dev = dh.device
+        want = (self.world > 1 and dev.type == "cuda") if fused is None else bool(fused)
+        if want and self.world > 1 and self.world <= 8:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = group if group is not None else dist.group.WORLD
+                buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+                self.handle = symm_mem.rendezvous(buf, grp)
+                self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+                self.buf = buf
+                self.fused = True
+            except Exception as e:   # no symmetric memory on this system / build: NCCL gather of the compact blocks instead
+                self.why = repr(e)
+                if fused:
+                    raise
+        if not self.fused:
+            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self.local = torch.empty(self.block_bytes, dtype=torch.uint8, device=dev)
+
+    def barrier(self):
+        """Device-side barrier over the ranks on the current stream (fused path) or a collective barrier."""
+        import torch.distributed as dist
+        if self.fused:
+            self.handle.barrier(channel=0)
+        elif self.world > 1:
+            dist.barrier(group=self.group)
+
+
+def sweep_sharded_compact(dh, mu1, pmax=4, group=None, state=None, fused=None, pre_barrier=True):
+    """Pure mu sweep sharded over the ranks with the gather FUSED into the sweep kernel (see module docstring).  Call from
+    every rank with the same ``mu1``; asynchronous on the current stream.  Returns (ShardedRecords, state) -- pass
+    ``state`` back in to reuse the buffers (and the symmetric-memory rendezvous) for the next sweep of the same size.
+
+    pre_barrier: ranks may still be reading the buffer of the previous sweep; a barrier first makes overwriting safe."""
+    import torch
+    import torch.distributed as dist
+    mu1 = np.atleast_1d(np.asarray(mu1, dtype=np.float64)) if not isinstance(mu1, torch.Tensor) else mu1
+    S = int(mu1.shape[0])
+    if state is None or state.n_states != S or state.pmax != pmax or state.n_sel != dh.n_sel:
+        state = CompactGather(dh, S, pmax, group, fused)
+    world, rank = state.world, state.rank
+    lo, hi = shard_bounds(S, world, rank)
+    shard = mu1[lo:hi]
+    if state.fused:
+        if pre_barrier:
+            state.barrier()
+        if hi > lo:
+            off = rank * state.block_bytes
+            # (dead phase slots are NOT written: they would double the NVLink traffic; host() masks them)
+            dh.sweep_compact(shard, pmax=pmax, dst=[p + off for p in state.peer_ptrs], n_total=state.smax, first=0, fill_dead=False)
+        state.barrier()   # every rank's stores have landed in every buffer once all kernels are done
+    else:
+        if hi > lo:
+            dh.sweep_compact(shard, pmax=pmax, dst=state.local, n_total=state.smax, first=0, fill_dead=False)
+        if world > 1:
+            dist.all_gather_into_tensor(state.buf, state.local, group=group)
+        else:
+            state.buf.copy_(state.local)
+    return ShardedRecords(state.buf, S, world, pmax, dh.n_sel, state.block_bytes, state.fused), state

@@ -199,6 +199,29 @@ int fhmc_pack_phase_soa16(const fhmc_sweep_out *out, long long n_states, int pma
                           int *max_nphase, void *stream);
 
 /*
+ * K1+K3+K2 with COMPACT records (new; the result set {status, nphase, fe, avg, bounds} of the reference's reweight()/thermo()/
+ * is_safe() loop, GH:268-289, 451-596, for many state points): every state point of `states` is written as a phase-major
+ * narrow record (layout of fhmc_pack_phase_soa16 for n_total records) at index first + s, by the sweep kernel itself, into
+ * EVERY destination buffer.  With n_dst == 1 this is the sweep + repack of the host pipeline in one kernel; with the peers'
+ * buffers in dst[] (pointers a process obtained by mapping its NVLink peers' memory) it is the sweep fused with the final
+ * gather of a sharded sweep: no collective afterwards, only a barrier.
+ *   fill_dead: also write NaN / -1 into the phase slots >= nphase (otherwise the caller has filled the buffers with 0xFF
+ *   bytes, which read as NaN / -1);  max_nphase: nullable device int, raised to the largest phase count (caller zeroes it).
+ * workspace: device, 256-byte aligned, fhmc_sweep_compact_workspace() bytes.  desc->pmax <= 8 and desc->n <= 32767.
+ */
+typedef struct fhmc_compact_out {
+    void *dst[8];
+    int n_dst;
+    long long n_total;
+    long long first;
+    int fill_dead;
+    int *max_nphase;
+} fhmc_compact_out;
+size_t fhmc_sweep_compact_workspace(const fhmc_hist_desc *desc, long long n_states);
+int fhmc_sweep_1d_compact(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states, const fhmc_compact_out *out,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
+/*
  * Host-buffer mu sweep (new; replaces the user's Python loop of reweight()/thermo()/is_safe() calls on host arrays,
  * GH:268-289, 451-596, README.md:60-85).  mu_host[n_states] and out_host are PINNED host memory; everything in between is
  * pipelined on three private streams (upload, compute, download) in chunks of `chunk` state points: H2D(mu) -> fhmc_sweep_1d -> fhmc_pack_phase_major

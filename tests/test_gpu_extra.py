@@ -390,3 +390,59 @@ def test_lean_solver_kernel_matches_group_kernel(monkeypatch):
     assert _lib.last_kernel() == "k_solve_lean"
     assert np.all(a["code"] == 0) and np.all(b["code"] == 0)
     assert np.allclose(a["mu_coex"], b["mu_coex"], rtol=0, atol=1e-12) and np.ptp(b["mu_coex"]) < 1e-9
+
+
+def _soa_equal_to_records(c, h, lo, S, pmax, status_mask=0xFFFF):
+    """compact views c (records lo .. lo+S-1) against the host() dict of a plain sweep of the same state points"""
+    st = c["status"].cpu().numpy()[lo:lo + S].astype(np.int64) & status_mask
+    assert np.array_equal(st, h["status"].astype(np.int64) & status_mask)
+    P = h["nphase"]
+    assert np.array_equal(c["nphase"].cpu().numpy()[lo:lo + S], P)
+    fe, av, bd = (c[k].cpu().numpy()[lo:lo + S] for k in ("fe", "avg", "bounds"))
+    for p in range(pmax):
+        live = (h["code"] == 0) & (P > p)
+        assert np.array_equal(fe[live, p], h["fe"][live, p]) and np.array_equal(av[live, p], h["avg"][live, p])
+        assert np.array_equal(bd[live, p], h["bounds"][live, p])
+        assert np.all(np.isnan(fe[~live, p])) and np.all(np.isnan(av[~live, p])) and np.all(bd[~live, p] == -1)
+
+
+def test_compact_records_written_by_the_sweep_kernel():
+    """fhmc_sweep_1d_compact: the headline kernel writes the phase-major narrow records itself (k_sweep_prod2<compact>) -- same
+    bits as a plain sweep followed by the repack; several destinations (as for a gather fused over NVLink peers), records at
+    an offset inside a larger layout, dead slots written by the kernel or left to a 0xFF-filled buffer; the general path
+    (small sweeps, three averaged quantities) through the same entry point."""
+    import torch
+    from fhmcanalysis_b200 import _lib, engine, synth
+    n = 1001
+    lnpi = synth.two_peak_lnpi(n)
+    N = np.arange(n, dtype=np.float64)
+    dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=10, sel=["N", N * N])
+    S = 200001
+    mu = np.concatenate([np.linspace(-0.03, 0.03, S - 4001), np.linspace(-6.0, 6.0, 4001)])   # strong tilts: queue / general evaluator
+    h = dh.sweep_auto(mu, pmax=4).host()
+    assert h["fe"].shape[1] == 4
+    top = torch.zeros(1, dtype=torch.int32, device="cuda")
+    c = dh.sweep_compact(mu, pmax=4, max_nphase=top)
+    assert _lib.last_kernel() == "k_sweep_prod2<compact>"
+    _soa_equal_to_records(c, h, 0, S, 4)
+    assert int(top.item()) == int(h["nphase"][h["code"] == 0].max())
+    # two destinations, records at an offset, dead slots left to the 0xFF fill
+    n_total, first = S + 5000, 1234
+    nbytes = int(_lib.load().fhmc_pack_soa16_bytes(n_total, 4, 2))
+    d0 = torch.full((nbytes,), 0xFF, dtype=torch.uint8, device="cuda")
+    d1 = torch.full((nbytes,), 0xFF, dtype=torch.uint8, device="cuda")
+    dh.sweep_compact(mu, pmax=4, dst=[d0.data_ptr(), d1.data_ptr()], n_total=n_total, first=first, fill_dead=False)
+    torch.cuda.synchronize()
+    assert torch.equal(d0, d1)
+    v = engine.soa16_views(d0, n_total, 4, 2)
+    _soa_equal_to_records(v, h, first, S, 4)
+    fe_all = v["fe"].cpu().numpy()
+    assert np.all(np.isnan(fe_all[:first])) and np.all(np.isnan(fe_all[first + S:]))      # nothing outside the launch's range
+    # general path: a small sweep, and three averaged quantities (no two-point product-form instantiation)
+    c = dh.sweep_compact(mu[:3000], pmax=4)
+    assert _lib.last_kernel() != "k_sweep_prod2<compact>"
+    _soa_equal_to_records(c, dh.sweep(mu[:3000], pmax=4).host(), 0, 3000, 4)      # the same kernel choice inside: same bits
+    dh3 = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=10, sel=["N", N * N, -2.0 * N])
+    h3 = dh3.sweep_auto(mu, pmax=4).host()
+    c3 = dh3.sweep_compact(mu, pmax=4)
+    _soa_equal_to_records(c3, h3, 0, S, 4)

@@ -34,6 +34,35 @@ def _fake_records(lo, hi, pmax, nsel):
             "min_idx": torch.arange(S * (pmax + 1), dtype=torch.int32).reshape(S, pmax + 1) + 3 * lo}
 
 
+def _soa16_bytes(S, pmax, nsel):
+    return ((4 * S + 15) & ~15) + pmax * S * (8 * (1 + nsel) + 4)      # fhmc_pack_soa16_bytes (include/fhmc_b200.h)
+
+
+def _fake_compact(lo, hi, pmax, nsel):
+    s = np.arange(lo, hi)
+    nph = (s % pmax + 1).astype(np.uint8)
+    st = np.where(s % 11 == 0, 4, 0).astype(np.uint16) | np.where(s % 2 == 0, 0x100, 0).astype(np.uint16)
+    fe = s[:, None] * 0.25 + np.arange(pmax)[None, :]
+    avg = s[:, None, None] * 1.5 + np.arange(pmax * nsel).reshape(1, pmax, nsel)
+    bounds = (s[:, None, None] % 100 + np.arange(pmax * 2).reshape(1, pmax, 2)).astype(np.int16)
+    return {"status": st, "nphase": nph, "fe": fe, "avg": avg, "bounds": bounds}
+
+
+def _pack_soa16(block, rec, smax, pmax, nsel):
+    """NumPy writer of the fhmc_pack_phase_soa16 layout for smax records (only live phase slots are stored)."""
+    from fhmcanalysis_b200.engine import soa16_views
+    v = soa16_views(block, smax, pmax, nsel)
+    m = len(rec["status"])
+    v["status"][:m] = torch.from_numpy(rec["status"].view(np.int16))
+    v["nphase"][:m] = torch.from_numpy(rec["nphase"])
+    live = np.arange(pmax)[None, :] < np.where((rec["status"] & 0xFF) == 0, rec["nphase"], 0)[:, None]
+    for p in range(pmax):
+        rows = torch.from_numpy(np.where(live[:, p])[0])
+        v["fe"][rows, p] = torch.from_numpy(rec["fe"][live[:, p], p])
+        v["avg"][rows, p] = torch.from_numpy(rec["avg"][live[:, p], p])
+        v["bounds"][rows, p] = torch.from_numpy(rec["bounds"][live[:, p], p])
+
+
 def _worker(rank, world, port, S, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -48,6 +77,27 @@ def _worker(rank, world, port, S, q):
     exp = {k: torch.cat([_fake_records(*parallel.shard_bounds(S, world, r), pmax, nsel)[k] for r in range(world)]) for k in ref}
     ok = all(torch.equal(out[k].reshape(exp[k].shape).to(exp[k].dtype), exp[k]) for k in exp)
     ok = ok and torch.equal(out["lnnorm"], ref["lnnorm"]) and torch.equal(out["fe"], ref["fe"])
+    # fewer state points than ranks: the rank with the EMPTY shard still joins the collective (no deadlock, no error)
+    lo1, hi1 = parallel.shard_bounds(1, world, rank)
+    f1, i1 = parallel.pack_records(_fake_records(lo1, hi1, pmax, nsel))
+    F1, I1 = parallel.all_gather_records(f1, i1, 1)
+    ok = ok and F1.shape[0] == 1 and I1.shape[0] == 1 and torch.equal(F1[0], parallel.pack_records(_fake_records(0, 1, pmax, nsel))[0][0])
+    # compact gather (NCCL-style path on CPU tensors): every rank packs its shard as a narrow phase-major block, one
+    # all_gather_into_tensor of the blocks, ShardedRecords.host() reassembles and masks the phase slots that do not exist
+    sizes = parallel.shard_sizes(S, world)
+    smax = max(sizes)
+    bb = (_soa16_bytes(smax, pmax, nsel) + 255) & ~255
+    block = torch.full((bb,), 0x5A, dtype=torch.uint8)                    # junk where nothing is stored
+    _pack_soa16(block, _fake_compact(lo, hi, pmax, nsel), smax, pmax, nsel)
+    full = torch.empty(world * bb, dtype=torch.uint8)
+    dist.all_gather_into_tensor(full, block)
+    got = parallel.ShardedRecords(full, S, world, pmax, nsel, bb, False).host()
+    exp = _fake_compact(0, S, pmax, nsel)
+    live = np.arange(pmax)[None, :] < np.where((exp["status"] & 0xFF) == 0, exp["nphase"], 0)[:, None]
+    ok = ok and np.array_equal(got["status"], exp["status"]) and np.array_equal(got["nphase"], exp["nphase"])
+    ok = ok and np.array_equal(got["fe"][live], exp["fe"][live]) and np.all(np.isnan(got["fe"][~live]))
+    ok = ok and np.array_equal(got["avg"][live], exp["avg"][live]) and np.array_equal(got["bounds"][live], exp["bounds"][live])
+    ok = ok and np.all(got["bounds"][~live] == -1) and got["fe"].shape == (S, pmax)
     q.put((rank, bool(ok), int(F.shape[0])))
     dist.destroy_process_group()
 
