@@ -1,21 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the histogram-reweighting hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload config2|config3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Workload (config.workload): BASELINE config 2 -- synthetic 1-component N_tot ln(PI), N_max = 1000 (1001 bins),
 smooth = 10; a "step" is one pass of the fused sweep (reweight + normalise + phase split + per-phase lnZ +
-<N>, <N^2>) over 10^6 state points mu in [-0.03, 0.03] PER GPU (weak scaling: state points are independent,
-each rank owns a contiguous slice of the N*10^6-point sweep; no collective on the data path, one NCCL
-all_gather of the packed results after the timed region, timed separately).
+<N>, <N^2>) over 10^6 state points mu in [-0.03, 0.03] PER GPU (weak scaling: the N*10^6-point mu list is cut into one
+contiguous shard per rank by the product's own `parallel.sweep_sharded_compact`; state points are independent, there is no
+collective on the data path, and the ONE exchange of the path -- the gather of the complete result records to every rank --
+is fused into the sweep kernel as plain stores into the peers' NVLink-mapped buffers).
 
 Timed numbers
-  value      state points/s, inputs resident in HBM, CUDA events around each step on the launch stream,
-             L2 flushed (256 MiB write) before every step, max over ranks.
+  value      state points/s through `parallel.sweep_sharded_compact` (what a multi-GPU user calls): inputs resident in
+             HBM, CUDA events around each step on the launch stream, L2 flushed (256 MiB write) before every step, max
+             over ranks.  At N > 1 it INCLUDES the gather (value_with_gather repeats it; value_compute_only is the same
+             sweep without the peer stores).  `strong` = the 10^6-point sweep of config 2 cut over the N GPUs.
   e2e        the same metric through the public batched API with HOST buffers: pinned-host mu -> device,
-             kernel, packed results -> pinned host, every step.
-  roofline   fp64-exp issue roofline: algorithmic exps = 1001 per state point, peak = the
-             register-resident exp micro-benchmark run in this same process (DFMA peak beside it).
+             kernel, compact results -> pinned host, every step (one C-ABI call, fhmc_sweep_host_compact16).
+  roofline   fp64 ISSUE roofline of the dominant kernel: frac = fp64-pipe instructions the kernel executes per second /
+             the DFMA issue peak measured in this process; algorithmic_frac = 1001 exp per state point against the
+             measured exp-issue peak.
+  extra      configs 3 (Taylor grid), 4 (coexistence curve) and 5 (2-D joint reweight) at N = 1, each with its own
+             roofline, parity sample and cpu_baseline; `sharded` = the same three through the sharded entry points at N > 1.
   cpu_baseline / --impl reference
              the compiled reference (oracle/_ref; else the C port) driven like its notebooks
              (fresh copy -> reweight -> thermo -> is_safe) on a bounded sample over all host cores.
@@ -41,11 +47,11 @@ MU_LO, MU_HI = -0.03, 0.03
 PMAX = 4
 METRIC = "reweighted state points/sec (lnPI+thermo) at N_max=1000"
 UNIT = "state points/s"
-# warp instructions per state point of k_sweep_prod2<2,1> on this workload (ncu --set full, profiles/r01b_prod2_sweep_ncu_summary.txt)
-FP64_INSTR_PER_POINT = 4355
-INSTR_PER_POINT = 9653
-PROFILE_SOURCE = "profiles/r01b_prod2_sweep_ncu_summary.txt"
 E2E_FIELDS = ("status", "nphase", "bounds", "fe", "avg")   # what the e2e arm copies back to the host every step
+# config 3 (Taylor grid), config 4 (coexistence curve), config 5 (2-D joint histogram): SURVEY 8(d)
+C3_MU1, C3_NB, C3_ND, C3_PMAX = -2.9, 4096, 4096, 8
+C4_BINS, C4_T = 2001, 10000
+C5_N, C5_S = 512, 100000
 
 
 def workload_arrays():
@@ -53,6 +59,28 @@ def workload_arrays():
     lnpi = synth.two_peak_lnpi(N_BINS)
     mom = synth.one_comp_moments(N_BINS)
     return lnpi, mom
+
+
+def instr_counts():
+    """Executed-instruction counts per unit of work of each timed kernel, from the committed ncu captures
+    (profiles/kernel_instr_counts.json: kernel name -> fp64 / all thread-level instructions per unit + the source digest)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "kernel_instr_counts.json")))
+    except Exception:
+        return {}
+
+
+def c3_axes():
+    return np.linspace(0.95, 1.05, C3_NB), np.linspace(0.2, 0.8, C3_ND)
+
+
+def c4_betas():
+    return 1.0 / np.linspace(0.90, 1.06, C4_T)
+
+
+def c5_pairs():
+    g1, g2 = np.meshgrid(np.linspace(-0.02, 0.02, 316), np.linspace(-0.02, 0.02, 317), indexing="ij")
+    return g1.ravel()[:C5_S].copy(), g2.ravel()[:C5_S].copy()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -117,16 +145,25 @@ def _cpu_chunk(args):
     return len(mus), time.perf_counter() - t0, idx, rec
 
 
-def cpu_arm(sample_per_core, cores=None, matched=False, keep=None):
-    """Time the CPU reference on `cores` processes; returns dict(value, cores, kind, sample).  keep: path of an .npz that
-    receives the sample's outputs (indices into the 10^6-point grid + records) for the GPU arm's parity check."""
-    import multiprocessing as mp
+def _n_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+
+
+def _cpu_kind():
     from oracle import ref
     kind = "reference" if ref.available() else "port"
     if kind == "port":
         from oracle import fhmc_oracle
         fhmc_oracle.build()
-    cores = cores or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
+    return kind
+
+
+def cpu_arm(sample_per_core, cores=None, matched=False, keep=None):
+    """Time the CPU reference on `cores` processes; returns dict(value, cores, kind, sample).  keep: path of an .npz that
+    receives the sample's outputs (indices into the 10^6-point grid + records) for the GPU arm's parity check."""
+    import multiprocessing as mp
+    kind = _cpu_kind()
+    cores = cores or _n_cores()
     total = sample_per_core * cores
     idx = sample_indices(total)
     chunks = [(kind, idx[c::cores], matched) for c in range(cores)]
@@ -202,6 +239,222 @@ def parity_block(cpu_npz, gpu, tag, rtol=1e-10):
     return {"checked": tag, "n": int(m), "int_mismatches": int(bad), "max_rel": rel, "rtol": rtol, "ok": bool(bad == 0 and rel <= rtol)}
 
 
+# ------------------------------------------------------------------------------------------------
+# CPU leg, part 2: configs 3, 4, 5 -- the reference (or the oracle) at the sampled state points of the GPU arm's extra
+# blocks: outputs compared with the GPU records of the same run, and timed as the per-config CPU baseline.
+# ------------------------------------------------------------------------------------------------
+def _c3_hist_arrays():
+    from fhmcanalysis_b200 import synth
+    return synth.two_peak_lnpi(N_BINS), synth.two_comp_moments(N_BINS)
+
+
+def _c3_chunk(args):
+    kind, cells = args
+    lnpi, mom = _c3_hist_arrays()
+    betas, dmus = c3_axes()
+    out = []
+    t0 = time.perf_counter()
+    if kind == "reference":
+        from oracle import ref
+        base = ref.make_histogram(lnpi, mom, 1.0, [-3.0, -2.5], SMOOTH)
+        base.reweight(C3_MU1)
+        for ib, idm in cells:
+            try:   # the notebook loop: extrapolate a clone (order 2, ln(PI) only), thermo, is_safe
+                hn = base.temp_dmu_extrap(float(betas[ib]), np.array([dmus[idm]]), 2, 10.0, True, True, True, False)
+                hn.thermo(props=False)
+                safe = bool(hn.is_safe())
+                th = hn.data["thermo"]
+                out.append({"ok": True, "nphase": len(th), "safe": safe, "max_idx": [int(x) for x in hn.data["ln(PI)_maxima_idx"]],
+                            "min_idx": [int(x) for x in hn.data["ln(PI)_minima_idx"]],
+                            "bounds": [[int(x) for x in th[p]["bound_idx"]] for p in range(len(th))],
+                            "fe": [float(th[p]["F.E./kT"]) for p in range(len(th))]})
+            except Exception as e:
+                out.append({"ok": False, "error": repr(e)[:80]})
+    else:
+        from oracle import fhmc_oracle as fo
+        N = np.arange(N_BINS, dtype=float)
+        A = fo.taylor_coefficients(mom, 0.5)
+        coef = np.stack([N, A["A_b"], A["A_d"], A["A_bb"], A["A_bd"], A["A_dd"]])
+        for ib, idm in cells:
+            xb, xd = betas[ib] - 1.0, dmus[idm] - 0.5
+            xi = np.array([xb * C3_MU1, xb, xd + xb * xd, 0.5 * xb * xb, xb * xd, 0.5 * xd * xd])
+            r = fo.state_point(lnpi, np.arange(N_BINS), 1.0, -3.0, C3_MU1, SMOOTH, coef=coef, xi=xi)
+            if r["status"] != 0:
+                out.append({"ok": False, "error": "oracle status %d" % r["status"]})
+            else:
+                out.append({"ok": True, "nphase": int(r["nphase"]), "safe": bool(r["safe"]), "max_idx": r["max_idx"].tolist(),
+                            "min_idx": r["min_idx"].tolist(), "bounds": np.asarray(r["bounds"]).reshape(-1, 2).tolist(), "fe": r["fe"].tolist()})
+    return out, time.perf_counter() - t0
+
+
+def _c4_arrays():
+    from fhmcanalysis_b200 import synth
+    return synth.two_peak_lnpi(C4_BINS, scale=2.0), synth.one_comp_moments(C4_BINS, max_order=3)
+
+
+def _c4_chunk(args):
+    """Per sampled temperature: (a) the reference's own find_phase_eq (Nelder-Mead, GH:598-668) from a two-decimal guess,
+    timed; (b) the tightened oracle (root of the signed dF.E. by brentq) around the GPU's root and the oracle
+    record at the GPU's root."""
+    kind, ks, mu_gpu = args
+    from oracle import fhmc_oracle as fo
+    lnpi, mom = _c4_arrays()
+    betas = c4_betas()
+    n = C4_BINS
+    N = np.arange(n, dtype=float)
+    A = fo.taylor_coefficients(mom)
+    sel = np.stack([N, N * N, mom[0, 0, 0, 0, 1]])
+    dsel = np.stack([np.zeros(n), np.zeros(n), -(mom[0, 0, 0, 0, 2] - mom[0, 0, 0, 0, 1] ** 2)])
+    out = []
+    t_ref, n_ref = 0.0, 0
+    base = None
+    if kind == "reference":
+        from oracle import ref
+        base = ref.make_histogram(lnpi, mom, 1.0, [0.0], SMOOTH)
+    for k, mu in zip(ks, mu_gpu):
+        xb = betas[k] - 1.0
+        rec = {"k": int(k)}
+        if base is not None:
+            t0 = time.perf_counter()
+            try:
+                eq = base.find_phase_eq(1e-10, round(float(mu), 2), float(betas[k]), [], 2, 10.0, True, False)
+                rec["mu_ref"] = float(eq.data["curr_mu"][0])
+            except Exception as e:
+                rec["ref_error"] = repr(e)[:80]
+            t_ref += time.perf_counter() - t0
+            n_ref += 1
+
+        def coef_fn(m, xb=xb):
+            return np.stack([N, A["A_b"], A["A_bb"]]), np.array([xb * m, xb, 0.5 * xb * xb])
+        t0 = time.perf_counter()
+        mu_t = None
+        for half in (1e-3, 1e-4, 1e-5, 1e-6):
+            try:
+                mu_t = fo.find_phase_eq_tight(lnpi, N, 1.0, 0.0, SMOOTH, mu - half, mu + half, coef_fn=coef_fn)
+                break
+            except (RuntimeError, ValueError):
+                continue
+        if base is None:
+            t_ref += time.perf_counter() - t0
+            n_ref += 1
+        rec["mu_tight"] = mu_t
+        coef, xi = coef_fn(mu)
+        r = fo.state_point(lnpi, np.arange(n), 1.0, 0.0, float(mu), SMOOTH, sel=sel + xb * dsel, coef=coef, xi=xi)
+        rec.update({"status": int(r["status"]), "nphase": int(r["nphase"]), "safe": bool(r["safe"]), "max_idx": r["max_idx"].tolist(),
+                    "min_idx": r["min_idx"].tolist(), "bounds": np.asarray(r["bounds"]).reshape(-1, 2).tolist(),
+                    "fe": r["fe"].tolist(), "avg": r["avg"].tolist()})
+        out.append(rec)
+    return out, t_ref, n_ref
+
+
+def _c5_chunk(args):
+    ks, = args
+    from oracle import fhmc_oracle as fo
+    from fhmcanalysis_b200 import synth
+    lnpi, bounds = synth.joint_2d(C5_N, C5_N, 640)
+    a1, a2 = c5_pairs()
+    op = np.arange(C5_N, dtype=float)
+    t0 = time.perf_counter()
+    out = [fo.reweight_2d(lnpi, bounds, op, op, float(a1[k]), float(a2[k])).tolist() for k in ks]
+    return out, time.perf_counter() - t0
+
+
+def extras_worker(in_npz, out_json):
+    """Second half of the cpu_baseline leg (see above).  in_npz: the GPU arm's records at the sampled state points."""
+    import multiprocessing as mp
+    z = np.load(in_npz)
+    kind = _cpu_kind()
+    cores = _n_cores()
+    ctx = mp.get_context("fork")
+    res = {}
+    with ctx.Pool(cores) as pool:
+        # ---- config 3 ----
+        if "c3_cells" in z.files:
+            cells = z["c3_cells"]
+            m = len(cells)
+            t0 = time.perf_counter()
+            parts = pool.map(_c3_chunk, [(kind, cells[c::cores]) for c in range(cores)])
+            wall = time.perf_counter() - t0
+            recs = [None] * m
+            for c, (o, _) in enumerate(parts):
+                for j, r in zip(range(c, m, cores), o):
+                    recs[j] = r
+            bad, rel, nok = 0, 0.0, 0
+            for j, r in enumerate(recs):
+                g_ok = int(z["c3_code"][j]) == 0
+                if not r["ok"] or not g_ok:
+                    bad += int(bool(r["ok"]) != g_ok)
+                    continue
+                nok += 1
+                P = r["nphase"]
+                bad += int(int(z["c3_nphase"][j]) != P) + int(bool(z["c3_safe"][j]) != r["safe"])
+                if int(z["c3_nphase"][j]) != P or P > C3_PMAX:
+                    continue
+                bad += int(z["c3_max_idx"][j, :P].tolist() != r["max_idx"]) + int(z["c3_bounds"][j, :P].tolist() != r["bounds"])
+                bad += int(z["c3_min_idx"][j, :len(r["min_idx"])].tolist() != r["min_idx"])
+                fe = np.asarray(r["fe"])
+                rel = max(rel, float(np.max(np.abs(z["c3_fe"][j, :P] - fe) / np.maximum(np.abs(fe), 1e-300))))
+            res["config3"] = {"parity": {"checked": "sampled grid cells of the timed launch vs %s (temp_dmu_extrap order 2 -> thermo -> is_safe per cell)" % kind,
+                                         "n": m, "n_both_ok": nok, "int_mismatches": bad, "max_rel": rel, "rtol": 1e-9, "ok": bool(bad == 0 and rel <= 1e-9)},
+                              "cpu_baseline": {"value": m / wall, "unit": UNIT, "cores": cores, "kind": kind,
+                                               "sample": "%d grid cells, %d processes, %.1f s wall" % (m, cores, wall)}}
+        # ---- config 4 ----
+        if "c4_k" in z.files:
+            ks, mu = z["c4_k"], z["c4_mu"]
+            m = len(ks)
+            t0 = time.perf_counter()
+            parts = pool.map(_c4_chunk, [(kind, ks[c::cores], mu[c::cores]) for c in range(cores)])
+            wall = time.perf_counter() - t0
+            recs = {}
+            t_ref, n_ref = 0.0, 0
+            for o, tr, nr in parts:
+                t_ref, n_ref = max(t_ref, tr), n_ref + nr
+                for r in o:
+                    recs[r["k"]] = r
+            bad, rel, dmu_tight, dmu_ref, n_ref_ok = 0, 0.0, 0.0, 0.0, 0
+            for j, k in enumerate(ks):
+                r = recs[int(k)]
+                if r["mu_tight"] is None or r["status"] != 0:
+                    bad += 1
+                    continue
+                dmu_tight = max(dmu_tight, abs(mu[j] - r["mu_tight"]) / max(1.0, abs(r["mu_tight"])))
+                if "mu_ref" in r:
+                    dmu_ref, n_ref_ok = max(dmu_ref, abs(mu[j] - r["mu_ref"])), n_ref_ok + 1
+                P = r["nphase"]
+                bad += int(int(z["c4_nphase"][j]) != P) + int(bool(z["c4_safe"][j]) != r["safe"])
+                if int(z["c4_nphase"][j]) != P:
+                    continue
+                bad += int(z["c4_max_idx"][j, :P].tolist() != r["max_idx"]) + int(z["c4_bounds"][j, :P].tolist() != r["bounds"])
+                fe, avg = np.asarray(r["fe"]), np.asarray(r["avg"])
+                rel = max(rel, float(np.max(np.abs(z["c4_fe"][j, :P] - fe) / np.maximum(np.abs(fe), 1e-12))))
+                rel = max(rel, float(np.max(np.abs(z["c4_avg"][j, :P] - avg) / np.maximum(np.abs(avg), 1e-300))))
+            res["config4"] = {"parity": {"checked": "sampled solves of the timed launch vs the tightened oracle (brentq on the signed dF.E., SURVEY 7.3) and the oracle record at mu_coex; "
+                                                    "max_abs_dmu_vs_reference_fmin = distance to the reference's own Nelder-Mead result (its xtol is 1e-4)",
+                                         "n": m, "int_mismatches": bad, "max_rel": rel, "max_rel_dmu_vs_tight": dmu_tight, "rtol": 1e-10,
+                                         "max_abs_dmu_vs_reference_fmin": dmu_ref, "n_reference_fmin_ok": n_ref_ok,
+                                         "ok": bool(bad == 0 and rel <= 1e-10 and dmu_tight <= 1e-10 and (n_ref_ok == 0 or dmu_ref <= 1e-3))},
+                              "cpu_baseline": {"value": n_ref / t_ref if t_ref > 0 else None, "unit": "coexistence points/s", "cores": cores, "kind": kind,
+                                               "sample": "%d solves (%s), %d processes, slowest process %.1f s" % (
+                                                   n_ref, "reference find_phase_eq(1e-10, guess = mu_coex rounded to 2 decimals, beta, order 2)" if kind == "reference" else "brentq oracle", cores, t_ref)}}
+        # ---- config 5 ----
+        if "c5_k" in z.files:
+            ks = z["c5_k"]
+            m = len(ks)
+            t0 = time.perf_counter()
+            parts = pool.map(_c5_chunk, [(ks[c::cores],) for c in range(cores)])
+            wall = time.perf_counter() - t0
+            want = np.zeros((m, 3))
+            for c, (o, _) in enumerate(parts):
+                want[c::cores] = np.asarray(o).reshape(-1, 3)
+            got = z["c5_out"]
+            rel = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)))
+            res["config5"] = {"parity": {"checked": "sampled (mu1, mu2) pairs of the timed launch vs the C oracle (dense log-sum-exp; the reference has no 2-D reweight)",
+                                         "n": m, "int_mismatches": 0, "max_rel": rel, "rtol": 1e-10, "ok": bool(rel <= 1e-10)},
+                              "cpu_baseline": {"value": m / wall, "unit": UNIT, "cores": cores, "kind": "port",
+                                               "sample": "%d state points, %d processes, %.1f s wall" % (m, cores, wall)}}
+    json.dump(res, open(out_json, "w"))
+
+
 def sha16(*arrays):
     h = hashlib.sha256()
     for a in arrays:
@@ -256,10 +509,210 @@ class ClockSampler(object):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def _event_ms(torch, fn, reps, warm):
+    """Median CUDA-event time of fn() on the current stream."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def _roof(counts, key, units_per_s, peaks, algo_exp_per_unit=None):
+    """Roofline object of an extra block: frac = executed fp64-pipe instructions / measured DFMA issue peak (instruction counts
+    per unit from the committed ncu capture named in `source`); algorithmic_frac = algorithmic exps / measured exp peak."""
+    c = counts.get(key, {})
+    r = {"bound": "fp64_issue", "kernel": key, "peak": peaks["dfma_per_s"] / 1e9, "unit": "G fp64-pipe instr/s (per lane)", "traffic": None,
+         "achieved": None, "frac": None, "instr_count_source": c.get("source")}
+    if c.get("fp64_per_unit"):
+        r["achieved"] = units_per_s * c["fp64_per_unit"] / 1e9
+        r["frac"] = units_per_s * c["fp64_per_unit"] / peaks["dfma_per_s"]
+        r["fp64_pipe_instr_per_unit"], r["instr_per_unit"], r["per"] = c["fp64_per_unit"], c.get("instr_per_unit"), c.get("unit")
+    if algo_exp_per_unit:
+        r["algorithmic_exp_per_unit"] = algo_exp_per_unit
+        r["algorithmic_frac"] = units_per_s * algo_exp_per_unit / peaks["exp_per_s"]
+    return r
+
+
+def extra_blocks(torch, dev, peaks, counts, histogram, engine, _lib):
+    """Configs 3, 4, 5 on one GPU: device-timed value, e2e where host buffers make sense, and the sampled records the CPU leg
+    checks.  Returns (blocks, sample arrays for the CPU leg)."""
+    from fhmcanalysis_b200 import synth
+    blocks, smp = {}, {}
+    # ---- config 3: 2-component Taylor grid 4096 beta x 4096 dmu2, order-2 lnPI (skip_mom), mu1 fixed ----------------------
+    try:
+        lnpi, mom2 = synth.two_peak_lnpi(N_BINS), synth.two_comp_moments(N_BINS)
+        h = histogram.from_arrays(lnpi, mom2, 1.0, [-3.0, -2.5], SMOOTH)
+        h.reweight(C3_MU1)
+        betas, dmus = c3_axes()
+        dh = h.device_histogram(beta=betas, dmu=dmus, order=2, moments=())
+        st = dh.make_states(np.array([C3_MU1]), betas, dmus, grid=True)
+        S = int(st.n_states)
+        res = engine.SweepResult(S, C3_PMAX, dh.n_sel, dev)
+        ms = _event_ms(torch, lambda: dh.sweep(None, states=st, out=res, pmax=C3_PMAX), reps=3, warm=1)
+        kern = _lib.last_kernel()
+        code = (res.status & 0xFF)
+        ib, idm = np.meshgrid(np.arange(37, C3_NB, 256), np.arange(91, C3_ND, 256), indexing="ij")
+        cells = np.stack([ib.ravel(), idm.ravel()], axis=1)
+        flat = torch.from_numpy(cells[:, 0] * C3_ND + cells[:, 1]).to(dev)
+        smp["c3_cells"] = cells
+        smp["c3_code"] = code[flat].cpu().numpy()
+        smp["c3_safe"] = ((res.status[flat] & 0x100) != 0).cpu().numpy()
+        for k in ("nphase", "max_idx", "min_idx", "bounds", "fe"):
+            smp["c3_" + k] = getattr(res, k)[flat].cpu().numpy()
+        v = S / (ms * 1e-3)
+        blocks["config3"] = {"workload": "config3: synthetic 2-comp Taylor grid, 4096 beta x 4096 dmu2 at mu1=-2.9, N_max=1000, smooth=10, order-2 lnPI (skip_mom), pmax 8",
+                             "value": v, "unit": UNIT, "ms": ms, "state_points": S, "kernel": kern, "gpu_launches": 1,
+                             "ok_fraction": float((code == 0).double().mean().item()),
+                             "fast_kernel_fraction": float(((res.status & 0x1000) != 0).double().mean().item()),
+                             "roofline": _roof(counts, "k_sweep_fast<taylor>", v, peaks, N_BINS),
+                             "e2e": None, "e2e_note": "the full record set of 1.7x10^7 cells is 3.6 GB; grids are consumed on the device (gc_binary.make_grid_multi) -- no host-buffer form is timed"}
+        del res
+    except Exception as e:
+        blocks["config3"] = {"value": None, "error": repr(e)}
+    # ---- config 4: coexistence curve, 10^4 temperatures, N_max = 2000, order-2 beta extrapolation, cold guesses ----------
+    try:
+        lnpi4, mom4 = synth.two_peak_lnpi(C4_BINS, scale=2.0), synth.one_comp_moments(C4_BINS, max_order=3)
+        h4 = histogram.from_arrays(lnpi4, mom4, 1.0, [0.0], SMOOTH)
+        betas4 = c4_betas()
+        dh4 = h4.device_histogram(beta=betas4, order=2, moments=("N", "N2", "U"))
+        g4 = np.zeros_like(betas4)
+        hold = {}
+
+        def solve(cont):
+            hold["r"] = dh4.find_phase_eq(g4, beta=betas4, lnz_tol=1e-10, pmax=4, continuation=cont)
+        ms_cold = _event_ms(torch, lambda: solve(False), reps=3, warm=1)
+        kern = _lib.last_kernel()
+        hr = hold["r"].host()
+        st4 = hr["status"].view(np.uint32)
+        conv = (hr["code"] == 0) & ((st4 & _lib.ST_JUMP) == 0)
+        evals = float(np.mean(hr["iters"]))
+        t0 = time.perf_counter()
+        for _ in range(3):
+            out4 = h4.find_phase_eq_batch(betas4, 0.0, order=2, lnZ_tol=1e-10)     # host arrays in, host records out (staged continuation)
+        e2e_s = (time.perf_counter() - t0) / 3
+        ks = np.where(conv)[0][::max(1, int(conv.sum()) // 64)][:64]
+        smp["c4_k"], smp["c4_mu"] = ks, hr["mu_coex"][ks]
+        smp["c4_safe"] = hr["safe"][ks]
+        for k in ("nphase", "max_idx", "bounds", "fe", "avg"):
+            smp["c4_" + k] = hr[k][ks]
+        v = C4_T / (ms_cold * 1e-3)
+        blocks["config4"] = {"workload": "config4: coexistence curve, 10^4 temperatures T in [0.90,1.06], N_max=2000, smooth=10, order-2 beta extrapolation, lnZ_tol=1e-10, every guess = 0 (cold), one launch",
+                             "value": v, "unit": "coexistence points/s", "ms": ms_cold, "solves": C4_T, "kernel": kern, "gpu_launches": 1,
+                             "converged_fraction": float(conv.mean()), "jump_terminated_fraction": float(np.mean((hr["code"] == 0) & ~conv)),
+                             "mean_evaluations": evals, "max_abs_dfe_converged": float(np.max(np.abs(hr["dfe"][conv]))) if conv.any() else None,
+                             "roofline": _roof(counts, "k_solve_lean", v, peaks, 2 * C4_BINS * evals),
+                             "e2e": {"value": C4_T / e2e_s, "unit": "coexistence points/s", "path": "histogram.find_phase_eq_batch (host arrays in, host records out, staged continuation)",
+                                     "converged_fraction": float(np.mean(out4["converged"])), "mean_evaluations_last_stage": float(np.mean(out4["iters"])),
+                                     "h2d_bytes_per_step": int(dh4.h2d_bytes + 3 * 8 * C4_T), "d2h_bytes_per_step": int(hold["r"].nbytes() + 20 * C4_T)}}
+    except Exception as e:
+        blocks["config4"] = {"value": None, "error": repr(e)}
+    # ---- config 5: 2-D joint (N1, N2) 512 x 512, 10^5 (mu1, mu2) pairs ---------------------------------------------------
+    try:
+        lnpi2d, bounds = synth.joint_2d(C5_N, C5_N, 640)
+        a1, a2 = c5_pairs()
+        op = np.arange(C5_N, dtype=np.float64)
+        tl, tb = torch.from_numpy(lnpi2d).to(dev), torch.from_numpy(bounds).to(dev)
+        to, ta1, ta2 = torch.from_numpy(op).to(dev), torch.from_numpy(a1).to(dev), torch.from_numpy(a2).to(dev)
+        hold = {}
+
+        def rw():
+            hold["o"] = engine.reweight_2d(tl, tb, to, to, ta1, ta2, None, return_device=True, product=True)
+        ms = _event_ms(torch, rw, reps=5, warm=2)
+        kern = _lib.last_kernel()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            engine.reweight_2d(lnpi2d, bounds, op, op, a1, a2, None)     # host arrays in, host array out
+        e2e_s = (time.perf_counter() - t0) / 3
+        ks = np.arange(13, C5_S, C5_S // 64)[:64]
+        smp["c5_k"], smp["c5_out"] = ks, hold["o"][torch.from_numpy(ks).to(dev)].cpu().numpy()
+        support = int(np.sum(bounds[:, 1] - bounds[:, 0]))
+        v = C5_S / (ms * 1e-3)
+        hbm = None
+        try:
+            hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+        except Exception:
+            pass
+        roof = _roof(counts, "k_rw2d_prod", v, peaks, support)
+        roof["hbm_if_streamed"] = {"algorithmic_bytes_per_state_point": 8 * C5_N * C5_N, "equivalent_gbs": v * 8.0 * C5_N * C5_N / 1e9, "peak_gbs": hbm,
+                                   "frac": (v * 8.0 * C5_N * C5_N / 1e9 / hbm) if hbm else None,
+                                   "note": "SURVEY 8(d) assigns HBM if the histogram were streamed per state point; a staged row chunk is reused by 512 state points, so the limiter is fp64 issue (DRAM 0.3 % in the ncu capture)"}
+        blocks["config5"] = {"workload": "config5: two_dim joint (N1,N2) 512x512 lnPI (triangle N1+N2>640 = -inf), 10^5 (mu1,mu2) pairs, lnZ + <N1> + <N2>",
+                             "value": v, "unit": UNIT, "ms": ms, "state_points": C5_S, "support_bins": support, "kernel": kern, "gpu_launches": 3,
+                             "roofline": roof,
+                             "e2e": {"value": C5_S / e2e_s, "unit": UNIT, "path": "engine.reweight_2d (host arrays in, host array out)",
+                                     "h2d_bytes_per_step": int(lnpi2d.nbytes + bounds.nbytes + 2 * op.nbytes + a1.nbytes + a2.nbytes), "d2h_bytes_per_step": int(3 * 8 * C5_S)}}
+    except Exception as e:
+        blocks["config5"] = {"value": None, "error": repr(e)}
+    return blocks, smp
+
+
+def sharded_blocks(torch, dist, dev, world, histogram, engine, parallel):
+    """Configs 3, 4, 5 through the product's sharded entry points at N > 1 (gathers included; device tensors out)."""
+    from fhmcanalysis_b200 import synth
+    out = {}
+
+    def timed(fn, reps=3, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    try:
+        lnpi, mom2 = synth.two_peak_lnpi(N_BINS), synth.two_comp_moments(N_BINS)
+        h = histogram.from_arrays(lnpi, mom2, 1.0, [-3.0, -2.5], SMOOTH)
+        h.reweight(C3_MU1)
+        betas, dmus = c3_axes()
+        dh = h.device_histogram(beta=betas, dmu=dmus, order=2, moments=())
+        ms = timed(lambda: parallel.sweep_grid_sharded(lambda: dh, C3_MU1, betas, dmus, pmax=C3_PMAX, to_host=False), reps=2)
+        out["config3"] = {"value": C3_NB * C3_ND / (ms * 1e-3), "unit": UNIT, "ms": ms, "scaling": "strong",
+                          "path": "parallel.sweep_grid_sharded: beta rows cut over the ranks, full records all-gathered (NCCL) to every rank"}
+    except Exception as e:
+        out["config3"] = {"value": None, "error": repr(e)}
+    try:
+        lnpi4, mom4 = synth.two_peak_lnpi(C4_BINS, scale=2.0), synth.one_comp_moments(C4_BINS, max_order=3)
+        h4 = histogram.from_arrays(lnpi4, mom4, 1.0, [0.0], SMOOTH)
+        betas4 = c4_betas()
+        dh4 = h4.device_histogram(beta=betas4, order=2, moments=("N", "N2", "U"))
+        ms = timed(lambda: parallel.find_phase_eq_sharded(lambda: dh4, 0.0, betas4, lnz_tol=1e-10, pmax=4, to_host=False, continuation=False))
+        out["config4"] = {"value": C4_T / (ms * 1e-3), "unit": "coexistence points/s", "ms": ms, "scaling": "strong",
+                          "path": "parallel.find_phase_eq_sharded: temperatures cut over the ranks (cold guesses), records all-gathered"}
+    except Exception as e:
+        out["config4"] = {"value": None, "error": repr(e)}
+    try:
+        lnpi2d, bounds = synth.joint_2d(C5_N, C5_N, 640)
+        a1, a2 = c5_pairs()
+        op = np.arange(C5_N, dtype=np.float64)
+        tl, tb = torch.from_numpy(lnpi2d).to(dev), torch.from_numpy(bounds).to(dev)
+        to, ta1, ta2 = torch.from_numpy(op).to(dev), torch.from_numpy(a1).to(dev), torch.from_numpy(a2).to(dev)
+        ms = timed(lambda: parallel.reweight_2d_sharded(tl, tb, to, to, ta1, ta2, device=dev, product=True, to_host=False), reps=5, warm=2)
+        out["config5"] = {"value": C5_S / (ms * 1e-3), "unit": UNIT, "ms": ms, "scaling": "strong",
+                          "path": "parallel.reweight_2d_sharded: the 10^5 (mu1,mu2) pairs cut over the ranks, histogram replicated, results all-gathered"}
+    except Exception as e:
+        out["config5"] = {"value": None, "error": repr(e)}
+    return out
+
+
 def run_gpu_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from fhmcanalysis_b200 import _lib, engine
+    from fhmcanalysis_b200 import _lib, engine, parallel
     from fhmcanalysis_b200.moments.histogram.one_dim.ntot.gc_hist import histogram
 
     if not torch.cuda.is_available():
@@ -272,9 +725,10 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     # CPU baseline first, on rank 0 at N=1 only (bounded sample), before the GPU is busy
     cpu = None
+    tmpdir = tempfile.mkdtemp(prefix="fhmc_bench_")
     if world == 1 and not args.no_cpu_baseline:
         try:
-            keep_path = os.path.join(tempfile.mkdtemp(prefix="fhmc_bench_"), "cpu_sample.npz")
+            keep_path = os.path.join(tmpdir, "cpu_sample.npz")
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-worker", "--keep", keep_path],
                                  capture_output=True, text=True, timeout=600)
             cpu = json.loads(out.stdout.strip().splitlines()[-1])
@@ -287,23 +741,42 @@ def run_gpu_arm(args, rank, world, local_rank):
     moments = ("N", "N2")
     dh = hist.device_histogram(moments=moments, device=dev)
     S = args.points
-    # this rank's slice of the global sweep
-    mu_all_lo = MU_LO + (MU_HI - MU_LO) * rank / world
-    mu_all_hi = MU_LO + (MU_HI - MU_LO) * (rank + 1) / world
-    mu_host = torch.from_numpy(np.linspace(mu_all_lo, mu_all_hi, S, endpoint=(rank == world - 1))).pin_memory()
-    mu_dev = mu_host.to(dev)
-    states = dh.make_states(mu_dev)
-    out = engine.SweepResult(S, PMAX, dh.n_sel, dev)
+    counts = instr_counts()
+    # the global sweep: world * S state points over the mu range of config 2; every rank holds the list, the product's sharded
+    # entry point takes this rank's contiguous slice
+    mu_all = torch.from_numpy(np.linspace(MU_LO, MU_HI, world * S)).to(dev)
+    lo, hi = parallel.shard_bounds(world * S, world, rank)
+    mu_host = mu_all[lo:hi].cpu().pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     peaks = engine.measure_peaks(dev)
+    hold = {"state": None, "rec": None}
 
-    def step():
-        dh.sweep(None, states=states, out=out, pmax=PMAX, lanes=args.lanes)
+    def step():   # the product's multi-GPU call: sweep of this rank's shard, complete compact records gathered to every rank
+        hold["rec"], hold["state"] = parallel.sweep_sharded_compact(dh, mu_all, pmax=PMAX, state=hold["state"])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    def timed_loop(fn, steps):
+        """K steps, CUDA events around each on the launch stream, L2 flushed before each; returns per-rank mean ms and the
+        max-over-ranks total."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            flush.zero_()          # L2 flush: inputs (8 MB of mu + 32 KB blob) are far smaller than the 126 MB L2
+            ev[k][0].record()
+            fn()
+            ev[k][1].record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = [a.elapsed_time(b) for a, b in ev]
+        t = torch.tensor([float(np.sum(ms))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(np.mean(ms)), float(t.item()) / steps, wall
 
     sampler = ClockSampler(local_rank)
     sampler.start()            # samples cover warm-up + timed region + e2e loop (same kernel under load throughout)
@@ -315,34 +788,41 @@ def run_gpu_arm(args, rank, world, local_rank):
         n_warm += 1
         if n_warm % 8 == 0:
             torch.cuda.synchronize(dev)
-    barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()          # L2 flush: inputs (8 MB of mu + 32 KB blob) are far smaller than the 126 MB L2
-        ev[k][0].record()
-        step()
-        ev[k][1].record()
-    barrier()
-    wall = time.perf_counter() - t_wall0
+    kern_ms, ms_per_step, wall = timed_loop(step, args.steps)
     timed_kernel = _lib.last_kernel()
-    kern_ms = [a.elapsed_time(b) for a, b in ev]
-    t_ms = torch.tensor([float(np.sum(kern_ms))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(t_ms.item())
-    ms_per_step = total_ms / args.steps
     value = world * S / (ms_per_step * 1e-3)
+    fused = bool(hold["state"].fused)
+    rec_bytes = int(hold["state"].block_bytes)
+
+    # the same sweep without the peer stores (compute only), and the strong-scaling form of config 2 (10^6 points over N GPUs)
+    compute_only = strong = None
+    if world > 1:
+        local = torch.empty(rec_bytes, dtype=torch.uint8, device=dev)
+        shard = mu_all[lo:hi]
+        smax = hold["state"].smax
+        for _ in range(3):
+            dh.sweep_compact(shard, pmax=PMAX, dst=local, n_total=smax, fill_dead=False)
+        _, ms_c, _ = timed_loop(lambda: dh.sweep_compact(shard, pmax=PMAX, dst=local, n_total=smax, fill_dead=False), args.steps)
+        compute_only = {"value": world * S / (ms_c * 1e-3), "ms_per_step": ms_c}
+        mu_strong = torch.from_numpy(np.linspace(MU_LO, MU_HI, S)).to(dev)
+        sh = {"state": None}
+
+        def strong_step():
+            _, sh["state"] = parallel.sweep_sharded_compact(dh, mu_strong, pmax=PMAX, state=sh["state"])
+        for _ in range(3):
+            strong_step()
+        _, ms_s, _ = timed_loop(strong_step, args.steps)
+        strong = {"value": S / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s, "state_points_total": S, "scaling": "strong",
+                  "note": "config 2's 10^6-point sweep cut over the N GPUs, gather included"}
 
     # ---- e2e through the public batched API with host buffers ------------------------------------
     # the per-state-point outputs SURVEY 8(d) config 2 lists: nphase, bounds, is_safe (status bit), lnZ per phase,
-    # <N>, <N^2> per phase.  (extrema index lists and the normalisation constant stay on the device.)
-    # Only phase slots that exist cross PCIe (phase-major repack on the device, engine.sweep_host_compact).
+    # <N>, <N^2> per phase.  Only phase slots that exist cross PCIe (compact records written by the sweep kernel).
     host_out = {"r": None}
     h2d = mu_host.numel() * 8 + dh.h2d_bytes
 
     def e2e_step():
-        # public host-buffer entry point (one C-ABI call): chunked, double-buffered H2D(mu) -> kernel -> repack -> D2H(results)
+        # public host-buffer entry point (one C-ABI call): chunked H2D(mu) -> sweep kernel (compact records) -> D2H(results)
         host_out["r"] = dh.sweep_host_compact(mu_host, pmax=PMAX, lanes=args.lanes, out=host_out["r"])
 
     for _ in range(2):
@@ -360,37 +840,46 @@ def run_gpu_arm(args, rank, world, local_rank):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * S / (float(e2e_ms.item()) * 1e-3)
     d2h = int(host_out["r"]["d2h_bytes"])
-    e2e_launches = 2 * ((S + (1 << 17) - 1) >> 17)      # sweep + repack kernel per chunk
+    e2e_launches = (S + (1 << 17) - 1) >> 17      # one sweep kernel per chunk
     clocks = sampler.stop()
 
-    # ---- the one collective of the path: final gather of packed results (not in `value`) ----------
-    gather_ms = None
+    # ---- ceiling of the e2e path: all ranks copy a result-sized buffer device -> pinned host at the same time --------------
+    pin = torch.empty(d2h, dtype=torch.uint8).pin_memory()
+    src = torch.empty(d2h, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        pin.copy_(src, non_blocking=True)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(10):
+        pin.copy_(src, non_blocking=True)
+    c1.record()
+    barrier()
+    d2h_ms = torch.tensor([c0.elapsed_time(c1) / 10], dtype=torch.float64, device=dev)
     if world > 1:
-        packed = torch.cat([out.lnnorm.view(-1), out.fe.view(-1), out.avg.view(-1)])
-        gathered = torch.empty(world * packed.numel(), dtype=packed.dtype, device=dev)
-        dist.all_gather_into_tensor(gathered, packed)
-        torch.cuda.synchronize(dev)
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        dist.all_gather_into_tensor(gathered, packed)
-        g1.record()
-        g1.synchronize()
-        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        gather_ms = float(gt.item())
+        dist.all_reduce(d2h_ms, op=dist.ReduceOp.MAX)
+    d2h_ms = float(d2h_ms.item())
+    del pin, src
 
-    # sanity: the timed kernel really produced results
-    hrec = out.host()
-    h_status = hrec["status"]
-    ok_frac = float(np.mean((h_status & 0xFF) == 0))
-    fast_frac = float(np.mean((h_status & 0x1000) != 0))
+    # ---- results of the timed sweep: sanity + consistency of the gathered buffers across the ranks -----------------------
+    hrec = hold["rec"].host()        # all world * S records, from THIS rank's gathered buffer
+    ok_frac = float(np.mean(hrec["code"] == 0))
+    fast_frac = float(np.mean((hrec["status"] & 0x1000) != 0))
+    gather_check = None
+    if world > 1:
+        live = torch.from_numpy(np.concatenate([hrec["fe"][:, :2].ravel(), hrec["avg"][:, :2].ravel(), hrec["nphase"].astype(np.float64)])).to(dev)
+        ck = torch.nan_to_num(live).sum().reshape(1)
+        cks = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(cks, ck)
+        gather_check = {"identical_on_all_ranks": bool((cks == cks[0]).all().item()), "records_per_rank": int(world * S)}
 
     # ---- parity in the same run: the records the TIMED kernel left behind (and the e2e arm's host records) against the
     #      outputs of the cpu_baseline leg at the same state points -------------------------
     parity = None
     if rank == 0 and cpu is not None and cpu.get("keep") and os.path.exists(cpu["keep"]):
         try:
-            parity = parity_block(cpu["keep"], hrec, "records of the timed kernel (%s) vs cpu_baseline outputs (%s), same mu" % (timed_kernel, cpu["kind"]))
+            g = {"nphase": hrec["nphase"].astype(np.int32), "safe": hrec["safe"], "bounds": hrec["bounds"], "fe": hrec["fe"], "avg": hrec["avg"]}
+            parity = parity_block(cpu["keep"], g, "records of the timed kernel (%s) vs cpu_baseline outputs (%s), same mu" % (timed_kernel, cpu["kind"]))
             e2e_rec = {"nphase": host_out["r"]["nphase"].numpy().astype(np.int32),
                        "safe": (host_out["r"]["status"].numpy().astype(np.int64) & 0x100) != 0,
                        "bounds": host_out["r"]["bounds"].numpy(), "fe": host_out["r"]["fe"].numpy(), "avg": host_out["r"]["avg"].numpy()}
@@ -399,35 +888,46 @@ def run_gpu_arm(args, rank, world, local_rank):
         except Exception as e:
             parity = {"checked": False, "error": repr(e)}
 
-    # ---- second half of the BASELINE metric: coexistence points/s (config 4: 10^4 temperatures, N_max = 2000, smooth 10,
-    #      order-2 beta extrapolation, one batched find_phase_eq launch, guesses = mu_ref for every temperature) ----------
-    coex = None
-    if rank == 0:
+    # ---- the full-record form of the same sweep (extrema lists + normalisation constant as well: 184 B per state point) ---
+    full = None
+    if world == 1:
         try:
-            from fhmcanalysis_b200 import synth
-            h4 = histogram.from_arrays(synth.two_peak_lnpi(2001, scale=2.0), synth.one_comp_moments(2001, max_order=3), 1.0, [0.0], SMOOTH)
-            betas4 = 1.0 / np.linspace(0.90, 1.06, 10000)
-            dh4 = h4.device_histogram(beta=betas4, order=2, moments=("N", "N2", "U"), device=dev)
-            g4 = np.zeros_like(betas4)
-            r4 = dh4.find_phase_eq(g4, beta=betas4, lnz_tol=1e-10, pmax=4)
-            torch.cuda.synchronize(dev)
-            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            c0.record()
+            states = dh.make_states(mu_all)
+            fout = engine.SweepResult(S, PMAX, dh.n_sel, dev)
             for _ in range(3):
-                r4 = dh4.find_phase_eq(g4, beta=betas4, lnz_tol=1e-10, pmax=4)
-            c1.record()
-            c1.synchronize()
-            hr = r4.host()
-            okc = hr["code"] == 0
-            coex = {"value": 3 * len(betas4) / (c0.elapsed_time(c1) * 1e-3), "unit": "coexistence points/s", "solves": len(betas4),
-                    "converged_fraction": float(np.mean(okc)), "mean_evaluations": float(np.mean(hr["iters"])),
-                    "median_abs_dfe": float(np.median(np.abs(hr["dfe"][okc]))) if okc.any() else None,
-                    "workload": "config4: N_max=2000, smooth=10, T in [0.90,1.06], order-2 beta extrapolation, all guesses = 0"}
-        except Exception as e:  # secondary metric: never lose the headline line
-            coex = {"value": None, "error": repr(e)}
+                dh.sweep(None, states=states, out=fout, pmax=PMAX, lanes=args.lanes)
+            _, ms_f, _ = timed_loop(lambda: dh.sweep(None, states=states, out=fout, pmax=PMAX, lanes=args.lanes), min(args.steps, 20))
+            full = {"value": S / (ms_f * 1e-3), "ms_per_step": ms_f, "kernel": _lib.last_kernel(), "bytes_per_state_point": fout.nbytes() / S}
+            if cpu is not None and cpu.get("keep") and os.path.exists(cpu["keep"]):
+                pf = parity_block(cpu["keep"], fout.host(), "full records")
+                full["parity"] = {k: pf[k] for k in ("n", "int_mismatches", "max_rel", "ok")}
+            del fout
+        except Exception as e:
+            full = {"value": None, "error": repr(e)}
+
+    # ---- configs 3, 4, 5 -----------------------------------------------------------------------------------------------
+    extra = sharded = None
+    if world == 1 and not args.no_extra:
+        extra, smp = extra_blocks(torch, dev, peaks, counts, histogram, engine, _lib)
+        if not args.no_cpu_baseline and smp:
+            try:
+                in_npz, out_json = os.path.join(tmpdir, "extra_gpu.npz"), os.path.join(tmpdir, "extra_cpu.json")
+                np.savez(in_npz, **smp)
+                subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-extras-worker", "--keep", in_npz, "--out", out_json],
+                               capture_output=True, text=True, timeout=900, check=True)
+                for k, v in json.load(open(out_json)).items():
+                    if k in extra and extra[k].get("value") is not None:
+                        extra[k].update(v)
+            except Exception as e:
+                extra["cpu_leg_error"] = repr(e)
+    elif world > 1 and not args.no_extra:
+        sharded = sharded_blocks(torch, dist, dev, world, histogram, engine, parallel)
 
     if rank == 0:
-        exps = S * N_BINS / (np.mean(kern_ms) * 1e-3)   # this rank's kernel
+        cnt = counts.get(timed_kernel, counts.get("k_sweep_prod2", {}))
+        fp64_pp, instr_pp = cnt.get("fp64_per_unit"), cnt.get("instr_per_unit")
+        rate1 = S / (kern_ms * 1e-3)          # this rank's kernel
+        exps = rate1 * N_BINS
         mp_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak = None
         if os.path.exists(mp_path):
@@ -435,44 +935,59 @@ def run_gpu_arm(args, rank, world, local_rank):
                 hbm_peak = json.load(open(mp_path)).get("hbm_gbs")
             except Exception:
                 hbm_peak = None
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01b_sweep_dram_bytes.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        algo_bytes = S * (8 + out.nbytes() / S)
+        algo_bytes = S * 8 + rec_bytes * (world if fused else 1)     # mu in + compact records out (to every rank when fused)
+        coex = None
+        if extra and extra.get("config4", {}).get("value") is not None:
+            c4 = extra["config4"]
+            coex = {"value": c4["value"], "unit": c4["unit"], "solves": c4["solves"], "converged_fraction": c4["converged_fraction"],
+                    "mean_evaluations": c4["mean_evaluations"], "max_abs_dfe_converged": c4["max_abs_dfe_converged"], "workload": c4["workload"]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "gpu_launches": args.steps,
+            "data": "synthetic", "gpu_launches": args.steps * (1 + (2 if fused else 0)),
+            "value_with_gather": value if world > 1 else None,
+            "value_compute_only": compute_only["value"] if compute_only else value,
             "config": {"workload": "config2: synthetic 1-comp N_tot lnPI, N_max=1000 (1001 bins), smooth=10, 10^6-point mu sweep per GPU with thermo "
                                    "(<N>, <N^2>, per-phase lnZ, phase split, is_safe)",
                        "state_points_per_gpu": S, "bins": N_BINS, "smooth": SMOOTH, "pmax": PMAX, "moments": list(moments),
-                       "lanes_per_point": args.lanes or "auto", "e2e_outputs": list(E2E_FIELDS), "e2e_path": "fhmc_sweep_host_compact (C ABI, host buffers): per 2^17-point chunk H2D(mu) -> sweep kernel -> k_pack_phase_soa16 (status i16, nphase u8, bounds i16; fe/avg f64) -> D2H of the live phase blocks; upload, compute and download streams", "e2e_gpu_launches_per_step": e2e_launches, "l2": "flushed (256 MiB memset) before every timed step",
+                       "timed_call": "parallel.sweep_sharded_compact -> fhmc_sweep_1d_compact (%s): compact records {status i16, nphase u8, fe/avg f64, bounds i16} "
+                                     "written by the sweep kernel%s" % (timed_kernel, "; gather fused into the kernel as stores to every rank's NVLink-mapped buffer (symmetric memory) + 2 device barriers" if fused else
+                                                                        ("; NCCL all_gather of the compact blocks" if world > 1 else "")),
+                       "gather": ("fused_nvlink_stores" if fused else ("nccl_all_gather" if world > 1 else None)),
+                       "record_bytes_per_rank": rec_bytes, "compute_only_ms_per_step": compute_only["ms_per_step"] if compute_only else None,
+                       "lanes_per_point": args.lanes or "auto", "e2e_outputs": list(E2E_FIELDS),
+                       "e2e_path": "fhmc_sweep_host_compact16 (C ABI, host buffers): per 2^17-point chunk H2D(mu) -> sweep kernel writing compact records -> D2H of the live phase blocks; upload, compute and download streams",
+                       "e2e_gpu_launches_per_step": e2e_launches, "l2": "flushed (256 MiB memset) before every timed step",
                        "parallelism": "dp%d over state points, no data-path collective" % world,
-                       "final_gather_ms": gather_ms, "ok_fraction": ok_frac, "fast_kernel_fraction": fast_frac, "wall_s_timed_region": wall},
+                       "ok_fraction": ok_frac, "fast_kernel_fraction": fast_frac, "wall_s_timed_region": wall, "gather_check": gather_check},
             "clocks": clocks,
             "coexistence": coex,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "strong": strong,
+            "full_records": full,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "d2h_ceiling": {"ms_per_step": d2h_ms, "aggregate_gbs": world * d2h / (d2h_ms * 1e-3) / 1e9,
+                                    "value_if_copy_only": world * S / (d2h_ms * 1e-3),
+                                    "frac_of_ceiling": e2e_value / (world * S / (d2h_ms * 1e-3)),
+                                    "note": "all ranks copy one result-sized buffer device -> pinned host at the same time (plain cudaMemcpyAsync); e2e cannot exceed this"}},
             # Roofline of the dominant kernel: fp64 ISSUE.  frac = fp64-pipe instructions the kernel EXECUTES per second (count per
             # state point from the committed ncu capture of this build x measured state points/s) / the DFMA issue peak measured
             # in this process.  The algorithmic count of SURVEY 8(d) (1001 exp per state point against the measured exp-issue
             # peak) is kept beside it as algorithmic_frac: it exceeds 1 because the product form replaces most exps by FMAs.
             "roofline": {"bound": "fp64_issue", "kernel": timed_kernel,
-                         "achieved": S * FP64_INSTR_PER_POINT / (np.mean(kern_ms) * 1e-3) / 1e9, "peak": peaks["dfma_per_s"] / 1e9,
+                         "achieved": (rate1 * fp64_pp / 1e9) if fp64_pp else None, "peak": peaks["dfma_per_s"] / 1e9,
                          "unit": "G fp64-pipe instr/s (per lane)",
-                         "frac": S * FP64_INSTR_PER_POINT / (np.mean(kern_ms) * 1e-3) / peaks["dfma_per_s"], "traffic": traffic,
+                         "frac": (rate1 * fp64_pp / peaks["dfma_per_s"]) if fp64_pp else None, "traffic": cnt.get("dram_bytes_per_launch"),
                          "peak_source": "k_bench_dfma, register-resident DFMA chains, measured in this process (no fp64 figure in MEASURED_PEAKS.json)",
-                         "fp64_pipe_instr_per_state_point": FP64_INSTR_PER_POINT, "instr_per_state_point": INSTR_PER_POINT,
-                         "instr_count_source": PROFILE_SOURCE,
+                         "fp64_pipe_instr_per_state_point": fp64_pp, "instr_per_state_point": instr_pp,
+                         "instr_count_source": cnt.get("source"), "kernel_ms": kern_ms,
                          "algorithmic_frac": exps / peaks["exp_per_s"], "algorithmic_exp_per_state_point": N_BINS,
                          "algorithmic_achieved_gexp_s": exps / 1e9, "exp_peak_gexp_s": peaks["exp_per_s"] / 1e9,
-                         "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (np.mean(kern_ms) * 1e-3) / 1e9,
-                                 "peak_gbs": hbm_peak, "frac": (algo_bytes / (np.mean(kern_ms) * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
+                         "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (kern_ms * 1e-3) / 1e9,
+                                 "peak_gbs": hbm_peak, "frac": (algo_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
                                  "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else "absent"}},
             "parity": parity,
+            "extra": extra,
+            "sharded": sharded,
             "inputs_sha256_16": {"lnpi": sha16(lnpi), "mom": sha16(mom), "mu_rank0": sha16(mu_host.numpy())},
         }
         if cpu is not None:
@@ -513,14 +1028,20 @@ def main():
     ap.add_argument("--points", type=int, default=S_PER_GPU, help="state points per GPU per step")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per state point (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 3/4/5 blocks")
     ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-extras-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--keep", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--out", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.cpu_baseline_worker:
         print(json.dumps(cpu_arm(12000, keep=args.keep)))
+        return 0
+    if args.cpu_extras_worker:
+        extras_worker(args.keep, args.out)
         return 0
     guard_stdout()   # from here on only emit() reaches the caller's stdout
     if args.impl == "reference":

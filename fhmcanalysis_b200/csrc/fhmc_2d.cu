@@ -391,6 +391,7 @@ extern "C" int fhmc_reweight_2d(const double *lnpi, const int *bounds, int n1, i
     else FHMC_LAUNCH_2D(2);
 #undef FHMC_LAUNCH_2D
     if (check_cuda(cudaGetLastError(), "k_rw2d_partial launch")) return 1;
+    note_kernel("k_rw2d_partial");
     k_rw2d_merge<<<(unsigned)((n_states + 255) / 256), 256, 0, s>>>(a);
     return check_cuda(cudaGetLastError(), "k_rw2d_merge launch");
 }
@@ -456,6 +457,7 @@ extern "C" int fhmc_reweight_2d_prod(const double *lnpi, const int *bounds, int 
     else FHMC_LAUNCH_2DP(2);
 #undef FHMC_LAUNCH_2DP
     if (check_cuda(cudaGetLastError(), "k_rw2d_prod launch")) return 1;
+    note_kernel("k_rw2d_prod");
     Rw2dArgs mga;
     mga.lnpi = lnpi; mga.bounds = bounds; mga.op1 = op1; mga.op2 = op2; mga.props = props; mga.a1 = a1; mga.a2 = a2;
     mga.ws = a.ws; mga.out = out; mga.n_states = n_states; mga.n1 = n1; mga.n2 = n2; mga.n_prop = n_prop;

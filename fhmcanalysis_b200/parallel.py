@@ -99,7 +99,14 @@ def _cut(x, lo, hi):
     return x if x.size == 1 else x[lo:hi]
 
 
-def sweep_sharded(make_device_hist, mu1, beta=None, dmu=None, pmax=4, lanes=0, gather=True, group=None):
+def _deliver(out, to_host):
+    """Gathered records as NumPy arrays (to_host) or as the device tensors the collective left behind."""
+    if not to_host:
+        return out
+    return {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+
+
+def sweep_sharded(make_device_hist, mu1, beta=None, dmu=None, pmax=4, lanes=0, gather=True, group=None, to_host=True):
     """Run a flat state-point list sharded over the ranks of ``group`` (call from every rank); FULL records.
 
     make_device_hist: callable returning this rank's engine.DeviceHistogram (the blob is replicated by plain H2D).
@@ -119,11 +126,10 @@ def sweep_sharded(make_device_hist, mu1, beta=None, dmu=None, pmax=4, lanes=0, g
         i = torch.zeros((0, n_i), dtype=torch.int32, device=dh.device)
     if gather and world > 1:
         f, i = all_gather_records(f, i, S, group)
-    out = unpack_records(f, i, pmax, dh.n_sel)
-    return {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+    return _deliver(unpack_records(f, i, pmax, dh.n_sel), to_host)
 
 
-def sweep_grid_sharded(make_device_hist, mu1, betas, dmus, pmax=4, group=None):
+def sweep_grid_sharded(make_device_hist, mu1, betas, dmus, pmax=4, group=None, to_host=True):
     """(beta x dmu) Taylor grid (temp_dmu_extrap_multi order: dmu fastest) at fixed mu1, the BETA rows sharded over the ranks
     (BASELINE config 3).  Returns the gathered records as NumPy arrays of nb*nd state points on every rank."""
     import torch
@@ -144,11 +150,10 @@ def sweep_grid_sharded(make_device_hist, mu1, betas, dmus, pmax=4, group=None):
         # shards are whole beta rows: gather row blocks of nd state points each
         f = all_gather_rows(f.reshape(-1, nd, n_f), nb, group).reshape(-1, n_f)
         i = all_gather_rows(i.reshape(-1, nd, n_i), nb, group).reshape(-1, n_i)
-    out = unpack_records(f, i, pmax, dh.n_sel)
-    return {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+    return _deliver(unpack_records(f, i, pmax, dh.n_sel), to_host)
 
 
-def find_phase_eq_sharded(make_device_hist, mu_guess, betas, dmu=None, lnz_tol=1e-10, pmax=4, group=None, **kw):
+def find_phase_eq_sharded(make_device_hist, mu_guess, betas, dmu=None, lnz_tol=1e-10, pmax=4, group=None, to_host=True, **kw):
     """Batched coexistence solves (K4, BASELINE config 4) with the temperatures sharded over the ranks; every rank returns
     the gathered dict: mu_coex, dfe, iters, status/code/converged, nphase, fe, avg, bounds."""
     import torch
@@ -170,23 +175,26 @@ def find_phase_eq_sharded(make_device_hist, mu_guess, betas, dmu=None, lnz_tol=1
         i = torch.zeros((0, n_i), dtype=torch.int32, device=dh.device)
     f, i = all_gather_records(f, i, T, group)
     out = unpack_records(f[:, 2:], i[:, 1:], max(pmax, 2), dh.n_sel)
-    out = {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
-    out["mu_coex"], out["dfe"], out["iters"] = f[:, 0].cpu().numpy(), f[:, 1].cpu().numpy(), i[:, 0].cpu().numpy()
+    out["mu_coex"], out["dfe"], out["iters"] = f[:, 0], f[:, 1], i[:, 0]
+    if not to_host:
+        return out
+    out = _deliver(out, True)
     out["status"] = out["status"].view(np.uint32)
     out["code"] = (out["status"] & _lib.ST_CODE_MASK).astype(np.int32)
     out["converged"] = (out["code"] == 0) & ((out["status"] & _lib.ST_JUMP) == 0)
     return out
 
 
-def reweight_2d_sharded(lnpi, bounds, op1, op2, a1, a2, props=None, device=None, group=None, product=None):
+def reweight_2d_sharded(lnpi, bounds, op1, op2, a1, a2, props=None, device=None, group=None, product=None, to_host=True):
     """K5 (BASELINE config 5): the (a1, a2) state points of a 2-D joint-histogram reweight sharded over the ranks, the
     histogram replicated; returns the gathered [S, 3 + n_prop] array (lnZ, <op1>, <op2>, <prop>...) on every rank."""
     import torch
     from . import engine
     world, rank = _world(group)
-    a1 = np.atleast_1d(np.asarray(a1, dtype=np.float64))
-    a2 = np.atleast_1d(np.asarray(a2, dtype=np.float64))
-    S = len(a1)
+    if not isinstance(a1, torch.Tensor):   # (device tensors are sliced as they are: inputs already resident in HBM)
+        a1 = np.atleast_1d(np.asarray(a1, dtype=np.float64))
+        a2 = np.atleast_1d(np.asarray(a2, dtype=np.float64))
+    S = int(a1.shape[0])
     lo, hi = shard_bounds(S, world, rank)
     n_prop = 0 if props is None else len(props)
     dev = engine.require_cuda(device)
@@ -194,7 +202,8 @@ def reweight_2d_sharded(lnpi, bounds, op1, op2, a1, a2, props=None, device=None,
         out = engine.reweight_2d(lnpi, bounds, op1, op2, a1[lo:hi], a2[lo:hi], props, device=dev, return_device=True, product=product)
     else:
         out = torch.zeros((0, 3 + n_prop), dtype=torch.float64, device=dev)
-    return all_gather_rows(out, S, group).cpu().numpy()
+    full = all_gather_rows(out, S, group)
+    return full.cpu().numpy() if to_host else full
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -306,11 +315,10 @@ def sweep_sharded_compact(dh, mu1, pmax=4, group=None, state=None, fused=None, p
             # (dead phase slots are NOT written: they would double the NVLink traffic; host() masks them)
             dh.sweep_compact(shard, pmax=pmax, dst=[p + off for p in state.peer_ptrs], n_total=state.smax, first=0, fill_dead=False)
         state.barrier()   # every rank's stores have landed in every buffer once all kernels are done
+    elif world == 1:
+        dh.sweep_compact(shard, pmax=pmax, dst=state.buf, n_total=state.smax, first=0, fill_dead=False)
     else:
         if hi > lo:
             dh.sweep_compact(shard, pmax=pmax, dst=state.local, n_total=state.smax, first=0, fill_dead=False)
-        if world > 1:
-            dist.all_gather_into_tensor(state.buf, state.local, group=group)
-        else:
-            state.buf.copy_(state.local)
+        dist.all_gather_into_tensor(state.buf, state.local, group=group)
     return ShardedRecords(state.buf, S, world, pmax, dh.n_sel, state.block_bytes, state.fused), state

@@ -35,6 +35,7 @@ SOURCES = {
     "joint_hist": "moments/histogram/two_dim/joint_hist.pyx",
     "gc_hist_n1": "moments/histogram/one_dim/n1/gc_hist.pyx",      # N_1 order parameter
     "pore_hist": "moments/histogram/two_dim/h_ntot/pore_hist.pyx",  # 2-D normalise / masked averages
+    "fhmc_patch": "moments/win_patch/fhmc_patch.pyx",               # window patching shift solve
 }
 
 # (module, regex, replacement, expected count or None) -- porting edits only.
@@ -50,6 +51,15 @@ PATCHES = [
     ("gc_hist", r"dtype=np\.int\)", "dtype=np.int64)", None),
     ("gc_hist", r"np\.float, np\.float64", "float, np.float64", 1),
     ("joint_hist", r"dtype=np\.int\)", "dtype=np.int64)", None),
+]
+# window patching (fhmc_patch.pyx:636, 640, 668, 472-473): the same Py2 method binding; the fmin objective and
+# patch_window_pair are cdef functions -> def so that tests can drive them; np.float alias in window.__init__
+PATCHES += [
+    ("fhmc_patch", r"window\._cy_normalize = types\.MethodType\(_cython_normalize_lnPI, None, window\)",
+     "def _py_normalize_lnPI(self):\n\t_cython_normalize_lnPI(self)\nwindow._cy_normalize = _py_normalize_lnPI", 1),
+    ("fhmc_patch", r"cdef double window_patch_error \(", "def window_patch_error (", 1),
+    ("fhmc_patch", r"cdef patch_window_pair \(", "def patch_window_pair (", 1),
+    ("fhmc_patch", r"dtype=np\.float,", "dtype=float,", 2),
 ]
 # the N_1 module carries the same Py2/NumPy-1 idioms as ntot/gc_hist.pyx (n1/gc_hist.pyx:1734-1735, 1739, 156, 112)
 PATCHES += [("gc_hist_n1",) + p[1:] for p in PATCHES if p[0] == "gc_hist"]

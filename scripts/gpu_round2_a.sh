@@ -1,0 +1,9 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+(python -m pytest tests -m gpu -x -q 2>&1 | tail -15) > gpurun_out/r2b_pytest.log
+(python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5) > gpurun_out/r2b_smoke.log
+python bench.py > gpurun_out/r2b_bench.json 2> gpurun_out/r2b_bench.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2b_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extra > gpurun_out/r2b_ncu_bench.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_sweep_prod2 -s 1 -c 1 -f -o gpurun_out/r2b_prod2c python scripts/prof_compact.py > gpurun_out/r2b_ncu_full.log 2>&1
+tail -3 gpurun_out/r2b_pytest.log; cat gpurun_out/r2b_smoke.log; tail -c 600 gpurun_out/r2b_bench.err; head -c 1500 gpurun_out/r2b_bench.json
