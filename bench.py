@@ -559,7 +559,7 @@ def extra_blocks(torch, dev, peaks, counts, histogram, engine, _lib):
         ms = _event_ms(torch, lambda: dh.sweep(None, states=st, out=res, pmax=C3_PMAX), reps=3, warm=1)
         kern = _lib.last_kernel()
         code = (res.status & 0xFF)
-        ib, idm = np.meshgrid(np.arange(37, C3_NB, 256), np.arange(91, C3_ND, 256), indexing="ij")
+        ib, idm = np.meshgrid(np.arange(37, C3_NB, 128), np.arange(91, C3_ND, 128), indexing="ij")
         cells = np.stack([ib.ravel(), idm.ravel()], axis=1)
         flat = torch.from_numpy(cells[:, 0] * C3_ND + cells[:, 1]).to(dev)
         smp["c3_cells"] = cells
@@ -598,7 +598,7 @@ def extra_blocks(torch, dev, peaks, counts, histogram, engine, _lib):
         for _ in range(3):
             out4 = h4.find_phase_eq_batch(betas4, 0.0, order=2, lnZ_tol=1e-10)     # host arrays in, host records out (staged continuation)
         e2e_s = (time.perf_counter() - t0) / 3
-        ks = np.where(conv)[0][::max(1, int(conv.sum()) // 64)][:64]
+        ks = np.where(conv)[0][::max(1, int(conv.sum()) // 256)][:256]
         smp["c4_k"], smp["c4_mu"] = ks, hr["mu_coex"][ks]
         smp["c4_safe"] = hr["safe"][ks]
         for k in ("nphase", "max_idx", "bounds", "fe", "avg"):
@@ -631,7 +631,7 @@ def extra_blocks(torch, dev, peaks, counts, histogram, engine, _lib):
         for _ in range(3):
             engine.reweight_2d(lnpi2d, bounds, op, op, a1, a2, None)     # host arrays in, host array out
         e2e_s = (time.perf_counter() - t0) / 3
-        ks = np.arange(13, C5_S, C5_S // 64)[:64]
+        ks = np.arange(13, C5_S, C5_S // 1024)[:1024]
         smp["c5_k"], smp["c5_out"] = ks, hold["o"][torch.from_numpy(ks).to(dev)].cpu().numpy()
         support = int(np.sum(bounds[:, 1] - bounds[:, 0]))
         v = C5_S / (ms * 1e-3)

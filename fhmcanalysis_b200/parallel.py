@@ -81,6 +81,10 @@ def all_gather_rows(t, n_states, group=None):
         return t
     sizes = shard_sizes(n_states, world)
     smax = max(max(sizes), 1)
+    if min(sizes) == smax:   # equal shards: the collective writes the final tensor, no padding and no concatenation
+        full = torch.empty((world * smax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(full, t.contiguous(), group=group)
+        return full
     pad = torch.zeros((smax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     pad[:t.shape[0]] = t
     full = torch.empty((world * smax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)

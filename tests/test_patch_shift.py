@@ -62,3 +62,63 @@ def test_patch_shifts_against_oracle():
     big = [(np.arange(1000.0) * 0.01 + k, np.arange(1000.0) * 0.01 + 2.5 * k) for k in range(10000)]
     s, e = fp.patch_shifts(big)
     assert np.allclose(s, 1.5 * np.arange(10000), rtol=0, atol=1e-9) and np.all(e < 1e-18)
+
+
+# ---- pinned on the reference itself: oracle/_ref/fhmc_patch (compiled fhmc_patch.pyx) run on its own fixture windows
+#      unittests/reference/test_sim/{1,2} and on synthetic window pairs (tests/golden/make_golden_patch.py) ----------------
+def _golden_patch():
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "patch_vectors.npz"))
+    cases = []
+    for name in z["names"]:
+        name = str(name)
+        w = []
+        for k in ("w1", "w2"):
+            lb, ub, off = (int(v) for v in z["%s/%s/meta" % (name, k)])
+            w.append(_Win(lb, ub, z["%s/%s/lnpi" % (name, k)], off))
+        cases.append((name, w[0], w[1], z))
+    return cases
+
+
+def test_overlap_and_objective_match_compiled_reference():
+    """The slices overlap_slices() cuts and the oracle's restated objective reproduce ``window_patch_error`` of the compiled
+    reference at the recorded trial shifts (1e-12 relative); the pair the reference refuses raises the same assertion."""
+    from oracle import fhmc_oracle as fo
+    from fhmcanalysis_b200.moments.win_patch.fhmc_patch import overlap_slices
+    seen_sim = seen_raise = 0
+    for name, w1, w2, z in _golden_patch():
+        if name + "/raises" in z.files:
+            with pytest.raises(AssertionError, match="no overlap"):
+                overlap_slices(w1, w2)
+            seen_raise += 1
+            continue
+        s1, s2 = overlap_slices(w1, w2)
+        for x, want in zip(z[name + "/trial"], z[name + "/obj"]):
+            got = fo.window_patch_error(float(x), s1, s2)
+            assert abs(got - want) <= 1e-12 * max(1.0, abs(want)), (name, x)
+        shift, err2 = z[name + "/ref"]
+        # the reference's answer is the objective at ITS shift, per overlapping bin
+        assert abs(fo.window_patch_error(shift, s1, s2) / len(s1) - err2) <= 1e-12 * max(1.0, err2)
+        seen_sim += name.startswith("sim")
+    assert seen_sim >= 1 and seen_raise >= 1
+
+
+@pytest.mark.gpu
+def test_patch_window_pair_against_compiled_reference():
+    """fhmc_patch_shifts against patch_window_pair of the compiled reference: |shift - reference| <= the reference's own
+    xtol (1e-4); the parabola gives err2_ref - err2 = (shift_ref - shift)^2 exactly, checked to 1e-10; never worse than the
+    reference's minimum."""
+    from fhmcanalysis_b200.moments.win_patch import fhmc_patch as fp
+    n = 0
+    for name, w1, w2, z in _golden_patch():
+        if name + "/raises" in z.files:
+            with pytest.raises(AssertionError):
+                fp.patch_window_pair(w1, w2)
+            continue
+        shift_ref, err_ref = z[name + "/ref"]
+        shift, err2 = fp.patch_window_pair(w1, w2)
+        assert abs(shift - shift_ref) <= 1e-4, name
+        assert err2 <= err_ref + 1e-12 * max(1.0, err_ref)
+        assert abs((err_ref - err2) - (shift_ref - shift) ** 2) <= 1e-10 * max(1.0, err_ref), name
+        n += 1
+    assert n >= 5
