@@ -383,6 +383,8 @@ __global__ void __launch_bounds__(256) k_pack_phase_soa16(const __grid_constant_
 
 // compact-record instantiations of the headline kernel (fhmc_fast_prod_compact.cu)
 int launch_prod2_compact(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream, int *grid_out, bool dry);
+// the same on per-histogram tables (fhmc_tab.cu); needs args.d.mu_tables
+int launch_tab2_compact(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream, int *grid_out, bool dry);
 
 #define FHMC_FAST_MIN_STATES 4096
 
@@ -478,7 +480,9 @@ int fhmc_sweep_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_sta
 // path: plain sweep into the scratch, then the narrow repack)
 #define FHMC_COMPACT_SCRATCH_RECORDS 8192
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
-static size_t carve_records(unsigned char *base, long long c, int pmax, int nsel, fhmc_sweep_out *o)
+}  // extern "C"
+namespace fhmc {
+size_t carve_records(unsigned char *base, long long c, int pmax, int nsel, fhmc_sweep_out *o)
 {
     size_t off = 0;
     auto take = [&](size_t nbytes) { unsigned char *p = base ? base + off : nullptr; off += al256(nbytes); return p; };
@@ -495,6 +499,8 @@ static size_t carve_records(unsigned char *base, long long c, int pmax, int nsel
     if (o) *o = t;
     return off;
 }
+}  // namespace fhmc
+extern "C" {
 
 size_t fhmc_sweep_compact_workspace(const fhmc_hist_desc *desc, long long n_states)
 {
@@ -537,13 +543,17 @@ int fhmc_sweep_1d_compact(const fhmc_hist_desc *desc, const double *blob, const 
     // fused path: the product-form kernel writes the records itself
     if (states->n_states > (long long)di->sm_count * 2 * FHMC_CTA && !states->beta && !states->dmu) {
         int grid = 0;
-        int rc = launch_prod2_compact(args, di->sm_count, di->smem_optin, s, &grid, true);
+        const bool tab = desc->mu_tables != nullptr;
+        int rc = tab ? launch_tab2_compact(args, di->sm_count, di->smem_optin, s, &grid, true) : -1;
+        const bool use_tab = tab && rc == 0;
+        if (!use_tab) rc = launch_prod2_compact(args, di->sm_count, di->smem_optin, s, &grid, true);
         if (rc == 0) {
             const long long need = (long long)grid * (FHMC_CTA / 32);
             if (need <= FHMC_COMPACT_SCRATCH_RECORDS &&
                 carve_records(nullptr, FHMC_COMPACT_SCRATCH_RECORDS, desc->pmax, desc->n_sel, nullptr) <= workspace_bytes) {
                 carve_records(static_cast<unsigned char *>(workspace), FHMC_COMPACT_SCRATCH_RECORDS, desc->pmax, desc->n_sel, &args.out);
-                rc = launch_prod2_compact(args, di->sm_count, di->smem_optin, s, &grid, false);
+                rc = use_tab ? launch_tab2_compact(args, di->sm_count, di->smem_optin, s, &grid, false)
+                             : launch_prod2_compact(args, di->sm_count, di->smem_optin, s, &grid, false);
                 if (rc >= 0) return rc;
             }
         } else if (rc == 1) {

@@ -63,6 +63,7 @@ struct FastLayout {
     // REC == 2 (product form): per 4-bin block {key(Dmin), key(Dmax) | pad | P x4 | P*X_q x4 ...} doubles
     static constexpr int BW = 2 + 4 * (1 + NSEL);
     static constexpr int SEGB = 32;                     // blocks per anchor segment (128 bins)
+    static constexpr int GRPB = 8;                      // blocks per key group (k_sweep_prod2: one range test clears 32 bins)
     static constexpr int QN = FHMC_FAST_QUEUE;          // deferred-fallback queue entries
     static constexpr int QTILES = 4;                    // tiles between two looks at the queue
     // (three CTAs per SM with a 512-entry queue and an 80-register cap measured 10 % slower for REC == 2)
@@ -75,6 +76,7 @@ struct FastCtx {
     const double *g_hidx;     // hull vertex bin indices (global)
     int H;                    // hull vertices
     uint32_t s_prod, s_anch;  // REC == 2: per-block product rows, per-segment anchors (max lnPI of the segment)
+    uint32_t s_gkey;          // REC == 2: {min key(Dmin), max key(Dmax)} over each group of GRPB blocks
     double sdn_lim;           // REC == 2: largest |s dN| for which every segment can be walked in product form (see fast_prepare)
     double lmax;              // REC == 2: max |lnPI_i| (rounding margin of the extremum prefilter)
 };
@@ -139,7 +141,7 @@ __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned cha
         __syncthreads();
     }
     FastCtx cx;
-    cx.s_prod = cx.s_anch = 0;
+    cx.s_prod = cx.s_anch = cx.s_gkey = 0;
     cx.sdn_lim = 0.0;
     cx.lmax = 0.0;
     if (REC == 2) {
@@ -213,8 +215,23 @@ __device__ __forceinline__ FastCtx fast_prepare(const SweepArgs &a, unsigned cha
             }
         }
         __syncthreads();
+        // hull of the tilt ranges of GRPB consecutive blocks: a group no state point of the thread can have an extremum in is
+        // summed without looking at its blocks' keys
+        int *gkey = reinterpret_cast<int *>(s_rmax + 1);
+        for (int g = threadIdx.x; g < (nb + LY::GRPB - 1) / LY::GRPB; g += blockDim.x) {
+            int lo = 0x7fffffff, hi = (int)0x80000000;
+            for (int b = g * LY::GRPB; b < min(nb, (g + 1) * LY::GRPB); ++b) {
+                const int *kb = reinterpret_cast<const int *>(prod + (size_t)b * LY::BW);
+                lo = min(lo, kb[0]);
+                hi = max(hi, kb[1]);
+            }
+            gkey[2 * g] = lo;
+            gkey[2 * g + 1] = hi;
+        }
+        __syncthreads();
         cx.s_prod = smem_u32(prod);
         cx.s_anch = smem_u32(anch);
+        cx.s_gkey = smem_u32(gkey);
         // P_i = exp(lnPI_i - A_g) and the running factor t r^k must both stay normal numbers wherever their product
         // matters: the lnPI spread of a segment plus the growth of t over its 128 bins has to fit the fp64 exponent
         // range, and exp(|s dN| * 128) itself must stay finite (4.5).  State points beyond the limit take true exps.
@@ -730,6 +747,7 @@ static size_t fast_smem_bytes(int n_pad)
     if (REC == 2) {
         const size_t nb = (size_t)(n_pad / 4 + 1);
         b += (nb + 3) * LY::BW * 8 + (nb / LY::SEGB + 2) * 8 + 32;   // (+3 blocks: the key prefetch reads ahead)
+        b += (nb / LY::GRPB + 2) * 8;                                  // group keys
     }
     return b;
 }

@@ -43,6 +43,7 @@ struct ProdWalk {
         int *lst;   // COMPACT: this state point's lists {max_idx[PM], min_idx[PM + 1], bounds[2 PM]} (local memory)
     };
     static constexpr int PM = FHMC_COMPACT_PMAX, LST = 4 * FHMC_COMPACT_PMAX + 1;
+    static constexpr bool USES_LST = COMPACT;
     static constexpr unsigned F_BAD = 1u, F_ROBUST = 2u, F_CHAIN = 4u;
     __device__ __forceinline__ double u0(const PS &p) const
     {
@@ -58,12 +59,12 @@ struct ProdWalk {
 
     const SweepArgs &a;
     const FastCtx &cx;
-    PointEval<1, false> &pe;
-    const int n, last, pmax;
+    PointEval<1, false> *const pe_;   // prologue / epilogue only (setup, repair); null inside slow_range_call()
+    const int n, last, pmax, smooth;
     const uint32_t s_pk, tab;
 
-    __device__ ProdWalk(const SweepArgs &a_, const FastCtx &cx_, PointEval<1, false> &pe_)
-        : a(a_), cx(cx_), pe(pe_), n(a_.d.n), last(a_.d.n - 1), pmax(a_.d.pmax), s_pk(cx_.s_pk), tab(pe_.tab)
+    __device__ ProdWalk(const SweepArgs &a_, const FastCtx &cx_, PointEval<1, false> *pe, int smooth_, uint32_t tab_)
+        : a(a_), cx(cx_), pe_(pe), n(a_.d.n), last(a_.d.n - 1), pmax(a_.d.pmax), smooth(smooth_), s_pk(cx_.s_pk), tab(tab_)
     {
     }
 
@@ -147,7 +148,7 @@ struct ProdWalk {
         const double vm = vmargin(p);
         const double xg = is_max ? xc - vm : xc + vm;
         bool rb = true;
-        for (int d = d0; d <= pe.w; ++d) {
+        for (int d = d0; d <= smooth; ++d) {
             const int jl = (i - d < 0) ? 0 : i - d;
             const int jr = (i + d > last) ? last : i + d;
             double xl = load_u(p, jl, Nd), xr = load_u(p, jr, Nd);
@@ -275,6 +276,7 @@ struct ProdWalk {
     // ---- prologue -----------------------------------------------------------------------------------------------
     __device__ __forceinline__ void init(PS &p, long long sp, double mu1) const
     {
+        PointEval<1, false> &pe = *pe_;
         pe.setup(mu1, a.d.beta_ref, a.d.dmu_ref);
         p.s = pe.s;
         p.sp = sp;
@@ -323,41 +325,87 @@ struct ProdWalk {
             b = bend;
         }
     }
+    // The hot loop.  A group of GRPB blocks whose key hull clears both state points is summed with no test at all
+    // (6 LDS.128 + 24 DFMA + 2 DMUL per block for the two points); a group that may hold an extremum of either point is
+    // walked point by point by slow_group() (out of line: the hot loop stays a few hundred bytes of straight code).
     __device__ __forceinline__ void walk2(PS &p0, PS &p1) const
     {
+        constexpr int GB = LY::GRPB;
         const int nb = (n - 2) / 4;
-        const double r2a = p0.r1 * p0.r1, r2b = p1.r1 * p1.r1;   // (pinning these in registers costs a spill in the loop: measured slower)
-        uint32_t pb = cx.s_prod;
+        const double r2a = p0.r1 * p0.r1, r2b = p1.r1 * p1.r1;
+        uint32_t pb = cx.s_prod, pg = cx.s_gkey;
         int b = 0, i = 1;
         for (int g = 0; b < nb; ++g) {
             const int bend = min(nb, b + LY::SEGB);
             const bool ua = anchor(p0, g, i), ub = anchor(p1, g, i);
             if (!(ua & ub)) {   // rare: walk this segment point by point
-                segment_single(p0, ua, b, bend, i, pb);
-                segment_single(p1, ub, b, bend, i, pb);
+                slow_range(p0, ua, b, bend, i, pb);
+                slow_range(p1, ub, b, bend, i, pb);
                 i += 4 * (bend - b);
                 pb += BWB * (uint32_t)(bend - b);
+                pg += 8u * (uint32_t)((bend - b + GB - 1) / GB);
                 b = bend;
                 continue;
             }
-            int ka, kb;   // the range keys of the next block are fetched while this one is summed
-            asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(ka), "=r"(kb) : "r"(pb));
-            for (; b < bend; ++b, i += 4, pb += BWB) {
-                const bool fa = flagged(p0, ka, kb), fb = flagged(p1, ka, kb);
-                asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(ka), "=r"(kb) : "r"(pb + BWB));
-                double tb[4 * (1 + NA)];
-                load_block(pb, tb);
-                if (fa | fb) {
-                    if (fa) careful_block(p0, pb, i); else fast_block_regs(p0, tb, r2a);
-                    if (fb) careful_block(p1, pb, i); else fast_block_regs(p1, tb, r2b);
+            while (b < bend) {
+                const int ge = min(bend, b + GB);
+                int ka, kb;
+                asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(ka), "=r"(kb) : "r"(pg));
+                pg += 8u;
+                if (flagged(p0, ka, kb) | flagged(p1, ka, kb)) {
+                    // block by block with the blocks' own keys; a flagged block runs the exact tests for its point
+                    int ib = i;
+                    for (int k = b; k < ge; ++k, ib += 4, pb += BWB) {
+                        int kba, kbb;
+                        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(kba), "=r"(kbb) : "r"(pb));
+                        const bool fa = flagged(p0, kba, kbb), fb = flagged(p1, kba, kbb);
+                        double tb[4 * (1 + NA)];
+                        load_block(pb, tb);
+                        if (fa) careful_block(p0, pb, ib); else fast_block_regs(p0, tb, r2a);
+                        if (fb) careful_block(p1, pb, ib); else fast_block_regs(p1, tb, r2b);
+                        p0.t *= p0.r4;
+                        p1.t *= p1.r4;
+                    }
+                } else if (ge - b == GB) {
+#pragma unroll 2
+                    for (int k = 0; k < GB; ++k, pb += BWB) {
+                        double tb[4 * (1 + NA)];
+                        load_block(pb, tb);
+                        fast_block_regs(p0, tb, r2a);
+                        fast_block_regs(p1, tb, r2b);
+                        p0.t *= p0.r4;
+                        p1.t *= p1.r4;
+                    }
                 } else {
-                    fast_block_regs(p0, tb, r2a);
-                    fast_block_regs(p1, tb, r2b);
+                    for (int k = b; k < ge; ++k, pb += BWB) {
+                        double tb[4 * (1 + NA)];
+                        load_block(pb, tb);
+                        fast_block_regs(p0, tb, r2a);
+                        fast_block_regs(p1, tb, r2b);
+                        p0.t *= p0.r4;
+                        p1.t *= p1.r4;
+                    }
                 }
-                p0.t *= p0.r4;
-                p1.t *= p1.r4;
+                i += 4 * (ge - b);
+                b = ge;
             }
         }
+    }
+    // blocks [b, bend) for one point with per-block key tests, exact tests in flagged blocks (segment_single), out of line.
+    // The state travels through a copy so that the caller's PS never has its address taken.
+    __device__ __forceinline__ void slow_range(PS &p, bool usable, int b, int bend, int i, uint32_t pb) const
+    {
+        PS q = p;
+        slow_range_call(a, cx, smooth, tab, &q, usable, b, bend, i, pb);
+        p = q;
+    }
+    static __device__ __noinline__ void slow_range_call(const SweepArgs &a_, FastCtx cx_, int smooth_, uint32_t tab_, PS *q, bool usable,
+                                                        int b, int bend, int i, uint32_t pb)
+    {
+        const ProdWalk w(a_, cx_, nullptr, smooth_, tab_);
+        PS p = *q;
+        w.segment_single(p, usable, b, bend, i, pb);
+        *q = p;
     }
 
     // ---- epilogue: tail bins, validation with the exact rules of the generic path, record ------------------------
@@ -365,6 +413,7 @@ struct ProdWalk {
     __device__ __forceinline__ bool finish(PS &p) const
     {
         if (p.fl & F_BAD) return false;
+        PointEval<1, false> &pe = *pe_;
         pe.s = p.s;
         {
             int i = 1 + 4 * ((n - 2) / 4);
@@ -483,18 +532,12 @@ struct ProdWalk {
     }
 };
 
-// Two state points per thread: thread t of tile T owns state points T*512 + t and T*512 + 256 + t.
-template <int NSEL, bool SEL0N, bool COMPACT = false>
-__global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_prod2(const __grid_constant__ SweepArgs a)
+// Two state points per thread: thread t of tile T owns state points T*512 + t and T*512 + 256 + t.  W = ProdWalk or the
+// table-driven TabWalk (fhmc_tab.cuh): same tiles, same deferred queue, same drain.
+template <int NSEL, bool COMPACT, class W>
+__device__ __forceinline__ void prod2_tiles(const SweepArgs &a, const W &w, double *s_tab)
 {
-    using LY = FastLayout<NSEL, SEL0N, 0, 1, 2>;
-    using W = ProdWalk<NSEL, SEL0N, COMPACT>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const FastCtx cx = fast_prepare<NSEL, SEL0N, 0, 1, 2>(a, smem_raw);
-    double *s_tab = cx.s_tab;
-    PointEval<1, false> pe(a, a.blob, threadIdx.x & 31, s_tab);   // rare paths (repair) read HBM/L2
-    const W w(a, cx, pe);
-
+    using LY = typename W::LY;
     // deferred fallback queue, as in k_sweep_fast
     long long *queue = reinterpret_cast<long long *>(s_tab + 64);
     int *q_count = reinterpret_cast<int *>(queue + LY::QN);
@@ -534,7 +577,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_prod2(const __grid_consta
     };
     int tile_no = 0;
     const long long S = a.st.n_states;
-    int lst0[COMPACT ? W::LST : 1], lst1[COMPACT ? W::LST : 1];
+    int lst0[W::USES_LST ? W::LST : 1], lst1[W::USES_LST ? W::LST : 1];
     for (long long base = (long long)blockIdx.x * (2 * FHMC_CTA); base < S; base += (long long)gridDim.x * (2 * FHMC_CTA)) {
         const long long sp0 = base + threadIdx.x, sp1 = sp0 + FHMC_CTA;
         if (sp0 < S) {
@@ -574,6 +617,18 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_prod2(const __grid_consta
         for (int o = 16; o > 0; o >>= 1) top = max(top, __shfl_xor_sync(0xffffffffu, top, o));
         if ((threadIdx.x & 31) == 0 && top > 0) atomicMax(a.c.max_nphase, top);
     }
+}
+
+template <int NSEL, bool SEL0N, bool COMPACT = false>
+__global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_prod2(const __grid_constant__ SweepArgs a)
+{
+    using W = ProdWalk<NSEL, SEL0N, COMPACT>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const FastCtx cx = fast_prepare<NSEL, SEL0N, 0, 1, 2>(a, smem_raw);
+    double *s_tab = cx.s_tab;
+    PointEval<1, false> pe(a, a.blob, threadIdx.x & 31, s_tab);   // rare paths (repair) read HBM/L2
+    const W w(a, cx, &pe, a.d.smooth, pe.tab);
+    prod2_tiles<NSEL, COMPACT, W>(a, w, s_tab);
 }
 
 template <int NSEL, bool SEL0N, bool COMPACT = false>

@@ -228,6 +228,8 @@ class DeviceHistogram(object):
         # fhmc_fast_prod.cu) with two state points per thread where the sweep is large enough (> 512 points per SM), 2 = product form, one
         # point per thread, 1 = four multiplicative chains (fhmc_fast_rec.cu), 0/False = one true exp per bin
         self.use_recurrence = int(os.environ.get("FHMC_MU_RECURRENCE", "3"))
+        # per-histogram tables for compact-record mu sweeps (ensure_mu_tables); False keeps the table-free kernel
+        self.use_mu_tables = os.environ.get("FHMC_MU_TABLES", "1") != "0"
         blob = np.zeros((len(rows), n_pad), dtype=np.float64)
         for i, r in enumerate(rows):
             if r.shape != (n,):
@@ -283,6 +285,31 @@ class DeviceHistogram(object):
         if hasattr(self, "_blob_pin"):
             del self._blob_pin
 
+    def ensure_mu_tables(self):
+        """Per-histogram tables of the compact-record mu sweep (fhmc_mu_tables_build: product tables + the phase structure
+        of every elementary tilt interval), built once on the device and handed to the kernels through desc.mu_tables.
+        FHMC_MU_TABLES=0 keeps the table-free kernel (k_sweep_prod2)."""
+        if getattr(self, "_mu_tables_tried", False) or not self.use_mu_tables:
+            return
+        self._mu_tables_tried = True
+        self._mu_tables = None
+        if not self.use_mu_tables or self.desc.mu_recurrence < 2 or not self.desc.hull_len:
+            return
+        L = _lib.load()
+        t = torch()
+        nbytes = int(L.fhmc_mu_tables_bytes(ctypes.byref(self.desc)))
+        if nbytes == 0:
+            return
+        buf = t.empty(nbytes + 256, dtype=t.uint8, device=self.device)
+        ptr = (buf.data_ptr() + 255) & ~255
+        with t.cuda.device(self.device):
+            rc = L.fhmc_mu_tables_build(ctypes.byref(self.desc), _ptr(self.blob), ctypes.c_void_p(ptr), nbytes, _stream_ptr(self.device))
+        if rc == 2:
+            return
+        _lib.check(rc, "fhmc_mu_tables_build")
+        self._mu_tables = buf
+        self.desc.mu_tables = ptr
+
     # ------------------------------------------------------------------------------------------
     def _desc(self, pmax, complete=False, compare_raw=False, cutoff=None, smooth=None):
         d = _lib.HistDesc.from_buffer_copy(self.desc)
@@ -292,6 +319,8 @@ class DeviceHistogram(object):
         if cutoff is not None:
             d.cutoff = float(cutoff)
         if smooth is not None:
+            if int(smooth) != d.smooth:
+                d.mu_tables = None      # the tables belong to one window width
             d.smooth = int(smooth)
         return d
 
@@ -364,6 +393,7 @@ class DeviceHistogram(object):
         S = int(st.n_states)
         if S >= self.FAST_PATH_MIN_STATES:
             self.ensure_hull()
+            self.ensure_mu_tables()
         n_total = S + int(first) if n_total is None else int(n_total)
         d = self._desc(pmax)
         nbytes = int(L.fhmc_pack_soa16_bytes(n_total, pmax, self.n_sel))
@@ -480,6 +510,7 @@ class DeviceHistogram(object):
         chunk = int(min(chunk, max(S, 1)))
         if S >= self.FAST_PATH_MIN_STATES and lanes in (0, 1):
             self.ensure_hull()
+            self.ensure_mu_tables()
         n_chunks = (S + chunk - 1) // chunk
         if not hasattr(self, "_hpipe") or self._hpipe["key"] != (chunk, pmax):
             ws_bytes = int(L.fhmc_sweep_host_workspace(chunk, pmax, nsel))

@@ -109,6 +109,13 @@ typedef struct fhmc_hist_desc {
     /* fhmc_find_phase_eq_1d only: minimum width (bins) of a phase that counts in the coexistence objective.
      * 0 = 2*smooth (ntot/gc_hist.pyx:652); n1/gc_hist.pyx:1479 passes smooth itself.                                  */
     int min_width;
+    /* Optional accelerator for pure mu sweeps with compact records (fhmc_sweep_1d_compact, fhmc_sweep_host_compact*): per-histogram
+     * tables built once by fhmc_mu_tables_build() -- the product tables of the sweep kernel and, per elementary interval of
+     * the tilt -s dN between two consecutive chord slopes of ln(PI), the outcome of relextrema() + the phase bounds of
+     * thermo() (GH:317-415, 498-520).  NULL: not provided (the sweep kernel builds its tables per launch and tests for
+     * extrema as it walks).  The buffer must stay valid and unchanged while sweeps use it, and belongs to exactly this
+     * blob / n / smooth / sel_row combination.                                                                        */
+    const void *mu_tables;
 } fhmc_hist_desc;
 
 /*
@@ -218,6 +225,16 @@ typedef struct fhmc_compact_out {
     int *max_nphase;
 } fhmc_compact_out;
 size_t fhmc_sweep_compact_workspace(const fhmc_hist_desc *desc, long long n_states);
+/*
+ * Per-histogram tables for fhmc_hist_desc.mu_tables (new; the reference recomputes relextrema()/thermo() bounds from
+ * scratch at every mu, GH:317-415, 498-520 -- on uniformly spaced N they are piecewise constant in mu and change only at
+ * chord slopes of ln(PI), so they are evaluated once per interval by the general evaluator and looked up afterwards).
+ * desc must describe a pure mu sweep in product form (mu_recurrence >= 2, hull rows present, n_coef == 0, n_term <= 1,
+ * n_sel <= 2, n <= 32767); desc->mu_tables is ignored.  tables: device, 256-byte aligned, fhmc_mu_tables_bytes() bytes
+ * (0 = not applicable).  Asynchronous on `stream`; returns 0 ok, 1 error, 2 not applicable for this descriptor.
+ */
+size_t fhmc_mu_tables_bytes(const fhmc_hist_desc *desc);
+int fhmc_mu_tables_build(const fhmc_hist_desc *desc, const double *blob, void *tables, size_t tables_bytes, void *stream);
 int fhmc_sweep_1d_compact(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states, const fhmc_compact_out *out,
                           void *workspace, size_t workspace_bytes, void *stream);
 

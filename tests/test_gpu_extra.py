@@ -417,6 +417,7 @@ def test_compact_records_written_by_the_sweep_kernel():
     lnpi = synth.two_peak_lnpi(n)
     N = np.arange(n, dtype=np.float64)
     dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=10, sel=["N", N * N])
+    dh.use_mu_tables = False      # the table-driven kernel has its own test (tests/test_gpu_tables.py)
     S = 200001
     mu = np.concatenate([np.linspace(-0.03, 0.03, S - 4001), np.linspace(-6.0, 6.0, 4001)])   # strong tilts: queue / general evaluator
     h = dh.sweep_auto(mu, pmax=4).host()
