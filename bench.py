@@ -231,8 +231,11 @@ def parity_block(cpu_npz, gpu, tag, rtol=1e-10):
         bad += int(np.sum((gpu["min_idx"][idx] != ref["min_idx"])[live_m]))
     rel = 0.0
     with np.errstate(all="ignore"):
-        for a, b in ((gpu["fe"][idx], ref["fe"]), (gpu["avg"][idx][..., 0], ref["avg"][..., 0]), (gpu["avg"][idx][..., 1], ref["avg"][..., 1])):
-            d = np.abs(a - b)[live] / np.abs(b[live])
+        # F.E./kT = -(ln sum_phase - x_0) is a logarithm and crosses zero inside the sweep (2e-5 at mu = -0.0196 of config 2, where
+        # 2e-14 absolute reads as 1e-9 relative): its error is taken relative to max(|F.E.|, 1); the averages purely relative
+        for a, b, floor in ((gpu["fe"][idx], ref["fe"], 1.0), (gpu["avg"][idx][..., 0], ref["avg"][..., 0], 0.0),
+                            (gpu["avg"][idx][..., 1], ref["avg"][..., 1], 0.0)):
+            d = np.abs(a - b)[live] / np.maximum(np.abs(b[live]), floor)
             if d.size:
                 rel = max(rel, float(np.nanmax(d)))
             bad += int(np.sum(np.isnan(a[live])))

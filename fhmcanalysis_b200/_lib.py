@@ -7,7 +7,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfhmc_b200.so")
+LIB_PATH = os.environ.get("FHMC_LIB_PATH") or os.path.join(HERE, "libfhmc_b200.so")   # (override: A/B runs of experimental builds)
 
 MAX_TERMS = 8
 MAX_SEL = 4

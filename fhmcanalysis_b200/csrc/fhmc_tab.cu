@@ -148,4 +148,15 @@ int fhmc_mu_tables_build(const fhmc_hist_desc *desc, const double *blob, void *t
     return check_cuda(cudaGetLastError(), "k_tab_records launch");
 }
 
+#ifdef FHMC_TAB_PROFILE
+// probe builds only: per-phase cycle sums of k_sweep_tab2 (init, walk, finish, -, warp tiles)
+int fhmc_tab_profile(unsigned long long *out8, int reset)
+{
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    if (out8 && cudaMemcpyFromSymbol(out8, g_tab_prof, sizeof(g_tab_prof)) != cudaSuccess) return 1;
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_tab_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 }  // extern "C"

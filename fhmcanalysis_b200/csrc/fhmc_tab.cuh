@@ -24,6 +24,8 @@
 // the build runs fast_prepare() in one CTA and saves its shared-memory image; every sweep CTA stages that image with two
 // TMA bulk copies instead of recomputing it (r01b: ~40 us per launch and CTA, 105 us per 2^17-point chunk against 64 us).
 #pragma once
+#include <stdlib.h>
+
 #include "fhmc_prod.cuh"
 
 namespace fhmc {
@@ -295,6 +297,16 @@ __device__ __forceinline__ FastCtx tab_prepare(const SweepArgs &a, unsigned char
     cx.s_gkey = smem_u32(anch + nseg + 2);
     cx.sdn_lim = h->sdn_lim;
     cx.lmax = h->lmax;
+    // exp(A_{g+1} - A_g): the running factor crosses a segment border by one multiplication (TabWalk::next_anchor); 0 where
+    // the ratio leaves the fp64 range.  Kept where fast_prepare() keeps the group keys, which this kernel never reads.
+    {
+        double *ratio = anch + nseg + 2;
+        for (int g = threadIdx.x; g < nseg; g += blockDim.x) {
+            const double e = (g + 1 < nseg) ? exp(anch[g + 1] - anch[g]) : 0.0;
+            ratio[g] = (e > 1e-280 && e < 1e280) ? e : 0.0;
+        }
+        __syncthreads();
+    }
     tc.ep = reinterpret_cast<const double *>(tables + h->off_ep);
     tc.rec = reinterpret_cast<const short *>(tables + h->off_rec);
     tc.n_ep = h->n_ep;
@@ -318,6 +330,7 @@ struct TabWalk : ProdWalk<NSEL, SEL0N, true> {
     struct PS : B::PS {
         int Bn;             // next boundary bin: the running phase ends before it (n: none left)
         int nph;            // phases of the record
+        int ivl;            // elementary tilt interval of this state point
         const short *rec;
     };
     const TabCtx &tc;
@@ -329,7 +342,8 @@ struct TabWalk : ProdWalk<NSEL, SEL0N, true> {
     }
 
     // ---- prologue: interval lookup instead of hull search + key ranges ------------------------------------------------
-    __device__ __forceinline__ void init(PS &p, long long sp, double mu1) const
+    // hint: interval index of a neighbouring state point (-1: none); consecutive state points of a sweep mostly share it
+    __device__ __forceinline__ void init(PS &p, long long sp, double mu1, int hint = -1) const
     {
         p.s = __dmul_rn(__dsub_rn(mu1, this->a.d.mu1_ref), this->a.d.beta_ref);   // GH:77, evaluated left to right
         p.sp = sp;
@@ -345,10 +359,15 @@ struct TabWalk : ProdWalk<NSEL, SEL0N, true> {
         if (fabs(sdn) < this->cx.sdn_lim) p.fl |= B::F_CHAIN;
         const double av = -sdn;
         int lo = 0, hi = tc.n_ep;
+        if (hint >= 0) {   // the hinted interval holds the tilt: no search
+            const double h_lo = hint > 0 ? __ldg(tc.ep + hint - 1) : -CUDART_INF, h_hi = hint < tc.n_ep ? __ldg(tc.ep + hint) : CUDART_INF;
+            if (h_lo <= av && av < h_hi) lo = hi = hint;
+        }
         while (lo < hi) {   // number of endpoints <= tilt
             const int mid = (lo + hi) >> 1;
             if (__ldg(tc.ep + mid) <= av) lo = mid + 1; else hi = mid;
         }
+        p.ivl = lo;
         const double dl = tab_margin(this->cx.lmax, fabs(p.s), tc.Na);
         const double e_lo = lo > 0 ? __ldg(tc.ep + lo - 1) : -CUDART_INF, e_hi = lo < tc.n_ep ? __ldg(tc.ep + lo) : CUDART_INF;
         p.rec = tc.rec + (size_t)lo * FHMC_TAB_REC_I16;
@@ -358,7 +377,7 @@ struct TabWalk : ProdWalk<NSEL, SEL0N, true> {
         const bool cap = p.nph > this->pmax || (head.z & 0xffff) > this->pmax - 1 || (head.z >> 16) > this->pmax || (head.w & 0xffff) > this->pmax + 1;
         if (!(av - e_lo > dl && e_hi - av > dl) || (head.x & 0xffff) != 1 || cap) p.fl |= B::F_BAD;
         p.r1 = exp(sdn);
-        p.r4 = exp(4.0 * sdn);
+        p.r4 = (p.r1 * p.r1) * (p.r1 * p.r1);   // (3 ulp instead of 1: <= 1e-14 over the 32 blocks between two anchors)
         p.Bn = this->n;
         if (!(p.fl & B::F_BAD)) {
             double Nm;
@@ -368,6 +387,21 @@ struct TabWalk : ProdWalk<NSEL, SEL0N, true> {
             this->load_bin(p, 0, b0);
             this->accumulate(p, b0);
         }
+    }
+    // t at the first bin of segment g: carried over from the end of segment g - 1 (t has been advanced by r4 per block, so
+    // only the anchors' ratio is missing) when that segment was walked in product form and t is a comfortable normal
+    // number, else a true exp like ProdWalk::anchor().  Rounding: one more multiplication per 128 bins.
+    __device__ __forceinline__ bool next_anchor(PS &p, int g, int i, bool prev_usable) const
+    {
+        if (g > 0 && prev_usable) {
+            const double e = lds_f64(this->cx.s_gkey + 8u * (uint32_t)(g - 1));
+            const double t = p.t * e;
+            if (t > 1e-250 && t < 1e250) {
+                p.t = t;
+                return true;
+            }
+        }
+        return this->anchor(p, g, i);
     }
     // right end of the running phase p.P (the last phase ends at n and is closed by finish())
     __device__ __forceinline__ int next_boundary(const PS &p) const
@@ -431,9 +465,11 @@ struct TabWalk : ProdWalk<NSEL, SEL0N, true> {
         const int nb = (this->n - 2) / 4;
         uint32_t pb = this->cx.s_prod;
         int b = 0, i = 1;
+        bool u = false;
         for (int g = 0; b < nb; ++g) {
             const int bend = min(nb, b + LY::SEGB);
-            segment_single(p, this->anchor(p, g, i), b, bend, i, pb);
+            u = next_anchor(p, g, i, u);
+            segment_single(p, u, b, bend, i, pb);
             i += 4 * (bend - b);
             pb += BWB * (uint32_t)(bend - b);
             b = bend;
@@ -446,9 +482,11 @@ struct TabWalk : ProdWalk<NSEL, SEL0N, true> {
         const double r2a = p0.r1 * p0.r1, r2b = p1.r1 * p1.r1;
         uint32_t pb = this->cx.s_prod;
         int b = 0, i = 1;
+        bool ua = false, ub = false;
         for (int g = 0; b < nb; ++g) {
             const int bend = min(nb, b + LY::SEGB);
-            const bool ua = this->anchor(p0, g, i), ub = this->anchor(p1, g, i);
+            ua = next_anchor(p0, g, i, ua);
+            ub = next_anchor(p1, g, i, ub);
             if (!(ua & ub)) {   // rare: walk this segment point by point
                 segment_single(p0, ua, b, bend, i, pb);
                 segment_single(p1, ub, b, bend, i, pb);
@@ -462,28 +500,33 @@ struct TabWalk : ProdWalk<NSEL, SEL0N, true> {
                 int cnt = stop - b;
                 i += 4 * cnt;
                 b = stop;
-#pragma unroll 1
-                for (; cnt >= 2; cnt -= 2, pb += 2 * BWB) {
+                // software pipeline: the table entries of a block are fetched while the previous block is summed (an iteration
+                // that starts with its own loads waits out the shared-memory latency first: 360 cycles per two blocks at two
+                // warps per scheduler against 104 cycles of fp64 pipe).  The last prefetch of a run reads at most two blocks
+                // past it: still inside the product rows' allocation (fast_smem_bytes keeps three spare blocks).
+                if (cnt > 0) {
                     double ta[4 * (1 + NA)], tc2[4 * (1 + NA)];
                     this->load_block(pb, ta);
-                    this->load_block(pb + BWB, tc2);
-                    this->fast_block_regs(p0, ta, r2a);
-                    this->fast_block_regs(p1, ta, r2b);
-                    p0.t *= p0.r4;
-                    p1.t *= p1.r4;
-                    this->fast_block_regs(p0, tc2, r2a);
-                    this->fast_block_regs(p1, tc2, r2b);
-                    p0.t *= p0.r4;
-                    p1.t *= p1.r4;
-                }
-                if (cnt > 0) {
-                    double ta[4 * (1 + NA)];
-                    this->load_block(pb, ta);
-                    this->fast_block_regs(p0, ta, r2a);
-                    this->fast_block_regs(p1, ta, r2b);
-                    p0.t *= p0.r4;
-                    p1.t *= p1.r4;
-                    pb += BWB;
+#pragma unroll 1
+                    for (; cnt >= 2; cnt -= 2, pb += 2 * BWB) {
+                        this->load_block(pb + BWB, tc2);
+                        this->fast_block_regs(p0, ta, r2a);
+                        this->fast_block_regs(p1, ta, r2b);
+                        p0.t *= p0.r4;
+                        p1.t *= p1.r4;
+                        this->load_block(pb + 2 * BWB, ta);
+                        this->fast_block_regs(p0, tc2, r2a);
+                        this->fast_block_regs(p1, tc2, r2b);
+                        p0.t *= p0.r4;
+                        p1.t *= p1.r4;
+                    }
+                    if (cnt > 0) {
+                        this->fast_block_regs(p0, ta, r2a);
+                        this->fast_block_regs(p1, ta, r2b);
+                        p0.t *= p0.r4;
+                        p1.t *= p1.r4;
+                        pb += BWB;
+                    }
                 }
                 if (b < bend) {   // the block at `b` holds a boundary of at least one of the two points
                     double ta[4 * (1 + NA)];
@@ -517,8 +560,12 @@ struct TabWalk : ProdWalk<NSEL, SEL0N, true> {
         if ((p.fl & B::F_BAD) || p.P != p.nph) return false;
         const int nM = p.nph;
         int bb[2 * FHMC_COMPACT_PMAX];
+        {
+            const int4 lo4 = __ldg(reinterpret_cast<const int4 *>(p.rec + FHMC_TR_BOUNDS)), hi4 = __ldg(reinterpret_cast<const int4 *>(p.rec + FHMC_TR_BOUNDS) + 1);
+            const int wds[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
 #pragma unroll
-        for (int q = 0; q < 2 * FHMC_COMPACT_PMAX; ++q) bb[q] = (q < 2 * nM) ? (int)__ldg(p.rec + FHMC_TR_BOUNDS + q) : 0;
+            for (int q = 0; q < FHMC_COMPACT_PMAX; ++q) { bb[2 * q] = wds[q] & 0xffff; bb[2 * q + 1] = (wds[q] >> 16) & 0xffff; }
+        }
         unsigned flags = 0;
         const double c = add_shift(p.Mq, log(p.Stot));
         double Nd;
@@ -552,6 +599,108 @@ struct TabWalk : ProdWalk<NSEL, SEL0N, true> {
     }
 };
 
+#ifdef FHMC_TAB_PROFILE
+__device__ unsigned long long g_tab_prof[8];   // cycles (lane 0 of every warp): init, walk, finish, drain; [4] warp tiles
+#define TAB_PROF_T(k) { const long long t_ = clock64(); if (lane == 0) prof[k] += t_ - tp; tp = t_; }
+#else
+#define TAB_PROF_T(k)
+#endif
+
+// Warp-granular tiles: a warp owns 64 consecutive state points (lane l: points l and 32 + l of the warp tile), warp tiles are
+// dealt round-robin over all warps of the grid, and NOTHING synchronises the warps of a CTA after the tables are staged: the
+// per-warp fallback queue (at most the 64 points of the tile) is drained by the warp itself.  With CTA-wide tiles and a
+// barrier every second tile the eight warps of a CTA ran their prologues, product loops and epilogues in lockstep -- fp64
+// pipe saturated in the loop phase (math-pipe throttle) and idle in the latency-bound phases (r2f capture: 55 % active).
+// Independent warps drift apart (a warp that reaches the loop first finds the pipe free and gets further ahead), so one
+// warp's epilogue overlaps the others' loops.
+template <int NSEL, class W>
+__device__ __forceinline__ void tab2_warp_tiles(const SweepArgs &a, const W &w, double *s_tab)
+{
+    using LY = typename W::LY;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    long long *queue = reinterpret_cast<long long *>(s_tab + 64) + wib * 64;   // this warp's 64 entries of the queue area
+    static_assert(LY::QN >= (FHMC_CTA / 32) * 64, "queue area too small for the per-warp queues");
+    const long long S = a.st.n_states;
+    const long long slot = (long long)blockIdx.x * (FHMC_CTA / 32) + wib;          // scratch record of this warp
+    const long long nwarps = (long long)gridDim.x * (FHMC_CTA / 32);
+    int top = 0;
+#ifdef FHMC_TAB_STAGGER
+    // seed the phase offsets of the four warps that share a scheduler: warp pairs (w, w + 4) of the two resident CTAs
+    {
+        const int g = ((wib >> 2) & 1) * 2 + (int)((blockIdx.x / 148u) & 1u);
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)g * FHMC_TAB_STAGGER) __nanosleep(2000);
+    }
+#endif
+    // warp w of CTA c takes warp tiles (w * gridDim + c) + k * nwarps: the tiles of one round go to different SMs first
+#ifdef FHMC_TAB_PROFILE
+    long long prof[5] = {0, 0, 0, 0, 0}, tp = clock64();
+#endif
+    for (long long wt = (long long)wib * gridDim.x + blockIdx.x; wt * 64 < S; wt += nwarps) {
+        const long long sp0 = wt * 64 + lane, sp1 = sp0 + 32;
+        bool ok0 = true, ok1 = true;
+        if (sp0 < S) {
+            typename W::PS p0, p1;
+            w.init(p0, sp0, a.st.mu1[(sp0 / a.st.mu1_div) % a.st.n_mu1]);
+            if (sp1 < S) {
+                w.init(p1, sp1, a.st.mu1[(sp1 / a.st.mu1_div) % a.st.n_mu1], p0.ivl);
+                TAB_PROF_T(0)
+                if (!((p0.fl | p1.fl) & W::F_BAD)) {
+                    w.walk2(p0, p1);
+                } else {
+                    if (!(p0.fl & W::F_BAD)) w.walk1(p0);
+                    if (!(p1.fl & W::F_BAD)) w.walk1(p1);
+                }
+                TAB_PROF_T(1)
+                ok0 = w.finish(p0);
+                ok1 = w.finish(p1);
+                TAB_PROF_T(2)
+                if (ok1) top = max(top, p1.P);
+            } else {
+                if (!(p0.fl & W::F_BAD)) w.walk1(p0);
+                ok0 = w.finish(p0);
+            }
+            if (ok0) top = max(top, p0.P);
+        }
+#ifdef FHMC_TAB_PROFILE
+        if (lane == 0) prof[4] += 1;
+#endif
+        // anything unusual: the whole warp evaluates it with the general evaluator, point by point
+        const unsigned m0 = __ballot_sync(0xffffffffu, !ok0), m1 = __ballot_sync(0xffffffffu, !ok1);
+        if (m0 | m1) {
+            if (!ok0) queue[__popc(m0 & ((1u << lane) - 1u))] = sp0;
+            if (!ok1) queue[__popc(m0) + __popc(m1 & ((1u << lane) - 1u))] = sp1;
+            __syncwarp();
+            const int cnt = __popc(m0) + __popc(m1);
+            for (int k = 0; k < cnt; ++k) {
+                const long long qs = queue[k];
+                const double qm = a.st.mu1[(qs / a.st.mu1_div) % a.st.n_mu1];
+                run_generic_point_warp<false>(a, s_tab, lane, qm, a.d.beta_ref, a.d.dmu_ref, slot);
+                __syncwarp();
+                const unsigned st_ = a.out.status[slot];
+                const int nM = a.out.nphase[slot];
+                const int Pe = ((st_ & FHMC_ST_CODE_MASK) == FHMC_OK) ? min(max(nM, 0), a.d.pmax) : 0;
+                if (lane < Pe)
+                    w.put_phase(qs, lane, a.out.fe[slot * a.d.pmax + lane], 1.0, a.out.avg + (slot * a.d.pmax + lane) * NSEL);
+                // (a point that went through the walk first may have left fe / avg in slots the final record does not have:
+                // always blank the dead slots of a re-evaluated point)
+                if (lane == 0) w.put_compact_tail_fill(qs, st_, nM, a.out.bounds + slot * a.d.pmax * 2, true);
+                top = max(top, Pe);
+                __syncwarp();
+            }
+        }
+    }
+    if (a.c.max_nphase) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) top = max(top, __shfl_xor_sync(0xffffffffu, top, o));
+        if (lane == 0 && top > 0) atomicMax(a.c.max_nphase, top);
+    }
+#ifdef FHMC_TAB_PROFILE
+    if (lane == 0)
+        for (int k = 0; k < 5; ++k) atomicAdd(&g_tab_prof[k], (unsigned long long)prof[k]);
+#endif
+}
+
 template <int NSEL, bool SEL0N>
 __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_tab2(const __grid_constant__ SweepArgs a)
 {
@@ -562,7 +711,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_tab2(const __grid_constan
     const FastCtx cx = tab_prepare<NSEL, SEL0N>(a, smem_raw, tc, ok);
     double *s_tab = cx.s_tab;
     const W w(a, cx, nullptr, a.d.smooth, smem_u32(s_tab), tc, ok);
-    prod2_tiles<NSEL, true, W>(a, w, s_tab);
+    tab2_warp_tiles<NSEL, W>(a, w, s_tab);
 }
 
 template <int NSEL, bool SEL0N>
@@ -580,6 +729,7 @@ static int launch_tab2(const SweepArgs &args, int sm_count, int smem_optin, cuda
     if (grid_out) *grid_out = (int)grid;
     if (dry) return 0;
     if (grid > ntiles) grid = ntiles;
+    if (const char *e = getenv("FHMC_TAB_GRID")) { const long long g = atoll(e); if (g > 0 && g < grid) grid = g; }   // (probe: fewer resident warps)
     kern<<<(unsigned)grid, FHMC_CTA, smem, stream>>>(args);
     note_kernel("k_sweep_tab2<compact>");
     return check_cuda(cudaGetLastError(), "k_sweep_tab2 launch");
