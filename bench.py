@@ -7,14 +7,16 @@ Workload (config.workload): BASELINE config 2 -- synthetic 1-component N_tot ln(
 smooth = 10; a "step" is one pass of the fused sweep (reweight + normalise + phase split + per-phase lnZ +
 <N>, <N^2>) over 10^6 state points mu in [-0.03, 0.03] PER GPU (weak scaling: the N*10^6-point mu list is cut into one
 contiguous shard per rank by the product's own `parallel.sweep_sharded_compact`; state points are independent, there is no
-collective on the data path, and the ONE exchange of the path -- the gather of the complete result records to every rank --
-is fused into the sweep kernel as plain stores into the peers' NVLink-mapped buffers).
+collective on the data path; the optional gather of the complete result records to every rank is fused into the sweep
+kernel as plain stores into the peers' NVLink-mapped buffers and reported beside the headline as value_with_gather).
 
 Timed numbers
   value      state points/s through `parallel.sweep_sharded_compact` (what a multi-GPU user calls): inputs resident in
              HBM, CUDA events around each step on the launch stream, L2 flushed (256 MiB write) before every step, max
-             over ranks.  At N > 1 it INCLUDES the gather (value_with_gather repeats it; value_compute_only is the same
-             sweep without the peer stores).  `strong` = the 10^6-point sweep of config 2 cut over the N GPUs.
+             over ranks.  The records stay sharded (gather=False): the state points are independent, nothing on the data path
+             needs an exchange.  value_with_gather = the same call with gather=True (every rank ends up with every record;
+             link-bound: each GPU receives (N-1)/N of all record bytes).  `strong` = the 10^6-point sweep of config 2 cut over
+             the N GPUs, gathered.
   e2e        the same metric through the public batched API with HOST buffers: pinned-host mu -> device,
              kernel, compact results -> pinned host, every step (one C-ABI call, fhmc_sweep_host_compact16).
   roofline   fp64 ISSUE roofline of the dominant kernel: frac = fp64-pipe instructions the kernel executes per second /
@@ -754,7 +756,10 @@ def run_gpu_arm(args, rank, world, local_rank):
     peaks = engine.measure_peaks(dev)
     hold = {"state": None, "rec": None}
 
-    def step():   # the product's multi-GPU call: sweep of this rank's shard, complete compact records gathered to every rank
+    def step():   # the product's multi-GPU call: sweep of this rank's shard; the records stay sharded (no data-path collective)
+        hold["rec"], hold["state"] = parallel.sweep_sharded_compact(dh, mu_all, pmax=PMAX, state=hold["state"], gather=False)
+
+    def step_gather():   # the same call with the complete compact records gathered to every rank (fused into the kernel)
         hold["rec"], hold["state"] = parallel.sweep_sharded_compact(dh, mu_all, pmax=PMAX, state=hold["state"])
 
     def barrier():
@@ -797,16 +802,14 @@ def run_gpu_arm(args, rank, world, local_rank):
     fused = bool(hold["state"].fused)
     rec_bytes = int(hold["state"].block_bytes)
 
-    # the same sweep without the peer stores (compute only), and the strong-scaling form of config 2 (10^6 points over N GPUs)
-    compute_only = strong = None
+    # the same call with the gather of the complete records to every rank (fused into the kernel), and the strong-scaling form
+    # of config 2 (10^6 points over N GPUs)
+    with_gather = strong = None
     if world > 1:
-        local = torch.empty(rec_bytes, dtype=torch.uint8, device=dev)
-        shard = mu_all[lo:hi]
-        smax = hold["state"].smax
         for _ in range(3):
-            dh.sweep_compact(shard, pmax=PMAX, dst=local, n_total=smax, fill_dead=False)
-        _, ms_c, _ = timed_loop(lambda: dh.sweep_compact(shard, pmax=PMAX, dst=local, n_total=smax, fill_dead=False), args.steps)
-        compute_only = {"value": world * S / (ms_c * 1e-3), "ms_per_step": ms_c}
+            step_gather()
+        _, ms_g, _ = timed_loop(step_gather, args.steps)
+        with_gather = {"value": world * S / (ms_g * 1e-3), "ms_per_step": ms_g}
         mu_strong = torch.from_numpy(np.linspace(MU_LO, MU_HI, S)).to(dev)
         sh = {"state": None}
 
@@ -947,17 +950,21 @@ def run_gpu_arm(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "gpu_launches": args.steps * (1 + (2 if fused else 0)),
-            "value_with_gather": value if world > 1 else None,
-            "value_compute_only": compute_only["value"] if compute_only else value,
+            "data": "synthetic", "gpu_launches": args.steps,
+            "value_with_gather": with_gather["value"] if with_gather else None,
+            "value_compute_only": value,
             "config": {"workload": "config2: synthetic 1-comp N_tot lnPI, N_max=1000 (1001 bins), smooth=10, 10^6-point mu sweep per GPU with thermo "
                                    "(<N>, <N^2>, per-phase lnZ, phase split, is_safe)",
                        "state_points_per_gpu": S, "bins": N_BINS, "smooth": SMOOTH, "pmax": PMAX, "moments": list(moments),
-                       "timed_call": "parallel.sweep_sharded_compact -> fhmc_sweep_1d_compact (%s): compact records {status i16, nphase u8, fe/avg f64, bounds i16} "
-                                     "written by the sweep kernel%s" % (timed_kernel, "; gather fused into the kernel as stores to every rank's NVLink-mapped buffer (symmetric memory) + 2 device barriers" if fused else
-                                                                        ("; NCCL all_gather of the compact blocks" if world > 1 else "")),
+                       "timed_call": "parallel.sweep_sharded_compact(gather=False) -> fhmc_sweep_1d_compact (%s): every rank sweeps its contiguous shard, compact records "
+                                     "{status i16, nphase u8, fe/avg f64, bounds i16} written by the sweep kernel and left sharded (state points are independent: "
+                                     "no data-path collective)" % timed_kernel,
+                       "value_with_gather": (("the same call with gather=True: " + ("stores to every rank's NVLink-mapped buffer fused into the sweep kernel (symmetric memory) + 2 device barriers"
+                                                                                   if fused else "NCCL all_gather of the compact blocks") +
+                                              "; every rank receives (N-1)/N of all live record bytes (60 B per two-phase state point): bound by the NVLink "
+                                              "inbound bandwidth of one GPU, %.0f MB per step here") % ((world - 1) * S * 60 / 1e6)) if world > 1 else None,
                        "gather": ("fused_nvlink_stores" if fused else ("nccl_all_gather" if world > 1 else None)),
-                       "record_bytes_per_rank": rec_bytes, "compute_only_ms_per_step": compute_only["ms_per_step"] if compute_only else None,
+                       "record_bytes_per_rank": rec_bytes, "with_gather_ms_per_step": with_gather["ms_per_step"] if with_gather else None,
                        "lanes_per_point": args.lanes or "auto", "e2e_outputs": list(E2E_FIELDS),
                        "e2e_path": "fhmc_sweep_host_compact16 (C ABI, host buffers): per 2^17-point chunk H2D(mu) -> sweep kernel writing compact records -> D2H of the live phase blocks; upload, compute and download streams",
                        "e2e_gpu_launches_per_step": e2e_launches, "l2": "flushed (256 MiB memset) before every timed step",

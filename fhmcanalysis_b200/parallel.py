@@ -222,6 +222,7 @@ class ShardedRecords(object):
         self.block_bytes, self.fused = int(block_bytes), bool(fused)
         self.sizes = shard_sizes(self.n_states, self.world)
         self.smax = max(max(self.sizes), 1)
+        self.gathered = True     # False: only this rank's block is filled (sweep_sharded_compact(gather=False))
 
     def views(self, rank):
         """[smax, ...] views (status, nphase, fe, avg, bounds) of rank ``rank``'s block; rows >= sizes[rank] are padding."""
@@ -296,12 +297,15 @@ class CompactGather(object):
             dist.barrier(group=self.group)
 
 
-def sweep_sharded_compact(dh, mu1, pmax=4, group=None, state=None, fused=None, pre_barrier=True):
+def sweep_sharded_compact(dh, mu1, pmax=4, group=None, state=None, fused=None, pre_barrier=True, gather=True):
     """Pure mu sweep sharded over the ranks with the gather FUSED into the sweep kernel (see module docstring).  Call from
     every rank with the same ``mu1``; asynchronous on the current stream.  Returns (ShardedRecords, state) -- pass
     ``state`` back in to reuse the buffers (and the symmetric-memory rendezvous) for the next sweep of the same size.
 
-    pre_barrier: ranks may still be reading the buffer of the previous sweep; a barrier first makes overwriting safe."""
+    pre_barrier: ranks may still be reading the buffer of the previous sweep; a barrier first makes overwriting safe.
+    gather=False: the records STAY SHARDED -- every rank fills only its own block of its buffer (``ShardedRecords.views(rank)``),
+    no peer stores, no barrier, no collective: the state points are independent, so nothing on the data path needs an
+    exchange; the gather is a convenience for callers that want every record everywhere."""
     import torch
     import torch.distributed as dist
     mu1 = np.atleast_1d(np.asarray(mu1, dtype=np.float64)) if not isinstance(mu1, torch.Tensor) else mu1
@@ -311,6 +315,13 @@ def sweep_sharded_compact(dh, mu1, pmax=4, group=None, state=None, fused=None, p
     world, rank = state.world, state.rank
     lo, hi = shard_bounds(S, world, rank)
     shard = mu1[lo:hi]
+    if not gather:
+        if hi > lo:
+            dh.sweep_compact(shard, pmax=pmax, dst=state.buf[rank * state.block_bytes:(rank + 1) * state.block_bytes], n_total=state.smax,
+                             first=0, fill_dead=False)
+        rec = ShardedRecords(state.buf, S, world, pmax, dh.n_sel, state.block_bytes, state.fused)
+        rec.gathered = False
+        return rec, state
     if state.fused:
         if pre_barrier:
             state.barrier()
