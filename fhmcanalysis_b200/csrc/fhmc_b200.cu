@@ -386,6 +386,9 @@ int launch_prod2_compact(const SweepArgs &args, int sm_count, int smem_optin, cu
 // the same on per-histogram tables (fhmc_tab.cu); needs args.d.mu_tables
 int launch_tab2_compact(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream, int *grid_out, bool dry);
 
+// Taylor-extrapolated grids, rows combined per (mu_1, beta) (fhmc_rowc.cu)
+int launch_rowc(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream);
+
 #define FHMC_FAST_MIN_STATES 4096
 
 int choose_lanes(long long n_states, int bins, const DevInfo *di)
@@ -464,7 +467,10 @@ int fhmc_sweep_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_sta
             if (desc->hull_len >= 2 && desc->hull_row > 1 && desc->hull_row + 2 <= desc->n_rows)
                 rc = launch_fast_mu(args, di->sm_count, di->smem_optin, s);
         } else {
-            rc = launch_fast_taylor(args, di->sm_count, di->smem_optin, s);
+            // (beta x dmu_2) grids with dmu_2 fastest: coefficient rows combined once per grid row (fhmc_rowc.cu)
+            static const bool rowc_on = !(getenv("FHMC_ROWC") && getenv("FHMC_ROWC")[0] == '0');
+            if (rowc_on) rc = launch_rowc(args, di->sm_count, di->smem_optin, s);
+            if (rc < 0) rc = launch_fast_taylor(args, di->sm_count, di->smem_optin, s);
         }
         if (rc >= 0) return rc;
     }

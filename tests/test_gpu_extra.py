@@ -284,6 +284,29 @@ def test_fast_taylor_kernel_agrees_with_generic(golden, golden_meta):
         _agree(a, b, ("sw", order, moments))
 
 
+@pytest.mark.gpu
+def test_row_combined_taylor_grid_kernel_agrees_with_generic(golden, golden_meta):
+    """k_sweep_rowc (coefficient rows combined once per (mu_1, beta) row of a beta x dmu_2 grid, two state points per thread,
+    in-warp fallback on the combined rows) against the general evaluator on the flat rows: wide temperature range (monotone
+    and one-phase cells), a run length that is not a multiple of the 64-point warp tile, orders 1 and 2, a small pmax."""
+    from fhmcanalysis_b200 import _lib
+    from fhmcanalysis_b200.moments.histogram.one_dim.ntot.gc_hist import histogram
+    meta = golden_meta["c3"]
+    h = histogram.from_arrays(golden["c3/lnpi"], golden["c3/mom"], meta["beta_ref"], meta["mu_ref"], meta["smooth"])
+    h.reweight(meta["mu1"])
+    for order, nb, nd, pmax, brange in ((2, 24, 600, 8, (0.90, 1.10)), (1, 16, 1111, 8, (0.97, 1.03)), (2, 8, 520, 2, (0.98, 1.02))):
+        betas, dmus = np.linspace(brange[0], brange[1], nb), np.linspace(0.1, 0.9, nd)
+        dh = h.device_histogram(beta=betas, dmu=dmus, order=order, moments=())
+        st = dh.make_states(np.array([meta["mu1"]]), betas, dmus, grid=True)
+        a = dh.sweep(None, states=st, pmax=pmax, lanes=1).host()
+        assert _lib.last_kernel() == "k_sweep_rowc"
+        b = dh.sweep(None, states=st, pmax=pmax, lanes=-1).host()
+        assert _lib.last_kernel() == "k_sweep_1d<1>"
+        if pmax == 8:
+            assert np.mean(a["code"] == 0) > 0.9 and np.mean((a["status"] & 0x1000) != 0) > 0.5
+        _agree(a, b, ("rowc", order, nb, nd, pmax))
+
+
 def torch_int16():
     import torch
     return torch.int16
