@@ -577,7 +577,7 @@ def extra_blocks(torch, dev, peaks, counts, histogram, engine, _lib):
                              "value": v, "unit": UNIT, "ms": ms, "state_points": S, "kernel": kern, "gpu_launches": 1,
                              "ok_fraction": float((code == 0).double().mean().item()),
                              "fast_kernel_fraction": float(((res.status & 0x1000) != 0).double().mean().item()),
-                             "roofline": _roof(counts, "k_sweep_fast<taylor>", v, peaks, N_BINS),
+                             "roofline": _roof(counts, kern, v, peaks, N_BINS),
                              "e2e": None, "e2e_note": "the full record set of 1.7x10^7 cells is 3.6 GB; grids are consumed on the device (gc_binary.make_grid_multi) -- no host-buffer form is timed"}
         del res
     except Exception as e:

@@ -113,11 +113,16 @@ __global__ void __launch_bounds__(FHMC_CTA) k_lnpi_1d(const __grid_constant__ Sw
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_phase_moments(const double *__restrict__ lnpi, int n, const double *__restrict__ mom,
                                                        int n_arrays, const int *__restrict__ bounds, int n_phase,
-                                                       double *__restrict__ avg, double *__restrict__ lnsum)
+                                                       double *__restrict__ avg, double *__restrict__ lnsum,
+                                                       const unsigned *__restrict__ status_dev, const int *__restrict__ nphase_dev)
 {
     __shared__ double s_tab[64];
     stage_exp_table(s_tab);
     __syncthreads();
+    if (nphase_dev) {   // bounds are the record of a sweep that is still on the device: its phase count, none if it raised
+        const int P = ((*status_dev & FHMC_ST_CODE_MASK) == FHMC_OK) ? *nphase_dev : 0;
+        n_phase = min(n_phase, max(P, 0));
+    }
     const uint32_t tab = smem_u32(s_tab);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -613,7 +618,18 @@ int fhmc_phase_moments(const double *lnpi, int n, const double *mom, int n_array
     const long long jobs = (long long)n_phase * (n_arrays + 1);
     long long blocks = (jobs + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_phase_moments<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(lnpi, n, mom, n_arrays, bounds, n_phase, avg, lnsum);
+    k_phase_moments<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(lnpi, n, mom, n_arrays, bounds, n_phase, avg, lnsum, nullptr, nullptr);
+    return check_cuda(cudaGetLastError(), "k_phase_moments launch");
+}
+
+int fhmc_phase_moments_dev(const double *lnpi, int n, const double *mom, int n_arrays, const int *bounds, const unsigned *status,
+                           const int *nphase, int pmax, double *avg, double *lnsum, void *stream)
+{
+    if (!lnpi || n < 1 || !bounds || !status || !nphase || pmax < 1 || n_arrays < 0 || (n_arrays > 0 && (!mom || !avg))) { set_error("bad arguments"); return 1; }
+    const long long jobs = (long long)pmax * (n_arrays + 1);
+    long long blocks = (jobs + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_phase_moments<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(lnpi, n, mom, n_arrays, bounds, pmax, avg, lnsum, status, nphase);
     return check_cuda(cudaGetLastError(), "k_phase_moments launch");
 }
 

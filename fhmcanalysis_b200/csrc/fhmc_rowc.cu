@@ -18,6 +18,7 @@
 // The exponent shift comes from a subsampled maximum (every 8th bin); a term may exceed it by up to 2^900, a larger
 // miss saturates (the exponent offset is clamped) and sends the state point to the general evaluator.
 #include "fhmc_fast.cuh"
+#include "fhmc_exp256.cuh"
 
 namespace fhmc {
 
@@ -31,38 +32,47 @@ struct RowcPlan {
 struct RowcCtx {
     uint32_t sL;          // shared-memory address of row L; C2 at +oC2, C1 at +oC1
     uint32_t oC1, oC2;
-    uint32_t tabL;        // this lane's copy of the 2^(j/64) table: entry j at tabL + (j << 7)
+    uint32_t tabL;        // this lane's copy of the 2^(j/256) table: entry j at tabL + (j << 7)
     const double *rows;   // the same rows / the plain table for the general evaluator
     const double *tab64;
 };
 
-// exp_scaled_r() with the lane-replicated table and an upper clamp of the exponent offset (see the file header)
-__device__ __forceinline__ double exp_rowc(double u, int Mq, uint32_t tabL, const ExpRegs &c)
+// exp(u - Mq ln2) for the walk: k = rint(u * 256/ln2), two-constant Cody-Waite, |r| <= ln2/512, degree-4 polynomial
+// (remainder 3.8e-17), 2^(j/256) from the lane-replicated table, exponent by integer add with the offset clamped on both
+// sides (see the file header): 9 fp64-pipe instructions, one less than exp_scaled_r().
+struct ExpRegs256 {
+    double inv, nhi, nlo, c4, c3, c2;
+};
+__device__ __forceinline__ ExpRegs256 load_exp_regs256()
+{
+    ExpRegs256 r = {FHMC_EXP256_INV, -FHMC_EXP256_HI, -FHMC_EXP256_LO, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+    asm volatile("" : "+d"(r.inv), "+d"(r.nhi), "+d"(r.nlo), "+d"(r.c4), "+d"(r.c3), "+d"(r.c2));
+    return r;
+}
+__device__ __forceinline__ double exp_rowc(double u, int Mq, uint32_t tabL, const ExpRegs256 &c)
 {
     const double kd0 = fma(u, c.inv, FHMC_EXP_MAGIC);
     const int k = __double2loint(kd0);
     const double kd = kd0 - FHMC_EXP_MAGIC;
     double r = fma(kd, c.nhi, u);
     r = fma(kd, c.nlo, r);
-    double p = fma(r, c.c5, c.c4);
-    p = fma(p, r, c.c3);
+    double p = fma(r, c.c4, c.c3);
     p = fma(p, r, c.c2);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    const double T = lds_f64(tabL + ((k & 63) << 7));
+    const double T = lds_f64(tabL + ((k & 255) << 7));
     const double v = T * p;
-    const int q = min(max((k >> 6) - Mq, -1022), 1000);
+    const int q = min(max((k >> 8) - Mq, -1022), 1000);
     const int hi = __double2hiint(v) + (q << 20);
     return __hiloint2double(hi, __double2loint(v));
 }
-
 // per-state-point state of the walk (kept in registers: never pass its address to a non-inlined function)
 struct RowcPt {
     double dD, q2, Sacc, Stot, u0, xm, uc, dc;
     long long sp;
     int Mq, P, cntM, cntm;
     unsigned rescue;
-    bool bad;
+    bool bad, live;   // !live: a lane beyond the end of its run walks a copy of the last state point and writes nothing
 };
 
 template <bool HC2>
@@ -160,9 +170,12 @@ __device__ __noinline__ bool rowc_finish(const SweepArgs &a, const RowcCtx cx, i
     return true;
 }
 
-// The walk of one (TWO = false) or two state points of the calling thread over the combined rows.
-template <bool HC2, bool TWO>
-__device__ __forceinline__ void rowc_walk(const SweepArgs &a, const RowcCtx &cx, const ExpRegs &ec, RowcPt &A, RowcPt &B)
+// F.E./kT of a phase from its max-shifted sum (out of line: log() is ~60 instructions and sits on the rare flush path)
+__device__ __noinline__ double rowc_fe(double Sacc, int Mq, double u0) { return -(add_shift(Mq, log(Sacc)) - u0); }
+
+// The walk of the two state points of the calling thread over the combined rows.
+template <bool HC2, int NB>
+__device__ __forceinline__ void rowc_walk(const SweepArgs &a, const RowcCtx &cx, const ExpRegs256 &ec, RowcPt &A, RowcPt &B)
 {
     const int n = a.d.n, last = n - 1, pmax = a.d.pmax, w = a.d.smooth;
     const uint32_t sL = cx.sL, oC1 = cx.oC1, oC2 = cx.oC2, tabL = cx.tabL;
@@ -177,67 +190,82 @@ __device__ __forceinline__ void rowc_walk(const SweepArgs &a, const RowcCtx &cx,
         for (int i = 0; i < n; i += 8) {
             const uint32_t addr = sL + 8u * (uint32_t)i;
             const double L = lds_f64(addr), c1 = lds_f64(addr + oC1), c2 = HC2 ? lds_f64(addr + oC2) : 0.0;
-            mA = fmax(mA, uof(A, L, c1, c2));
-            if (TWO) mB = fmax(mB, uof(B, L, c1, c2));
+            const double va = uof(A, L, c1, c2), vb = uof(B, L, c1, c2);
+            mA = va > mA ? va : mA;
+            mB = vb > mB ? vb : mB;
         }
-        mA = fmax(mA, load_u(A, last));
-        A.Mq = shift_for_max(mA);
-        if (TWO) {
-            mB = fmax(mB, load_u(B, last));
-            B.Mq = shift_for_max(mB);
-        }
+        A.Mq = shift_for_max(fmax(mA, load_u(A, last)));
+        B.Mq = shift_for_max(fmax(mB, load_u(B, last)));
     }
     auto flush = [&](RowcPt &p) {
-        if (p.P < pmax && p.Sacc >= 1e-280) a.out.fe[p.sp * pmax + p.P] = -(add_shift(p.Mq, log(p.Sacc)) - p.u0);
+        if (p.P < pmax && p.Sacc >= 1e-280) { if (p.live) a.out.fe[p.sp * pmax + p.P] = rowc_fe(p.Sacc, p.Mq, p.u0); }
         else if (p.P < pmax && p.P < 32) p.rescue |= 1u << p.P;   // re-integrated about its own maximum in rowc_finish()
         else p.bad = true;
         p.Stot += p.Sacc;
         p.Sacc = 0.0;
         ++p.P;
     };
-    auto window = [&](const RowcPt &p, int i, double xc, bool is_max) {   // shifts 2..w (shift 1 already passed)
+    // bin i passed the strict 1-neighbour test: remaining shifts 2..w of argrelextrema, then the list entry; a confirmed
+    // minimum flushes the running sums (a minimum bin opens the phase to its right, GH:498-520)
+    auto confirm = [&](RowcPt &p, int i, double xc, bool is_max) {
         for (int d = 2; d <= w; ++d) {
             const int jl = (i - d < 0) ? 0 : i - d;
             const int jr = (i + d > last) ? last : i + d;
             const double xl = load_u(p, jl), xr = load_u(p, jr);
-            if (!(is_max ? (xc > xl && xc > xr) : (xc < xl && xc < xr))) return false;
+            if (!(is_max ? (xc > xl && xc > xr) : (xc < xl && xc < xr))) return;
         }
-        return true;
-    };
-    auto test_bin = [&](RowcPt &p, int i, double xm, double xc, double xp) {
-        const bool is_max = (xc > xm) && (xc > xp), is_min = (xc < xm) && (xc < xp);
-        if ((is_max || is_min) && window(p, i, xc, is_max)) {
-            if (is_max) {
-                if (1 + p.cntM <= pmax - 1) a.out.max_idx[p.sp * pmax + 1 + p.cntM] = i;
-                ++p.cntM;
-            } else {
-                if (1 + p.cntm <= pmax) a.out.min_idx[p.sp * (pmax + 1) + 1 + p.cntm] = i;
-                ++p.cntm;
-                flush(p);   // a minimum bin opens the phase to its right (GH:498-520)
-            }
+        if (is_max) {
+            if (p.live && 1 + p.cntM <= pmax - 1) a.out.max_idx[p.sp * pmax + 1 + p.cntM] = i;
+            ++p.cntM;
+        } else {
+            if (p.live && 1 + p.cntm <= pmax) a.out.min_idx[p.sp * (pmax + 1) + 1 + p.cntm] = i;
+            ++p.cntm;
+            flush(p);
         }
     };
     auto ex = [&](const RowcPt &p, double u) { return exp_rowc(u, p.Mq, tabL, ec); };
-    // one block of four bins i..i+3 of one state point: u of the bins i+1..i+4 given, p.xm / p.uc / p.dc carried
-    auto fast_block = [&](RowcPt &p, double u1, double u2, double u3, double u4, double d4) {
-        const double e0 = ex(p, p.uc), e1 = ex(p, u1), e2 = ex(p, u2), e3 = ex(p, u3);
-        p.Sacc += (e0 + e1) + (e2 + e3);
-        p.xm = u3;
-        p.uc = u4;
-        p.dc = d4;
+    // one block of NB bins i..i+NB-1 of one state point: un[] = u of the bins i+1..i+NB, p.xm / p.uc / p.dc carried
+    auto fast_block = [&](RowcPt &p, const double (&un)[NB], double dlast) {
+        double e[NB];
+        e[0] = ex(p, p.uc);
+#pragma unroll
+        for (int k = 1; k < NB; ++k) e[k] = ex(p, un[k - 1]);
+        p.Sacc += NB == 4 ? (e[0] + e[1]) + (e[2] + e[NB - 1]) : e[0] + e[1];
+        p.xm = un[NB - 2];
+        p.uc = un[NB - 1];
+        p.dc = dlast;
     };
-    auto slow_block = [&](RowcPt &p, int i, double u1, double u2, double u3, double u4, double d4) {
-        test_bin(p, i, p.xm, p.uc, u1);
-        p.Sacc += ex(p, p.uc);
-        test_bin(p, i + 1, p.uc, u1, u2);
-        p.Sacc += ex(p, u1);
-        test_bin(p, i + 2, u1, u2, u3);
-        p.Sacc += ex(p, u2);
-        test_bin(p, i + 3, u2, u3, u4);
-        p.Sacc += ex(p, u3);
-        p.xm = u3;
-        p.uc = u4;
-        p.dc = d4;
+    // a block in which successive differences change sign: exact strict 1-neighbour tests; only a bin that passes them
+    // (rare) takes the window test, in bin order, each bin's own term added after its test
+    auto slow_block = [&](RowcPt &p, int i, const double (&un)[NB], double dlast) {
+        double x[NB + 2], e[NB];
+        x[0] = p.xm;
+        x[1] = p.uc;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) x[k + 2] = un[k];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) e[k] = ex(p, x[k + 1]);
+        unsigned cM = 0, cm = 0;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            cM |= (x[k + 1] > x[k] && x[k + 1] > x[k + 2]) ? (1u << k) : 0u;
+            cm |= (x[k + 1] < x[k] && x[k + 1] < x[k + 2]) ? (1u << k) : 0u;
+        }
+        if ((cM | cm) == 0) {
+            p.Sacc += NB == 4 ? (e[0] + e[1]) + (e[2] + e[NB - 1]) : e[0] + e[1];
+        } else {
+            double xs[NB], es[NB];   // indexed by the loop counter below: local memory, on this rare path only
+#pragma unroll
+            for (int k = 0; k < NB; ++k) { xs[k] = x[k + 1]; es[k] = e[k]; }
+#pragma unroll 1
+            for (int k = 0; k < NB; ++k) {
+                if (((cM | cm) >> k) & 1u) confirm(p, i + k, xs[k], ((cM >> k) & 1u) != 0);
+                p.Sacc += es[k];
+            }
+        }
+        p.xm = un[NB - 2];
+        p.uc = un[NB - 1];
+        p.dc = dlast;
     };
     auto start = [&](RowcPt &p) {
         p.u0 = load_u(p, 0);
@@ -247,65 +275,71 @@ __device__ __forceinline__ void rowc_walk(const SweepArgs &a, const RowcCtx &cx,
         p.dc = __dsub_rn(p.uc, p.xm);   // sign(dc) is the exact order of (xm, uc)
     };
     if (n < 3) {
-        A.bad = true;
-        if (TWO) B.bad = true;
+        A.bad = B.bad = true;
         return;
     }
     start(A);
-    if (TWO) start(B);
+    start(B);
     int i = 1;
     uint32_t addr = sL + 16u;   // bin i + 1
-#pragma unroll 1
-    for (; i + 3 < last; i += 4, addr += 32u) {   // bins i..i+3 are interior, i+4 <= last exists
-        double L[4], c1[4], c2[4];
+    // sign bits of the NB + 1 successive differences around a block: any change means a strict 1-neighbour extremum may sit in it
+    auto flips = [&](const RowcPt &p, const double (&un)[NB], double &dlast) {
+        double d[NB];
+        d[0] = __dsub_rn(un[0], p.uc);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 1; k < NB; ++k) d[k] = __dsub_rn(un[k], un[k - 1]);
+        int f = __double2hiint(p.dc) ^ __double2hiint(d[0]);
+#pragma unroll
+        for (int k = 1; k < NB; ++k) f |= __double2hiint(d[k - 1]) ^ __double2hiint(d[k]);
+        dlast = d[NB - 1];
+        return f;
+    };
+#pragma unroll 1
+    for (; i + NB - 1 < last; i += NB, addr += 8u * NB) {   // bins i..i+NB-1 are interior, i+NB <= last exists
+        double L[NB], c1[NB], c2[NB];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
             L[k] = lds_f64(addr + 8u * k);
             c1[k] = lds_f64(addr + oC1 + 8u * k);
             c2[k] = HC2 ? lds_f64(addr + oC2 + 8u * k) : 0.0;
         }
-        double ua[4], ub[4];
+        double ua[NB], ub[NB];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < NB; ++k) {
             ua[k] = uof(A, L[k], c1[k], c2[k]);
-            if (TWO) ub[k] = uof(B, L[k], c1[k], c2[k]);
+            ub[k] = uof(B, L[k], c1[k], c2[k]);
         }
-        const double a1 = __dsub_rn(ua[0], A.uc), a2 = __dsub_rn(ua[1], ua[0]), a3 = __dsub_rn(ua[2], ua[1]), a4 = __dsub_rn(ua[3], ua[2]);
-        const int flipA = (__double2hiint(A.dc) ^ __double2hiint(a1)) | (__double2hiint(a1) ^ __double2hiint(a2)) |
-                          (__double2hiint(a2) ^ __double2hiint(a3)) | (__double2hiint(a3) ^ __double2hiint(a4));
-        if (TWO) {
-            const double b1 = __dsub_rn(ub[0], B.uc), b2 = __dsub_rn(ub[1], ub[0]), b3 = __dsub_rn(ub[2], ub[1]), b4 = __dsub_rn(ub[3], ub[2]);
-            const int flipB = (__double2hiint(B.dc) ^ __double2hiint(b1)) | (__double2hiint(b1) ^ __double2hiint(b2)) |
-                              (__double2hiint(b2) ^ __double2hiint(b3)) | (__double2hiint(b3) ^ __double2hiint(b4));
-            if ((flipA | flipB) < 0) {   // some pair of successive differences changes sign: look closely (per point)
-                if (flipA < 0) slow_block(A, i, ua[0], ua[1], ua[2], ua[3], a4); else fast_block(A, ua[0], ua[1], ua[2], ua[3], a4);
-                if (flipB < 0) slow_block(B, i, ub[0], ub[1], ub[2], ub[3], b4); else fast_block(B, ub[0], ub[1], ub[2], ub[3], b4);
-            } else {
-                fast_block(A, ua[0], ua[1], ua[2], ua[3], a4);
-                fast_block(B, ub[0], ub[1], ub[2], ub[3], b4);
-            }
+        double da, db;
+        const int flipA = flips(A, ua, da), flipB = flips(B, ub, db);
+        if ((flipA | flipB) < 0) {   // look closely (per point)
+            if (flipA < 0) slow_block(A, i, ua, da); else fast_block(A, ua, da);
+            if (flipB < 0) slow_block(B, i, ub, db); else fast_block(B, ub, db);
         } else {
-            if (flipA < 0) slow_block(A, i, ua[0], ua[1], ua[2], ua[3], a4); else fast_block(A, ua[0], ua[1], ua[2], ua[3], a4);
+            fast_block(A, ua, da);
+            fast_block(B, ub, db);
         }
     }
     auto tail = [&](RowcPt &p) {
+#pragma unroll 1
         for (int j = i; j < last; ++j) {
-            const double un = load_u(p, j + 1);
-            test_bin(p, j, p.xm, p.uc, un);
-            p.Sacc += ex(p, p.uc);
-            p.xm = p.uc;
+            const double un = load_u(p, j + 1), xc = p.uc;
+            const bool is_max = (xc > p.xm) && (xc > un), is_min = (xc < p.xm) && (xc < un);
+            if (is_max || is_min) confirm(p, j, xc, is_max);
+            p.Sacc += ex(p, xc);
+            p.xm = xc;
             p.uc = un;
         }
         p.Sacc += ex(p, p.uc);
         flush(p);
     };
     tail(A);
-    if (TWO) tail(B);
+    tail(B);
 }
 
-__device__ __forceinline__ void rowc_init(RowcPt &p, long long sp, double dmu, double dmu_ref)
+__device__ __forceinline__ void rowc_init(RowcPt &p, long long sp, double dmu, double dmu_ref, bool live)
 {
     p.sp = sp;
+    p.live = live;
     p.dD = dmu - dmu_ref;
     p.q2 = monomial(FHMC_M_DD2, 0.0, p.dD, 0.0);
     p.Sacc = p.Stot = 0.0;
@@ -316,37 +350,61 @@ __device__ __forceinline__ void rowc_init(RowcPt &p, long long sp, double dmu, d
     p.u0 = p.xm = p.uc = p.dc = 0.0;
 }
 
+// bytes of shared memory: two row buffers (L | C2 | C1 each), the plain 2^(j/64) table of the general evaluator, the
+// lane-replicated 2^(j/256) table, two release counters
+static size_t rowc_smem_bytes(int n_pad) { return ((size_t)6 * n_pad + 64 + 256 * 16) * 8 + 16; }
+
 template <bool HC2>
 __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_rowc(const __grid_constant__ SweepArgs a, const __grid_constant__ RowcPlan pl)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int n = a.d.n, npad = a.d.n_pad, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *rows = reinterpret_cast<double *>(smem_raw);   // L | C2 | C1
-    double *tab64 = rows + 3 * (size_t)npad;
-    double *tabR = tab64 + 64;                             // [64][16]: entry j of copy c at (j * 16 + c)
+    double *rows0 = reinterpret_cast<double *>(smem_raw);   // two buffers of L | C2 | C1
+    double *tab64 = rows0 + 6 * (size_t)npad;
+    double *tabR = tab64 + 64;                              // [256][16]: entry j of copy c at (j * 16 + c)
+    unsigned *released = reinterpret_cast<unsigned *>(tabR + 256 * 16);   // per buffer: warps that are done with a use of it
     stage_exp_table(tab64);
-    for (int j = threadIdx.x; j < 64 * 16; j += blockDim.x) tabR[j] = c_exp.tab[j >> 4];
-    const ExpRegs ec = load_exp_regs();
+    for (int j = threadIdx.x; j < 256 * 16; j += blockDim.x) tabR[j] = c_exp256[j >> 4];
+    if (threadIdx.x < 2) released[threadIdx.x] = 0u;
+    __syncthreads();   // the only CTA-wide barrier of the kernel
+    const ExpRegs256 ec = load_exp_regs256();
     RowcCtx cx;
-    cx.sL = smem_u32(rows);
     cx.oC2 = (uint32_t)npad * 8u;
     cx.oC1 = (uint32_t)npad * 16u;
     cx.tabL = smem_u32(tabR) + ((uint32_t)(lane & 15) << 3);
-    cx.rows = rows;
     cx.tab64 = tab64;
+    cx.rows = rows0;
+    cx.sL = smem_u32(rows0);
     const long long items = pl.n_runs * pl.chunks_per_run;
-    for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+    long long cur_run = -1;
+    unsigned epoch = 0;   // row builds so far; build e uses buffer e & 1
+    // contiguous items per CTA: the chunks of one run follow each other, so its rows are combined once
+    const long long it0 = items * blockIdx.x / gridDim.x, it1 = items * (blockIdx.x + 1) / gridDim.x;
+    for (long long it = it0; it < it1; ++it) {
         const long long run = it / pl.chunks_per_run;
         const int ch = (int)(it % pl.chunks_per_run);
         const long long sp0 = run * pl.n_run;
-        const double mu1 = a.st.mu1[(sp0 / a.st.mu1_div) % a.st.n_mu1];
-        const double beta = a.st.beta ? a.st.beta[(sp0 / a.st.beta_div) % a.st.n_beta] : a.d.beta_ref;
-        __syncthreads();   // every warp is done with the previous rows
-        {
-            // combine the coefficient rows of this (mu_1, beta): terms in descriptor order, each into the row of its power of dD
+        if (run != cur_run) {
+            // Every warp combines the coefficient rows of this (mu_1, beta) itself (all warps store identical values), so no
+            // warp waits for another one here; the two row buffers alternate, and a buffer is overwritten only after all
+            // warps of the CTA have released its previous use, two builds back (counter in shared memory).
+            __syncwarp();
+            if (cur_run >= 0 && lane == 0) {
+                __threadfence_block();
+                atomicAdd(&released[(epoch - 1) & 1u], 1u);
+            }
+            cur_run = run;
+            const unsigned b = epoch & 1u, need = (epoch >> 1) * (FHMC_CTA / 32);
+            if (lane == 0)
+                while (*reinterpret_cast<volatile unsigned *>(&released[b]) < need) { }
+            __syncwarp();
+            double *rows = rows0 + (size_t)b * 3 * npad;
+            const double mu1 = a.st.mu1[(sp0 / a.st.mu1_div) % a.st.n_mu1];
+            const double beta = a.st.beta ? a.st.beta[(sp0 / a.st.beta_div) % a.st.n_beta] : a.d.beta_ref;
+            // terms in descriptor order, each into the row of its power of dD
             const double s = __dmul_rn(__dsub_rn(mu1, a.d.mu1_ref), a.d.beta_ref);   // GH:77, evaluated left to right
             const double dB = beta - a.d.beta_ref;
-            for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+            for (int i = lane; i < npad; i += 32) {
                 double L = 0.0, C1 = 0.0, C2 = 0.0;
                 if (i < n) {
                     L = __dadd_rn(a.blob[i], __dmul_rn(s, a.blob[npad + i]));
@@ -363,31 +421,22 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_rowc(const __grid_constan
                 rows[npad + i] = C2;
                 rows[2 * npad + i] = C1;
             }
+            __syncwarp();
+            cx.rows = rows;
+            cx.sL = smem_u32(rows);
+            ++epoch;
         }
-        __syncthreads();
         const long long j0 = (long long)ch * pl.chunk, j1 = min(j0 + (long long)pl.chunk, pl.n_run);
         for (long long t = j0 + warp * 64; t < j1; t += (FHMC_CTA / 32) * 64) {
-            const long long jA = t + lane, jB = t + 32 + lane;
-            bool okA = true, okB = true;
-            if (t + 64 <= j1) {
-                RowcPt A, B;
-                rowc_init(A, sp0 + jA, a.st.dmu[jA], a.d.dmu_ref);
-                rowc_init(B, sp0 + jB, a.st.dmu[jB], a.d.dmu_ref);
-                rowc_walk<HC2, true>(a, cx, ec, A, B);
-                okA = !A.bad && rowc_finish<HC2>(a, cx, lane, A.sp, A.dD, A.q2, A.Mq, A.P, A.cntM, A.cntm, A.rescue, A.Stot, A.u0);
-                okB = !B.bad && rowc_finish<HC2>(a, cx, lane, B.sp, B.dD, B.q2, B.Mq, B.P, B.cntM, B.cntm, B.rescue, B.Stot, B.u0);
-            } else {   // last, partly filled tile of the run: one state point at a time
-                for (int h = 0; h < 2; ++h) {
-                    const long long j = h ? jB : jA;
-                    if (j < j1) {
-                        RowcPt A;
-                        rowc_init(A, sp0 + j, a.st.dmu[j], a.d.dmu_ref);
-                        rowc_walk<HC2, false>(a, cx, ec, A, A);
-                        const bool ok = !A.bad && rowc_finish<HC2>(a, cx, lane, A.sp, A.dD, A.q2, A.Mq, A.P, A.cntM, A.cntm, A.rescue, A.Stot, A.u0);
-                        if (h) okB = ok; else okA = ok;
-                    }
-                }
-            }
+            // a lane beyond the end of the run walks the run's last state point again without writing anything
+            const bool liveA = t + lane < j1, liveB = t + 32 + lane < j1;
+            const long long jA = liveA ? t + lane : j1 - 1, jB = liveB ? t + 32 + lane : j1 - 1;
+            RowcPt A, B;
+            rowc_init(A, sp0 + jA, a.st.dmu[jA], a.d.dmu_ref, liveA);
+            rowc_init(B, sp0 + jB, a.st.dmu[jB], a.d.dmu_ref, liveB);
+            rowc_walk<HC2, 4>(a, cx, ec, A, B);
+            const bool okA = !liveA || !A.bad && rowc_finish<HC2>(a, cx, lane, A.sp, A.dD, A.q2, A.Mq, A.P, A.cntM, A.cntm, A.rescue, A.Stot, A.u0);
+            const bool okB = !liveB || !B.bad && rowc_finish<HC2>(a, cx, lane, B.sp, B.dD, B.q2, B.Mq, B.P, B.cntM, B.cntm, B.rescue, B.Stot, B.u0);
             // anything unusual: the whole warp re-runs it with the general evaluator, on the combined rows
             __syncwarp();
             unsigned fA = __ballot_sync(0xffffffffu, !okA), fB = __ballot_sync(0xffffffffu, !okB);
@@ -397,7 +446,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_rowc(const __grid_constan
                 const int src = __ffs(f) - 1;
                 f &= f - 1;
                 const long long j = t + (second ? 32 : 0) + src;
-                rowc_generic(a, rows, tab64, lane, a.st.dmu[j], sp0 + j, HC2 ? 1 : 0);
+                rowc_generic(a, cx.rows, tab64, lane, a.st.dmu[j], sp0 + j, HC2 ? 1 : 0);
                 __syncwarp();
             }
         }
@@ -424,7 +473,7 @@ int launch_rowc(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_
         }
     }
     if (!has_dd && !hc2) return -1;
-    const size_t smem = ((size_t)3 * d.n_pad + 64 + 64 * 16) * 8;
+    const size_t smem = rowc_smem_bytes(d.n_pad);
     if (smem > (size_t)smem_optin) return -1;
     auto kern = hc2 ? k_sweep_rowc<true> : k_sweep_rowc<false>;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return 1;

@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Latency of the scalar drop-in API (fresh histogram -> reweight -> thermo(all moments) -> is_safe; find_phase_eq), with a
+cProfile breakdown (PROFILE=1)."""
+import cProfile
+import os
+import pstats
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from fhmcanalysis_b200 import synth  # noqa: E402
+from fhmcanalysis_b200.moments.histogram.one_dim.ntot.gc_hist import histogram  # noqa: E402
+
+lnpi1, mom1 = synth.two_peak_lnpi(1001), synth.one_comp_moments(1001)
+h1 = histogram.from_arrays(lnpi1, mom1, 1.0, [0.0], 10)
+
+
+def dropin():
+    hh = histogram.from_arrays(lnpi1, mom1, 1.0, [0.0], 10)
+    hh.reweight(0.01)
+    hh.thermo()
+    return hh.is_safe()
+
+
+def loop_same():
+    # the notebook loop: one histogram object, many state points (deepcopy per point like the reference's examples)
+    import copy
+    hh = copy.deepcopy(h1)
+    hh.reweight(0.01)
+    hh.thermo()
+    return hh.is_safe()
+
+
+for fn, name in ((dropin, "from_arrays+reweight+thermo+is_safe"), (loop_same, "deepcopy+reweight+thermo+is_safe")):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        fn()
+    print("%s: %.3f ms per state point" % (name, (time.perf_counter() - t0) / 50 * 1e3))
+t0 = time.perf_counter()
+for _ in range(10):
+    h1.find_phase_eq(1e-6, 0.0)
+print("find_phase_eq: %.3f ms" % ((time.perf_counter() - t0) / 10 * 1e3))
+if os.environ.get("PROFILE"):
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(50):
+        dropin()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(35)
