@@ -73,6 +73,14 @@ class SweepOut(ctypes.Structure):
                 ("status", "nphase", "nmin", "lnnorm", "fe", "avg", "bounds", "max_idx", "min_idx")]
 
 
+class ScalarIO(ctypes.Structure):
+    """fhmc_scalar_io (include/fhmc_b200.h): buffers of one fhmc_scalar_point call."""
+    _fields_ = [("blob", ctypes.c_void_p), ("mu1_dev", ctypes.c_void_p), ("mu1_pinned", ctypes.c_void_p), ("mu1", ctypes.c_double),
+                ("lnpi_host", ctypes.c_void_p), ("ntot_host", ctypes.c_void_p), ("rec", SweepOut), ("row", ctypes.c_void_p),
+                ("mom", ctypes.c_void_p), ("n_arrays", ctypes.c_int), ("avg", ctypes.c_void_p), ("lnsum", ctypes.c_void_p),
+                ("out_dev", ctypes.c_void_p), ("out_host", ctypes.c_void_p), ("out_bytes", ctypes.c_size_t)]
+
+
 EXPORTS = [
     "fhmc_version", "fhmc_last_error", "fhmc_last_kernel", "fhmc_device_info", "fhmc_sweep_1d", "fhmc_lnpi_1d",
     "fhmc_phase_moments", "fhmc_axpy_rows", "fhmc_find_phase_eq_1d", "fhmc_reweight_2d",
@@ -81,7 +89,7 @@ EXPORTS = [
     "fhmc_sweep_host_compact16", "fhmc_pack_soa16_bytes", "fhmc_pack_phase_soa16",
     "fhmc_patch_shifts", "fhmc_reweight_2d_prod", "fhmc_reweight_2d_prod_workspace",
     "fhmc_bench_dfma", "fhmc_bench_exp", "fhmc_lean_stats", "fhmc_sweep_1d_compact", "fhmc_sweep_compact_workspace",
-    "fhmc_mu_tables_bytes", "fhmc_mu_tables_build",
+    "fhmc_mu_tables_bytes", "fhmc_mu_tables_build", "fhmc_phase_moments_dev", "fhmc_scalar_point",
 ]
 
 _lib = None
@@ -160,6 +168,10 @@ def load():
     L.fhmc_mu_tables_bytes.argtypes = [ctypes.POINTER(HistDesc)]
     L.fhmc_mu_tables_build.restype = ci
     L.fhmc_mu_tables_build.argtypes = [ctypes.POINTER(HistDesc), vp, vp, ctypes.c_size_t, vp]
+    L.fhmc_phase_moments_dev.restype = ci
+    L.fhmc_phase_moments_dev.argtypes = [vp, ci, vp, ci, vp, vp, vp, ci, vp, vp, vp]
+    L.fhmc_scalar_point.restype = ci
+    L.fhmc_scalar_point.argtypes = [ctypes.POINTER(HistDesc), ctypes.POINTER(ScalarIO), ci, ci, vp]
     L.fhmc_lean_stats.restype = ci
     L.fhmc_lean_stats.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ci]
     _lib = L

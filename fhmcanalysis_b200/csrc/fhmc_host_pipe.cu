@@ -276,3 +276,37 @@ extern "C" int fhmc_sweep_host_compact16(const fhmc_hist_desc *desc, const doubl
     return sweep_host_impl(desc, blob, mu_host, n_states, lanes_per_point, chunk, workspace, workspace_bytes, out_host, flags_host,
                            guess_nphase, max_nphase_out, d2h_bytes_out, stream, true);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// fhmc_scalar_point: the scalar drop-in calls (histogram.reweight / normalize / relextrema / thermo on ONE state point,
+// GH:260-289, 317-415, 451-554) as one host call: H2D of what changed on the host side (ln(PI) row, N row, target mu_1),
+// sweep record (warp-per-point general evaluator), normalised row, per-phase averages of every moment array with the phase
+// bounds read from the record on the device, ONE D2H of the contiguous result range, one stream synchronisation.
+// The notebook loop of the reference costs a dozen synchronising copies per state point when each method uploads and
+// downloads on its own (0.86 ms measured); here a state point is two of these calls.
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int fhmc_scalar_point(const fhmc_hist_desc *desc, const fhmc_scalar_io *io, int want_row, int want_moments, void *stream)
+{
+    if (!desc || !io || !io->blob || !io->mu1_dev || !io->mu1_pinned || !io->out_dev || !io->out_host) { fhmc::set_error("fhmc_scalar_point: missing buffer"); return 1; }
+    if (want_moments && (!io->row || !io->lnsum || (io->n_arrays > 0 && (!io->mom || !io->avg)))) { fhmc::set_error("fhmc_scalar_point: missing moment buffers"); return 1; }
+    if (want_moments && !want_row) { fhmc::set_error("fhmc_scalar_point: the moments are averaged over the normalised row"); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t row_bytes = (size_t)desc->n * sizeof(double);
+    if (io->lnpi_host && fhmc::check_cuda(cudaMemcpyAsync(io->blob, io->lnpi_host, row_bytes, cudaMemcpyHostToDevice, s), "H2D ln(PI)")) return 1;
+    if (io->ntot_host && fhmc::check_cuda(cudaMemcpyAsync(io->blob + desc->n_pad, io->ntot_host, row_bytes, cudaMemcpyHostToDevice, s), "H2D N")) return 1;
+    *io->mu1_pinned = io->mu1;
+    if (fhmc::check_cuda(cudaMemcpyAsync(io->mu1_dev, io->mu1_pinned, sizeof(double), cudaMemcpyHostToDevice, s), "H2D mu_1")) return 1;
+    fhmc_states st;
+    memset(&st, 0, sizeof(st));
+    st.n_states = 1;
+    st.mu1 = io->mu1_dev;
+    st.n_mu1 = st.mu1_div = 1;
+    st.n_beta = st.beta_div = st.n_dmu = st.dmu_div = 1;
+    if (fhmc_sweep_1d(desc, io->blob, &st, &io->rec, 32, stream)) return 1;
+    if (want_row && fhmc_lnpi_1d(desc, io->blob, &st, io->rec.lnnorm, io->row, stream)) return 1;
+    if (want_moments &&
+        fhmc_phase_moments_dev(io->row, desc->n, io->mom, io->n_arrays, io->rec.bounds, io->rec.status, io->rec.nphase, desc->pmax,
+                               io->avg, io->lnsum, stream)) return 1;
+    if (fhmc::check_cuda(cudaMemcpyAsync(io->out_host, io->out_dev, io->out_bytes, cudaMemcpyDeviceToHost, s), "D2H results")) return 1;
+    return fhmc::check_cuda(cudaStreamSynchronize(s), "fhmc_scalar_point");
+}

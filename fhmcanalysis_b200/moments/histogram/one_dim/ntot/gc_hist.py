@@ -175,12 +175,22 @@ class histogram(TaylorMixin):
                                       self.data["curr_beta"], self.data["curr_mu"][0], dmu_ref, smooth=max(int(sm), 1),
                                       cutoff=cutoff, coef=coef, sel=sel, sel_kinds=sel_kinds, device=device)
 
+    def _scalar_point(self, mu1_target, **kw):
+        """One state point through the cached scalar path (engine.ScalarPath -> fhmc_scalar_point): the host arrays are the
+        source of truth, the device copies are refreshed only when their content key changed."""
+        lnpi = np.asarray(self.data["ln(PI)"], dtype=np.float64)
+        ntot = self.data[self._op_key]
+        if len(ntot) != len(lnpi):
+            # the reference's tests assign shorter arrays to data['ln(PI)'] (T1:155-198); normalize/relextrema/thermo
+            # never touch ntot (no reweighting shift: s = 0), so any N row of the right length will do
+            ntot = np.arange(len(lnpi))
+        sp = engine.ScalarPath.get(len(lnpi))
+        return sp.point(lnpi, ntot, self.data["curr_beta"], self.data["curr_mu"][0], self.metadata["smooth"], float(mu1_target), **kw)
+
     def _renormalised(self, mu1_target):
         """ln(PI) reweighted to mu1_target and normalised (K1): returns (array, lnNorm)."""
-        dh = self._device_hist()
-        res = dh.sweep(np.array([float(mu1_target)]), pmax=1, lanes=32, complete=True)
-        row = dh.lnpi_rows(res)[0].cpu().numpy()
-        return row, float(res.lnnorm.cpu().numpy()[0])
+        r = self._scalar_point(mu1_target, complete=True, want_row=True)
+        return r["row"], r["lnnorm"]
 
     # ------------------------------------------------------------------------------------------
     def mix(self, other, weights):
@@ -244,19 +254,29 @@ class histogram(TaylorMixin):
                 print(i, self.data["ln(PI)"][i] - self.data["ln(PI)"][0])
 
     # ------------------------------------------------------------------------------------------
-    def _split(self, compare_raw, want_norm):
-        """K3 (+K1 normalisation): extrema lists / bounds / F.E. of the current ln(PI)."""
+    def _split(self, compare_raw, want_norm, mom=None):
+        """K3 (+K1 normalisation, + K2 over the rows of ``mom``): extrema lists / bounds / F.E. of the current ln(PI)."""
         if int(self.metadata["smooth"]) < 1:
             raise ValueError("Order must be an int >= 1")  # scipy.signal.argrelextrema (GH:329)
-        dh = self._device_hist()
-        res = dh.sweep_auto(np.array([float(self.data["curr_mu"][0])]), pmax=8, lanes=32, compare_raw=compare_raw)
-        h = res.host()
-        code = int(h["code"][0])
-        P, nm = int(h["nphase"][0]), int(h["nmin"][0])
-        out = {"code": code, "maxima": h["max_idx"][0, :P].astype(np.int64), "minima": h["min_idx"][0, :nm].astype(np.int64),
-               "bounds": h["bounds"][0, :P].astype(np.int64), "fe": h["fe"][0, :P].copy(), "lnnorm": float(h["lnnorm"][0])}
-        if want_norm:
-            out["lnpi"] = dh.lnpi_rows(res)[0].cpu().numpy()
+        r = self._scalar_point(self.data["curr_mu"][0], compare_raw=compare_raw, want_row=want_norm, mom=mom)
+        if r["code"] == _lib.E_CAPACITY:
+            # more extrema than the scalar path's record holds (very noisy ln(PI)): the growing-capacity batched call
+            dh = self._device_hist()
+            res = dh.sweep_auto(np.array([float(self.data["curr_mu"][0])]), pmax=32, lanes=32, compare_raw=compare_raw)
+            h = res.host()
+            P, nm = int(h["nphase"][0]), int(h["nmin"][0])
+            out = {"code": int(h["code"][0]), "maxima": h["max_idx"][0, :P].astype(np.int64), "minima": h["min_idx"][0, :nm].astype(np.int64),
+                   "bounds": h["bounds"][0, :P].astype(np.int64), "fe": h["fe"][0, :P].copy(), "lnnorm": float(h["lnnorm"][0])}
+            if want_norm or mom is not None:
+                out["lnpi"] = dh.lnpi_rows(res)[0].cpu().numpy()
+            return out
+        P, nm = r["nphase"], r["nmin"]
+        out = {"code": r["code"], "maxima": r["max_idx"][:P].astype(np.int64), "minima": r["min_idx"][:nm].astype(np.int64),
+               "bounds": r["bounds"][:P].astype(np.int64), "fe": r["fe"][:P].copy(), "lnnorm": r["lnnorm"]}
+        if want_norm or mom is not None:
+            out["lnpi"] = r["row"]
+        if mom is not None:
+            out["avg"], out["lnsum"] = r["avg"], r["lnsum"]
         return out
 
     def relextrema(self):
@@ -312,9 +332,12 @@ class histogram(TaylorMixin):
     def thermo(self, props=True, complete=False, collect=None):
         """Integrate ln(PI) per phase and average every moment array (GH:451-554)."""
         n = len(self.data["ln(PI)"])
+        fused = None
         if not complete:
+            use_mom = props and collect is None and np.shape(self.data["mom"])[-1] == n
             try:
-                s = self._split(compare_raw=False, want_norm=True)
+                s = self._split(compare_raw=False, want_norm=True,
+                                mom=np.asarray(self.data["mom"], dtype=np.float64).reshape(-1, n) if use_mom else None)
             except ValueError as e:
                 raise Exception("Unable to find relative extrema : " + str(e))
             self.data["ln(PI)"] = s["lnpi"]  # GH:475: thermo leaves the normalised array behind
@@ -332,6 +355,8 @@ class histogram(TaylorMixin):
                     raise IndexError("index out of bounds")
                 raise Exception("Unable to find relative extrema : " + msg)
             bounds, fe = [tuple(int(v) for v in b) for b in s["bounds"]], s["fe"]
+            if "avg" in s:
+                fused = s["avg"]       # averaged on the device in the same call, over the bounds of the record
             if collect is not None:
                 collect(hist=self)
                 bounds = self._bounds_from_lists(n, self.data["ln(PI)_maxima_idx"], self.data["ln(PI)_minima_idx"])
@@ -342,7 +367,9 @@ class histogram(TaylorMixin):
         nphases = len(bounds)
         phase = {}
         avg = None
-        if props or fe is None:
+        if fused is not None:
+            avg = fused
+        elif props or fe is None:
             mom = np.asarray(self.data["mom"], dtype=np.float64) if props else None
             avg, lnsum = engine.phase_moments(self.data["ln(PI)"], mom.reshape(-1, n) if props else None, np.array(bounds))
             if fe is None:

@@ -179,6 +179,38 @@ int fhmc_lnpi_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_stat
  */
 int fhmc_phase_moments(const double *lnpi, int n, const double *mom, int n_arrays, const int *bounds,
                        int n_phase, double *avg, double *lnsum, void *stream);
+/* The same with the phase count still on the device: `bounds`, `status`, `nphase` point into the record of a sweep
+ * (fhmc_sweep_out of ONE state point, capacity pmax); phases >= *nphase (or all, if the status code is not FHMC_OK) are skipped. */
+int fhmc_phase_moments_dev(const double *lnpi, int n, const double *mom, int n_arrays, const int *bounds, const unsigned *status,
+                           const int *nphase, int pmax, double *avg, double *lnsum, void *stream);
+
+/*
+ * One scalar drop-in call (histogram.reweight / normalize / relextrema / thermo for ONE state point, GH:260-289, 317-415,
+ * 451-554) as ONE host call: uploads what changed on the host (lnpi_host / ntot_host non-NULL: pinned rows of desc->n
+ * doubles copied into blob rows 0 / 1), sets the target mu_1, runs fhmc_sweep_1d (one warp, general evaluator),
+ * fhmc_lnpi_1d (want_row) and fhmc_phase_moments_dev (want_moments: averages of the n_arrays rows of `mom` over the phases
+ * of the record), copies the contiguous device range [out_dev, out_dev + out_bytes) -- which the caller lays out to hold
+ * rec, row, avg and lnsum -- to out_host (pinned) and synchronises `stream`.
+ */
+typedef struct fhmc_scalar_io {
+    double *blob;              /* device [>= 2][n_pad]: row 0 ln(PI), row 1 N (+ whatever desc describes)   */
+    double *mu1_dev;           /* device [1]                                                               */
+    double *mu1_pinned;        /* pinned host [1]: staging of mu1                                          */
+    double mu1;                /* target mu_1 of the state point                                           */
+    const double *lnpi_host;   /* pinned host [n] or NULL (blob row 0 is current)                          */
+    const double *ntot_host;   /* pinned host [n] or NULL (blob row 1 is current)                          */
+    fhmc_sweep_out rec;        /* device record of one state point, capacity desc->pmax                    */
+    double *row;               /* device [n]: normalised reweighted ln(PI)            (want_row)            */
+    const double *mom;         /* device [n_arrays][n] or NULL                        (want_moments)        */
+    int n_arrays;
+    double *avg;               /* device [pmax][n_arrays]                                                   */
+    double *lnsum;             /* device [pmax]                                                             */
+    void *out_dev;             /* device range that holds rec / row / avg / lnsum ...                       */
+    void *out_host;            /* ... and its pinned host mirror                                            */
+    size_t out_bytes;
+} fhmc_scalar_io;
+int fhmc_scalar_point(const fhmc_hist_desc *desc, const fhmc_scalar_io *io, int want_row, int want_moments, void *stream);
+
 
 /*
  * Phase-major repack of sweep records for the trip to the host (new; no reference counterpart).  fhmc_sweep_out keeps

@@ -217,3 +217,52 @@ def test_batched_entry_points(golden, golden_meta, oracle):
         mu_t = oracle.find_phase_eq_tight(lnpi, N, meta["beta_ref"], 0.0, meta["smooth"], res["mu_coex"][k] - 0.01,
                                           res["mu_coex"][k] + 0.01, coef_fn=coef_fn)
         assert abs(res["mu_coex"][k] - mu_t) < 1e-10 * max(1.0, abs(mu_t))
+
+
+def test_scalar_path_cache_follows_the_host_arrays(golden):
+    """The scalar calls keep ln(PI), N and the moment tensor resident on the device between calls (engine.ScalarPath),
+    keyed on the CONTENT of the host arrays, which stay the source of truth (T1:155, 206-209 overwrite hist.data[...]).
+    Every kind of host-side change must reach the next call: a new array object, an in-place write of one element, a
+    change confined to the low-order moments (invisible to a floating-point checksum next to the N^2 U^2 rows, the bug
+    this test pins), two histogram objects of the same length taking turns, and a shorter ln(PI)."""
+    from fhmcanalysis_b200 import engine
+    a, b = _hist(golden, smooth=3), _hist(golden, smooth=3)
+    n = len(a.data["ln(PI)"])
+    lnpi0, mom0 = a.data["ln(PI)"].copy(), a.data["mom"].copy()
+
+    def fresh_thermo(lnpi, mom):
+        """the same state point through the batched kernels with nothing cached (a new DeviceHistogram per call)"""
+        dh = engine.DeviceHistogram(lnpi, np.arange(n), 1.0, 5.0, smooth=3)
+        h = dh.sweep(np.array([5.0]), pmax=8, lanes=32).host()
+        P = int(h["nphase"][0])
+        row = dh.lnpi_rows(dh.sweep(np.array([5.0]), pmax=8, lanes=32))[0].cpu().numpy()
+        avg, _ = engine.phase_moments(row, mom.reshape(-1, n), h["bounds"][0, :P])
+        return P, h["fe"][0, :P], avg
+
+    def check(hist):
+        lnpi, mom = np.array(hist.data["ln(PI)"], dtype=np.float64), np.array(hist.data["mom"], dtype=np.float64)
+        hist.thermo()
+        P, fe, avg = fresh_thermo(lnpi, mom)
+        assert len(hist.data["thermo"]) == P
+        for p in range(P):
+            assert np.isclose(hist.data["thermo"][p]["F.E./kT"], fe[p], rtol=1e-12, atol=1e-12)
+            assert np.allclose(hist.data["thermo"][p]["mom"].reshape(-1), avg[p], rtol=1e-12, atol=0, equal_nan=True)
+
+    check(a)
+    a.data["mom"][0, 1, 0, 0, 0, 7] += 1.0e-3             # one low-order entry, in place
+    check(a)
+    a.data["mom"] = mom0 * 1.0                            # new object, old content
+    check(a)
+    a.data["mom"][1, 1, 0, 0, 0] *= 1.5                   # a whole low-order row; the high-order rows (1e10 larger) untouched
+    check(a)
+    b.data["ln(PI)"] = lnpi0 + 1.0e-3 * np.sin(np.arange(n))      # the other object takes a turn with other arrays
+    check(b)
+    check(a)
+    a.data["ln(PI)"][n // 2] += 0.25                      # in-place write of one bin
+    check(a)
+    a.reweight(5.01)
+    check(a)
+    b.data["ln(PI)"] = T1.astype(np.float64)              # shorter array, as T1:155 does
+    b.metadata["smooth"] = 1
+    b.relextrema()
+    assert b.data["ln(PI)_maxima_idx"].tolist() == [10, 25] and b.data["ln(PI)_minima_idx"].tolist() == [0, 20, 30]
