@@ -709,8 +709,15 @@ class ScalarPath(object):
 
     @classmethod
     def get(cls, n, device=None):
+        if device is None:
+            t = torch()
+            if cls._cache:                      # (a CUDA context exists: the cheap query is enough)
+                key = (t.cuda.current_device(), int(n))
+                sp = cls._cache.get(key)
+                if sp is not None:
+                    return sp
         dev = require_cuda(device)
-        key = (str(dev), int(n))
+        key = (dev.index if dev.index is not None else torch().cuda.current_device(), int(n))
         sp = cls._cache.get(key)
         if sp is None:
             sp = cls._cache[key] = cls(int(n), dev)
@@ -719,6 +726,7 @@ class ScalarPath(object):
     def __init__(self, n, device):
         t = torch()
         self.n, self.n_pad, self.device = n, n + (n & 1), device
+        self._index = device.index if device.index is not None else t.cuda.current_device()
         self.blob = t.zeros((2, self.n_pad), dtype=t.float64, device=device)
         self.mu1_dev = t.zeros(1, dtype=t.float64, device=device)
         self.stage = t.zeros(2 * self.n_pad + 2, dtype=t.float64).pin_memory()     # ln(PI) | N | mu_1
@@ -749,6 +757,8 @@ class ScalarPath(object):
         self.out_host = t.zeros(off, dtype=t.uint8).pin_memory()
         self.out_np = self.out_host.numpy()
         self._layout = layout
+        self._views = [(name, self.out_np[o:o + nb].view(dt).reshape(shape)[0] if len(shape) > 1 else self.out_np[o:o + nb].view(dt))
+                       for name, dt, shape, o, nb in layout]
         base = self.out_dev.data_ptr()
         ptr = {name: base + o for name, _, _, o, _ in layout}
         self.rec = _lib.SweepOut(*[ptr.get(k) for k in SweepResult.FIELDS])
@@ -810,21 +820,26 @@ class ScalarPath(object):
         io.mom = self.mom_dev.data_ptr() if want_mom else None
         io.n_arrays = self.n_arrays if want_mom else 0
         io.out_dev, io.out_host, io.out_bytes = base, self.out_host.data_ptr(), self.out_bytes
-        with torch().cuda.device(self.device):
+        tc = torch().cuda
+        if tc.current_device() == self._index:
             rc = L.fhmc_scalar_point(ctypes.byref(d), ctypes.byref(io), 1 if (want_row or want_mom) else 0, 1 if want_mom else 0,
-                                     _stream_ptr(self.device))
+                                     tc.current_stream().cuda_stream)
+        else:
+            with tc.device(self.device):
+                rc = L.fhmc_scalar_point(ctypes.byref(d), ctypes.byref(io), 1 if (want_row or want_mom) else 0, 1 if want_mom else 0,
+                                         tc.current_stream().cuda_stream)
         if rc != 0:
             self.lnpi_key = self.ntot_key = None     # the uploads may not have happened
         _lib.check(rc, "fhmc_scalar_point")
         hb = self.out_np
         out = {}
-        for name, dt, shape, off, nb in self._layout:
-            out[name] = hb[off:off + nb].view(dt).reshape(shape)[0].copy()
-        status = int(out["status"]) & 0xFFFFFFFF
+        for name, view in self._views:
+            out[name] = view.copy()
+        status = int(out["status"][0]) & 0xFFFFFFFF
         out["status"] = status
         out["code"] = status & ST_CODE_MASK
         out["safe"] = (status & ST_SAFE) != 0
-        out["nphase"], out["nmin"], out["lnnorm"] = int(out["nphase"]), int(out["nmin"]), float(out["lnnorm"])
+        out["nphase"], out["nmin"], out["lnnorm"] = int(out["nphase"][0]), int(out["nmin"][0]), float(out["lnnorm"][0])
         if want_row or want_mom:
             out["row"] = hb[self._off_row:self._off_row + 8 * n].view(np.float64).copy()
         if want_mom:

@@ -47,7 +47,14 @@ t0 = time.perf_counter()
 for _ in range(10):
     h1.find_phase_eq(1e-6, 0.0)
 print("find_phase_eq: %.3f ms" % ((time.perf_counter() - t0) / 10 * 1e3))
-if os.environ.get("PROFILE"):
+if os.environ.get("PROFILE") == "2":
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(20):
+        h1.find_phase_eq(1e-6, 0.0)
+    pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
+elif os.environ.get("PROFILE"):
     pr = cProfile.Profile()
     pr.enable()
     for _ in range(50):
