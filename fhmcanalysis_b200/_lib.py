@@ -89,7 +89,7 @@ EXPORTS = [
     "fhmc_sweep_host_compact16", "fhmc_pack_soa16_bytes", "fhmc_pack_phase_soa16",
     "fhmc_patch_shifts", "fhmc_reweight_2d_prod", "fhmc_reweight_2d_prod_workspace",
     "fhmc_bench_dfma", "fhmc_bench_exp", "fhmc_lean_stats", "fhmc_sweep_1d_compact", "fhmc_sweep_compact_workspace",
-    "fhmc_mu_tables_bytes", "fhmc_mu_tables_build", "fhmc_phase_moments_dev", "fhmc_scalar_point",
+    "fhmc_mu_tables_bytes", "fhmc_mu_tables_build", "fhmc_phase_moments_dev", "fhmc_scalar_point", "fhmc_find_phase_eq_curve",
 ]
 
 _lib = None
@@ -130,6 +130,9 @@ def load():
     L.fhmc_find_phase_eq_1d.restype = ci
     L.fhmc_find_phase_eq_1d.argtypes = [ctypes.POINTER(HistDesc), vp, ctypes.POINTER(States), cd, cd, ci,
                                         vp, vp, vp, ctypes.POINTER(SweepOut), vp]
+    L.fhmc_find_phase_eq_curve.restype = ci
+    L.fhmc_find_phase_eq_curve.argtypes = [ctypes.POINTER(HistDesc), vp, ctypes.POINTER(States), cd, cd, ci, ci,
+                                           vp, vp, vp, ctypes.POINTER(SweepOut), vp]
     L.fhmc_reweight_2d.restype = ci
     L.fhmc_reweight_2d_workspace.restype = ctypes.c_size_t
     L.fhmc_reweight_2d_workspace.argtypes = [ci, ci, ci, cll]

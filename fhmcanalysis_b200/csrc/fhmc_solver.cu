@@ -105,9 +105,9 @@ static int launch_solver(const SolveArgs &sa, size_t smem, const DevCaps &caps, 
 
 using namespace fhmc;
 
-extern "C" int fhmc_find_phase_eq_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states,
-                                     double lnz_tol, double mu_step, int max_iter, double *mu_coex, double *dfe,
-                                     int *iters, const fhmc_sweep_out *out, void *stream)
+static int find_phase_eq_impl(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states, double lnz_tol, double mu_step,
+                              int max_iter, int cont_stride, double *mu_coex, double *dfe, int *iters, const fhmc_sweep_out *out,
+                              void *stream)
 {
     if (!desc || !blob || !states || !out || !mu_coex || !dfe || !iters) { set_error("null pointer"); return 1; }
     if (desc->n_sel < 1) { set_error("solver needs quantity 0 to be N_tot (its phase averages give the Newton slope)"); return 1; }
@@ -136,6 +136,8 @@ extern "C" int fhmc_find_phase_eq_1d(const fhmc_hist_desc *desc, const double *b
     sa.mu_coex = mu_coex;
     sa.dfe = dfe;
     sa.iters = iters;
+    sa.cont_stride = cont_stride > 1 ? cont_stride : 0;
+    if (sa.cont_stride && check_cuda(cudaMemsetAsync(iters, 0, sizeof(int) * (size_t)states->n_states, (cudaStream_t)stream), "cudaMemsetAsync")) return 1;
     const bool taylor = desc->n_coef > 0 || desc->n_term > 1;
     const long long T = states->n_states;
     cudaStream_t s = (cudaStream_t)stream;
@@ -146,6 +148,7 @@ extern "C" int fhmc_find_phase_eq_1d(const fhmc_hist_desc *desc, const double *b
         const int rc = launch_solver_lean(sa, caps.sm_count, caps.smem_optin, s);
         if (rc >= 0) return rc;
     }
+    sa.cont_stride = 0;   // the group kernels solve every record from its own guess
     note_kernel("k_find_phase_eq");
     if (forced == 1) return taylor ? launch_solver<1, true>(sa, smem, caps, s) : launch_solver<1, false>(sa, smem, caps, s);
     if (forced == 4) return taylor ? launch_solver<4, true>(sa, smem, caps, s) : launch_solver<4, false>(sa, smem, caps, s);
@@ -154,4 +157,19 @@ extern "C" int fhmc_find_phase_eq_1d(const fhmc_hist_desc *desc, const double *b
     if (T * 4 <= (long long)caps.sm_count * 2048 * 4)
         return taylor ? launch_solver<4, true>(sa, smem, caps, s) : launch_solver<4, false>(sa, smem, caps, s);
     return taylor ? launch_solver<1, true>(sa, smem, caps, s) : launch_solver<1, false>(sa, smem, caps, s);
+}
+
+extern "C" int fhmc_find_phase_eq_1d(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states,
+                                     double lnz_tol, double mu_step, int max_iter, double *mu_coex, double *dfe,
+                                     int *iters, const fhmc_sweep_out *out, void *stream)
+{
+    return find_phase_eq_impl(desc, blob, states, lnz_tol, mu_step, max_iter, 0, mu_coex, dfe, iters, out, stream);
+}
+
+extern "C" int fhmc_find_phase_eq_curve(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states,
+                                        double lnz_tol, double mu_step, int max_iter, int seed_stride, double *mu_coex, double *dfe,
+                                        int *iters, const fhmc_sweep_out *out, void *stream)
+{
+    if (seed_stride < 2) { set_error("seed_stride must be >= 2"); return 1; }
+    return find_phase_eq_impl(desc, blob, states, lnz_tol, mu_step, max_iter, seed_stride, mu_coex, dfe, iters, out, stream);
 }

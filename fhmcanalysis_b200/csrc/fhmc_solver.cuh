@@ -10,6 +10,11 @@ struct SolveArgs {
     int max_iter;
     double *mu_coex, *dfe;
     int *iters;
+    // Continuation along a coexistence CURVE (fhmc_find_phase_eq_curve; 0 = off): the solves form a list ordered in beta;
+    // every cont_stride-th one (and the last) is a seed solved from its own guess, every other solve starts from the linear
+    // interpolation in beta of the roots of the two seeds around it.  iters[] doubles as the "finished" flag (zeroed
+    // before the launch, written last).
+    int cont_stride;
 };
 
 
@@ -136,14 +141,19 @@ __device__ __forceinline__ void solve_one(const SolveArgs &sa, long long rec, do
     }
     if (!converged && code == FHMC_E_NO_COEX && it >= sa.max_iter) code = FHMC_E_NO_COEX + 1;  // iteration cap
     commit();
+    if (sa.cont_stride > 0) {   // other warps wait for this record: everything above must be visible before the flag below
+        __threadfence();
+        __syncwarp();
+    }
     if (leader) {
         sa.mu_coex[rec] = mu_good;
         sa.dfe[rec] = d;
-        sa.iters[rec] = nevals;
         if (code != FHMC_OK) a.out.status[rec] = (a.out.status[rec] & ~FHMC_ST_CODE_MASK) | (unsigned)code;
         // the search ended on a JUMP of the free-energy difference (a phase boundary moved by a bin, a phase appeared or
         // vanished): mu_coex is the edge of the jump, |dfe| > lnz_tol.  Callers tell these from converged roots by this bit.
         else if (!(fabs(d) <= sa.lnz_tol)) a.out.status[rec] |= FHMC_ST_JUMP;
+        if (sa.cont_stride > 0) __threadfence();
+        *reinterpret_cast<volatile int *>(sa.iters + rec) = nevals;   // last: the record's "finished" flag
     }
 }
 

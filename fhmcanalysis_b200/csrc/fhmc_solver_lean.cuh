@@ -38,12 +38,44 @@ __global__ void __launch_bounds__(CTA, 1) k_solve_lean(const __grid_constant__ S
     for (;;) {
         unsigned nxt = 0;
         if (lane == 0) nxt = atomicAdd(counter, 1u);
-        const long long rec = (long long)__shfl_sync(0xffffffffu, nxt, 0);
-        if (rec >= T) break;
+        const long long q = (long long)__shfl_sync(0xffffffffu, nxt, 0);
+        if (q >= T) break;
         const fhmc_states &st = a.st;
-        const double mu = st.mu1[(rec / st.mu1_div) % st.n_mu1];
+        long long rec = q;
+        long long dep_l = -1, dep_r = -1;
+        if (sa.cont_stride > 1) {
+            // queue order: the seeds (every cont_stride-th solve and the last one) first, then the rest in list order, so the
+            // seeds an item waits for were always handed out before it
+            const long long S = sa.cont_stride, n_seed = (T - 1) / S + 1, extra = ((T - 1) % S) ? 1 : 0;
+            if (q < n_seed) rec = q * S;
+            else if (q < n_seed + extra) rec = T - 1;
+            else {
+                const long long j = q - n_seed - extra;          // j-th solve that is not a multiple of S ...
+                rec = j + j / (S - 1) + 1;
+                // (T-1, when it is the extra seed, is the largest such solve and lies beyond the end of this part of the queue)
+                dep_l = (rec / S) * S;
+                dep_r = dep_l + S < T ? dep_l + S : T - 1;
+            }
+        }
+        double mu = st.mu1[(rec / st.mu1_div) % st.n_mu1];
         const double beta = st.beta ? st.beta[(rec / st.beta_div) % st.n_beta] : a.d.beta_ref;
         const double dmu = st.dmu ? st.dmu[(rec / st.dmu_div) % st.n_dmu] : a.d.dmu_ref;
+        if (dep_l >= 0) {
+            if (lane == 0) {
+                while (*reinterpret_cast<volatile int *>(sa.iters + dep_l) == 0) __nanosleep(100);
+                while (*reinterpret_cast<volatile int *>(sa.iters + dep_r) == 0) __nanosleep(100);
+                __threadfence();
+            }
+            __syncwarp();
+            const unsigned sl = __ldcg(a.out.status + dep_l), sr = __ldcg(a.out.status + dep_r);
+            const bool gl = (sl & (FHMC_ST_CODE_MASK | FHMC_ST_JUMP)) == 0, gr = (sr & (FHMC_ST_CODE_MASK | FHMC_ST_JUMP)) == 0;
+            const double ml = __ldcg(sa.mu_coex + dep_l), mr = __ldcg(sa.mu_coex + dep_r);
+            const double bl = st.beta ? st.beta[(dep_l / st.beta_div) % st.n_beta] : a.d.beta_ref;
+            const double br = st.beta ? st.beta[(dep_r / st.beta_div) % st.n_beta] : a.d.beta_ref;
+            if (gl && gr && br != bl) mu = ml + (mr - ml) * ((beta - bl) / (br - bl));
+            else if (gl) mu = ml;
+            else if (gr) mu = mr;
+        }
         bool in_scratch = false;
 #ifdef FHMC_LEAN_PROFILE
         const long long t_solve0 = clock64();

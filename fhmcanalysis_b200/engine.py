@@ -628,7 +628,7 @@ class DeviceHistogram(object):
         return st
 
     def find_phase_eq(self, mu_guess, beta=None, dmu=None, lnz_tol=1e-10, mu_step=None, max_iter=200, pmax=4,
-                      smooth=None, cutoff=None, min_width=None, continuation=None, stride=32):
+                      smooth=None, cutoff=None, min_width=None, continuation=None, stride=32, seed_stride=32):
         """K4: one coexistence solve per entry of (mu_guess, beta, dmu) (flat lists).  Returns a SweepResult at coexistence
         with extra['mu_coex', 'dfe', 'iters'] (iters = evaluations of the last stage).
 
@@ -636,7 +636,9 @@ class DeviceHistogram(object):
         every `stride`-th temperature (in order of beta) is solved first and the guesses of all solves are interpolated
         from those roots -- what a user's notebook does by hand when it feeds the previous temperature's mu into the next
         call, done hierarchically so that both stages stay batched.  The second stage then needs ~3 evaluations per
-        solve instead of ~6.5 and never visits the monotone ln(PI) far from coexistence."""
+        solve instead of ~6.5 and never visits the monotone ln(PI) far from coexistence.  A list that is already ordered
+        in beta takes ONE launch: every ``seed_stride``-th solve is a seed, the others wait inside the kernel for the two
+        seeds around them and start from the interpolated root (``fhmc_find_phase_eq_curve``)."""
         t = torch()
         if self.n_sel < 1:
             raise ValueError("the solver needs quantity 0 to be N_tot (construct DeviceHistogram with sel=['N', ...])")
@@ -646,8 +648,16 @@ class DeviceHistogram(object):
             if host_in and beta is not None and np.size(beta) >= 8 * stride and (dmu is None or np.size(dmu) == 1):
                 g = np.atleast_1d(np.asarray(mu_guess, dtype=np.float64))
                 continuation = bool(np.all(g == g.flat[0]))
-        if continuation and host_in and beta is not None and np.size(beta) > stride:
+        if continuation and host_in and beta is not None and np.size(beta) > stride and (dmu is None or np.size(dmu) == 1):
             b = np.atleast_1d(np.asarray(beta, dtype=np.float64))
+            db = np.diff(b)
+            if b.ndim == 1 and (np.all(db > 0) or np.all(db < 0)):
+                # the list already runs along the curve: one launch, the seeds (every seed_stride-th solve) and the
+                # interpolated guesses of the other solves are handled inside the kernel (fhmc_find_phase_eq_curve)
+                out = self._find_phase_eq_once(mu_guess, beta, dmu, lnz_tol, mu_step, max_iter, pmax, smooth, cutoff, min_width,
+                                               seed_stride=max(2, int(seed_stride)))
+                out.extra["coarse_solves"] = (len(b) - 1) // max(2, int(seed_stride)) + 1
+                return out
             g = np.broadcast_to(np.atleast_1d(np.asarray(mu_guess, dtype=np.float64)), b.shape)
             d = None if dmu is None else np.broadcast_to(np.atleast_1d(np.asarray(dmu, dtype=np.float64)), b.shape)
             order = np.argsort(b, kind="stable")
@@ -667,7 +677,7 @@ class DeviceHistogram(object):
                 return out
         return self._find_phase_eq_once(mu_guess, beta, dmu, lnz_tol, mu_step, max_iter, pmax, smooth, cutoff, min_width)
 
-    def _find_phase_eq_once(self, mu_guess, beta, dmu, lnz_tol, mu_step, max_iter, pmax, smooth, cutoff, min_width):
+    def _find_phase_eq_once(self, mu_guess, beta, dmu, lnz_tol, mu_step, max_iter, pmax, smooth, cutoff, min_width, seed_stride=0):
         L = _lib.load()
         t = torch()
         if any(isinstance(x, t.Tensor) for x in (mu_guess, beta, dmu)):
@@ -685,9 +695,14 @@ class DeviceHistogram(object):
             mu_step = 0.05 / abs(self.desc.beta_ref)   # first blind search step (doubles until <N> brackets the window)
         cs = out.c_struct()
         with t.cuda.device(self.device):
-            rc = L.fhmc_find_phase_eq_1d(ctypes.byref(d), _ptr(self.blob), ctypes.byref(st), float(lnz_tol),
-                                         float(mu_step), int(max_iter), _ptr(mu_coex), _ptr(dfe), _ptr(iters),
-                                         ctypes.byref(cs), _stream_ptr(self.device))
+            if seed_stride and seed_stride > 1:
+                rc = L.fhmc_find_phase_eq_curve(ctypes.byref(d), _ptr(self.blob), ctypes.byref(st), float(lnz_tol),
+                                                float(mu_step), int(max_iter), int(seed_stride), _ptr(mu_coex), _ptr(dfe), _ptr(iters),
+                                                ctypes.byref(cs), _stream_ptr(self.device))
+            else:
+                rc = L.fhmc_find_phase_eq_1d(ctypes.byref(d), _ptr(self.blob), ctypes.byref(st), float(lnz_tol),
+                                             float(mu_step), int(max_iter), _ptr(mu_coex), _ptr(dfe), _ptr(iters),
+                                             ctypes.byref(cs), _stream_ptr(self.device))
         _lib.check(rc, "fhmc_find_phase_eq_1d")
         out.extra = {"mu_coex": mu_coex, "dfe": dfe, "iters": iters}
         out._states = st

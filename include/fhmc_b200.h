@@ -314,6 +314,15 @@ int fhmc_find_phase_eq_1d(const fhmc_hist_desc *desc, const double *blob, const 
                           double lnz_tol, double mu_step, int max_iter,
                           double *mu_coex, double *dfe, int *iters,
                           const fhmc_sweep_out *out, void *stream);
+/* The same for a coexistence CURVE: the flat list of solves is ordered along the curve (beta monotone).  Every
+ * seed_stride-th solve and the last one are "seeds", solved from their own mu_guess; every other solve starts from the
+ * linear interpolation in beta of the roots of the two seeds around it (a seed that did not converge is left out; with no
+ * usable seed the solve's own guess is used) -- what a notebook does when it feeds the previous temperature's mu into the
+ * next find_phase_eq call (GH:598-668 needs a good guess), done inside ONE launch: seeds are handed out first, the other
+ * solves wait for their two seeds only.  Same outputs as fhmc_find_phase_eq_1d (roots agree to lnz_tol; deterministic). */
+int fhmc_find_phase_eq_curve(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states,
+                             double lnz_tol, double mu_step, int max_iter, int seed_stride, double *mu_coex, double *dfe,
+                             int *iters, const fhmc_sweep_out *out, void *stream);
 
 /*
  * K5: 2-D joint histogram lnPI(op1,op2) (container: two_dim/joint_hist.pyx:201-247) reweighted to

@@ -110,7 +110,7 @@ def _check_against_tight_oracle(oracle, lnpi, mom, betas, res, idx, smooth):
             return np.stack([N, A["A_b"], A["A_bb"]]), np.array([xb * mu, xb, 0.5 * xb * xb])
         mu = res["mu_coex"][k]
         mu_t = None
-        for half in (1e-3, 1e-4, 1e-5, 1e-6):
+        for half in (1e-7, 1e-6, 1e-5, 1e-4, 1e-3):     # the root nearest to the solver's
             try:
                 mu_t = oracle.find_phase_eq_tight(lnpi, N, 1.0, 0.0, smooth, mu - half, mu + half, coef_fn=coef_fn)
                 break
@@ -152,10 +152,28 @@ def test_config4_coexistence_curve_at_size(oracle):
     idx = np.where(conv)[0][::83]
     assert len(idx) >= 100
     _check_against_tight_oracle(oracle, lnpi, mom, betas, cold, idx, smooth)
-    # staged continuation (coarse subset first, interpolated guesses): same roots, fewer evaluations
+    # continuation along the curve (seeds first, interpolated guesses for the other solves): same roots, fewer evaluations.
+    # The list is ordered in beta, so this is ONE launch of fhmc_find_phase_eq_curve (seeds and waiting inside the kernel).
     st = h4.find_phase_eq_batch(betas, 0.0, order=2, lnZ_tol=tol)           # automatic for one cold guess
+    assert _lib.last_kernel() == "k_solve_lean"
     both = conv & st["converged"]
     assert both.mean() > 0.98 and st["iters"].mean() < 0.6 * cold["iters"].mean()
     same = np.abs(st["mu_coex"][both] - cold["mu_coex"][both]) <= 1e-9
     assert same.mean() > 0.995      # (a noisy ln(PI) near the critical temperature can hold more than one root)
     _check_against_tight_oracle(oracle, lnpi, mom, betas, st, np.where(st["converged"])[0][::89], smooth)
+    again = h4.find_phase_eq_batch(betas, 0.0, order=2, lnZ_tol=tol)
+    assert np.array_equal(again["mu_coex"], st["mu_coex"]) and np.array_equal(again["iters"], st["iters"])     # deterministic
+    # a list that is NOT ordered in beta takes the host-staged form of the same continuation (two launches): same roots
+    perm = np.random.default_rng(5).permutation(T)[:3000]
+    sh = h4.find_phase_eq_batch(betas[perm], 0.0, order=2, lnZ_tol=tol)
+    b2 = sh["converged"] & st["converged"][perm]
+    assert b2.mean() > 0.97 and np.mean(np.abs(sh["mu_coex"][b2] - st["mu_coex"][perm][b2]) <= 1e-9) > 0.99
+    # seed stride that does not divide the list, a list shorter than the stride, a two-entry list
+    dh = h4.device_histogram(beta=betas, order=2, moments=("N",))
+    for sub, stride in ((slice(100, 1131), 7), (slice(4000, 4011), 32), (slice(5000, 5002), 2)):
+        bsub = betas[sub]
+        a1 = dh._find_phase_eq_once(np.zeros_like(bsub), bsub, None, tol, None, 200, 4, None, None, None, seed_stride=stride).host()
+        a0 = dh._find_phase_eq_once(np.zeros_like(bsub), bsub, None, tol, None, 200, 4, None, None, None).host()
+        ok = (a1["code"] == 0) & (a0["code"] == 0) & (np.abs(a1["dfe"]) <= tol) & (np.abs(a0["dfe"]) <= tol)
+        assert ok.mean() > 0.9 and np.all(a1["iters"] > 0)
+        assert np.mean(np.abs(a1["mu_coex"][ok] - a0["mu_coex"][ok]) <= 1e-9) > 0.98
