@@ -5,16 +5,18 @@
 //     lnPI'(N) = L(N) + dD * C1(N) + (dD^2 / 2) * C2(N)
 //     L  = fl(lnPI + fl(s N)) + sum over the terms without dD  (dB mu_1 N, dB A_b, dB^2/2 A_bb, ...)
 //     C1 = A_d + dB * A_bd,     C2 = A_dd
-// so a CTA combines the coefficient rows ONCE per row of the grid (n bins x <= 8 terms, against n_dmu x n bins of
-// walking) and a bin then costs 2 fp64 instructions for u instead of 8 and three 8-byte broadcast loads instead of four
-// 16-byte ones.  Everything else is the walk of fhmc_fast.cuh (one exp pass, sign-of-difference prefilter, exact windowed
-// tests, repair(), re-test on the normalised values) with three changes that the profile of the Taylor kernel asked for:
+// so the coefficient rows are combined ONCE per row of the grid (n bins x <= 8 terms, against n_dmu x n bins of walking)
+// and a bin then costs 2 fp64 instructions for u instead of 8 and three 8-byte broadcast loads instead of four 16-byte
+// ones.  Everything else is the walk of fhmc_fast.cuh (one exp pass, sign-of-difference prefilter, exact windowed tests,
+// repair(), re-test on the normalised values) with the changes that the profile of the Taylor kernel asked for:
 //   * two state points per thread: every row load serves both, their independent exp chains interleave;
-//   * a lane-replicated 2^(j/64) table (16 copies, lane l reads copy l mod 16): the per-lane table look-up of exp is
-//     conflict-free (it cost ~6 shared-memory wavefronts per warp and bin, as much as the row loads);
+//   * a lane-replicated 2^(j/256) table (16 copies, lane l reads copy l mod 16): the per-lane table look-up of exp is
+//     conflict-free (it cost ~6 shared-memory wavefronts per warp and bin, as much as the row loads), and the larger
+//     table pays for one polynomial degree (9 fp64-pipe instructions per exp);
 //   * no CTA-wide fallback queue: a state point that is not a plain case is re-run on the spot by its whole warp with the
-//     general evaluator -- on the SAME combined rows, so both paths see bit-identical u -- and nothing synchronises the
-//     warps of a CTA between two row builds.
+//     general evaluator -- on the SAME combined rows, so both paths see bit-identical u;
+//   * no CTA barrier per grid row: every warp combines the rows of its next grid row itself (all warps store identical
+//     values) into one of two alternating row buffers, guarded by release counters in shared memory.
 // The exponent shift comes from a subsampled maximum (every 8th bin); a term may exceed it by up to 2^900, a larger
 // miss saturates (the exponent offset is clamped) and sends the state point to the general evaluator.
 #include "fhmc_fast.cuh"
