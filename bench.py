@@ -603,7 +603,7 @@ def extra_blocks(torch, dev, peaks, counts, histogram, engine, _lib):
         hc = hold["r"].host()
         conv_c = (hc["code"] == 0) & ((hc["status"].view(np.uint32) & _lib.ST_JUMP) == 0)
         evals_cold = float(np.mean(hc["iters"]))
-        # the product's default for a list ordered along the curve: ONE launch of fhmc_find_phase_eq_curve (every 32nd solve a
+        # the product's default for a list ordered along the curve: ONE launch of fhmc_find_phase_eq_curve (every 64th solve a
         # cold seed, the others start from the interpolated roots of their two seeds, inside the kernel)
         ms_curve = _event_ms(torch, lambda: solve(None), reps=3, warm=1)
         kern = _lib.last_kernel()
@@ -623,7 +623,7 @@ def extra_blocks(torch, dev, peaks, counts, histogram, engine, _lib):
         for k in ("nphase", "max_idx", "bounds", "fe", "avg"):
             smp["c4_" + k] = hr[k][ks]
         v = C4_T / (ms_curve * 1e-3)
-        blocks["config4"] = {"workload": "config4: coexistence curve, 10^4 temperatures T in [0.90,1.06], N_max=2000, smooth=10, order-2 beta extrapolation, lnZ_tol=1e-10, every guess = 0 (cold), one launch (fhmc_find_phase_eq_curve: seeds every 32nd temperature, in-kernel continuation)",
+        blocks["config4"] = {"workload": "config4: coexistence curve, 10^4 temperatures T in [0.90,1.06], N_max=2000, smooth=10, order-2 beta extrapolation, lnZ_tol=1e-10, every guess = 0 (cold), one launch (fhmc_find_phase_eq_curve: seeds every 64th temperature, in-kernel continuation)",
                              "value": v, "unit": "coexistence points/s", "ms": ms_curve, "solves": C4_T, "kernel": kern, "gpu_launches": 1,
                              "every_solve_cold": {"value": C4_T / (ms_cold * 1e-3), "ms": ms_cold, "mean_evaluations": evals_cold, "converged_fraction": float(conv_c.mean()),
                                                   "note": "fhmc_find_phase_eq_1d: every solve from its own guess 0 (the r02a figure)"},

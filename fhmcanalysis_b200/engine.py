@@ -628,7 +628,7 @@ class DeviceHistogram(object):
         return st
 
     def find_phase_eq(self, mu_guess, beta=None, dmu=None, lnz_tol=1e-10, mu_step=None, max_iter=200, pmax=4,
-                      smooth=None, cutoff=None, min_width=None, continuation=None, stride=32, seed_stride=32):
+                      smooth=None, cutoff=None, min_width=None, continuation=None, stride=32, seed_stride=64):
         """K4: one coexistence solve per entry of (mu_guess, beta, dmu) (flat lists).  Returns a SweepResult at coexistence
         with extra['mu_coex', 'dfe', 'iters'] (iters = evaluations of the last stage).
 

@@ -58,7 +58,7 @@ def main():
         out.append({"config": "3: synthetic 2-comp Taylor grid 4096 beta x 4096 dmu2, N_max=1000, " + tag, "state_points": S, "ms": ms,
                     "value": S / (ms * 1e-3), "unit": "state points/s", "ok_fraction": okf, "blob_rows": dh.n_rows,
                     "roofline": {"bound": "fp64_exp", "achieved_gexp_s": exps / 1e9, "peak_gexp_s": peaks["exp_per_s"] / 1e9,
-                                 "frac": exps / peaks["exp_per_s"], "note": "k_sweep_fast Taylor variant (sub-sampled max pre-pass + one true exp per bin)"}})
+                                 "frac": exps / peaks["exp_per_s"], "note": "k_sweep_rowc for the lnPI-only grid (rows combined per grid row), k_sweep_fast Taylor variant with averaged quantities; one true exp per bin"}})
         del res
 
     # ---- config 4: coexistence curve over 10^4 temperatures, N_max=2000, smooth=10, order 2 --------------

@@ -41,7 +41,7 @@ def run(stride):
 ms0, h0 = run(0)
 conv0 = (h0["code"] == 0) & ((h0["status"].view(np.uint32) & _lib.ST_JUMP) == 0)
 print("cold: %.3f ms  %.3g solves/s  evals %.2f  converged %.4f" % (ms0, 1e4 / ms0 * 1e3, h0["iters"].mean(), conv0.mean()))
-for stride in (4, 8, 16, 32, 64):
+for stride in (32, 64, 128, 256, 512, 1024):
     ms, h = run(stride)
     conv = (h["code"] == 0) & ((h["status"].view(np.uint32) & _lib.ST_JUMP) == 0)
     both = conv & conv0

@@ -22,5 +22,17 @@ o2 = h.reweight_batch(np.linspace(-0.1, 0.1, 300), beta=np.array([1.01]), order=
 l2, b2 = synth.joint_2d(67, 45, 70)
 x = engine.reweight_2d(l2, b2, np.arange(67.0), np.arange(45.0), np.linspace(-0.1, 0.1, 333), np.linspace(0.1, -0.1, 333), np.random.default_rng(0).random((2, 67, 45)))
 h2 = h.mix(h, [0.4, 0.6])
+# r02: compact records on per-histogram tables, the row-combined Taylor grid kernel, the curve solver, the scalar path
+dhc = histogram.from_arrays(lnpi, mom, 1.0, [0.0], 4).device_histogram(moments=("N", "N2"))
+c = dhc.sweep_compact(np.linspace(-0.2, 0.2, 5000), pmax=4)
+n2 = 301
+h2c = histogram.from_arrays(synth.two_peak_lnpi(n2), synth.two_comp_moments(n2), 1.0, [-3.0, -2.5], 5)
+h2c.reweight(-2.9)
+bs, ds = np.linspace(0.97, 1.03, 3), np.linspace(0.2, 0.8, 600)
+dg = h2c.device_histogram(beta=bs, dmu=ds, order=2, moments=())
+g = dg.sweep(None, states=dg.make_states(np.array([-2.9]), bs, ds, grid=True), pmax=8, lanes=1)
+n4 = 401
+h4 = histogram.from_arrays(synth.two_peak_lnpi(n4, scale=0.4), synth.one_comp_moments(n4, 3), 1.0, [0.0], 5)
+cv = h4.find_phase_eq_batch(1.0 / np.linspace(0.95, 1.03, 300), 0.0, order=2)
 torch.cuda.synchronize()
-print("sanitize case done", int(o["code"].sum()), float(x[0, 0]))
+print("sanitize case done", int(o["code"].sum()), float(x[0, 0]), int((cv["code"] == 0).sum()))
