@@ -704,7 +704,7 @@ def sharded_blocks(torch, dist, dev, world, histogram, engine, parallel):
         dh = h.device_histogram(beta=betas, dmu=dmus, order=2, moments=())
         ms = timed(lambda: parallel.sweep_grid_sharded(lambda: dh, C3_MU1, betas, dmus, pmax=C3_PMAX, to_host=False), reps=2)
         out["config3"] = {"value": C3_NB * C3_ND / (ms * 1e-3), "unit": UNIT, "ms": ms, "scaling": "strong",
-                          "path": "parallel.sweep_grid_sharded: beta rows cut over the ranks, full records all-gathered (NCCL) to every rank"}
+                          "path": "parallel.sweep_grid_sharded: beta rows cut over the ranks, full records (the per-phase columns that exist anywhere on the grid) all-gathered (NCCL) to every rank"}
     except Exception as e:
         out["config3"] = {"value": None, "error": repr(e)}
     try:

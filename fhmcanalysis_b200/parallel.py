@@ -11,7 +11,10 @@ range, runs the same kernels on it, and the only communication is the final gath
   Where symmetric memory is not available the records are written locally and gathered with ONE NCCL
   ``all_gather_into_tensor`` of the compact blocks (gloo in the CPU tests of this host-side logic).
 * ``sweep_sharded`` / ``find_phase_eq_sharded`` / ``reweight_2d_sharded`` / ``sweep_grid_sharded``: full records (or the
-  solver's / the 2-D kernel's outputs) gathered with padded ``all_gather_into_tensor`` calls, one per dtype.
+  solver's / the 2-D kernel's outputs) gathered with padded ``all_gather_into_tensor`` calls, one per dtype.  The two sweeps
+  first agree (one MAX all-reduce of two integers) on the largest phase / minima count any record has and gather only that
+  many per-phase columns: the capacity pmax = 8 of a Taylor grid holds two or three phases, 96-120 instead of 216 bytes per
+  state point on the wire.
 
 Layout of a gathered compact result: ``world`` blocks of ``fhmc_pack_soa16_bytes(smax, pmax, n_sel)`` bytes, block r = the
 narrow phase-major records of rank r's shard (``smax`` = largest shard).  ``ShardedRecords.host()`` concatenates them.
@@ -42,10 +45,35 @@ FLOAT_FIELDS = ("lnnorm", "fe", "avg")
 INT_FIELDS = ("status", "nphase", "nmin", "bounds", "max_idx", "min_idx")
 
 
-def pack_records(rec):
-    """dict of per-state-point tensors [S, ...] -> (float64 [S, F], int32 [S, I]) rows, one per state point."""
+def live_widths(nphase, nmin, pmax, group=None):
+    """(P, M): the largest phase count and the largest minima count over ALL ranks' records, clamped to the capacities
+    pmax / pmax + 1 -- the widths worth gathering (one MAX all-reduce of two integers; synchronises).  ``nphase`` / ``nmin``
+    are this rank's tensors (possibly empty)."""
+    import torch
+    import torch.distributed as dist
+    if nphase.numel():
+        w = torch.stack([nphase.max(), nmin.max()]).to(torch.int64)
+    else:
+        w = torch.zeros(2, dtype=torch.int64, device=nphase.device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(w, op=dist.ReduceOp.MAX, group=group)
+    P, M = (int(x) for x in w.tolist())
+    return max(1, min(int(pmax), P)), max(1, min(int(pmax) + 1, M))
+
+
+def pack_records(rec, widths=None):
+    """dict of per-state-point tensors [S, ...] -> (float64 [S, F], int32 [S, I]) rows, one per state point.
+    widths = (P, M) from live_widths(): only the first P phase slots (fe, avg, bounds, max_idx) and the first M entries of
+    min_idx are packed -- with pmax = 8 and two-phase records that is 96 instead of 216 bytes per state point on the wire."""
     import torch
     S = rec["lnnorm"].shape[0]
+    if widths is not None:
+        P, M = widths
+        rec = dict(rec)
+        for k in ("fe", "avg", "bounds", "max_idx"):
+            if rec.get(k) is not None:
+                rec[k] = rec[k][:, :P]
+        rec["min_idx"] = rec["min_idx"][:, :M]
 
     def rows(x):   # (S may be 0: an explicit width instead of -1)
         return x.reshape(S, int(np.prod(x.shape[1:])))
@@ -54,16 +82,20 @@ def pack_records(rec):
     return f, i
 
 
-def unpack_records(f, i, pmax, n_sel):
+def unpack_records(f, i, pmax, n_sel, widths=None):
+    """Inverse of pack_records.  With ``widths`` the per-phase arrays come back with P (min_idx: M) columns."""
     S = f.shape[0]
+    mcols = pmax + 1
+    if widths is not None:
+        pmax, mcols = widths
     out, c = {}, 0
     out["lnnorm"] = f[:, 0]
     out["fe"] = f[:, 1:1 + pmax]
     c = 1 + pmax
     out["avg"] = f[:, c:c + pmax * n_sel].reshape(S, pmax, n_sel) if n_sel else None
-    widths = (("status", 1), ("nphase", 1), ("nmin", 1), ("bounds", 2 * pmax), ("max_idx", pmax), ("min_idx", pmax + 1))
+    cols = (("status", 1), ("nphase", 1), ("nmin", 1), ("bounds", 2 * pmax), ("max_idx", pmax), ("min_idx", mcols))
     c = 0
-    for k, w in widths:
+    for k, w in cols:
         out[k] = i[:, c:c + w]
         c += w
     out["status"], out["nphase"], out["nmin"] = out["status"][:, 0], out["nphase"][:, 0], out["nmin"][:, 0]
@@ -96,6 +128,15 @@ def all_gather_records(f, i, n_states, group=None):
     return all_gather_rows(f, n_states, group), all_gather_rows(i, n_states, group)
 
 
+def _empty_records(pmax, n_sel, device):
+    """Zero-row record tensors of a rank whose shard is empty (it still joins the collectives)."""
+    import torch
+    z = lambda *shape, dt=torch.float64: torch.zeros(shape, dtype=dt, device=device)
+    i32 = torch.int32
+    return {"lnnorm": z(0), "fe": z(0, pmax), "avg": z(0, pmax, n_sel) if n_sel else None, "status": z(0, dt=i32), "nphase": z(0, dt=i32),
+            "nmin": z(0, dt=i32), "bounds": z(0, pmax, 2, dt=i32), "max_idx": z(0, pmax, dt=i32), "min_idx": z(0, pmax + 1, dt=i32)}
+
+
 def _cut(x, lo, hi):
     if x is None:
         return None
@@ -103,11 +144,22 @@ def _cut(x, lo, hi):
     return x if x.size == 1 else x[lo:hi]
 
 
-def _deliver(out, to_host):
-    """Gathered records as NumPy arrays (to_host) or as the device tensors the collective left behind."""
+def _deliver(out, to_host, pmax=None):
+    """Gathered records as NumPy arrays (to_host; per-phase arrays padded back to the capacity ``pmax`` with NaN / -1 where
+    only the live widths were gathered) or as the device tensors the collective left behind (``out['widths']`` = (P, M))."""
     if not to_host:
         return out
-    return {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+    res = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items() if k != "widths"}
+    if pmax is not None and out.get("widths") is not None:
+        def pad(a, n, fill):
+            if a is None or a.shape[1] >= n:
+                return a
+            full = np.full((a.shape[0], n) + a.shape[2:], fill, dtype=a.dtype)
+            full[:, :a.shape[1]] = a
+            return full
+        for k, n, fill in (("fe", pmax, np.nan), ("avg", pmax, np.nan), ("bounds", pmax, -1), ("max_idx", pmax, -1), ("min_idx", pmax + 1, -1)):
+            res[k] = pad(res.get(k), n, fill)
+    return res
 
 
 def sweep_sharded(make_device_hist, mu1, beta=None, dmu=None, pmax=4, lanes=0, gather=True, group=None, to_host=True):
@@ -121,16 +173,20 @@ def sweep_sharded(make_device_hist, mu1, beta=None, dmu=None, pmax=4, lanes=0, g
     S = len(mu1)
     lo, hi = shard_bounds(S, world, rank)
     dh = make_device_hist()
-    n_f, n_i = 1 + pmax + pmax * dh.n_sel, 3 + 2 * pmax + pmax + pmax + 1
+    widths = None
     if hi > lo:
         res = dh.sweep(mu1[lo:hi], _cut(beta, lo, hi), _cut(dmu, lo, hi), pmax=pmax, lanes=lanes)
-        f, i = pack_records({k: getattr(res, k) for k in FLOAT_FIELDS + INT_FIELDS})
-    else:   # more ranks than state points: nothing to compute here, but the collective below needs every rank
-        f = torch.zeros((0, n_f), dtype=torch.float64, device=dh.device)
-        i = torch.zeros((0, n_i), dtype=torch.int32, device=dh.device)
+        rec = {k: getattr(res, k) for k in FLOAT_FIELDS + INT_FIELDS}
+    else:   # more ranks than state points: nothing to compute here, but the collectives below need every rank
+        rec = _empty_records(pmax, dh.n_sel, dh.device)
+    if gather and world > 1:
+        widths = live_widths(rec["nphase"], rec["nmin"], pmax, group)     # only the phase slots that exist go on the wire
+    f, i = pack_records(rec, widths)
     if gather and world > 1:
         f, i = all_gather_records(f, i, S, group)
-    return _deliver(unpack_records(f, i, pmax, dh.n_sel), to_host)
+    out = unpack_records(f, i, pmax, dh.n_sel, widths)
+    out["widths"] = widths
+    return _deliver(out, to_host, pmax)
 
 
 def sweep_grid_sharded(make_device_hist, mu1, betas, dmus, pmax=4, group=None, to_host=True):
@@ -143,18 +199,24 @@ def sweep_grid_sharded(make_device_hist, mu1, betas, dmus, pmax=4, group=None, t
     nb, nd = len(betas), len(dmus)
     lo, hi = shard_bounds(nb, world, rank)
     dh = make_device_hist()
-    n_f, n_i = 1 + pmax + pmax * dh.n_sel, 3 + 2 * pmax + pmax + pmax + 1
+    widths = None
     if hi > lo:
         res = dh.sweep(np.atleast_1d(mu1), betas[lo:hi], dmus, grid=True, pmax=pmax)
-        f, i = pack_records({k: getattr(res, k) for k in FLOAT_FIELDS + INT_FIELDS})
+        rec = {k: getattr(res, k) for k in FLOAT_FIELDS + INT_FIELDS}
     else:
-        f = torch.zeros((0, n_f), dtype=torch.float64, device=dh.device)
-        i = torch.zeros((0, n_i), dtype=torch.int32, device=dh.device)
+        rec = _empty_records(pmax, dh.n_sel, dh.device)
+    if world > 1:
+        # only the phase slots that exist anywhere on the grid go on the wire (pmax = 8, two or three phases: 96-120 of 216 B)
+        widths = live_widths(rec["nphase"], rec["nmin"], pmax, group)
+    f, i = pack_records(rec, widths)
     if world > 1:
         # shards are whole beta rows: gather row blocks of nd state points each
+        n_f, n_i = f.shape[1], i.shape[1]
         f = all_gather_rows(f.reshape(-1, nd, n_f), nb, group).reshape(-1, n_f)
         i = all_gather_rows(i.reshape(-1, nd, n_i), nb, group).reshape(-1, n_i)
-    return _deliver(unpack_records(f, i, pmax, dh.n_sel), to_host)
+    out = unpack_records(f, i, pmax, dh.n_sel, widths)
+    out["widths"] = widths
+    return _deliver(out, to_host, pmax)
 
 
 def find_phase_eq_sharded(make_device_hist, mu_guess, betas, dmu=None, lnz_tol=1e-10, pmax=4, group=None, to_host=True, **kw):

@@ -98,6 +98,29 @@ def _worker(rank, world, port, S, q):
     ok = ok and np.array_equal(got["fe"][live], exp["fe"][live]) and np.all(np.isnan(got["fe"][~live]))
     ok = ok and np.array_equal(got["avg"][live], exp["avg"][live]) and np.array_equal(got["bounds"][live], exp["bounds"][live])
     ok = ok and np.all(got["bounds"][~live] == -1) and got["fe"].shape == (S, pmax)
+    # full records trimmed to the live widths: the ranks agree on the largest phase / minima count (MAX all-reduce), only
+    # that many per-phase columns are packed and gathered; _deliver pads them back to the capacity with NaN / -1
+    pm8 = 8
+    rec = _fake_records(lo, hi, pm8, nsel)
+    rec["nphase"] = rec["nphase"].clamp(max=2 + rank)          # rank 1 owns the only three-phase records
+    widths = parallel.live_widths(rec["nphase"], rec["nmin"], pm8)
+    ok = ok and widths == (3, 3)
+    ft, it = parallel.pack_records(rec, widths)
+    ok = ok and ft.shape[1] == 1 + 3 + 3 * nsel and it.shape[1] == 3 + 6 + 3 + 3
+    Ft, It = parallel.all_gather_records(ft, it, S)
+    trimmed = parallel.unpack_records(Ft, It, pm8, nsel, widths)
+    trimmed["widths"] = widths
+    host = parallel._deliver(trimmed, True, pm8)
+    exp8 = {k: torch.cat([_fake_records(*parallel.shard_bounds(S, world, r), pm8, nsel)[k] for r in range(world)]).numpy() for k in rec}
+    ok = ok and host["fe"].shape == (S, pm8) and np.array_equal(host["fe"][:, :3], exp8["fe"][:, :3]) and np.all(np.isnan(host["fe"][:, 3:]))
+    ok = ok and np.array_equal(host["avg"][:, :3], exp8["avg"][:, :3]) and np.array_equal(host["bounds"][:, :3], exp8["bounds"][:, :3])
+    ok = ok and np.all(host["bounds"][:, 3:] == -1) and np.array_equal(host["max_idx"][:, :3], exp8["max_idx"][:, :3])
+    ok = ok and host["min_idx"].shape == (S, pm8 + 1) and np.array_equal(host["min_idx"][:, :3], exp8["min_idx"][:, :3]) and np.all(host["min_idx"][:, 3:] == -1)
+    ok = ok and np.array_equal(host["lnnorm"], exp8["lnnorm"]) and np.array_equal(host["status"], exp8["status"])
+    # an empty shard joins the width agreement too
+    e = parallel._empty_records(pm8, nsel, torch.device("cpu"))
+    w1 = parallel.live_widths(rec["nphase"] if rank == 0 else e["nphase"], rec["nmin"] if rank == 0 else e["nmin"], pm8)
+    ok = ok and w1 == (2, 3)
     q.put((rank, bool(ok), int(F.shape[0])))
     dist.destroy_process_group()
 
