@@ -266,3 +266,29 @@ def test_scalar_path_cache_follows_the_host_arrays(golden):
     b.metadata["smooth"] = 1
     b.relextrema()
     assert b.data["ln(PI)_maxima_idx"].tolist() == [10, 25] and b.data["ln(PI)_minima_idx"].tolist() == [0, 20, 30]
+
+
+def test_scalar_path_more_extrema_than_its_record_holds(golden, oracle):
+    """A noisy ln(PI) with smooth = 1 has dozens of windowed extrema: the scalar path's record (capacity 8) reports
+    FHMC_E_CAPACITY and the drop-in methods fall back to the growing-capacity batched call; lists, bounds, F.E. and the
+    27 moment averages equal the oracle's."""
+    hist = _hist(golden, smooth=1)
+    n = len(hist.data["ln(PI)"])
+    rng = np.random.default_rng(11)
+    lnpi = -1.0e-4 * (np.arange(n) - 0.5 * n) ** 2 + 0.05 * rng.normal(size=n)
+    hist.data["ln(PI)"] = lnpi.copy()
+    mom = np.asarray(hist.data["mom"], dtype=np.float64).reshape(-1, n)
+    r = oracle.state_point(lnpi, np.arange(n), 1.0, 5.0, 5.0, 1, sel=mom)
+    assert r["status"] == 0 and r["nphase"] > 8
+    hist.relextrema()
+    assert hist.data["ln(PI)_maxima_idx"].tolist() == r["max_idx"].tolist()
+    assert hist.data["ln(PI)_minima_idx"].tolist() == r["min_idx"].tolist()
+    hist.data["ln(PI)"] = lnpi.copy()
+    hist.thermo()
+    th = hist.data["thermo"]
+    assert len(th) == r["nphase"]
+    bounds = np.asarray(r["bounds"]).reshape(-1, 2)
+    for p in range(r["nphase"]):
+        assert tuple(th[p]["bound_idx"]) == tuple(bounds[p])
+        assert np.isclose(th[p]["F.E./kT"], r["fe"][p], rtol=1e-10, atol=1e-12)
+        assert np.allclose(th[p]["mom"].reshape(-1), r["avg"][p], rtol=1e-10, atol=0)
