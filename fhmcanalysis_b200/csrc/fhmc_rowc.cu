@@ -75,6 +75,7 @@ struct RowcPt {
     int Mq, P, cntM, cntm;
     unsigned rescue;
     bool bad, live;   // !live: a lane beyond the end of its run walks a copy of the last state point and writes nothing
+    bool wig;         // some pair of successive differences of u changed sign (false: u is monotone, all differences share a sign bit)
 };
 
 template <bool HC2>
@@ -107,14 +108,14 @@ __device__ __noinline__ void rowc_generic(const SweepArgs &a, const double *rows
 // on fl(u - c), rescue of underflowed phases, is_safe).  false: not a plain case, re-run it with the general evaluator.
 template <bool HC2>
 __device__ __noinline__ bool rowc_finish(const SweepArgs &a, const RowcCtx cx, int lane, long long sp, double dD, double q2, int Mq,
-                                         int P, int cntM, int cntm, unsigned rescue, double Stot, double u0)
+                                         int P, int cntM, int cntm, unsigned rescue, double Stot, double u0, int mono)
 {
     const int n = a.d.n, last = n - 1, pmax = a.d.pmax, w = a.d.smooth;
     PointEval<1, true> pe(a, a.blob, lane, cx.tab64);   // repair() only: it reads no histogram value on these paths
     int *maxl = a.out.max_idx + sp * pmax;
     int *minl = a.out.min_idx + sp * (pmax + 1);
     int *bl = a.out.bounds + sp * pmax * 2;
-    if (!(Stot < 0x1p900) || !(Stot > 0.0)) return false;   // the subsampled shift missed the maximum by too much
+    if (!(Stot < 0x1p900) || !(Stot > 0x1p-900)) return false;   // the shift (subsampled maximum / carried over) was too far off
     const double c = add_shift(Mq, log(Stot));
     auto window_c = [&](int i, double xc, bool is_max) {   // all shifts 1..w on the normalised values
         for (int d = 1; d <= w; ++d) {
@@ -133,10 +134,23 @@ __device__ __noinline__ bool rowc_finish(const SweepArgs &a, const RowcCtx cx, i
         // max / min of the NORMALISED array (GH:382-386); genuine ties go to the general evaluator
         double vM = -CUDART_INF, vm = CUDART_INF;
         int cM = 0, cm = 0, pM = 0, pm = 0;
-        for (int j = 0; j < n; ++j) {
-            const double v = __dsub_rn(rowc_u<HC2>(cx, j, dD, q2), c);
-            if (v > vM) { vM = v; cM = 1; pM = j; } else if (v == vM) ++cM;
-            if (v < vm) { vm = v; cm = 1; pm = j; } else if (v == vm) ++cm;
+        if (mono != 0) {
+            // the walk saw no sign change between successive differences: u, and with it fl(u - c), is monotone (mono = 1:
+            // non-decreasing, 2: strictly decreasing), so the maximum and the minimum sit at the two ends and can only be
+            // tied with their neighbours there
+            const double v0 = __dsub_rn(rowc_u<HC2>(cx, 0, dD, q2), c), v1 = __dsub_rn(rowc_u<HC2>(cx, 1, dD, q2), c);
+            const double vl = __dsub_rn(rowc_u<HC2>(cx, last, dD, q2), c), vk = __dsub_rn(rowc_u<HC2>(cx, last - 1, dD, q2), c);
+            const bool up = mono == 1;
+            cM = (up ? vl > vk : v0 > v1) ? 1 : 2;
+            cm = (up ? v0 < v1 : vl < vk) ? 1 : 2;
+            pM = up ? last : 0;
+            pm = up ? 0 : last;
+        } else {
+            for (int j = 0; j < n; ++j) {
+                const double v = __dsub_rn(rowc_u<HC2>(cx, j, dD, q2), c);
+                if (v > vM) { vM = v; cM = 1; pM = j; } else if (v == vM) ++cM;
+                if (v < vm) { vm = v; cm = 1; pm = j; } else if (v == vm) ++cm;
+            }
         }
         rc = (cM == 1 && cm == 1) ? pe.repair(true, c, 0, 0, 0.0, 0.0, maxl, minl, bl, nM, nm, flags, part, 1, 1, pM, pm)
                                   : FHMC_NEED_SLOW;
@@ -177,7 +191,7 @@ __device__ __noinline__ double rowc_fe(double Sacc, int Mq, double u0) { return 
 
 // The walk of the two state points of the calling thread over the combined rows.
 template <bool HC2, int NB>
-__device__ __forceinline__ void rowc_walk(const SweepArgs &a, const RowcCtx &cx, const ExpRegs256 &ec, RowcPt &A, RowcPt &B)
+__device__ __forceinline__ void rowc_walk(const SweepArgs &a, const RowcCtx &cx, const ExpRegs256 &ec, RowcPt &A, RowcPt &B, bool have_shift)
 {
     const int n = a.d.n, last = n - 1, pmax = a.d.pmax, w = a.d.smooth;
     const uint32_t sL = cx.sL, oC1 = cx.oC1, oC2 = cx.oC2, tabL = cx.tabL;
@@ -186,8 +200,9 @@ __device__ __forceinline__ void rowc_walk(const SweepArgs &a, const RowcCtx &cx,
         return HC2 ? fma(p.q2, c2, t) : t;
     };
     auto load_u = [&](const RowcPt &p, int i) { return rowc_u<HC2>(cx, i, p.dD, p.q2); };
-    // ---- shift: maximum over every 8th bin (+ the last one) ---------------------------------------------------------
-    {
+    // ---- shift: maximum over every 8th bin (+ the last one), unless the caller carried one over from the thread's previous
+    // state points (512 positions earlier in the same run: ln Z moves by far less than the 2^+-900 a shift may be off)
+    if (!have_shift) {
         double mA = -CUDART_INF, mB = -CUDART_INF;
         for (int i = 0; i < n; i += 8) {
             const uint32_t addr = sL + 8u * (uint32_t)i;
@@ -240,6 +255,7 @@ __device__ __forceinline__ void rowc_walk(const SweepArgs &a, const RowcCtx &cx,
     // a block in which successive differences change sign: exact strict 1-neighbour tests; only a bin that passes them
     // (rare) takes the window test, in bin order, each bin's own term added after its test
     auto slow_block = [&](RowcPt &p, int i, const double (&un)[NB], double dlast) {
+        p.wig = true;
         double x[NB + 2], e[NB];
         x[0] = p.xm;
         x[1] = p.uc;
@@ -324,7 +340,9 @@ __device__ __forceinline__ void rowc_walk(const SweepArgs &a, const RowcCtx &cx,
     auto tail = [&](RowcPt &p) {
 #pragma unroll 1
         for (int j = i; j < last; ++j) {
-            const double un = load_u(p, j + 1), xc = p.uc;
+            const double un = load_u(p, j + 1), xc = p.uc, dn = __dsub_rn(un, xc);
+            if ((__double2hiint(dn) ^ __double2hiint(p.dc)) < 0) p.wig = true;
+            p.dc = dn;
             const bool is_max = (xc > p.xm) && (xc > un), is_min = (xc < p.xm) && (xc < un);
             if (is_max || is_min) confirm(p, j, xc, is_max);
             p.Sacc += ex(p, xc);
@@ -338,17 +356,18 @@ __device__ __forceinline__ void rowc_walk(const SweepArgs &a, const RowcCtx &cx,
     tail(B);
 }
 
-__device__ __forceinline__ void rowc_init(RowcPt &p, long long sp, double dmu, double dmu_ref, bool live)
+__device__ __forceinline__ void rowc_init(RowcPt &p, long long sp, double dmu, double dmu_ref, bool live, int Mq)
 {
     p.sp = sp;
     p.live = live;
+    p.wig = false;
     p.dD = dmu - dmu_ref;
     p.q2 = monomial(FHMC_M_DD2, 0.0, p.dD, 0.0);
     p.Sacc = p.Stot = 0.0;
     p.P = p.cntM = p.cntm = 0;
     p.rescue = 0;
     p.bad = false;
-    p.Mq = 0;
+    p.Mq = Mq;
     p.u0 = p.xm = p.uc = p.dc = 0.0;
 }
 
@@ -429,16 +448,23 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_rowc(const __grid_constan
             ++epoch;
         }
         const long long j0 = (long long)ch * pl.chunk, j1 = min(j0 + (long long)pl.chunk, pl.n_run);
+        int MqA = 0, MqB = 0;
+        bool carry = false;   // MqA / MqB: ln Z / ln 2 of the thread's previous two state points of this item
         for (long long t = j0 + warp * 64; t < j1; t += (FHMC_CTA / 32) * 64) {
             // a lane beyond the end of the run walks the run's last state point again without writing anything
             const bool liveA = t + lane < j1, liveB = t + 32 + lane < j1;
             const long long jA = liveA ? t + lane : j1 - 1, jB = liveB ? t + 32 + lane : j1 - 1;
             RowcPt A, B;
-            rowc_init(A, sp0 + jA, a.st.dmu[jA], a.d.dmu_ref, liveA);
-            rowc_init(B, sp0 + jB, a.st.dmu[jB], a.d.dmu_ref, liveB);
-            rowc_walk<HC2, 4>(a, cx, ec, A, B);
-            const bool okA = !liveA || !A.bad && rowc_finish<HC2>(a, cx, lane, A.sp, A.dD, A.q2, A.Mq, A.P, A.cntM, A.cntm, A.rescue, A.Stot, A.u0);
-            const bool okB = !liveB || !B.bad && rowc_finish<HC2>(a, cx, lane, B.sp, B.dD, B.q2, B.Mq, B.P, B.cntM, B.cntm, B.rescue, B.Stot, B.u0);
+            rowc_init(A, sp0 + jA, a.st.dmu[jA], a.d.dmu_ref, liveA, MqA);
+            rowc_init(B, sp0 + jB, a.st.dmu[jB], a.d.dmu_ref, liveB, MqB);
+            rowc_walk<HC2, 4>(a, cx, ec, A, B, carry);
+            const int monoA = A.wig ? 0 : (__double2hiint(A.dc) < 0 ? 2 : 1), monoB = B.wig ? 0 : (__double2hiint(B.dc) < 0 ? 2 : 1);
+            const bool okA = !liveA || !A.bad && rowc_finish<HC2>(a, cx, lane, A.sp, A.dD, A.q2, A.Mq, A.P, A.cntM, A.cntm, A.rescue, A.Stot, A.u0, monoA);
+            const bool okB = !liveB || !B.bad && rowc_finish<HC2>(a, cx, lane, B.sp, B.dD, B.q2, B.Mq, B.P, B.cntM, B.cntm, B.rescue, B.Stot, B.u0, monoB);
+            // next tile of this warp: shift = exponent of the sums just formed (both walks plain and in range), else a fresh pre-pass
+            carry = !A.bad && !B.bad && A.Stot < 0x1p900 && A.Stot > 0x1p-900 && B.Stot < 0x1p900 && B.Stot > 0x1p-900;
+            MqA = A.Mq + ((__double2hiint(A.Stot) >> 20) & 0x7ff) - 1022;
+            MqB = B.Mq + ((__double2hiint(B.Stot) >> 20) & 0x7ff) - 1022;
             // anything unusual: the whole warp re-runs it with the general evaluator, on the combined rows
             __syncwarp();
             unsigned fA = __ballot_sync(0xffffffffu, !okA), fB = __ballot_sync(0xffffffffu, !okB);

@@ -61,3 +61,24 @@ elif os.environ.get("PROFILE"):
         dropin()
     pr.disable()
     pstats.Stats(pr).sort_stats("cumulative").print_stats(35)
+if os.environ.get("PROFILE") == "3":
+    # cost of the pieces of one scalar call
+    from fhmcanalysis_b200 import engine
+    sp = engine.ScalarPath.get(1001)
+    N = np.arange(1001)
+    m2 = np.asarray(mom1, dtype=np.float64).reshape(-1, 1001)
+
+    def t(fn, reps=300):
+        for _ in range(20):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps * 1e6
+    print("point(complete, row)          %.1f us" % t(lambda: sp.point(lnpi1, N, 1.0, 0.0, 10, 0.01, complete=True, want_row=True)))
+    print("point(split only)             %.1f us" % t(lambda: sp.point(lnpi1, N, 1.0, 0.0, 10, 0.0)))
+    print("point(split, row, 27 moments) %.1f us" % t(lambda: sp.point(lnpi1, N, 1.0, 0.0, 10, 0.0, want_row=True, mom=m2)))
+    print("key(lnpi) %.1f us  key(N) %.1f us  key(mom) %.1f us" % (t(lambda: sp._key(lnpi1)), t(lambda: sp._key(np.ascontiguousarray(N, dtype=np.float64))), t(lambda: sp._mom_key(m2))))
+    hh = histogram.from_arrays(lnpi1, mom1, 1.0, [0.0], 10)
+    print("from_arrays %.1f us" % t(lambda: histogram.from_arrays(lnpi1, mom1, 1.0, [0.0], 10)))
+    print("reweight %.1f us  thermo %.1f us  is_safe %.1f us" % (t(lambda: hh.reweight(0.01)), t(lambda: hh.thermo()), t(lambda: hh.is_safe())))
