@@ -720,7 +720,8 @@ class ScalarPath(object):
     synchronisation) into a pinned result buffer."""
 
     PMAX = 8
-    _cache = {}
+    MAX_CACHED = 16      # histogram lengths kept resident per process (least recently used goes first)
+    _cache = {}          # insertion-ordered: (device index, n) -> ScalarPath.  Not thread-safe: one scalar call at a time per process
 
     @classmethod
     def get(cls, n, device=None):
@@ -730,11 +731,15 @@ class ScalarPath(object):
                 key = (t.cuda.current_device(), int(n))
                 sp = cls._cache.get(key)
                 if sp is not None:
+                    if len(cls._cache) > 1:
+                        cls._cache[key] = cls._cache.pop(key)     # most recently used last
                     return sp
         dev = require_cuda(device)
         key = (dev.index if dev.index is not None else torch().cuda.current_device(), int(n))
         sp = cls._cache.get(key)
         if sp is None:
+            while len(cls._cache) >= cls.MAX_CACHED:
+                cls._cache.pop(next(iter(cls._cache)))
             sp = cls._cache[key] = cls(int(n), dev)
         return sp
 

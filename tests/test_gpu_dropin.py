@@ -292,3 +292,21 @@ def test_scalar_path_more_extrema_than_its_record_holds(golden, oracle):
         assert tuple(th[p]["bound_idx"]) == tuple(bounds[p])
         assert np.isclose(th[p]["F.E./kT"], r["fe"][p], rtol=1e-10, atol=1e-12)
         assert np.allclose(th[p]["mom"].reshape(-1), r["avg"][p], rtol=1e-10, atol=0)
+
+
+def test_scalar_path_cache_is_bounded(golden):
+    """One resident ScalarPath per histogram length, at most MAX_CACHED of them (least recently used evicted)."""
+    from fhmcanalysis_b200 import engine
+    import FHMCAnalysis.moments.histogram.one_dim.ntot.gc_hist as oneDH
+    old = engine.ScalarPath.MAX_CACHED
+    engine.ScalarPath.MAX_CACHED = 3
+    try:
+        for n in (40, 41, 42, 43, 44, 41):
+            x = np.arange(n, dtype=np.float64)
+            h = oneDH.histogram.from_arrays(-0.01 * (x - 0.5 * n) ** 2, np.ones((1, 2, 1, 2, 2, n)), 1.0, [0.0], 2)
+            h.normalize()
+            assert np.isclose(np.log(np.sum(np.exp(h.data["ln(PI)"]))), 0.0, atol=1e-12)
+            assert len(engine.ScalarPath._cache) <= 3
+        assert [k[1] for k in engine.ScalarPath._cache][-1] == 41
+    finally:
+        engine.ScalarPath.MAX_CACHED = old
