@@ -613,10 +613,13 @@ def extra_blocks(torch, dev, peaks, counts, histogram, engine, _lib):
         evals = float(np.mean(hr["iters"]))
         both = conv & conv_c
         same_root = float(np.mean(np.abs(hr["mu_coex"][both] - hc["mu_coex"][both]) <= 1e-9)) if both.any() else None
+        for _ in range(3):     # warm-up (pinned staging buffers, first-call attribute queries)
+            h4.find_phase_eq_batch(betas4, 0.0, order=2, lnZ_tol=1e-10)
+        torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        for _ in range(3):
-            out4 = h4.find_phase_eq_batch(betas4, 0.0, order=2, lnZ_tol=1e-10)     # host arrays in, host records out (staged continuation)
-        e2e_s = (time.perf_counter() - t0) / 3
+        for _ in range(5):
+            out4 = h4.find_phase_eq_batch(betas4, 0.0, order=2, lnZ_tol=1e-10)     # host arrays in, host records out (one launch, in-kernel continuation)
+        e2e_s = (time.perf_counter() - t0) / 5
         ks = np.where(conv)[0][::max(1, int(conv.sum()) // 256)][:256]
         smp["c4_k"], smp["c4_mu"] = ks, hr["mu_coex"][ks]
         smp["c4_safe"] = hr["safe"][ks]
@@ -631,7 +634,7 @@ def extra_blocks(torch, dev, peaks, counts, histogram, engine, _lib):
                              "converged_fraction": float(conv.mean()), "jump_terminated_fraction": float(np.mean((hr["code"] == 0) & ~conv)),
                              "mean_evaluations": evals, "max_abs_dfe_converged": float(np.max(np.abs(hr["dfe"][conv]))) if conv.any() else None,
                              "roofline": _roof(counts, "k_solve_lean/evaluation", v * evals, peaks, 2 * C4_BINS),
-                             "e2e": {"value": C4_T / e2e_s, "unit": "coexistence points/s", "path": "histogram.find_phase_eq_batch (host arrays in, host records out, staged continuation)",
+                             "e2e": {"value": C4_T / e2e_s, "unit": "coexistence points/s", "path": "histogram.find_phase_eq_batch (host arrays in, host records out; histogram blob rebuilt and uploaded per call, one launch with in-kernel continuation)",
                                      "converged_fraction": float(np.mean(out4["converged"])), "mean_evaluations_last_stage": float(np.mean(out4["iters"])),
                                      "h2d_bytes_per_step": int(dh4.h2d_bytes + 3 * 8 * C4_T), "d2h_bytes_per_step": int(hold["r"].nbytes() + 20 * C4_T)}}
     except Exception as e:
@@ -649,10 +652,13 @@ def extra_blocks(torch, dev, peaks, counts, histogram, engine, _lib):
             hold["o"] = engine.reweight_2d(tl, tb, to, to, ta1, ta2, None, return_device=True, product=True)
         ms = _event_ms(torch, rw, reps=5, warm=2)
         kern = _lib.last_kernel()
+        for _ in range(3):     # warm-up
+            engine.reweight_2d(lnpi2d, bounds, op, op, a1, a2, None)
+        torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        for _ in range(3):
+        for _ in range(5):
             engine.reweight_2d(lnpi2d, bounds, op, op, a1, a2, None)     # host arrays in, host array out
-        e2e_s = (time.perf_counter() - t0) / 3
+        e2e_s = (time.perf_counter() - t0) / 5
         ks = np.arange(13, C5_S, C5_S // 1024)[:1024]
         smp["c5_k"], smp["c5_out"] = ks, hold["o"][torch.from_numpy(ks).to(dev)].cpu().numpy()
         support = int(np.sum(bounds[:, 1] - bounds[:, 0]))
