@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SOURCES = ["fhmc_b200.cu", "fhmc_solver.cu", "fhmc_solver_lean.cu", "fhmc_solver_lean2.cu", "fhmc_2d.cu", "fhmc_fast_taylor.cu", "fhmc_rowc.cu", "fhmc_fast_rec.cu", "fhmc_fast_prod.cu", "fhmc_fast_prod_compact.cu", "fhmc_tab.cu", "fhmc_masked2d.cu", "fhmc_host_pipe.cu", "fhmc_patch.cu"]
+SOURCES = ["fhmc_b200.cu", "fhmc_solver.cu", "fhmc_solver_lean.cu", "fhmc_solver_lean2.cu", "fhmc_2d.cu", "fhmc_fast_taylor.cu", "fhmc_rowc.cu", "fhmc_fast_rec.cu", "fhmc_fast_prod.cu", "fhmc_fast_prod_compact.cu", "fhmc_tab.cu", "fhmc_cell.cu", "fhmc_masked2d.cu", "fhmc_host_pipe.cu", "fhmc_patch.cu"]
 HEADERS = ["fhmc_common.cuh", "fhmc_point.cuh", "fhmc_fast.cuh", "fhmc_prod.cuh", "fhmc_tab.cuh", "fhmc_solver.cuh", "fhmc_lean.cuh", "fhmc_solver_lean.cuh"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "csrc")]

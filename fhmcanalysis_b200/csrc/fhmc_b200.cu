@@ -390,6 +390,8 @@ __global__ void __launch_bounds__(256) k_pack_phase_soa16(const __grid_constant_
 int launch_prod2_compact(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream, int *grid_out, bool dry);
 // the same on per-histogram tables (fhmc_tab.cu); needs args.d.mu_tables
 int launch_tab2_compact(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream, int *grid_out, bool dry);
+// dense sweeps on tilt cells + the table walk over whatever the cells leave (fhmc_cell.cu); needs args.d.mu_cells and args.c.ix_*
+int launch_cell_compact(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream);
 
 // Taylor-extrapolated grids, rows combined per (mu_1, beta) (fhmc_rowc.cu)
 int launch_rowc(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream);
@@ -511,6 +513,8 @@ size_t carve_records(unsigned char *base, long long c, int pmax, int nsel, fhmc_
     return off;
 }
 }  // namespace fhmc
+static size_t cell_index_bytes(long long n_states) { return (((size_t)8 * (size_t)n_states + 255) & ~(size_t)255) + 256; }
+
 extern "C" {
 
 size_t fhmc_sweep_compact_workspace(const fhmc_hist_desc *desc, long long n_states)
@@ -521,7 +525,9 @@ size_t fhmc_sweep_compact_workspace(const fhmc_hist_desc *desc, long long n_stat
                        desc->pmax <= FHMC_COMPACT_PMAX && desc->n <= 32767;
     const long long c = (fused && n_states > FHMC_COMPACT_SCRATCH_RECORDS) ? FHMC_COMPACT_SCRATCH_RECORDS
                         : (n_states > FHMC_COMPACT_SCRATCH_RECORDS ? n_states : FHMC_COMPACT_SCRATCH_RECORDS);
-    return carve_records(nullptr, c, desc->pmax, desc->n_sel, nullptr);
+    // + the index list of the state points the tilt cells leave to the table walk
+    const size_t ix = (fused && desc->mu_tables && desc->mu_cells) ? cell_index_bytes(n_states) : 0;
+    return carve_records(nullptr, c, desc->pmax, desc->n_sel, nullptr) + ix;
 }
 
 int fhmc_sweep_1d_compact(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states, const fhmc_compact_out *cout,
@@ -562,7 +568,18 @@ int fhmc_sweep_1d_compact(const fhmc_hist_desc *desc, const double *blob, const 
             const long long need = (long long)grid * (FHMC_CTA / 32);
             if (need <= FHMC_COMPACT_SCRATCH_RECORDS &&
                 carve_records(nullptr, FHMC_COMPACT_SCRATCH_RECORDS, desc->pmax, desc->n_sel, nullptr) <= workspace_bytes) {
-                carve_records(static_cast<unsigned char *>(workspace), FHMC_COMPACT_SCRATCH_RECORDS, desc->pmax, desc->n_sel, &args.out);
+                const size_t rec_bytes = carve_records(static_cast<unsigned char *>(workspace), FHMC_COMPACT_SCRATCH_RECORDS, desc->pmax,
+                                                       desc->n_sel, &args.out);
+                if (use_tab && desc->mu_cells && rec_bytes + cell_index_bytes(states->n_states) <= workspace_bytes) {
+                    // dense sweep on tilt cells; what they leave goes through the table walk in the same call
+                    unsigned char *ix = static_cast<unsigned char *>(workspace) + rec_bytes;
+                    args.c.ix_list = reinterpret_cast<long long *>(ix);
+                    args.c.ix_count = reinterpret_cast<int *>(ix + cell_index_bytes(states->n_states) - 256);
+                    rc = launch_cell_compact(args, di->sm_count, di->smem_optin, s);
+                    if (rc >= 0) return rc;
+                    args.c.ix_list = nullptr;
+                    args.c.ix_count = nullptr;
+                }
                 rc = use_tab ? launch_tab2_compact(args, di->sm_count, di->smem_optin, s, &grid, false)
                              : launch_prod2_compact(args, di->sm_count, di->smem_optin, s, &grid, false);
                 if (rc >= 0) return rc;

@@ -31,6 +31,10 @@ struct CompactArgs {
     long long first;     // record index of state point 0 of this launch
     int fill_dead;       // write NaN / -1 into the phase slots >= nphase
     int *max_nphase;     // device int raised (atomicMax) to the largest phase count; nullable
+    // k_sweep_cell (fhmc_cell.cu): state points it leaves to the table walk -- list[0 .. *count) (it appends; the indexed
+    // instantiation of k_sweep_tab2 reads).  Null everywhere else.
+    long long *ix_list;
+    int *ix_count;
 };
 
 struct SweepArgs {

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(FHMC_CTA, 1) k_tab_image(const __grid_constant
 }
 
 // build, kernel 2: rank sort of the raw endpoints (ties broken by position); +inf entries end up behind the finite ones
-__global__ void __launch_bounds__(256) k_tab_rank(unsigned char *tables)
+static __global__ void __launch_bounds__(256) k_tab_rank(unsigned char *tables)
 {
     MuTabHeader *h = reinterpret_cast<MuTabHeader *>(tables);
     const int E = h->ep_cap;
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) k_tab_rank(unsigned char *tables)
 }
 
 // build, kernel 3: one representative mu per elementary interval (k = number of endpoints <= tilt)
-__global__ void __launch_bounds__(256) k_tab_mu(unsigned char *tables, double mu1_ref, double beta_ref)
+static __global__ void __launch_bounds__(256) k_tab_mu(unsigned char *tables, double mu1_ref, double beta_ref)
 {
     const MuTabHeader *h = reinterpret_cast<const MuTabHeader *>(tables);
     const double *ep = reinterpret_cast<const double *>(tables + h->off_ep);
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) k_tab_mu(unsigned char *tables, double mu
 }
 
 // build, kernel 4: the general evaluator's records of the representatives -> interval records
-__global__ void __launch_bounds__(128) k_tab_records(unsigned char *tables, fhmc_sweep_out out, int pmax, double mu1_ref, double beta_ref,
+static __global__ void __launch_bounds__(128) k_tab_records(unsigned char *tables, fhmc_sweep_out out, int pmax, double mu1_ref, double beta_ref,
                                                      const double *hull_slope, const double *hull_idx, int hull_len)
 {
     const MuTabHeader *h = reinterpret_cast<const MuTabHeader *>(tables);
@@ -613,14 +613,15 @@ __device__ unsigned long long g_tab_prof[8];   // cycles (lane 0 of every warp):
 // pipe saturated in the loop phase (math-pipe throttle) and idle in the latency-bound phases (r2f capture: 55 % active).
 // Independent warps drift apart (a warp that reaches the loop first finds the pipe free and gets further ahead), so one
 // warp's epilogue overlaps the others' loops.
-template <int NSEL, class W>
+// IDX: the state points are list[0 .. *count) of SweepArgs::c (what k_sweep_cell left over) instead of 0 .. n_states - 1.
+template <int NSEL, class W, bool IDX = false>
 __device__ __forceinline__ void tab2_warp_tiles(const SweepArgs &a, const W &w, double *s_tab)
 {
     using LY = typename W::LY;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     long long *queue = reinterpret_cast<long long *>(s_tab + 64) + wib * 64;   // this warp's 64 entries of the queue area
     static_assert(LY::QN >= (FHMC_CTA / 32) * 64, "queue area too small for the per-warp queues");
-    const long long S = a.st.n_states;
+    const long long S = IDX ? (long long)*a.c.ix_count : a.st.n_states;
     const long long slot = (long long)blockIdx.x * (FHMC_CTA / 32) + wib;          // scratch record of this warp
     const long long nwarps = (long long)gridDim.x * (FHMC_CTA / 32);
     int top = 0;
@@ -637,12 +638,13 @@ __device__ __forceinline__ void tab2_warp_tiles(const SweepArgs &a, const W &w, 
     long long prof[5] = {0, 0, 0, 0, 0}, tp = clock64();
 #endif
     for (long long wt = (long long)wib * gridDim.x + blockIdx.x; wt * 64 < S; wt += nwarps) {
-        const long long sp0 = wt * 64 + lane, sp1 = sp0 + 32;
+        const long long k0 = wt * 64 + lane, k1 = k0 + 32;
+        const long long sp0 = (IDX && k0 < S) ? a.c.ix_list[k0] : k0, sp1 = (IDX && k1 < S) ? a.c.ix_list[k1] : k1;
         bool ok0 = true, ok1 = true;
-        if (sp0 < S) {
+        if (k0 < S) {
             typename W::PS p0, p1;
             w.init(p0, sp0, a.st.mu1[(sp0 / a.st.mu1_div) % a.st.n_mu1]);
-            if (sp1 < S) {
+            if (k1 < S) {
                 w.init(p1, sp1, a.st.mu1[(sp1 / a.st.mu1_div) % a.st.n_mu1], p0.ivl);
                 TAB_PROF_T(0)
                 if (!((p0.fl | p1.fl) & W::F_BAD)) {
@@ -712,6 +714,38 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_tab2(const __grid_constan
     double *s_tab = cx.s_tab;
     const W w(a, cx, nullptr, a.d.smooth, smem_u32(s_tab), tc, ok);
     tab2_warp_tiles<NSEL, W>(a, w, s_tab);
+}
+
+// the same over an index list (the leftovers of k_sweep_cell): nothing staged when the list is empty
+template <int NSEL, bool SEL0N>
+__global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_tab2_idx(const __grid_constant__ SweepArgs a)
+{
+    using W = TabWalk<NSEL, SEL0N>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if ((long long)blockIdx.x * 64 >= (long long)*a.c.ix_count) return;   // this CTA's first warp tile is tile blockIdx.x (uniform per CTA)
+    TabCtx tc;
+    bool ok;
+    const FastCtx cx = tab_prepare<NSEL, SEL0N>(a, smem_raw, tc, ok);
+    double *s_tab = cx.s_tab;
+    const W w(a, cx, nullptr, a.d.smooth, smem_u32(s_tab), tc, ok);
+    tab2_warp_tiles<NSEL, W, true>(a, w, s_tab);
+}
+
+template <int NSEL, bool SEL0N>
+static int launch_tab2_idx(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream)
+{
+    const size_t smem = fast_smem_bytes<NSEL, SEL0N, 0, 1, 2>(args.d.n_pad);
+    if (smem > (size_t)smem_optin) return -1;
+    auto kern = k_sweep_tab2_idx<NSEL, SEL0N>;
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return 1;
+    int occ = 0;
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FHMC_CTA, smem), "occupancy query")) return 1;
+    if (occ < 1) return -1;
+    const long long ntiles = (args.st.n_states + 63) / 64;   // (the list cannot be longer than the sweep)
+    long long grid = (long long)sm_count * occ;
+    if (grid > ntiles) grid = ntiles;
+    kern<<<(unsigned)grid, FHMC_CTA, smem, stream>>>(args);
+    return check_cuda(cudaGetLastError(), "k_sweep_tab2_idx launch");
 }
 
 template <int NSEL, bool SEL0N>

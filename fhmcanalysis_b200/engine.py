@@ -161,6 +161,7 @@ def soa16_views(buf, S, pmax, nsel):
     out = {}
     out["status"] = t.as_strided(buf[:4 * S].view(t.int16), (S,), (2,))
     out["nphase"] = t.as_strided(buf[:4 * S], (S,), (4,), buf.storage_offset() + 2)
+    out["path"] = t.as_strided(buf[:4 * S], (S,), (4,), buf.storage_offset() + 3)   # diagnostic: 1 = written by the tilt cells
     f0 = (4 * S + 15) & ~15
     F = buf[f0:f0 + pmax * S * nf * 8].view(t.float64)
     B = buf[f0 + pmax * S * nf * 8:f0 + pmax * S * nf * 8 + pmax * S * 4].view(t.int16)
@@ -230,6 +231,8 @@ class DeviceHistogram(object):
         self.use_recurrence = int(os.environ.get("FHMC_MU_RECURRENCE", "3"))
         # per-histogram tables for compact-record mu sweeps (ensure_mu_tables); False keeps the table-free kernel
         self.use_mu_tables = os.environ.get("FHMC_MU_TABLES", "1") != "0"
+        # tilt cells on top of the tables for dense sweeps (ensure_mu_cells); False keeps the table walk
+        self.use_mu_cells = os.environ.get("FHMC_MU_CELLS", "1") != "0"
         blob = np.zeros((len(rows), n_pad), dtype=np.float64)
         for i, r in enumerate(rows):
             if r.shape != (n,):
@@ -310,6 +313,61 @@ class DeviceHistogram(object):
         self._mu_tables = buf
         self.desc.mu_tables = ptr
 
+    CELLS_MIN_STATES = 1 << 16   # the fused compact kernels start at 2 x 256 state points per SM; cells pay from about here
+    CELLS_MAX_EXTRA = 32768   # cells beyond one per elementary interval (0.67 KB each at two averaged quantities)
+
+    def ensure_mu_cells(self, mu):
+        """Tilt cells of a dense compact-record mu sweep (fhmc_mu_cells_build): moment expansions of the per-phase sums about the
+        centres of small tilt cells covering the mu range of ``mu`` (a device tensor or host array), handed to the kernels through
+        desc.mu_cells.  Built once per range: a later sweep inside the range reuses them, one that leaves it rebuilds them for
+        the union.  The range of a device tensor is read back once per (storage, version); state points outside the cells are
+        still evaluated (by the table walk), so a stale range costs speed, never correctness.  FHMC_MU_CELLS=0 / use_mu_cells =
+        False keeps the table walk (k_sweep_tab2)."""
+        if not self.use_mu_cells or not self.desc.mu_tables:
+            return
+        t = torch()
+        if isinstance(mu, t.Tensor):
+            if mu.numel() == 0:
+                return
+            key = (mu.data_ptr(), mu.numel(), mu._version)
+            if key == getattr(self, "_cells_key", None):
+                return
+            lo, hi = (float(x) for x in t.aminmax(mu))
+        else:
+            mu = np.asarray(mu, dtype=np.float64)
+            if mu.size == 0:
+                return
+            key = None
+            lo, hi = float(mu.min()), float(mu.max())
+        if not (np.isfinite(lo) and np.isfinite(hi)):
+            return
+        self._cells_key = key
+        have = getattr(self, "_cells_range", None)
+        if have is not None and have[0] <= lo and hi <= have[1]:
+            return
+        if have is not None:   # grow: cover both
+            lo, hi = min(lo, have[0]), max(hi, have[1])
+        L = _lib.load()
+        d = self.desc
+        Nrow = self.blob_host[1, :self.n]
+        tilt_range = abs((hi - lo) * d.beta_ref * (Nrow[1] - Nrow[0]))
+        extra = int(min(self.CELLS_MAX_EXTRA, tilt_range * self.n / 0.19 + 64))
+        nbytes = int(L.fhmc_mu_cells_bytes(ctypes.byref(d), extra))
+        if nbytes == 0:
+            return
+        buf = t.empty(nbytes + 256, dtype=t.uint8, device=self.device)
+        ptr = (buf.data_ptr() + 255) & ~255
+        with t.cuda.device(self.device):
+            rc = L.fhmc_mu_cells_build(ctypes.byref(d), _ptr(self.blob), ctypes.c_void_p(ptr), nbytes, extra, lo, hi, _stream_ptr(self.device))
+        if rc == 2:
+            return
+        _lib.check(rc, "fhmc_mu_cells_build")
+        # (the previous buffer may still be read by a sweep queued on this stream: the caching allocator reuses it only in
+        # stream order)
+        self._mu_cells = buf
+        self._cells_range = (lo, hi)
+        self.desc.mu_cells = ptr
+
     # ------------------------------------------------------------------------------------------
     def _desc(self, pmax, complete=False, compare_raw=False, cutoff=None, smooth=None):
         d = _lib.HistDesc.from_buffer_copy(self.desc)
@@ -321,6 +379,7 @@ class DeviceHistogram(object):
         if smooth is not None:
             if int(smooth) != d.smooth:
                 d.mu_tables = None      # the tables belong to one window width
+                d.mu_cells = None
             d.smooth = int(smooth)
         return d
 
@@ -394,6 +453,10 @@ class DeviceHistogram(object):
         if S >= self.FAST_PATH_MIN_STATES:
             self.ensure_hull()
             self.ensure_mu_tables()
+            if S >= self.CELLS_MIN_STATES and not st.beta and not st.dmu:
+                keep = getattr(st, "_keep", None)
+                on_dev = isinstance(mu1, t.Tensor) and mu1.is_cuda
+                self.ensure_mu_cells(keep[0] if (on_dev or mu1 is None) and keep is not None else mu1)
         n_total = S + int(first) if n_total is None else int(n_total)
         d = self._desc(pmax)
         nbytes = int(L.fhmc_pack_soa16_bytes(n_total, pmax, self.n_sel))

@@ -116,6 +116,12 @@ typedef struct fhmc_hist_desc {
      * extrema as it walks).  The buffer must stay valid and unchanged while sweeps use it, and belongs to exactly this
      * blob / n / smooth / sel_row combination.                                                                        */
     const void *mu_tables;
+    /* Optional second level on top of mu_tables, for DENSE mu sweeps (fhmc_sweep_1d_compact): moment expansions of the per-phase
+     * sums about the centres of small tilt cells, built by fhmc_mu_cells_build() for one range of mu.  Inside an elementary
+     * interval the phase bounds are fixed, so every per-phase sum  sum_i exp(lnPI_i + s N_i) X_q(i)  is an entire function of s:
+     * a state point then costs one degree-7 polynomial per phase and quantity instead of a walk over the bins (GH:71-78,
+     * 498-554).  State points outside the range, or that fail a rounding-margin test, take the table walk.  NULL: not provided. */
+    const void *mu_cells;
 } fhmc_hist_desc;
 
 /*
@@ -229,7 +235,7 @@ int fhmc_pack_phase_major(const fhmc_sweep_out *out, long long n_states, int pma
 
 /*
  * Narrow variant of the repack: 4 + P (8 + 8 n_sel + 4) bytes per state point with P live phases.
- *   packed: { u16 status (FHMC_ST_* fit 15 bits); u8 nphase; u8 0 }[S], padded to 16 bytes  |
+ *   packed: { u16 status (FHMC_ST_* fit 15 bits); u8 nphase; u8 path (diagnostic: 1 = written by the tilt cells, else 0) }[S], padded to 16 bytes  |
  *           for p in 0..pmax-1: { f64 fe; f64 avg[n_sel]; }[S]  |  for p in 0..pmax-1: { i16 bounds[2]; }[S]
  * (bin indices must fit int16: n <= 32767).  Slots p >= nphase[s] hold NaN / -1 as in fhmc_pack_phase_major.
  */
@@ -269,6 +275,17 @@ size_t fhmc_mu_tables_bytes(const fhmc_hist_desc *desc);
 int fhmc_mu_tables_build(const fhmc_hist_desc *desc, const double *blob, void *tables, size_t tables_bytes, void *stream);
 int fhmc_sweep_1d_compact(const fhmc_hist_desc *desc, const double *blob, const fhmc_states *states, const fhmc_compact_out *out,
                           void *workspace, size_t workspace_bytes, void *stream);
+/*
+ * Tilt cells for fhmc_hist_desc.mu_cells (new; see the field): moment expansions of the per-phase sums of reweight() + thermo()
+ * (GH:71-78, 498-554) about the centres of small cells of the tilt, for the state points with mu1 in [mu_lo, mu_hi].  desc must
+ * carry the mu_tables the cells refine (same blob); desc->mu_cells is ignored.  cells: device, 256-byte aligned,
+ * fhmc_mu_cells_bytes(desc, extra_pieces) bytes -- room for one cell per elementary interval plus extra_pieces (a one-phase
+ * interval needs a cell per 0.2 / n of tilt; intervals that do not fit any more are left to the table walk).  Asynchronous on
+ * `stream`; returns 0 ok, 1 error, 2 not applicable.  The buffer belongs to exactly this blob / tables combination.
+ */
+size_t fhmc_mu_cells_bytes(const fhmc_hist_desc *desc, int extra_pieces);
+int fhmc_mu_cells_build(const fhmc_hist_desc *desc, const double *blob, void *cells, size_t cells_bytes, int extra_pieces,
+                        double mu_lo, double mu_hi, void *stream);
 
 /*
  * Host-buffer mu sweep (new; replaces the user's Python loop of reweight()/thermo()/is_safe() calls on host arrays,

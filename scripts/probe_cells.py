@@ -1,0 +1,55 @@
+"""Kernel time of the dense compact mu sweep on tilt cells (k_sweep_cell) against the table walk, and the cost of building the cells."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from fhmcanalysis_b200 import _lib, engine, synth
+
+n = 1001
+lnpi = synth.two_peak_lnpi(n)
+N = np.arange(n, dtype=np.float64)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+
+def timed(fn, reps=20):
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+for S in (100000, 1000000, 4000000):
+    mu = torch.linspace(-0.03, 0.03, S, dtype=torch.float64, device="cuda")
+    for cells in (False, True):
+        dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=10, sel=["N", N * N])
+        dh.use_mu_cells = cells
+        st = dh.make_states(mu)
+        buf = torch.empty(int(_lib.load().fhmc_pack_soa16_bytes(S, 4, 2)), dtype=torch.uint8, device="cuda")
+        fn = lambda: dh.sweep_compact(None, pmax=4, dst=buf, states=st, fill_dead=False)
+        r = fn()
+        torch.cuda.synchronize()
+        med, best = timed(fn)
+        frac = float(r["path"].double().mean()) if cells else 0.0
+        print("S %8d cells %d  %-26s median %.1f us  min %.1f us -> %.3e points/s  cell fraction %.4f" % (S, cells, _lib.last_kernel(), 1e3 * med, 1e3 * best, S / (1e-3 * med), frac), flush=True)
+        if cells:
+            def rebuild():
+                dh._cells_range = None
+                dh._cells_key = None
+                dh.ensure_mu_cells(mu)
+            med, best = timed(rebuild, 10)
+            print("   cells build (aminmax + readback + 3 kernels): median %.1f us  min %.1f us;  range %r" % (1e3 * med, 1e3 * best, dh._cells_range))
+            hdr = dh._mu_cells[(-dh._mu_cells.data_ptr()) % 256:][:64].cpu().numpy().view(np.int32)
+            print("   header: n_pieces %d n_blocks %d truncated %d (piece_cap %d)" % (hdr[6], hdr[7], hdr[8], hdr[4]))
+            def cold():
+                dh._cells_range = None
+                dh._cells_key = None
+                fn()
+            med, best = timed(cold, 10)
+            print("   cold step (cells rebuilt inside): median %.1f us  min %.1f us -> %.3e points/s" % (1e3 * med, 1e3 * best, S / (1e-3 * med)))

@@ -8,11 +8,12 @@ pytestmark = pytest.mark.gpu
 S_MIN = 80000   # the fused compact kernels take sweeps of more than 2 x 256 state points per SM (148 SMs)
 
 
-def _both(lnpi, N, mu, smooth, sel=None, beta=1.0, mu_ref=0.0, pmax=4):
+def _both(lnpi, N, mu, smooth, sel=None, beta=1.0, mu_ref=0.0, pmax=4, cells=False):
     """compact records through the table-driven kernel + plain records of the general one-lane kernel"""
     from fhmcanalysis_b200 import _lib, engine
     sel = ["N", N * N] if sel is None else sel
     dh = engine.DeviceHistogram(lnpi, N, beta, mu_ref, smooth=smooth, sel=sel)
+    dh.use_mu_cells = cells     # False: the table walk itself (tests/test_gpu_cells.py runs the same cases on the tilt cells)
     c = dh.sweep_compact(mu, pmax=pmax)
     kern = _lib.last_kernel()
     g = dh.sweep(mu, pmax=pmax, lanes=-1).host()
