@@ -38,23 +38,28 @@ struct CellHeader {   // 256 bytes at the start of the cells buffer
     int iv_cap, piece_cap, block_cap;
     int n_pieces, n_blocks;               // (device)
     int truncated;                        // capacity reached: the upper intervals of the range are not covered (device)
-    int pad0;
-    long long off_iv, off_piece, off_coef;
+    int grid_n;                           // cells of the lookup grid over [a_lo, a_hi]
+    long long off_iv, off_piece, off_coef, off_pstart, off_grid;
     double a_lo, a_hi;                    // covered tilt range (device)
-    double pad1[20];
+    double inv_g;                         // grid cells per unit of tilt (device)
+    double pad1[17];
 };
 static_assert(sizeof(CellHeader) <= 256, "header must fit its slot");
 
-struct CellIv {     // per elementary interval
+struct CellIv {     // per elementary interval (build only)
     int first, m;   // pieces first .. first + m - 1 (m == 0: not covered)
     int bfirst, nph;
     double a0, inv_w;
 };
+// One cell.  [safe_lo, safe_hi]: the tilts of the cell that are further from both ends of its elementary interval than the
+// rounding margin of the table walk (tab_margin at the largest |s| of the cell, doubled) -- the margin test of a state point is
+// one range check.  The words the sweep needs from the interval record travel with the cell.
 struct CellPiece {
-    double s_c;
+    double s_c, safe_lo, safe_hi;
     int block, ivl;
+    short nph, lastmax, hidx, cntM, cntm, nmin, pad0, pad1;
 };
-static_assert(sizeof(CellIv) == 32 && sizeof(CellPiece) == 16, "cell table strides");
+static_assert(sizeof(CellIv) == 32 && sizeof(CellPiece) == 48, "cell table strides");
 
 // centre and half width (bins) of the phase [left, right)
 __device__ __forceinline__ void cell_geom(int left, int right, double &c, double &R)
@@ -154,27 +159,65 @@ __global__ void __launch_bounds__(1024) k_cell_plan(const unsigned char *tables,
         h->truncated = s_trunc;
         h->a_lo = a_lo;
         h->a_hi = a_hi;
+        h->inv_g = (double)h0.grid_n / (a_hi - a_lo);
     }
 }
 
-// build 2: the pieces of every covered interval (a thread per interval)
+// build 2: the pieces of every covered interval (a thread per interval), in tilt order; pstart[] = their lower ends
 __global__ void __launch_bounds__(256) k_cell_pieces(const unsigned char *tables, unsigned char *cells)
 {
     const MuTabHeader *th = reinterpret_cast<const MuTabHeader *>(tables);
     const CellHeader *h = reinterpret_cast<const CellHeader *>(cells);
+    const double *ep = reinterpret_cast<const double *>(tables + th->off_ep);
+    const short *rec = reinterpret_cast<const short *>(tables + th->off_rec);
     const CellIv *iv = reinterpret_cast<const CellIv *>(cells + h->off_iv);
     CellPiece *pc = reinterpret_cast<CellPiece *>(cells + h->off_piece);
+    double *pstart = reinterpret_cast<double *>(cells + h->off_pstart);
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > th->n_ep) return;
     const CellIv c = iv[k];
+    if (c.m < 1) return;
+    const short *r = rec + (size_t)k * FHMC_TAB_REC_I16;
+    const double e_lo = k > 0 ? ep[k - 1] : -CUDART_INF, e_hi = k < th->n_ep ? ep[k] : CUDART_INF;
+    const double w = 1.0 / c.inv_w;
     for (int j = 0; j < c.m; ++j) {
         CellPiece p;
-        const double a_c = c.a0 + ((double)j + 0.5) / c.inv_w;
+        const double p_lo = c.a0 + (double)j * w, p_hi = c.a0 + (double)(j + 1) * w;
+        const double a_c = c.a0 + ((double)j + 0.5) * w;
         p.s_c = -a_c / th->dN;
+        const double s_abs = fmax(fabs(p_lo), fabs(p_hi)) / th->dN;
+        const double dl = 2.0 * tab_margin(th->lmax, s_abs, th->Na);
+        p.safe_lo = fmax(p_lo, e_lo + dl);
+        p.safe_hi = fmin(p_hi, e_hi - dl);
         p.block = c.bfirst + j * c.nph;
         p.ivl = k;
+        p.nph = (short)c.nph;
+        p.lastmax = r[FHMC_TR_LASTMAX];
+        p.hidx = r[FHMC_TR_HIDX];
+        p.cntM = r[FHMC_TR_CNTM];
+        p.cntm = r[FHMC_TR_CNTMIN];
+        p.nmin = r[FHMC_TR_NMIN];
+        p.pad0 = p.pad1 = 0;
         pc[c.first + j] = p;
+        pstart[c.first + j] = p_lo;
     }
+}
+
+// build 2b: lookup grid over [a_lo, a_hi]: gfirst[g] = last piece whose lower end is <= the lower edge of grid cell g (0 if none)
+__global__ void __launch_bounds__(256) k_cell_grid(unsigned char *cells)
+{
+    const CellHeader *h = reinterpret_cast<const CellHeader *>(cells);
+    const double *pstart = reinterpret_cast<const double *>(cells + h->off_pstart);
+    int *gfirst = reinterpret_cast<int *>(cells + h->off_grid);
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > h->grid_n) return;
+    const double edge = h->a_lo + (double)g / h->inv_g;
+    int lo = 0, hi = h->n_pieces;   // number of pieces with pstart <= edge
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pstart[mid] <= edge) lo = mid + 1; else hi = mid;
+    }
+    gfirst[g] = max(lo - 1, 0);
 }
 
 // build 3: the expansion coefficients, a warp per piece
@@ -228,9 +271,14 @@ __global__ void __launch_bounds__(256) k_cell_coef(const unsigned char *tables, 
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
             }
+            // normalised by C_0 = sum_i w_i: the sum is C_0 (1 + eps) with |eps| <= e^|y| - 1, its log ln C_0 + log1p(eps) by a short
+            // series (no log() per state point), and the averages are ratios of the normalised polynomials
+            const double C0 = acc[0], invC0 = 1.0 / C0;
+#pragma unroll
+            for (int q = 0; q < (1 + NSEL) * K; ++q) acc[q] *= invC0;
             double *b = coef + (size_t)(p.block + ph) * BLK;
             if (lane == 0) {
-                b[0] = M;
+                b[0] = M + log(C0);   // ln S_p at the cell centre
                 b[1] = N0 + c * dN;   // N at the phase centre
                 b[2] = dN * R;        // y = d * b[2]
                 b[3] = 0.0;
@@ -245,64 +293,73 @@ __global__ void __launch_bounds__(256) k_cell_coef(const unsigned char *tables, 
 // ---------------------------------------------------------------------------------------------------------------------
 // sweep: a thread per state point
 // ---------------------------------------------------------------------------------------------------------------------
+#ifndef FHMC_CELL_MINB
+#define FHMC_CELL_MINB 4
+#endif
 template <int NSEL>
-__global__ void __launch_bounds__(256) k_sweep_cell(const __grid_constant__ SweepArgs a)
+__global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid_constant__ SweepArgs a)
 {
     constexpr int K = FHMC_CELL_K, BLK = cell_blk(NSEL);
     const unsigned char *tables = static_cast<const unsigned char *>(a.d.mu_tables);
     const unsigned char *cells = static_cast<const unsigned char *>(a.d.mu_cells);
     const MuTabHeader *th = reinterpret_cast<const MuTabHeader *>(tables);
     const CellHeader *ch = reinterpret_cast<const CellHeader *>(cells);
-    const double *ep = reinterpret_cast<const double *>(tables + th->off_ep);
     const short *rec = reinterpret_cast<const short *>(tables + th->off_rec);
-    const CellIv *civ = reinterpret_cast<const CellIv *>(cells + ch->off_iv);
     const CellPiece *cpc = reinterpret_cast<const CellPiece *>(cells + ch->off_piece);
     const double *coef = reinterpret_cast<const double *>(cells + ch->off_coef);
-    const int n = a.d.n, last = n - 1, pmax = a.d.pmax, ne = th->n_ep;
-    const double dN = th->dN, Na = th->Na, lmax = th->lmax;
+    const double *pstart = reinterpret_cast<const double *>(cells + ch->off_pstart);
+    const int *gfirst = reinterpret_cast<const int *>(cells + ch->off_grid);
+    const int n = a.d.n, last = n - 1, pmax = a.d.pmax, grid_n = ch->grid_n;
+    const double dN = th->dN, Na = th->Na, lmax = th->lmax, a_lo = ch->a_lo, a_hi = ch->a_hi, inv_g = ch->inv_g;
     const double *lnpi = a.blob, *Nrow = a.blob + a.d.n_pad;
     const bool usable = th->magic == FHMC_TAB_MAGIC && !th->bad && th->n == n && th->smooth == a.d.smooth && ch->magic == FHMC_CELL_MAGIC &&
                         ch->n_sel == NSEL && th->n_sel == NSEL && (NSEL < 1 || th->sel_row[0] == a.d.sel_row[0]) &&
-                        (NSEL < 2 || th->sel_row[1] == a.d.sel_row[1]) && n >= 3;
+                        (NSEL < 2 || th->sel_row[1] == a.d.sel_row[1]) && n >= 3 && ch->n_pieces > 0;
     const double l0 = lnpi[0], N_0 = Nrow[0], l_last = lnpi[last], N_last = Nrow[last];
     const int lane = threadIdx.x & 31;
     const long long S = a.st.n_states;
     const long long cN = a.c.n_total;
     int top = 0;
-    for (long long base = (long long)blockIdx.x * blockDim.x; base < S; base += (long long)gridDim.x * blockDim.x) {
+    // flat list of mu (the usual case): no 64-bit division per state point; the next round's mu is fetched a round ahead
+    const bool flat = a.st.mu1_div == 1 && a.st.n_mu1 >= S;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    auto load_mu = [&](long long q) -> double {
+        if (q >= S) return 0.0;
+        return flat ? __ldg(a.st.mu1 + q) : a.st.mu1[(q / a.st.mu1_div) % a.st.n_mu1];
+    };
+    double mu_next = load_mu((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < S; base += stride) {
         const long long sp = base + threadIdx.x;
         bool done = true;
+        const double mu1 = mu_next;
+        mu_next = load_mu(sp + stride);
         if (sp < S) {
             done = false;
-            const double mu1 = a.st.mu1[(sp / a.st.mu1_div) % a.st.n_mu1];
             const double s = __dmul_rn(__dsub_rn(mu1, a.d.mu1_ref), a.d.beta_ref);   // GH:77, evaluated left to right
             const double sdn = s * dN, av = -sdn;
             do {
-                if (!usable || !(fabs(4.0 * sdn) < 200.0)) break;
-                int lo = 0, hi = ne;
-                while (lo < hi) {   // number of endpoints <= tilt
-                    const int mid = (lo + hi) >> 1;
-                    if (__ldg(ep + mid) <= av) lo = mid + 1; else hi = mid;
+                if (!usable || !(fabs(4.0 * sdn) < 200.0) || !(av >= a_lo && av <= a_hi)) break;
+                // the cell of this tilt: lookup grid, then a bisection over the few cells that start inside the grid cell
+                const int g = min((int)((av - a_lo) * inv_g), grid_n - 1);
+                int lo = __ldg(gfirst + g), hi = __ldg(gfirst + g + 1);
+                while (lo < hi) {   // last cell with pstart <= tilt, in [lo, hi]
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (__ldg(pstart + mid) <= av) lo = mid; else hi = mid - 1;
                 }
-                const double dl = tab_margin(lmax, fabs(s), Na);
-                const double e_lo = lo > 0 ? __ldg(ep + lo - 1) : -CUDART_INF, e_hi = lo < ne ? __ldg(ep + lo) : CUDART_INF;
-                const short *r = rec + (size_t)lo * FHMC_TAB_REC_I16;
-                const int4 head = __ldg(reinterpret_cast<const int4 *>(r));   // {valid, nphase}, {hidx, lastmax}, {cntM, cntm}, {nmin, -}
-                const int nph = head.x >> 16;
+                const CellPiece *cp = cpc + lo;
+                const double2 w0 = __ldg(reinterpret_cast<const double2 *>(cp));       // {s_c, safe_lo}
+                const int4 w1 = __ldg(reinterpret_cast<const int4 *>(cp) + 1);         // {safe_hi lo, safe_hi hi, block, ivl}
+                const int4 w2 = __ldg(reinterpret_cast<const int4 *>(cp) + 2);         // {nph | lastmax, hidx | cntM, cntm | nmin, -}
+                const double s_c = w0.x, safe_hi = __hiloint2double(w1.y, w1.x);
+                // margin test of the table walk (the tilt is further from both interval ends than rounding can move a comparison)
+                if (!(av >= w0.y && av <= safe_hi)) break;
+                const int nph = w2.x & 0xffff, lastmax = (w2.x >> 16) & 0xffff, hidx = w2.y & 0xffff;
                 // (the capacity rules of PointEval::repair() for the caller's pmax: such a state point is a capacity error)
-                const bool cap = nph > pmax || (head.z & 0xffff) > pmax - 1 || (head.z >> 16) > pmax || (head.w & 0xffff) > pmax + 1;
-                if (!(av - e_lo > dl && e_hi - av > dl) || (head.x & 0xffff) != 1 || cap) break;
-                const int4 c0 = __ldg(reinterpret_cast<const int4 *>(civ + lo));           // {first, m, bfirst, nph}
-                const double2 c1 = __ldg(reinterpret_cast<const double2 *>(civ + lo) + 1);   // {a0, inv_w}
-                if (c0.y < 1 || c0.w != nph) break;
-                const double fj = (av - c1.x) * c1.y;
-                if (!(fj >= 0.0 && fj <= (double)c0.y)) break;   // outside the range the cells were built for
-                const int j = min((int)fj, c0.y - 1);
-                const int4 pw = __ldg(reinterpret_cast<const int4 *>(cpc + c0.x + j));   // {s_c lo, s_c hi, block, ivl}
-                const double s_c = __hiloint2double(pw.y, pw.x);
+                if (nph > pmax || ((w2.y >> 16) & 0xffff) > pmax - 1 || (w2.z & 0xffff) > pmax || ((w2.z >> 16) & 0xffff) > pmax + 1) break;
+                const short *r = rec + (size_t)w1.w * FHMC_TAB_REC_I16;
                 const double d = s - s_c;
+                const double dl = tab_margin(lmax, fabs(s), Na);
                 // is_safe (GH:586-591): fl(fl(u_M - c) - fl(u_last - c)) < cutoff, decided without c when it is not a rounding matter
-                const int hidx = head.y & 0xffff, lastmax = head.y >> 16;
                 const double u_last = __dadd_rn(l_last, __dmul_rn(s, N_last));
                 unsigned flags = FHMC_ST_FAST;
                 if (lastmax != last) {
@@ -315,7 +372,7 @@ __global__ void __launch_bounds__(256) k_sweep_cell(const __grid_constant__ Swee
                 }
                 const double u0 = __dadd_rn(l0, __dmul_rn(s, N_0));
                 const int Mq = shift_for_max(__dadd_rn(__ldg(lnpi + hidx), __dmul_rn(s, __ldg(Nrow + hidx))));
-                const double *b = coef + (size_t)pw.z * BLK;
+                const double *b = coef + (size_t)w1.z * BLK;
                 // bounds of the phases, as the interval record holds them ({left, right} as two int16 per word)
                 int wds[8];
                 {
@@ -348,14 +405,27 @@ __global__ void __launch_bounds__(256) k_sweep_cell(const __grid_constant__ Swee
                         v = fma(v, y, k23.y);
                         v = fma(v, y, k23.x);
                         v = fma(v, y, k01.y);
-                        v = fma(v, y, k01.x);
-                        P[q] = v;
+                        P[q] = q == 0 ? v * y : fma(v, y, k01.x);   // (quantity 0: eps = P_0 / C_0 - 1, its constant term is 1)
                     }
-                    if (!(P[0] > 0.0)) { good = false; break; }
-                    const double lnS = (g0.x - u0) + fma(d, g0.y, log(P[0]));   // ln S_p - u_0
+                    const double eps = P[0];
+                    if (!(fabs(eps) < 0.06)) { good = false; break; }   // (|eps| <= e^0.05 - 1 by construction)
+                    // log1p(eps), |eps| < 0.06: alternating series through eps^13 / 13 (next term < 1e-17 relative)
+                    double l1 = fma(eps, 1.0 / 13.0, -1.0 / 12.0);
+                    l1 = fma(l1, eps, 1.0 / 11.0);
+                    l1 = fma(l1, eps, -1.0 / 10.0);
+                    l1 = fma(l1, eps, 1.0 / 9.0);
+                    l1 = fma(l1, eps, -1.0 / 8.0);
+                    l1 = fma(l1, eps, 1.0 / 7.0);
+                    l1 = fma(l1, eps, -1.0 / 6.0);
+                    l1 = fma(l1, eps, 1.0 / 5.0);
+                    l1 = fma(l1, eps, -1.0 / 4.0);
+                    l1 = fma(l1, eps, 1.0 / 3.0);
+                    l1 = fma(l1, eps, -0.5);
+                    l1 = fma(l1 * eps, eps, eps);
+                    const double lnS = (g0.x - u0) + fma(d, g0.y, l1);   // ln S_p - u_0
                     // (diagnostic bit of the walk: this phase's sum underflows next to the global maximum's shift)
                     if (lnS + u0 - (double)Mq * 0.6931471805599453 < -644.7236) flags |= FHMC_ST_RESCUED;
-                    const double inv = 1.0 / P[0];
+                    const double inv = 1.0 / (1.0 + eps);
                     for (int dd = 0; dd < a.c.n_dst; ++dd) {
                         double *f = reinterpret_cast<double *>(a.c.dst[dd] + fbase) + ((long long)ph * cN + rix) * (1 + NSEL);
                         f[0] = -lnS;
@@ -420,6 +490,11 @@ static CellLayout cell_layout(const fhmc_hist_desc &d, int extra_pieces)
     h.off_iv = take((size_t)h.iv_cap * sizeof(CellIv));
     h.off_piece = take((size_t)h.piece_cap * sizeof(CellPiece));
     h.off_coef = take((size_t)h.block_cap * h.blk * 8);
+    h.off_pstart = take((size_t)(h.piece_cap + 1) * 8);
+    int g = 1024;
+    while (g < 4 * h.piece_cap && g < 65536) g <<= 1;
+    h.grid_n = g;
+    h.off_grid = take((size_t)(g + 2) * 4);
     L.total = off;
     return L;
 }
@@ -431,8 +506,20 @@ int launch_cell_compact(const SweepArgs &args, int sm_count, int smem_optin, cud
     if (!d.mu_tables || !d.mu_cells || d.pmax > FHMC_COMPACT_PMAX || d.n_sel > 2 || !args.c.ix_list || !args.c.ix_count) return -1;
     if (check_cuda(cudaMemsetAsync(args.c.ix_count, 0, sizeof(int), stream), "cudaMemsetAsync")) return 1;
     const long long S = args.st.n_states;
+    // persistent grid: exactly the CTAs that are resident at once (a partial last wave would idle a third of the SMs)
+    static int occ_cache[3] = {0, 0, 0};
+    const int q = d.n_sel;
+    if (occ_cache[q] == 0) {
+        int occ = 0;
+        cudaError_t e = q == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_cell<0>, 256, 0)
+                      : q == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_cell<1>, 256, 0)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_cell<2>, 256, 0);
+        if (check_cuda(e, "occupancy query")) return 1;
+        occ_cache[q] = occ > 0 ? occ : 1;
+    }
     long long grid = (S + 255) / 256;
-    if (grid > (long long)sm_count * 8) grid = (long long)sm_count * 8;
+    if (grid > (long long)sm_count * occ_cache[q]) grid = (long long)sm_count * occ_cache[q];
+    if (const char *e = getenv("FHMC_CELL_GRID")) { const long long g = atoll(e); if (g > 0) grid = g; }   // (probe)
     switch (d.n_sel) {
     case 0: k_sweep_cell<0><<<(unsigned)grid, 256, 0, stream>>>(args); break;
     case 1: k_sweep_cell<1><<<(unsigned)grid, 256, 0, stream>>>(args); break;
@@ -479,6 +566,7 @@ int fhmc_mu_cells_build(const fhmc_hist_desc *desc, const double *blob, void *ce
     if (check_cuda(cudaMemcpyAsync(cb, &L.h, sizeof(CellHeader), cudaMemcpyHostToDevice, s), "cudaMemcpyAsync")) return 1;
     k_cell_plan<<<1, 1024, 0, s>>>(tb, cb, L.h, mu_lo, mu_hi, desc->mu1_ref, desc->beta_ref);
     k_cell_pieces<<<(L.h.iv_cap + 255) / 256, 256, 0, s>>>(tb, cb);
+    k_cell_grid<<<(L.h.grid_n + 1 + 255) / 256, 256, 0, s>>>(cb);
     const int r0 = desc->n_sel > 0 ? desc->sel_row[0] : 0, r1 = desc->n_sel > 1 ? desc->sel_row[1] : 0;
     const int grid = 148 * 4;
     switch (desc->n_sel) {

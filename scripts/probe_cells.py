@@ -53,3 +53,24 @@ for S in (100000, 1000000, 4000000):
                 fn()
             med, best = timed(cold, 10)
             print("   cold step (cells rebuilt inside): median %.1f us  min %.1f us -> %.3e points/s" % (1e3 * med, 1e3 * best, S / (1e-3 * med)))
+
+# host cost of one call (no synchronisation inside the loop) and back-to-back device time per call
+import time
+S = 1000000
+mu = torch.linspace(-0.03, 0.03, S, dtype=torch.float64, device="cuda")
+dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=10, sel=["N", N * N])
+st = dh.make_states(mu)
+buf = torch.empty(int(_lib.load().fhmc_pack_soa16_bytes(S, 4, 2)), dtype=torch.uint8, device="cuda")
+fn = lambda: dh.sweep_compact(None, pmax=4, dst=buf, states=st, fill_dead=False)
+fn(); torch.cuda.synchronize()
+for reps in (20, 200):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    print("back to back x%d: host %.1f us per call, device %.1f us per call" % (reps, 1e6 * (t1 - t0) / reps, 1e3 * a.elapsed_time(b) / reps))
