@@ -72,6 +72,36 @@ def instr_counts():
         return {}
 
 
+def roofline_block(kernel, rate1, fp64_pp, instr_pp, cnt, peaks, kern_ms, exps, algo_bytes, hbm_peak):
+    """Roofline of the timed kernel.  The table walk (k_sweep_tab2) sums over the bins per state point and is bound by fp64 ISSUE:
+    frac = fp64-pipe instructions it EXECUTES per second (count per state point from the committed ncu capture x measured state
+    points/s) / the DFMA issue peak measured in this process.  The tilt-cell kernel (k_sweep_cell) evaluates a handful of
+    polynomials per state point whatever the histogram length: what is left is the record traffic, so its bound is HBM --
+    achieved = algorithmic bytes (8 B of mu in, 4 + 28 B per existing phase out) / the timed duration against MEASURED_PEAKS.json
+    hbm_gbs; the fp64 figures stay beside it.  algorithmic_frac = SURVEY 8(d)'s count (1001 exp per state point) against the
+    measured exp-issue peak: it exceeds 1 because neither kernel evaluates one exp per bin and state point."""
+    fp64 = {"achieved": (rate1 * fp64_pp / 1e9) if fp64_pp else None, "peak": peaks["dfma_per_s"] / 1e9, "unit": "G fp64-pipe instr/s (per lane)",
+            "frac": (rate1 * fp64_pp / peaks["dfma_per_s"]) if fp64_pp else None,
+            "peak_source": "k_bench_dfma, register-resident DFMA chains, measured in this process (no fp64 figure in MEASURED_PEAKS.json)",
+            "fp64_pipe_instr_per_state_point": fp64_pp, "instr_per_state_point": instr_pp, "instr_count_source": cnt.get("source")}
+    gbs = algo_bytes / (kern_ms * 1e-3) / 1e9
+    hbm = {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": (gbs / hbm_peak) if hbm_peak else None,
+           "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else "absent"}
+    common = {"kernel": kernel, "traffic": cnt.get("dram_bytes_per_launch"), "kernel_ms": kern_ms,
+              "algorithmic_frac": exps / peaks["exp_per_s"], "algorithmic_exp_per_state_point": N_BINS,
+              "algorithmic_achieved_gexp_s": exps / 1e9, "exp_peak_gexp_s": peaks["exp_per_s"] / 1e9}
+    if kernel.startswith("k_sweep_cell"):
+        out = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm["frac"],
+               "peak_source": hbm["peak_source"], "algorithmic_bytes_per_launch": algo_bytes,
+               "note": "kernel_ms is the whole timed call on the device (count reset + k_sweep_cell + the indexed table walk over its leftovers)",
+               "fp64_issue": fp64}
+    else:
+        out = dict(fp64)
+        out.update({"bound": "fp64_issue", "hbm": hbm})
+    out.update(common)
+    return out
+
+
 def c3_axes():
     return np.linspace(0.95, 1.05, C3_NB), np.linspace(0.2, 0.8, C3_ND)
 
@@ -824,6 +854,32 @@ def run_gpu_arm(args, rank, world, local_rank):
     value = world * S / (ms_per_step * 1e-3)
     fused = bool(hold["state"].fused)
     rec_bytes = int(hold["state"].block_bytes)
+    # bytes the timed call must move per rank: 8 B of mu in, a record of 4 + 28 B per phase that exists out
+    nph_sum = int(hold["rec"].views(rank)["nphase"][:S].sum().item()) if hasattr(hold["rec"], "views") else 2 * S
+    cell_frac = float(hold["rec"].views(rank)["path"][:S].double().mean().item()) if hasattr(hold["rec"], "views") else None
+
+    # the same call (a) with the tilt cells dropped before every step, so that the range read-back and the cell build run inside the
+    # timed region, and (b) without the cells: the table walk (k_sweep_tab2), the r02f headline kernel
+    variants = {}
+    if dh.desc.mu_cells:
+        def step_cold():
+            dh._cells_range = None
+            dh._cells_key = None
+            step()
+        for _ in range(3):
+            step_cold()
+        _, ms_c, _ = timed_loop(step_cold, min(args.steps, 50))
+        variants["cells_rebuilt_every_step"] = {"value": world * S / (ms_c * 1e-3), "ms_per_step": ms_c,
+                                                "note": "the cells are dropped before every step: torch.aminmax of mu + read-back + fhmc_mu_cells_build (4 kernels) inside the timed region"}
+        saved = (dh.desc.mu_cells, dh.use_mu_cells)
+        dh.desc.mu_cells, dh.use_mu_cells = None, False
+        for _ in range(3):
+            step()
+        _, ms_t, _ = timed_loop(step, min(args.steps, 50))
+        variants["table_walk"] = {"value": world * S / (ms_t * 1e-3), "ms_per_step": ms_t, "kernel": _lib.last_kernel(),
+                                  "note": "use_mu_cells = False: every state point walks the bins on the per-histogram tables (the r02f headline)"}
+        dh.desc.mu_cells, dh.use_mu_cells = saved
+        step()
 
     # the same call with the gather of the complete records to every rank (fused into the kernel), and the strong-scaling form
     # of config 2 (10^6 points over N GPUs)
@@ -964,7 +1020,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                 hbm_peak = json.load(open(mp_path)).get("hbm_gbs")
             except Exception:
                 hbm_peak = None
-        algo_bytes = S * 8 + rec_bytes * (world if fused else 1)     # mu in + compact records out (to every rank when fused)
+        algo_bytes = S * 8 + S * 4 + 28 * nph_sum     # mu in + the compact records that exist out (4 B head + 28 B per phase)
         coex = None
         if extra and extra.get("config4", {}).get("value") is not None:
             c4 = extra["config4"]
@@ -992,7 +1048,10 @@ def run_gpu_arm(args, rank, world, local_rank):
                        "e2e_path": "fhmc_sweep_host_compact16 (C ABI, host buffers): per 2^17-point chunk H2D(mu) -> sweep kernel writing compact records -> D2H of the live phase blocks; upload, compute and download streams",
                        "e2e_gpu_launches_per_step": e2e_launches, "l2": "flushed (256 MiB memset) before every timed step",
                        "parallelism": "dp%d over state points, no data-path collective" % world,
-                       "ok_fraction": ok_frac, "fast_kernel_fraction": fast_frac, "wall_s_timed_region": wall, "gather_check": gather_check},
+                       "ok_fraction": ok_frac, "fast_kernel_fraction": fast_frac, "cell_kernel_fraction": cell_frac,
+                       "tables": "per-histogram state built before the first step: interval records (fhmc_mu_tables_build) and, for the mu range of the sweep, tilt cells "
+                                 "(fhmc_mu_cells_build); every state point of every step is evaluated from its mu; variants.cells_rebuilt_every_step has the cell build inside the timed region",
+                       "wall_s_timed_region": wall, "gather_check": gather_check},
             "clocks": clocks,
             "coexistence": coex,
             "strong": strong,
@@ -1006,18 +1065,8 @@ def run_gpu_arm(args, rank, world, local_rank):
             # state point from the committed ncu capture of this build x measured state points/s) / the DFMA issue peak measured
             # in this process.  The algorithmic count of SURVEY 8(d) (1001 exp per state point against the measured exp-issue
             # peak) is kept beside it as algorithmic_frac: it exceeds 1 because the product form replaces most exps by FMAs.
-            "roofline": {"bound": "fp64_issue", "kernel": timed_kernel,
-                         "achieved": (rate1 * fp64_pp / 1e9) if fp64_pp else None, "peak": peaks["dfma_per_s"] / 1e9,
-                         "unit": "G fp64-pipe instr/s (per lane)",
-                         "frac": (rate1 * fp64_pp / peaks["dfma_per_s"]) if fp64_pp else None, "traffic": cnt.get("dram_bytes_per_launch"),
-                         "peak_source": "k_bench_dfma, register-resident DFMA chains, measured in this process (no fp64 figure in MEASURED_PEAKS.json)",
-                         "fp64_pipe_instr_per_state_point": fp64_pp, "instr_per_state_point": instr_pp,
-                         "instr_count_source": cnt.get("source"), "kernel_ms": kern_ms,
-                         "algorithmic_frac": exps / peaks["exp_per_s"], "algorithmic_exp_per_state_point": N_BINS,
-                         "algorithmic_achieved_gexp_s": exps / 1e9, "exp_peak_gexp_s": peaks["exp_per_s"] / 1e9,
-                         "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (kern_ms * 1e-3) / 1e9,
-                                 "peak_gbs": hbm_peak, "frac": (algo_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
-                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else "absent"}},
+            "roofline": roofline_block(timed_kernel, rate1, fp64_pp, instr_pp, cnt, peaks, kern_ms, exps, algo_bytes, hbm_peak),
+            "variants": variants,
             "parity": parity,
             "extra": extra,
             "sharded": sharded,

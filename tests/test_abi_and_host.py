@@ -30,8 +30,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from fhmcanalysis_b200 import _lib
-    # sizes implied by the header: 4+8+8+2+4+8 ints + 4 ints + 4 doubles + hull_row/hull_len/mu_recurrence/min_width + mu_tables
-    assert ctypes.sizeof(_lib.HistDesc) == (4 + 8 + 8 + 2 + 4 + 8 + 4) * 4 + 4 * 8 + 4 * 4 + 8
+    # sizes implied by the header: 4+8+8+2+4+8 ints + 4 ints + 4 doubles + hull_row/hull_len/mu_recurrence/min_width + mu_tables + mu_cells
+    assert ctypes.sizeof(_lib.HistDesc) == (4 + 8 + 8 + 2 + 4 + 8 + 4) * 4 + 4 * 8 + 4 * 4 + 8 + 8
     assert ctypes.sizeof(_lib.States) == 10 * 8
     assert ctypes.sizeof(_lib.SweepOut) == 9 * 8
 
