@@ -573,8 +573,7 @@ int fhmc_sweep_1d_compact(const fhmc_hist_desc *desc, const double *blob, const 
                 if (use_tab && desc->mu_cells && rec_bytes + cell_index_bytes(states->n_states) <= workspace_bytes) {
                     // dense sweep on tilt cells; what they leave goes through the table walk in the same call
                     unsigned char *ix = static_cast<unsigned char *>(workspace) + rec_bytes;
-                    args.c.ix_list = reinterpret_cast<long long *>(ix);
-                    args.c.ix_count = reinterpret_cast<int *>(ix + cell_index_bytes(states->n_states) - 256);
+                    args.c.ix_list = reinterpret_cast<long long *>(ix);   // (its counter lives in the cells buffer)
                     rc = launch_cell_compact(args, di->sm_count, di->smem_optin, s);
                     if (rc >= 0) return rc;
                     args.c.ix_list = nullptr;

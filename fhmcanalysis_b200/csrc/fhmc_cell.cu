@@ -22,6 +22,7 @@
 // without a valid record, failed margin tests, is_safe closer to its cutoff than rounding) is appended to an index list and
 // walked by k_sweep_tab2_idx -- the parity-pinned table walk with its own fallback to the general evaluator -- in the same
 // call.
+#include <stddef.h>
 #include <string.h>
 
 #include "fhmc_tab.cuh"
@@ -39,10 +40,12 @@ struct CellHeader {   // 256 bytes at the start of the cells buffer
     int n_pieces, n_blocks;               // (device)
     int truncated;                        // capacity reached: the upper intervals of the range are not covered (device)
     int grid_n;                           // cells of the lookup grid over [a_lo, a_hi]
+    int q_count, q_ticket;                // sweeps: entries of the leftover list / CTAs of the indexed walk that are through; both
+                                          // are zero between two sweeps (the last CTA of the walk resets them)
     long long off_iv, off_piece, off_coef, off_pstart, off_grid;
     double a_lo, a_hi;                    // covered tilt range (device)
     double inv_g;                         // grid cells per unit of tilt (device)
-    double pad1[17];
+    double pad1[16];
 };
 static_assert(sizeof(CellHeader) <= 256, "header must fit its slot");
 
@@ -58,8 +61,9 @@ struct CellPiece {
     double s_c, safe_lo, safe_hi;
     int block, ivl;
     short nph, lastmax, hidx, cntM, cntm, nmin, pad0, pad1;
+    double lM, NM, lH, NH;   // ln(PI) and N at the last maximum (is_safe) and at the hull vertex (the shift of the RESCUED bit)
 };
-static_assert(sizeof(CellIv) == 32 && sizeof(CellPiece) == 48, "cell table strides");
+static_assert(sizeof(CellIv) == 32 && sizeof(CellPiece) == 80, "cell table strides");
 
 // centre and half width (bins) of the phase [left, right)
 __device__ __forceinline__ void cell_geom(int left, int right, double &c, double &R)
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(1024) k_cell_plan(const unsigned char *tables,
 }
 
 // build 2: the pieces of every covered interval (a thread per interval), in tilt order; pstart[] = their lower ends
-__global__ void __launch_bounds__(256) k_cell_pieces(const unsigned char *tables, unsigned char *cells)
+__global__ void __launch_bounds__(256) k_cell_pieces(const unsigned char *tables, unsigned char *cells, const double *blob, int n_pad)
 {
     const MuTabHeader *th = reinterpret_cast<const MuTabHeader *>(tables);
     const CellHeader *h = reinterpret_cast<const CellHeader *>(cells);
@@ -198,6 +202,10 @@ __global__ void __launch_bounds__(256) k_cell_pieces(const unsigned char *tables
         p.cntm = r[FHMC_TR_CNTMIN];
         p.nmin = r[FHMC_TR_NMIN];
         p.pad0 = p.pad1 = 0;
+        p.lM = blob[p.lastmax];
+        p.NM = blob[n_pad + p.lastmax];
+        p.lH = blob[p.hidx];
+        p.NH = blob[n_pad + p.hidx];
         pc[c.first + j] = p;
         pstart[c.first + j] = p_lo;
     }
@@ -281,7 +289,8 @@ __global__ void __launch_bounds__(256) k_cell_coef(const unsigned char *tables, 
                 b[0] = M + log(C0);   // ln S_p at the cell centre
                 b[1] = N0 + c * dN;   // N at the phase centre
                 b[2] = dN * R;        // y = d * b[2]
-                b[3] = 0.0;
+                reinterpret_cast<int *>(b + 3)[0] = (left & 0xffff) | (right << 16);   // {left, right} as two int16: the record's bounds word
+                reinterpret_cast<int *>(b + 3)[1] = 0;
             }
 #pragma unroll
             for (int q = 0; q < (1 + NSEL) * K; ++q)
@@ -300,11 +309,13 @@ template <int NSEL>
 __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid_constant__ SweepArgs a)
 {
     constexpr int K = FHMC_CELL_K, BLK = cell_blk(NSEL);
+    // the indexed walk behind this kernel is launched with programmatic stream serialisation: its CTAs may be placed as soon as
+    // SMs drain here (it waits for this grid's completion itself before it reads the leftover list)
+    asm volatile("griddepcontrol.launch_dependents;");
     const unsigned char *tables = static_cast<const unsigned char *>(a.d.mu_tables);
     const unsigned char *cells = static_cast<const unsigned char *>(a.d.mu_cells);
     const MuTabHeader *th = reinterpret_cast<const MuTabHeader *>(tables);
     const CellHeader *ch = reinterpret_cast<const CellHeader *>(cells);
-    const short *rec = reinterpret_cast<const short *>(tables + th->off_rec);
     const CellPiece *cpc = reinterpret_cast<const CellPiece *>(cells + ch->off_piece);
     const double *coef = reinterpret_cast<const double *>(cells + ch->off_coef);
     const double *pstart = reinterpret_cast<const double *>(cells + ch->off_pstart);
@@ -322,18 +333,22 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
     int top = 0;
     // flat list of mu (the usual case): no 64-bit division per state point; the next round's mu is fetched a round ahead
     const bool flat = a.st.mu1_div == 1 && a.st.n_mu1 >= S;
-    const long long stride = (long long)gridDim.x * blockDim.x;
+    // Blocked partition: a CTA owns one contiguous run of state points.  Neighbouring state points of a sweep share their cell, so
+    // after the first round the coefficient blocks a warp needs are in this SM's L1 (with a grid-stride loop every round of every
+    // CTA lands in another cell and waits for L2).
+    const long long run = (((S + gridDim.x - 1) / gridDim.x) + 255) & ~255ll;
+    const long long first = (long long)blockIdx.x * run, end = first + run < S ? first + run : S;
     auto load_mu = [&](long long q) -> double {
-        if (q >= S) return 0.0;
+        if (q >= end) return 0.0;
         return flat ? __ldg(a.st.mu1 + q) : a.st.mu1[(q / a.st.mu1_div) % a.st.n_mu1];
     };
-    double mu_next = load_mu((long long)blockIdx.x * blockDim.x + threadIdx.x);
-    for (long long base = (long long)blockIdx.x * blockDim.x; base < S; base += stride) {
+    double mu_next = load_mu(first + threadIdx.x);
+    for (long long base = first; base < end; base += 256) {
         const long long sp = base + threadIdx.x;
         bool done = true;
         const double mu1 = mu_next;
-        mu_next = load_mu(sp + stride);
-        if (sp < S) {
+        mu_next = load_mu(sp + 256);
+        if (sp < end) {
             done = false;
             const double s = __dmul_rn(__dsub_rn(mu1, a.d.mu1_ref), a.d.beta_ref);   // GH:77, evaluated left to right
             const double sdn = s * dN, av = -sdn;
@@ -350,20 +365,21 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
                 const double2 w0 = __ldg(reinterpret_cast<const double2 *>(cp));       // {s_c, safe_lo}
                 const int4 w1 = __ldg(reinterpret_cast<const int4 *>(cp) + 1);         // {safe_hi lo, safe_hi hi, block, ivl}
                 const int4 w2 = __ldg(reinterpret_cast<const int4 *>(cp) + 2);         // {nph | lastmax, hidx | cntM, cntm | nmin, -}
+                const double2 w3 = __ldg(reinterpret_cast<const double2 *>(cp) + 3);   // {lnPI, N} at the last maximum
+                const double2 w4 = __ldg(reinterpret_cast<const double2 *>(cp) + 4);   // {lnPI, N} at the hull vertex
                 const double s_c = w0.x, safe_hi = __hiloint2double(w1.y, w1.x);
                 // margin test of the table walk (the tilt is further from both interval ends than rounding can move a comparison)
                 if (!(av >= w0.y && av <= safe_hi)) break;
-                const int nph = w2.x & 0xffff, lastmax = (w2.x >> 16) & 0xffff, hidx = w2.y & 0xffff;
+                const int nph = w2.x & 0xffff, lastmax = (w2.x >> 16) & 0xffff;
                 // (the capacity rules of PointEval::repair() for the caller's pmax: such a state point is a capacity error)
                 if (nph > pmax || ((w2.y >> 16) & 0xffff) > pmax - 1 || (w2.z & 0xffff) > pmax || ((w2.z >> 16) & 0xffff) > pmax + 1) break;
-                const short *r = rec + (size_t)w1.w * FHMC_TAB_REC_I16;
                 const double d = s - s_c;
                 const double dl = tab_margin(lmax, fabs(s), Na);
                 // is_safe (GH:586-591): fl(fl(u_M - c) - fl(u_last - c)) < cutoff, decided without c when it is not a rounding matter
                 const double u_last = __dadd_rn(l_last, __dmul_rn(s, N_last));
                 unsigned flags = FHMC_ST_FAST;
                 if (lastmax != last) {
-                    const double uM = __dadd_rn(__ldg(lnpi + lastmax), __dmul_rn(s, __ldg(Nrow + lastmax)));
+                    const double uM = __dadd_rn(w3.x, __dmul_rn(s, w3.y));
                     const double D = uM - u_last;
                     if (fabs(D - a.d.cutoff) <= 2.0 * dl) break;
                     if (!(D < a.d.cutoff)) flags |= FHMC_ST_SAFE;
@@ -371,20 +387,13 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
                     flags |= FHMC_ST_SAFE;
                 }
                 const double u0 = __dadd_rn(l0, __dmul_rn(s, N_0));
-                const int Mq = shift_for_max(__dadd_rn(__ldg(lnpi + hidx), __dmul_rn(s, __ldg(Nrow + hidx))));
+                const int Mq = shift_for_max(__dadd_rn(w4.x, __dmul_rn(s, w4.y)));
                 const double *b = coef + (size_t)w1.z * BLK;
-                // bounds of the phases, as the interval record holds them ({left, right} as two int16 per word)
-                int wds[8];
-                {
-                    const int4 lo4 = __ldg(reinterpret_cast<const int4 *>(r + FHMC_TR_BOUNDS));
-                    wds[0] = lo4.x; wds[1] = lo4.y; wds[2] = lo4.z; wds[3] = lo4.w;
-                    wds[4] = wds[5] = wds[6] = wds[7] = 0;
-                    if (nph > 4) {
-                        const int4 hi4 = __ldg(reinterpret_cast<const int4 *>(r + FHMC_TR_BOUNDS) + 1);
-                        wds[4] = hi4.x; wds[5] = hi4.y; wds[6] = hi4.z; wds[7] = hi4.w;
-                    }
-                }
                 const long long fbase = (4 * cN + 15) & ~15ll, bbase = fbase + (long long)pmax * cN * (1 + NSEL) * 8, rix = a.c.first + sp;
+                // first destination: running pointers over the phase blocks (the other destinations of a fused gather are
+                // addressed per phase)
+                double *f0 = reinterpret_cast<double *>(a.c.dst[0] + fbase) + rix * (1 + NSEL);
+                int *b0 = reinterpret_cast<int *>(a.c.dst[0] + bbase) + rix;
                 bool good = true;
                 // (a state point that gives up after its first phases has left them in the record: the table walk that takes it
                 // over finds the same phases in the same interval record and overwrites every one of them)
@@ -393,6 +402,7 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
                     if (ph >= nph) break;
                     const double2 g0 = __ldg(reinterpret_cast<const double2 *>(b)), g1 = __ldg(reinterpret_cast<const double2 *>(b) + 1);
                     const double y = d * g1.x;
+                    const int bword = __double2loint(g1.y);   // {left, right} of this phase
                     if (!(fabs(y) <= FHMC_CELL_YMAX * (1.0 + 1e-6))) { good = false; break; }
                     double P[1 + NSEL];
 #pragma unroll
@@ -426,13 +436,19 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
                     // (diagnostic bit of the walk: this phase's sum underflows next to the global maximum's shift)
                     if (lnS + u0 - (double)Mq * 0.6931471805599453 < -644.7236) flags |= FHMC_ST_RESCUED;
                     const double inv = 1.0 / (1.0 + eps);
-                    for (int dd = 0; dd < a.c.n_dst; ++dd) {
+                    f0[0] = -lnS;
+#pragma unroll
+                    for (int q = 0; q < NSEL; ++q) f0[1 + q] = P[1 + q] * inv;
+                    *b0 = bword;
+                    for (int dd = 1; dd < a.c.n_dst; ++dd) {
                         double *f = reinterpret_cast<double *>(a.c.dst[dd] + fbase) + ((long long)ph * cN + rix) * (1 + NSEL);
                         f[0] = -lnS;
 #pragma unroll
                         for (int q = 0; q < NSEL; ++q) f[1 + q] = P[1 + q] * inv;
-                        reinterpret_cast<int *>(a.c.dst[dd] + bbase)[(long long)ph * cN + rix] = wds[ph];
+                        reinterpret_cast<int *>(a.c.dst[dd] + bbase)[(long long)ph * cN + rix] = bword;
                     }
+                    f0 += cN * (1 + NSEL);
+                    b0 += cN;
                     b += BLK;
                 }
                 if (!good) break;
@@ -457,7 +473,7 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
             int pos = 0;
             if (lane == 0) pos = atomicAdd(a.c.ix_count, __popc(m));
             pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (!done) a.c.ix_list[pos + __popc(m & ((1u << lane) - 1u))] = sp;
+            if (!done && pos >= 0 && pos + 32 <= S + 32) a.c.ix_list[pos + __popc(m & ((1u << lane) - 1u))] = sp;   // (the list holds S + 32 entries)
         }
     }
     if (a.c.max_nphase) {
@@ -500,11 +516,14 @@ static CellLayout cell_layout(const fhmc_hist_desc &d, int extra_pieces)
 }
 
 // cells + index list of the leftovers: returns 0 ok, 1 error, -1 not applicable
-int launch_cell_compact(const SweepArgs &args, int sm_count, int smem_optin, cudaStream_t stream)
+int launch_cell_compact(const SweepArgs &args_in, int sm_count, int smem_optin, cudaStream_t stream)
 {
-    const fhmc_hist_desc &d = args.d;
-    if (!d.mu_tables || !d.mu_cells || d.pmax > FHMC_COMPACT_PMAX || d.n_sel > 2 || !args.c.ix_list || !args.c.ix_count) return -1;
-    if (check_cuda(cudaMemsetAsync(args.c.ix_count, 0, sizeof(int), stream), "cudaMemsetAsync")) return 1;
+    const fhmc_hist_desc &d = args_in.d;
+    if (!d.mu_tables || !d.mu_cells || d.pmax > FHMC_COMPACT_PMAX || d.n_sel > 2 || !args_in.c.ix_list) return -1;
+    // the list's counter lives in the cells buffer (zero between sweeps: fhmc_mu_cells_build zeroes it, the last CTA of the
+    // indexed walk resets it) -- sweeps that share a cells buffer must therefore be ordered on one stream
+    SweepArgs args = args_in;
+    args.c.ix_count = reinterpret_cast<int *>(static_cast<unsigned char *>(const_cast<void *>(d.mu_cells)) + offsetof(CellHeader, q_count));
     const long long S = args.st.n_states;
     // persistent grid: exactly the CTAs that are resident at once (a partial last wave would idle a third of the SMs)
     static int occ_cache[3] = {0, 0, 0};
@@ -565,7 +584,7 @@ int fhmc_mu_cells_build(const fhmc_hist_desc *desc, const double *blob, void *ce
     const unsigned char *tb = static_cast<const unsigned char *>(desc->mu_tables);
     if (check_cuda(cudaMemcpyAsync(cb, &L.h, sizeof(CellHeader), cudaMemcpyHostToDevice, s), "cudaMemcpyAsync")) return 1;
     k_cell_plan<<<1, 1024, 0, s>>>(tb, cb, L.h, mu_lo, mu_hi, desc->mu1_ref, desc->beta_ref);
-    k_cell_pieces<<<(L.h.iv_cap + 255) / 256, 256, 0, s>>>(tb, cb);
+    k_cell_pieces<<<(L.h.iv_cap + 255) / 256, 256, 0, s>>>(tb, cb, blob, desc->n_pad);
     k_cell_grid<<<(L.h.grid_n + 1 + 255) / 256, 256, 0, s>>>(cb);
     const int r0 = desc->n_sel > 0 ? desc->sel_row[0] : 0, r1 = desc->n_sel > 1 ? desc->sel_row[1] : 0;
     const int grid = 148 * 4;

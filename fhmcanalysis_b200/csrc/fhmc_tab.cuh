@@ -25,6 +25,7 @@
 // TMA bulk copies instead of recomputing it (r01b: ~40 us per launch and CTA, 105 us per 2^17-point chunk against 64 us).
 #pragma once
 #include <stdlib.h>
+#include <string.h>
 
 #include "fhmc_prod.cuh"
 
@@ -621,7 +622,7 @@ __device__ __forceinline__ void tab2_warp_tiles(const SweepArgs &a, const W &w, 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     long long *queue = reinterpret_cast<long long *>(s_tab + 64) + wib * 64;   // this warp's 64 entries of the queue area
     static_assert(LY::QN >= (FHMC_CTA / 32) * 64, "queue area too small for the per-warp queues");
-    const long long S = IDX ? (long long)*a.c.ix_count : a.st.n_states;
+    const long long S = IDX ? min((long long)*reinterpret_cast<volatile int *>(a.c.ix_count), a.st.n_states) : a.st.n_states;
     const long long slot = (long long)blockIdx.x * (FHMC_CTA / 32) + wib;          // scratch record of this warp
     const long long nwarps = (long long)gridDim.x * (FHMC_CTA / 32);
     int top = 0;
@@ -722,13 +723,27 @@ __global__ void __launch_bounds__(FHMC_CTA, 2) k_sweep_tab2_idx(const __grid_con
 {
     using W = TabWalk<NSEL, SEL0N>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    if ((long long)blockIdx.x * 64 >= (long long)*a.c.ix_count) return;   // this CTA's first warp tile is tile blockIdx.x (uniform per CTA)
-    TabCtx tc;
-    bool ok;
-    const FastCtx cx = tab_prepare<NSEL, SEL0N>(a, smem_raw, tc, ok);
-    double *s_tab = cx.s_tab;
-    const W w(a, cx, nullptr, a.d.smooth, smem_u32(s_tab), tc, ok);
-    tab2_warp_tiles<NSEL, W, true>(a, w, s_tab);
+    // launched behind k_sweep_cell with programmatic stream serialisation: wait for that grid (and its list) to be complete
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const long long cnt = min((long long)*reinterpret_cast<volatile int *>(a.c.ix_count), a.st.n_states);
+    if ((long long)blockIdx.x * 64 < cnt) {   // this CTA's first warp tile is tile blockIdx.x (uniform per CTA)
+        TabCtx tc;
+        bool ok;
+        const FastCtx cx = tab_prepare<NSEL, SEL0N>(a, smem_raw, tc, ok);
+        double *s_tab = cx.s_tab;
+        const W w(a, cx, nullptr, a.d.smooth, smem_u32(s_tab), tc, ok);
+        tab2_warp_tiles<NSEL, W, true>(a, w, s_tab);
+    }
+    // the last CTA through resets the counter and the ticket for the next sweep (every CTA has read the count by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.c.ix_count + 1, 1) == (int)gridDim.x - 1) {
+            a.c.ix_count[0] = 0;
+            a.c.ix_count[1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 template <int NSEL, bool SEL0N>
@@ -744,8 +759,18 @@ static int launch_tab2_idx(const SweepArgs &args, int sm_count, int smem_optin, 
     const long long ntiles = (args.st.n_states + 63) / 64;   // (the list cannot be longer than the sweep)
     long long grid = (long long)sm_count * occ;
     if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, FHMC_CTA, smem, stream>>>(args);
-    return check_cuda(cudaGetLastError(), "k_sweep_tab2_idx launch");
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(FHMC_CTA);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return check_cuda(cudaLaunchKernelEx(&cfg, kern, args), "k_sweep_tab2_idx launch");
 }
 
 template <int NSEL, bool SEL0N>
