@@ -521,8 +521,10 @@ size_t fhmc_sweep_compact_workspace(const fhmc_hist_desc *desc, long long n_stat
 {
     if (!desc || n_states < 0 || desc->pmax < 1) return 0;
     // the fused kernel needs FHMC_COMPACT_SCRATCH_RECORDS records; anything it does not cover needs a record per state point
+    // (the same size threshold as fhmc_sweep_1d_compact: smaller sweeps take the general path, one scratch record per state point)
+    const DevInfo *di = dev_info();
     const bool fused = desc->mu_recurrence >= 2 && desc->n_coef == 0 && desc->n_term <= 1 && !desc->complete && desc->n_sel <= 2 &&
-                       desc->pmax <= FHMC_COMPACT_PMAX && desc->n <= 32767;
+                       desc->pmax <= FHMC_COMPACT_PMAX && desc->n <= 32767 && di && n_states > (long long)di->sm_count * 2 * FHMC_CTA;
     const long long c = (fused && n_states > FHMC_COMPACT_SCRATCH_RECORDS) ? FHMC_COMPACT_SCRATCH_RECORDS
                         : (n_states > FHMC_COMPACT_SCRATCH_RECORDS ? n_states : FHMC_COMPACT_SCRATCH_RECORDS);
     // + the index list of the state points the tilt cells leave to the table walk

@@ -169,3 +169,18 @@ def test_cells_capacity_and_small_pmax():
         if pmax == 1:
             assert np.any(g["code"] == 8)
             assert not np.any(c["path"].cpu().numpy()[g["code"] == 8])
+
+
+def test_compact_sweep_below_the_fused_threshold_sizes_its_workspace():
+    """Sweeps of 8192 < S <= 2 x 256 state points per SM take the general path (a scratch record per state point): the workspace
+    query must say so (it used to answer with the fused path's size and the call failed with 'workspace too small')."""
+    from fhmcanalysis_b200 import engine, synth
+    n = 1001
+    lnpi = synth.two_peak_lnpi(n)
+    N = np.arange(n, dtype=np.float64)
+    for S in (9000, 30000, 70000):
+        mu = np.linspace(-0.03, 0.03, S)
+        dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=10, sel=["N", N * N])
+        c = dh.sweep_compact(mu, pmax=4)
+        g = dh.sweep(mu, pmax=4, lanes=-1).host()
+        _check(c, g, 4)
