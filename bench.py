@@ -863,14 +863,13 @@ def run_gpu_arm(args, rank, world, local_rank):
     variants = {}
     if dh.desc.mu_cells:
         def step_cold():
-            dh._cells_range = None
             dh._cells_key = None
             step()
         for _ in range(3):
             step_cold()
         _, ms_c, _ = timed_loop(step_cold, min(args.steps, 50))
         variants["cells_rebuilt_every_step"] = {"value": world * S / (ms_c * 1e-3), "ms_per_step": ms_c,
-                                                "note": "the cells are dropped before every step: torch.aminmax of mu + read-back + fhmc_mu_cells_build (4 kernels) inside the timed region"}
+                                                "note": "the cells are dropped before every step: fhmc_mu_cells_build_for (range of mu on the device + 4 build kernels, no read-back) inside the timed region"}
         saved = (dh.desc.mu_cells, dh.use_mu_cells)
         dh.desc.mu_cells, dh.use_mu_cells = None, False
         for _ in range(3):

@@ -89,7 +89,7 @@ EXPORTS = [
     "fhmc_sweep_host_compact16", "fhmc_pack_soa16_bytes", "fhmc_pack_phase_soa16",
     "fhmc_patch_shifts", "fhmc_reweight_2d_prod", "fhmc_reweight_2d_prod_workspace",
     "fhmc_bench_dfma", "fhmc_bench_exp", "fhmc_lean_stats", "fhmc_sweep_1d_compact", "fhmc_sweep_compact_workspace",
-    "fhmc_mu_tables_bytes", "fhmc_mu_tables_build", "fhmc_mu_cells_bytes", "fhmc_mu_cells_build", "fhmc_phase_moments_dev", "fhmc_scalar_point", "fhmc_find_phase_eq_curve",
+    "fhmc_mu_tables_bytes", "fhmc_mu_tables_build", "fhmc_mu_cells_bytes", "fhmc_mu_cells_build", "fhmc_mu_cells_build_for", "fhmc_phase_moments_dev", "fhmc_scalar_point", "fhmc_find_phase_eq_curve",
 ]
 
 _lib = None
@@ -175,6 +175,8 @@ def load():
     L.fhmc_mu_cells_bytes.argtypes = [ctypes.POINTER(HistDesc), ci]
     L.fhmc_mu_cells_build.restype = ci
     L.fhmc_mu_cells_build.argtypes = [ctypes.POINTER(HistDesc), vp, vp, ctypes.c_size_t, ci, ctypes.c_double, ctypes.c_double, vp]
+    L.fhmc_mu_cells_build_for.restype = ci
+    L.fhmc_mu_cells_build_for.argtypes = [ctypes.POINTER(HistDesc), vp, vp, ctypes.c_size_t, ci, vp, cll, vp]
     L.fhmc_phase_moments_dev.restype = ci
     L.fhmc_phase_moments_dev.argtypes = [vp, ci, vp, ci, vp, vp, vp, ci, vp, vp, vp]
     L.fhmc_scalar_point.restype = ci

@@ -45,7 +45,8 @@ struct CellHeader {   // 256 bytes at the start of the cells buffer
     long long off_iv, off_piece, off_coef, off_pstart, off_grid;
     double a_lo, a_hi;                    // covered tilt range (device)
     double inv_g;                         // grid cells per unit of tilt (device)
-    double pad1[16];
+    unsigned long long kmin, kmax;        // order-preserving keys of min / max mu of the sweep (k_cell_range; device)
+    double pad1[14];
 };
 static_assert(sizeof(CellHeader) <= 256, "header must fit its slot");
 
@@ -75,11 +76,62 @@ __device__ __forceinline__ void cell_geom(int left, int right, double &c, double
 __host__ __device__ constexpr int cell_blk(int nsel) { return 4 + FHMC_CELL_K * (1 + nsel); }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// build 1 (one CTA): pieces per interval for the tilt range of [mu_lo, mu_hi], exclusive scans
+// build 0 (device-side range): min / max of the finite mu of a sweep, as order-preserving integer keys
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long cell_key(double x)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double cell_unkey(unsigned long long k)
+{
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+__global__ void __launch_bounds__(256) k_cell_range(const double *mu, long long n, unsigned char *cells)
+{
+    CellHeader *h = reinterpret_cast<CellHeader *>(cells);
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double x = __ldg(mu + i);
+        if (fabs(x) < CUDART_INF) {
+            const unsigned long long k = cell_key(x);
+            lo = min(lo, k);
+            hi = max(hi, k);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    __shared__ unsigned long long s_lo[8], s_hi[8];
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { lo = min(lo, s_lo[w]); hi = max(hi, s_hi[w]); }
+        if (lo <= hi) {
+            atomicMin(&h->kmin, lo);
+            atomicMax(&h->kmax, hi);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// build 1 (one CTA): pieces per interval for the tilt range of [mu_lo, mu_hi] (dev_range: of the keys k_cell_range left in
+// the header), exclusive scans
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_cell_plan(const unsigned char *tables, unsigned char *cells, CellHeader h0, double mu_lo, double mu_hi,
-                                                    double mu1_ref, double beta_ref)
+                                                    double mu1_ref, double beta_ref, int dev_range)
 {
+    bool have_range = true;
+    if (dev_range) {
+        const CellHeader *hr = reinterpret_cast<const CellHeader *>(cells);
+        have_range = hr->kmin <= hr->kmax;
+        mu_lo = have_range ? cell_unkey(hr->kmin) : 0.0;
+        mu_hi = have_range ? cell_unkey(hr->kmax) : 0.0;
+    }
+    __syncthreads();   // (every thread has read the keys before thread 0 rewrites the header)
     const MuTabHeader *th = reinterpret_cast<const MuTabHeader *>(tables);
     const double *ep = reinterpret_cast<const double *>(tables + th->off_ep);
     const short *rec = reinterpret_cast<const short *>(tables + th->off_rec);
@@ -92,7 +144,7 @@ __global__ void __launch_bounds__(1024) k_cell_plan(const unsigned char *tables,
     const double pad = 1e-9 * fmax(1.0, fmax(fabs(a_lo), fabs(a_hi)));
     a_lo -= pad;
     a_hi += pad;
-    const bool usable = th->magic == FHMC_TAB_MAGIC && !th->bad && niv <= h0.iv_cap;
+    const bool usable = th->magic == FHMC_TAB_MAGIC && !th->bad && niv <= h0.iv_cap && have_range;
     const int per = (niv + (int)blockDim.x - 1) / (int)blockDim.x;
     const int k_lo = (int)threadIdx.x * per, k_hi = min(niv, k_lo + per);
     int np = 0, nb = 0;
@@ -228,22 +280,22 @@ __global__ void __launch_bounds__(256) k_cell_grid(unsigned char *cells)
     gfirst[g] = max(lo - 1, 0);
 }
 
-// build 3: the expansion coefficients, a warp per piece
+// build 3: the expansion coefficients, a CTA (8 warps) per cell: one pass over the bins of every phase
 template <int NSEL>
 __global__ void __launch_bounds__(256) k_cell_coef(const unsigned char *tables, unsigned char *cells, const double *blob, int n_pad, int row0, int row1)
 {
-    constexpr int K = FHMC_CELL_K, BLK = cell_blk(NSEL);
+    constexpr int K = FHMC_CELL_K, BLK = cell_blk(NSEL), NV = (1 + NSEL) * K;
     const MuTabHeader *th = reinterpret_cast<const MuTabHeader *>(tables);
     const short *rec = reinterpret_cast<const short *>(tables + th->off_rec);
     const CellHeader *h = reinterpret_cast<const CellHeader *>(cells);
     const CellPiece *pc = reinterpret_cast<const CellPiece *>(cells + h->off_piece);
     double *coef = reinterpret_cast<double *>(cells + h->off_coef);
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const double *lnpi = blob, *Nrow = blob + n_pad;
     const double *xr[2] = {blob + (size_t)row0 * n_pad, blob + (size_t)row1 * n_pad};
     const double N0 = Nrow[0], dN = th->dN;
-    for (int pi = warp; pi < h->n_pieces; pi += nwarp) {
+    __shared__ double s_red[8][NV + 1];
+    for (int pi = blockIdx.x; pi < h->n_pieces; pi += gridDim.x) {
         const CellPiece p = pc[pi];
         const short *r = rec + (size_t)p.ivl * FHMC_TAB_REC_I16;
         const int P = r[FHMC_TR_NPHASE];
@@ -252,14 +304,19 @@ __global__ void __launch_bounds__(256) k_cell_coef(const unsigned char *tables, 
             double c, R;
             cell_geom(left, right, c, R);
             double M = -CUDART_INF;
-            for (int i = left + lane; i < right; i += 32) M = fmax(M, lnpi[i] + p.s_c * Nrow[i]);
+            for (int i = left + (int)threadIdx.x; i < right; i += 256) M = fmax(M, lnpi[i] + p.s_c * Nrow[i]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) M = fmax(M, __shfl_xor_sync(0xffffffffu, M, o));
-            double acc[(1 + NSEL) * K];
+            __syncthreads();   // (s_red of the previous phase has been read)
+            if (lane == 0) s_red[wib][NV] = M;
+            __syncthreads();
 #pragma unroll
-            for (int q = 0; q < (1 + NSEL) * K; ++q) acc[q] = 0.0;
+            for (int w = 0; w < 8; ++w) M = fmax(M, s_red[w][NV]);
+            double acc[NV];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) acc[q] = 0.0;
             const double invR = 1.0 / R;
-            for (int i = left + lane; i < right; i += 32) {
+            for (int i = left + (int)threadIdx.x; i < right; i += 256) {
                 const double w = exp(lnpi[i] + p.s_c * Nrow[i] - M);
                 const double x = ((double)i - c) * invR;
                 double wq[1 + NSEL];
@@ -275,26 +332,31 @@ __global__ void __launch_bounds__(256) k_cell_coef(const unsigned char *tables, 
                 }
             }
 #pragma unroll
-            for (int q = 0; q < (1 + NSEL) * K; ++q) {
+            for (int q = 0; q < NV; ++q) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
             }
-            // normalised by C_0 = sum_i w_i: the sum is C_0 (1 + eps) with |eps| <= e^|y| - 1, its log ln C_0 + log1p(eps) by a short
-            // series (no log() per state point), and the averages are ratios of the normalised polynomials
-            const double C0 = acc[0], invC0 = 1.0 / C0;
 #pragma unroll
-            for (int q = 0; q < (1 + NSEL) * K; ++q) acc[q] *= invC0;
-            double *b = coef + (size_t)(p.block + ph) * BLK;
-            if (lane == 0) {
-                b[0] = M + log(C0);   // ln S_p at the cell centre
-                b[1] = N0 + c * dN;   // N at the phase centre
-                b[2] = dN * R;        // y = d * b[2]
-                reinterpret_cast<int *>(b + 3)[0] = (left & 0xffff) | (right << 16);   // {left, right} as two int16: the record's bounds word
-                reinterpret_cast<int *>(b + 3)[1] = 0;
+            for (int q = 0; q < NV; ++q)
+                if (lane == (q & 31)) s_red[wib][q] = acc[q];
+            __syncthreads();
+            if (wib == 0 && lane < NV) {
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) v += s_red[w][lane];
+                // normalised by C_0 = sum_i w_i: the sum is C_0 (1 + eps) with |eps| <= e^|y| - 1, its log ln C_0 + log1p(eps) by a
+                // short series (no log() per state point), and the averages are ratios of the normalised polynomials
+                const double C0 = __shfl_sync((1u << NV) - 1u, v, 0);
+                double *b = coef + (size_t)(p.block + ph) * BLK;
+                b[4 + lane] = v / C0;
+                if (lane == 0) {
+                    b[0] = M + log(C0);   // ln S_p at the cell centre
+                    b[1] = N0 + c * dN;   // N at the phase centre
+                    b[2] = dN * R;        // y = d * b[2]
+                    reinterpret_cast<int *>(b + 3)[0] = (left & 0xffff) | (right << 16);   // {left, right} as two int16: the record's bounds word
+                    reinterpret_cast<int *>(b + 3)[1] = 0;
+                }
             }
-#pragma unroll
-            for (int q = 0; q < (1 + NSEL) * K; ++q)
-                if (lane == (q & 31)) b[4 + q] = acc[q];
         }
     }
 }
@@ -570,20 +632,26 @@ size_t fhmc_mu_cells_bytes(const fhmc_hist_desc *desc, int extra_pieces)
     return cell_layout(*desc, extra_pieces).total;
 }
 
-int fhmc_mu_cells_build(const fhmc_hist_desc *desc, const double *blob, void *cells, size_t cells_bytes, int extra_pieces, double mu_lo,
-                        double mu_hi, void *stream)
+static int cells_build_impl(const fhmc_hist_desc *desc, const double *blob, void *cells, size_t cells_bytes, int extra_pieces, double mu_lo,
+                            double mu_hi, const double *mu_dev, long long n_mu, void *stream)
 {
     if (!desc || !blob || !cells) { set_error("null argument"); return 1; }
     if (!desc->mu_tables || fhmc_mu_tables_bytes(desc) == 0) { set_error("mu cells need the mu tables of the same descriptor"); return 2; }
-    if (!(mu_lo <= mu_hi)) { set_error("mu cells: empty or non-finite range"); return 1; }
+    if (!mu_dev && !(mu_lo <= mu_hi)) { set_error("mu cells: empty or non-finite range"); return 1; }
     if ((uintptr_t)cells & 255) { set_error("cells must be a 256-byte aligned device pointer"); return 1; }
-    const CellLayout L = cell_layout(*desc, extra_pieces);
+    CellLayout L = cell_layout(*desc, extra_pieces);
     if (cells_bytes < L.total) { set_error("cells buffer too small: need fhmc_mu_cells_bytes() bytes"); return 1; }
     cudaStream_t s = (cudaStream_t)stream;
     unsigned char *cb = static_cast<unsigned char *>(cells);
     const unsigned char *tb = static_cast<const unsigned char *>(desc->mu_tables);
+    L.h.kmin = ~0ull;
+    L.h.kmax = 0ull;
     if (check_cuda(cudaMemcpyAsync(cb, &L.h, sizeof(CellHeader), cudaMemcpyHostToDevice, s), "cudaMemcpyAsync")) return 1;
-    k_cell_plan<<<1, 1024, 0, s>>>(tb, cb, L.h, mu_lo, mu_hi, desc->mu1_ref, desc->beta_ref);
+    if (mu_dev) {
+        long long g = (n_mu + 1023) / 1024;
+        k_cell_range<<<(unsigned)(g < 1 ? 1 : (g > 592 ? 592 : g)), 256, 0, s>>>(mu_dev, n_mu, cb);
+    }
+    k_cell_plan<<<1, 1024, 0, s>>>(tb, cb, L.h, mu_lo, mu_hi, desc->mu1_ref, desc->beta_ref, mu_dev ? 1 : 0);
     k_cell_pieces<<<(L.h.iv_cap + 255) / 256, 256, 0, s>>>(tb, cb, blob, desc->n_pad);
     k_cell_grid<<<(L.h.grid_n + 1 + 255) / 256, 256, 0, s>>>(cb);
     const int r0 = desc->n_sel > 0 ? desc->sel_row[0] : 0, r1 = desc->n_sel > 1 ? desc->sel_row[1] : 0;
@@ -594,6 +662,19 @@ int fhmc_mu_cells_build(const fhmc_hist_desc *desc, const double *blob, void *ce
     default: k_cell_coef<2><<<grid, 256, 0, s>>>(tb, cb, blob, desc->n_pad, r0, r1); break;
     }
     return check_cuda(cudaGetLastError(), "mu cells build launch");
+}
+
+int fhmc_mu_cells_build(const fhmc_hist_desc *desc, const double *blob, void *cells, size_t cells_bytes, int extra_pieces, double mu_lo,
+                        double mu_hi, void *stream)
+{
+    return cells_build_impl(desc, blob, cells, cells_bytes, extra_pieces, mu_lo, mu_hi, nullptr, 0, stream);
+}
+
+int fhmc_mu_cells_build_for(const fhmc_hist_desc *desc, const double *blob, void *cells, size_t cells_bytes, int extra_pieces,
+                            const double *mu_dev, long long n_mu, void *stream)
+{
+    if (!mu_dev || n_mu < 1) { set_error("mu cells: no state points"); return 1; }
+    return cells_build_impl(desc, blob, cells, cells_bytes, extra_pieces, 0.0, 0.0, mu_dev, n_mu, stream);
 }
 
 }  // extern "C"

@@ -313,59 +313,42 @@ class DeviceHistogram(object):
         self._mu_tables = buf
         self.desc.mu_tables = ptr
 
-    CELLS_MIN_STATES = 1 << 16   # the fused compact kernels start at 2 x 256 state points per SM; cells pay from about here
-    CELLS_MAX_EXTRA = 32768   # cells beyond one per elementary interval (0.67 KB each at two averaged quantities)
+    CELLS_MIN_STATES = 1 << 17   # building the cells costs about as much as walking 1.4x10^5 state points
+    CELLS_EXTRA = 32768          # cells beyond one per elementary interval the buffer has room for (0.8 KB each at two quantities)
 
     def ensure_mu_cells(self, mu):
-        """Tilt cells of a dense compact-record mu sweep (fhmc_mu_cells_build): moment expansions of the per-phase sums about the
-        centres of small tilt cells covering the mu range of ``mu`` (a device tensor or host array), handed to the kernels through
-        desc.mu_cells.  Built once per range: a later sweep inside the range reuses them, one that leaves it rebuilds them for
-        the union.  The range of a device tensor is read back once per (storage, version); state points outside the cells are
-        still evaluated (by the table walk), so a stale range costs speed, never correctness.  FHMC_MU_CELLS=0 / use_mu_cells =
-        False keeps the table walk (k_sweep_tab2)."""
+        """Tilt cells of a dense compact-record mu sweep (fhmc_mu_cells_build_for): moment expansions of the per-phase sums about
+        the centres of small tilt cells covering the range of the device tensor ``mu``, handed to the kernels through
+        desc.mu_cells.  Everything happens on the device, in stream order (no read-back): the cells are rebuilt whenever the sweep
+        is not the tensor they were built for -- (storage, length, version) -- and reused otherwise.  State points the cells do not
+        cover are still evaluated (by the table walk), so a stale key costs speed, never correctness.  FHMC_MU_CELLS=0 /
+        use_mu_cells = False keeps the table walk (k_sweep_tab2)."""
         if not self.use_mu_cells or not self.desc.mu_tables:
             return
         t = torch()
-        if isinstance(mu, t.Tensor):
-            if mu.numel() == 0:
-                return
-            key = (mu.data_ptr(), mu.numel(), mu._version)
-            if key == getattr(self, "_cells_key", None):
-                return
-            lo, hi = (float(x) for x in t.aminmax(mu))
-        else:
-            mu = np.asarray(mu, dtype=np.float64)
-            if mu.size == 0:
-                return
-            key = None
-            lo, hi = float(mu.min()), float(mu.max())
-        if not (np.isfinite(lo) and np.isfinite(hi)):
+        if not isinstance(mu, t.Tensor) or not mu.is_cuda or mu.numel() == 0 or mu.dtype != t.float64 or not mu.is_contiguous():
             return
-        self._cells_key = key
-        have = getattr(self, "_cells_range", None)
-        if have is not None and have[0] <= lo and hi <= have[1]:
+        key = (mu.data_ptr(), mu.numel(), mu._version)
+        if key == getattr(self, "_cells_key", None) and self.desc.mu_cells:
             return
-        if have is not None:   # grow: cover both
-            lo, hi = min(lo, have[0]), max(hi, have[1])
         L = _lib.load()
         d = self.desc
-        Nrow = self.blob_host[1, :self.n]
-        tilt_range = abs((hi - lo) * d.beta_ref * (Nrow[1] - Nrow[0]))
-        extra = int(min(self.CELLS_MAX_EXTRA, tilt_range * self.n / 0.19 + 64))
-        nbytes = int(L.fhmc_mu_cells_bytes(ctypes.byref(d), extra))
-        if nbytes == 0:
-            return
-        buf = t.empty(nbytes + 256, dtype=t.uint8, device=self.device)
-        ptr = (buf.data_ptr() + 255) & ~255
+        if getattr(self, "_mu_cells", None) is None:
+            nbytes = int(L.fhmc_mu_cells_bytes(ctypes.byref(d), self.CELLS_EXTRA))
+            if nbytes == 0:
+                self.use_mu_cells = False
+                return
+            self._mu_cells = t.empty(nbytes + 256, dtype=t.uint8, device=self.device)
+            self._mu_cells_bytes = nbytes
+        ptr = (self._mu_cells.data_ptr() + 255) & ~255
         with t.cuda.device(self.device):
-            rc = L.fhmc_mu_cells_build(ctypes.byref(d), _ptr(self.blob), ctypes.c_void_p(ptr), nbytes, extra, lo, hi, _stream_ptr(self.device))
+            rc = L.fhmc_mu_cells_build_for(ctypes.byref(d), _ptr(self.blob), ctypes.c_void_p(ptr), self._mu_cells_bytes, self.CELLS_EXTRA,
+                                           ctypes.c_void_p(mu.data_ptr()), mu.numel(), _stream_ptr(self.device))
         if rc == 2:
+            self.use_mu_cells = False
             return
-        _lib.check(rc, "fhmc_mu_cells_build")
-        # (the previous buffer may still be read by a sweep queued on this stream: the caching allocator reuses it only in
-        # stream order)
-        self._mu_cells = buf
-        self._cells_range = (lo, hi)
+        _lib.check(rc, "fhmc_mu_cells_build_for")
+        self._cells_key = key
         self.desc.mu_cells = ptr
 
     # ------------------------------------------------------------------------------------------
@@ -455,8 +438,8 @@ class DeviceHistogram(object):
             self.ensure_mu_tables()
             if S >= self.CELLS_MIN_STATES and not st.beta and not st.dmu:
                 keep = getattr(st, "_keep", None)
-                on_dev = isinstance(mu1, t.Tensor) and mu1.is_cuda
-                self.ensure_mu_cells(keep[0] if (on_dev or mu1 is None) and keep is not None else mu1)
+                if keep is not None and st.n_mu1 == S and st.mu1_div == 1:
+                    self.ensure_mu_cells(keep[0])
         n_total = S + int(first) if n_total is None else int(n_total)
         d = self._desc(pmax)
         nbytes = int(L.fhmc_pack_soa16_bytes(n_total, pmax, self.n_sel))

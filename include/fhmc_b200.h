@@ -286,6 +286,9 @@ int fhmc_sweep_1d_compact(const fhmc_hist_desc *desc, const double *blob, const 
 size_t fhmc_mu_cells_bytes(const fhmc_hist_desc *desc, int extra_pieces);
 int fhmc_mu_cells_build(const fhmc_hist_desc *desc, const double *blob, void *cells, size_t cells_bytes, int extra_pieces,
                         double mu_lo, double mu_hi, void *stream);
+/* the same for the range of the finite values of a device array of mu1 (read on the device: nothing synchronises) */
+int fhmc_mu_cells_build_for(const fhmc_hist_desc *desc, const double *blob, void *cells, size_t cells_bytes, int extra_pieces,
+                            const double *mu_dev, long long n_mu, void *stream);
 
 /*
  * Host-buffer mu sweep (new; replaces the user's Python loop of reweight()/thermo()/is_safe() calls on host arrays,

@@ -40,15 +40,13 @@ for S in (100000, 1000000, 4000000):
         print("S %8d cells %d  %-26s median %.1f us  min %.1f us -> %.3e points/s  cell fraction %.4f" % (S, cells, _lib.last_kernel(), 1e3 * med, 1e3 * best, S / (1e-3 * med), frac), flush=True)
         if cells:
             def rebuild():
-                dh._cells_range = None
                 dh._cells_key = None
                 dh.ensure_mu_cells(mu)
             med, best = timed(rebuild, 10)
-            print("   cells build (aminmax + readback + 3 kernels): median %.1f us  min %.1f us;  range %r" % (1e3 * med, 1e3 * best, dh._cells_range))
+            print("   cells build (range on the device + 4 kernels): median %.1f us  min %.1f us" % (1e3 * med, 1e3 * best))
             hdr = dh._mu_cells[(-dh._mu_cells.data_ptr()) % 256:][:64].cpu().numpy().view(np.int32)
             print("   header: n_pieces %d n_blocks %d truncated %d (piece_cap %d)" % (hdr[6], hdr[7], hdr[8], hdr[4]))
             def cold():
-                dh._cells_range = None
                 dh._cells_key = None
                 fn()
             med, best = timed(cold, 10)

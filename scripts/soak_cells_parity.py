@@ -32,6 +32,7 @@ def main():
         nsel = int(rng.integers(0, 3))
         sel = [["N", N * N], [np.sqrt(N + 1.0)], []][2 - nsel] if nsel < 2 else ["N", N * N]
         dh = engine.DeviceHistogram(lnpi, N, beta, mu_ref, smooth=smooth, sel=sel)
+        dh.CELLS_MIN_STATES = 1
         pmax = int(rng.choice([4, 8]))
         c = dh.sweep_compact(mus, pmax=pmax)
         kern = _lib.last_kernel()

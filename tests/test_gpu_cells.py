@@ -110,19 +110,19 @@ def test_cells_ties_spacing_offsets_and_ranges():
     dh, c, g, kern = _both(lnpi, N2, mu2, 5, sel=[N2, N2 * N2], beta=0.8, mu_ref=-0.3, cells=True)
     assert kern == "k_sweep_cell<compact>"
     assert _check(c, g, 4) > 0.99 and _cell_fraction(c) > 0.95
-    first = dh._cells_range
-    # a second range, partly outside: rebuilt for the union
+    # a second range, partly outside the first: the cells follow the sweep
     mu3 = np.linspace(0.1, 0.45, S)
     c3 = dh.sweep_compact(mu3, pmax=4)
     g3 = dh.sweep(mu3, pmax=4, lanes=-1).host()
-    assert dh._cells_range[0] <= first[0] and dh._cells_range[1] >= 0.45
     assert _check(c3, g3, 4) > 0.99 and _cell_fraction(c3) > 0.95
     # every state point the same
     mu4 = np.full(S, 0.0123)
     c4 = dh.sweep_compact(mu4, pmax=4)
     g4 = dh.sweep(mu4, pmax=4, lanes=-1).host()
     _check(c4, g4, 4)
-    # device tensor input: cached by (storage, version); an in-place change of the tensor is seen
+    assert _cell_fraction(c4) > 0.99
+    # device tensor input: cached by (storage, version); an in-place change of the tensor is seen; cells built for another sweep are
+    # still correct for this one (state points outside them take the table walk)
     import torch
     mu_d = torch.from_numpy(mu2).cuda()
     c5 = dh.sweep_compact(mu_d, pmax=4)
@@ -132,11 +132,18 @@ def test_cells_ties_spacing_offsets_and_ranges():
     mu_d.mul_(3.0)
     c6 = dh.sweep_compact(mu_d, pmax=4)
     g6 = dh.sweep(mu_d, pmax=4, lanes=-1).host()
-    assert dh._cells_key != key and dh._cells_range[0] <= -0.6 and dh._cells_range[1] >= 0.6
-    _check(c6, g6, 4)
+    assert dh._cells_key != key
+    assert _check(c6, g6, 4) > 0.99 and _cell_fraction(c6) > 0.95
+    stale = dh._cells_key
+    mu_e = torch.from_numpy(np.linspace(-0.9, 0.9, S)).cuda()
+    dh._cells_key = (mu_e.data_ptr(), mu_e.numel(), mu_e._version)     # pretend the cells (range [-0.6, 0.6]) belong to this sweep
+    c7 = dh.sweep_compact(mu_e, pmax=4)
+    g7 = dh.sweep(mu_e, pmax=4, lanes=-1).host()
+    assert _check(c7, g7, 4) > 0.99 and 0.5 < _cell_fraction(c7) < 0.75
     # one quantity that is not N; no quantity
     for sel in ([N2 * N2], []):
         dhq = engine.DeviceHistogram(lnpi, N2, 0.8, -0.3, smooth=5, sel=sel)
+        dhq.CELLS_MIN_STATES = 1
         cq = dhq.sweep_compact(mu2, pmax=4)
         assert _lib.last_kernel() == "k_sweep_cell<compact>"
         gq = dhq.sweep(mu2, pmax=4, lanes=-1).host()
@@ -163,6 +170,7 @@ def test_cells_capacity_and_small_pmax():
     mu = np.linspace(-0.03, 0.03, S_MIN + 5)
     for pmax in (1, 8):
         dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=10, sel=["N", N * N])
+        dh.CELLS_MIN_STATES = 1
         c = dh.sweep_compact(mu, pmax=pmax)
         g = dh.sweep(mu, pmax=pmax, lanes=-1).host()
         _check(c, g, pmax)

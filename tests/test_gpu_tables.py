@@ -14,6 +14,7 @@ def _both(lnpi, N, mu, smooth, sel=None, beta=1.0, mu_ref=0.0, pmax=4, cells=Fal
     sel = ["N", N * N] if sel is None else sel
     dh = engine.DeviceHistogram(lnpi, N, beta, mu_ref, smooth=smooth, sel=sel)
     dh.use_mu_cells = cells     # False: the table walk itself (tests/test_gpu_cells.py runs the same cases on the tilt cells)
+    dh.CELLS_MIN_STATES = 1     # (the engine builds cells from 2^17 state points on; the test sweeps are shorter)
     c = dh.sweep_compact(mu, pmax=pmax)
     kern = _lib.last_kernel()
     g = dh.sweep(mu, pmax=pmax, lanes=-1).host()
