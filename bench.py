@@ -1028,7 +1028,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "gpu_launches": args.steps,
+            "data": "synthetic", "gpu_launches": args.steps * (2 if timed_kernel.startswith("k_sweep_cell") else 1),   # (k_sweep_cell + k_sweep_tab2_idx per step)
             "value_with_gather": with_gather["value"] if with_gather else None,
             "value_compute_only": value,
             "config": {"workload": "config2: synthetic 1-comp N_tot lnPI, N_max=1000 (1001 bins), smooth=10, 10^6-point mu sweep per GPU with thermo "

@@ -545,6 +545,213 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same sweep with the phase loop uniform across the warp and the fp64 fields of a phase leaving through a shared-memory
+// transpose: the 32 state points of a warp fill 32 (1 + NSEL) consecutive doubles of the phase block, written as 16-byte
+// chunks (full 32-byte sectors) instead of (1 + NSEL) 8-byte stores per lane at a stride of 8 (1 + NSEL) bytes -- a third of the
+// store sectors at NSEL = 2, which is what bounds a gather fused into the sweep (every record crosses NVLink to every peer).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NSEL>
+__global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell_t(const __grid_constant__ SweepArgs a)
+{
+    constexpr int K = FHMC_CELL_K, BLK = cell_blk(NSEL), NF = 1 + NSEL, CHUNKS = 16 * NF;
+    asm volatile("griddepcontrol.launch_dependents;");
+    __shared__ __align__(16) double s_slab[8][32 * NF];
+    const unsigned char *tables = static_cast<const unsigned char *>(a.d.mu_tables);
+    const unsigned char *cells = static_cast<const unsigned char *>(a.d.mu_cells);
+    const MuTabHeader *th = reinterpret_cast<const MuTabHeader *>(tables);
+    const CellHeader *ch = reinterpret_cast<const CellHeader *>(cells);
+    const CellPiece *cpc = reinterpret_cast<const CellPiece *>(cells + ch->off_piece);
+    const double *coef = reinterpret_cast<const double *>(cells + ch->off_coef);
+    const double *pstart = reinterpret_cast<const double *>(cells + ch->off_pstart);
+    const int *gfirst = reinterpret_cast<const int *>(cells + ch->off_grid);
+    const int n = a.d.n, last = n - 1, pmax = a.d.pmax, grid_n = ch->grid_n;
+    const double dN = th->dN, Na = th->Na, lmax = th->lmax, a_lo = ch->a_lo, a_hi = ch->a_hi, inv_g = ch->inv_g;
+    const double *lnpi = a.blob, *Nrow = a.blob + a.d.n_pad;
+    const bool usable = th->magic == FHMC_TAB_MAGIC && !th->bad && th->n == n && th->smooth == a.d.smooth && ch->magic == FHMC_CELL_MAGIC &&
+                        ch->n_sel == NSEL && th->n_sel == NSEL && (NSEL < 1 || th->sel_row[0] == a.d.sel_row[0]) &&
+                        (NSEL < 2 || th->sel_row[1] == a.d.sel_row[1]) && n >= 3 && ch->n_pieces > 0;
+    const double l0 = lnpi[0], N_0 = Nrow[0], l_last = lnpi[last], N_last = Nrow[last];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *slab = s_slab[wib];
+    const long long S = a.st.n_states;
+    const long long cN = a.c.n_total;
+    const long long fbase = (4 * cN + 15) & ~15ll, bbase = fbase + (long long)pmax * cN * NF * 8;
+    int top = 0;
+    const bool flat = a.st.mu1_div == 1 && a.st.n_mu1 >= S;
+    const long long run = (((S + gridDim.x - 1) / gridDim.x) + 255) & ~255ll;
+    const long long first = (long long)blockIdx.x * run, end = first + run < S ? first + run : S;
+    auto load_mu = [&](long long q) -> double {
+        if (q >= end) return 0.0;
+        return flat ? __ldg(a.st.mu1 + q) : a.st.mu1[(q / a.st.mu1_div) % a.st.n_mu1];
+    };
+    if (!usable) {   // cells that do not belong to this descriptor: every state point is left to the table walk
+        for (long long base = first; base < end; base += 256) {
+            const long long sp = base + threadIdx.x;
+            const unsigned m = __ballot_sync(0xffffffffu, sp < end);
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(a.c.ix_count, __popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (sp < end && pos >= 0 && pos + 32 <= S + 32) a.c.ix_list[pos + __popc(m & ((1u << lane) - 1u))] = sp;
+        }
+        return;
+    }
+    double mu_next = load_mu(first + threadIdx.x);
+    for (long long base = first; base < end; base += 256) {
+        const long long sp = base + threadIdx.x;
+        const double mu1 = mu_next;
+        mu_next = load_mu(sp + 256);
+        const bool mine = sp < end;
+        const double s = __dmul_rn(__dsub_rn(mu1, a.d.mu1_ref), a.d.beta_ref);   // GH:77, evaluated left to right
+        const double sdn = s * dN, av = -sdn;
+        bool act = mine && usable && (fabs(4.0 * sdn) < 200.0) && (av >= a_lo && av <= a_hi);
+        // the cell of this tilt: lookup grid, then a bisection over the few cells that start inside the grid cell
+        const int g = act ? min((int)((av - a_lo) * inv_g), grid_n - 1) : 0;
+        int lo = __ldg(gfirst + g), hi = act ? __ldg(gfirst + g + 1) : lo;
+        while (lo < hi) {   // last cell with pstart <= tilt, in [lo, hi]
+            const int mid = (lo + hi + 1) >> 1;
+            if (__ldg(pstart + mid) <= av) lo = mid; else hi = mid - 1;
+        }
+        const CellPiece *cp = cpc + lo;
+        const double2 w0 = __ldg(reinterpret_cast<const double2 *>(cp));       // {s_c, safe_lo}
+        const int4 w1 = __ldg(reinterpret_cast<const int4 *>(cp) + 1);         // {safe_hi lo, safe_hi hi, block, ivl}
+        const int4 w2 = __ldg(reinterpret_cast<const int4 *>(cp) + 2);         // {nph | lastmax, hidx | cntM, cntm | nmin, -}
+        const double2 w3 = __ldg(reinterpret_cast<const double2 *>(cp) + 3);   // {lnPI, N} at the last maximum
+        const double2 w4 = __ldg(reinterpret_cast<const double2 *>(cp) + 4);   // {lnPI, N} at the hull vertex
+        const double s_c = w0.x, safe_hi = __hiloint2double(w1.y, w1.x);
+        const int nph = w2.x & 0xffff, lastmax = (w2.x >> 16) & 0xffff;
+        // margin test of the table walk; the capacity rules of PointEval::repair() for the caller's pmax
+        act = act && (av >= w0.y && av <= safe_hi) &&
+              !(nph > pmax || ((w2.y >> 16) & 0xffff) > pmax - 1 || (w2.z & 0xffff) > pmax || ((w2.z >> 16) & 0xffff) > pmax + 1);
+        const double d = s - s_c;
+        const double dl = tab_margin(lmax, fabs(s), Na);
+        // is_safe (GH:586-591): fl(fl(u_M - c) - fl(u_last - c)) < cutoff, decided without c when it is not a rounding matter
+        const double u_last = __dadd_rn(l_last, __dmul_rn(s, N_last));
+        unsigned flags = FHMC_ST_FAST;
+        if (lastmax != last) {
+            const double D = __dadd_rn(w3.x, __dmul_rn(s, w3.y)) - u_last;
+            if (fabs(D - a.d.cutoff) <= 2.0 * dl) act = false;
+            if (!(D < a.d.cutoff)) flags |= FHMC_ST_SAFE;
+        } else if (!(0.0 < a.d.cutoff)) {
+            flags |= FHMC_ST_SAFE;
+        }
+        const double u0 = __dadd_rn(l0, __dmul_rn(s, N_0));
+        const int Mq = shift_for_max(__dadd_rn(w4.x, __dmul_rn(s, w4.y)));
+        const double *b = coef + (size_t)w1.z * BLK;
+        const long long rix = a.c.first + sp, rix0 = rix - lane;
+        const int nph_l = act ? nph : 0;
+        const int nmax = __reduce_max_sync(0xffffffffu, nph_l);
+        for (int ph = 0; ph < nmax; ++ph, b += BLK) {   // (uniform across the warp)
+            bool on = act && ph < nph_l;
+            double v[NF];
+#pragma unroll
+            for (int q = 0; q < NF; ++q) v[q] = 0.0;
+            int bword = 0;
+            if (on) {
+                const double2 g0 = __ldg(reinterpret_cast<const double2 *>(b)), g1 = __ldg(reinterpret_cast<const double2 *>(b) + 1);
+                const double y = d * g1.x;
+                bword = __double2loint(g1.y);   // {left, right} of this phase
+                double P[NF];
+#pragma unroll
+                for (int q = 0; q < NF; ++q) {
+                    const double2 *cq = reinterpret_cast<const double2 *>(b + 4 + q * K);
+                    const double2 k01 = __ldg(cq), k23 = __ldg(cq + 1), k45 = __ldg(cq + 2), k67 = __ldg(cq + 3);
+                    double t = fma(k67.y, y, k67.x);
+                    t = fma(t, y, k45.y);
+                    t = fma(t, y, k45.x);
+                    t = fma(t, y, k23.y);
+                    t = fma(t, y, k23.x);
+                    t = fma(t, y, k01.y);
+                    P[q] = q == 0 ? t * y : fma(t, y, k01.x);   // (quantity 0: eps = P_0 / C_0 - 1, its constant term is 1)
+                }
+                const double eps = P[0];
+                if (!(fabs(y) <= FHMC_CELL_YMAX * (1.0 + 1e-6)) || !(fabs(eps) < 0.06)) {   // (|eps| <= e^0.05 - 1 by construction)
+                    act = false;
+                    on = false;
+                } else {
+                    // log1p(eps), |eps| < 0.06: alternating series through eps^13 / 13 (next term < 1e-17 relative)
+                    double l1 = fma(eps, 1.0 / 13.0, -1.0 / 12.0);
+                    l1 = fma(l1, eps, 1.0 / 11.0);
+                    l1 = fma(l1, eps, -1.0 / 10.0);
+                    l1 = fma(l1, eps, 1.0 / 9.0);
+                    l1 = fma(l1, eps, -1.0 / 8.0);
+                    l1 = fma(l1, eps, 1.0 / 7.0);
+                    l1 = fma(l1, eps, -1.0 / 6.0);
+                    l1 = fma(l1, eps, 1.0 / 5.0);
+                    l1 = fma(l1, eps, -1.0 / 4.0);
+                    l1 = fma(l1, eps, 1.0 / 3.0);
+                    l1 = fma(l1, eps, -0.5);
+                    l1 = fma(l1 * eps, eps, eps);
+                    const double lnS = (g0.x - u0) + fma(d, g0.y, l1);   // ln S_p - u_0
+                    // (diagnostic bit of the walk: this phase's sum underflows next to the global maximum's shift)
+                    if (lnS + u0 - (double)Mq * 0.6931471805599453 < -644.7236) flags |= FHMC_ST_RESCUED;
+                    const double inv = 1.0 / (1.0 + eps);
+                    v[0] = -lnS;
+#pragma unroll
+                    for (int q = 0; q < NSEL; ++q) v[1 + q] = P[1 + q] * inv;
+                }
+            }
+            const long long prow = (long long)ph * cN;
+            // all 32 state points of the warp have this phase and the warp's slice of the block starts on a 16-byte boundary:
+            // transpose through shared memory and write full 16-byte chunks; else every lane writes its own fields
+            const bool whole = __all_sync(0xffffffffu, on) && ((NF & 1) == 0 || (((prow + rix0) & 1) == 0));
+            if (whole) {
+#pragma unroll
+                for (int q = 0; q < NF; ++q) slab[NF * lane + q] = v[q];
+                __syncwarp();
+                double2 c[(CHUNKS + 31) / 32];
+#pragma unroll
+                for (int r = 0; r < (CHUNKS + 31) / 32; ++r)
+                    c[r] = (lane + 32 * r < CHUNKS) ? reinterpret_cast<const double2 *>(slab)[lane + 32 * r] : make_double2(0.0, 0.0);
+                __syncwarp();
+                for (int dd = 0; dd < a.c.n_dst; ++dd) {
+                    double2 *o = reinterpret_cast<double2 *>(reinterpret_cast<double *>(a.c.dst[dd] + fbase) + (prow + rix0) * NF);
+#pragma unroll
+                    for (int r = 0; r < (CHUNKS + 31) / 32; ++r)
+                        if (lane + 32 * r < CHUNKS) o[lane + 32 * r] = c[r];
+                }
+            } else if (on) {
+                for (int dd = 0; dd < a.c.n_dst; ++dd) {
+                    double *f = reinterpret_cast<double *>(a.c.dst[dd] + fbase) + (prow + rix) * NF;
+#pragma unroll
+                    for (int q = 0; q < NF; ++q) f[q] = v[q];
+                }
+            }
+            if (on)
+                for (int dd = 0; dd < a.c.n_dst; ++dd) reinterpret_cast<int *>(a.c.dst[dd] + bbase)[prow + rix] = bword;
+        }
+        // (a state point that gave up after its first phases has left them in the record: the table walk that takes it over finds
+        // the same phases in the same interval record and overwrites every one of them)
+        if (act) {
+            const uchar4 hd = make_uchar4((unsigned char)(flags & 0xFFu), (unsigned char)((flags >> 8) & 0xFFu), (unsigned char)nph, 1);   // (byte 3: written by the tilt cells -- diagnostic)
+            for (int dd = 0; dd < a.c.n_dst; ++dd) {
+                reinterpret_cast<uchar4 *>(a.c.dst[dd])[rix] = hd;
+                if (a.c.fill_dead)
+                    for (int ph = nph; ph < pmax; ++ph) {
+                        double *f = reinterpret_cast<double *>(a.c.dst[dd] + fbase) + ((long long)ph * cN + rix) * NF;
+#pragma unroll
+                        for (int q = 0; q < NF; ++q) f[q] = CUDART_NAN;
+                        reinterpret_cast<int *>(a.c.dst[dd] + bbase)[(long long)ph * cN + rix] = -1;
+                    }
+            }
+            top = max(top, nph);
+        }
+        // leftovers: appended to the index list of the table walk (one atomic per warp)
+        const unsigned m = __ballot_sync(0xffffffffu, mine && !act);
+        if (m) {
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(a.c.ix_count, __popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (mine && !act && pos >= 0 && pos + 32 <= S + 32) a.c.ix_list[pos + __popc(m & ((1u << lane) - 1u))] = sp;
+        }
+    }
+    if (a.c.max_nphase) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) top = max(top, __shfl_xor_sync(0xffffffffu, top, o));
+        if (lane == 0 && top > 0) atomicMax(a.c.max_nphase, top);
+    }
+}
+
 struct CellLayout {
     CellHeader h;
     size_t total;
@@ -588,23 +795,41 @@ int launch_cell_compact(const SweepArgs &args_in, int sm_count, int smem_optin, 
     args.c.ix_count = reinterpret_cast<int *>(static_cast<unsigned char *>(const_cast<void *>(d.mu_cells)) + offsetof(CellHeader, q_count));
     const long long S = args.st.n_states;
     // persistent grid: exactly the CTAs that are resident at once (a partial last wave would idle a third of the SMs)
-    static int occ_cache[3] = {0, 0, 0};
+    // the transposing variant when the records also go to NVLink peers (FHMC_CELL_T = 1 / 0 forces it on / off)
+    static int t_mode = -1;
+    if (t_mode < 0) { const char *e = getenv("FHMC_CELL_T"); t_mode = e ? (atoi(e) ? 1 : 0) : 2; }
+    const bool tr = t_mode == 1 || (t_mode == 2 && args.c.n_dst > 1);
+    static int occ_cache[2][3] = {{0, 0, 0}, {0, 0, 0}};
     const int q = d.n_sel;
-    if (occ_cache[q] == 0) {
+    if (occ_cache[tr][q] == 0) {
         int occ = 0;
-        cudaError_t e = q == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_cell<0>, 256, 0)
-                      : q == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_cell<1>, 256, 0)
-                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_cell<2>, 256, 0);
+        cudaError_t e;
+        if (tr)
+            e = q == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_cell_t<0>, 256, 0)
+              : q == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_cell_t<1>, 256, 0)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_cell_t<2>, 256, 0);
+        else
+            e = q == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_cell<0>, 256, 0)
+              : q == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_cell<1>, 256, 0)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_cell<2>, 256, 0);
         if (check_cuda(e, "occupancy query")) return 1;
-        occ_cache[q] = occ > 0 ? occ : 1;
+        occ_cache[tr][q] = occ > 0 ? occ : 1;
     }
     long long grid = (S + 255) / 256;
-    if (grid > (long long)sm_count * occ_cache[q]) grid = (long long)sm_count * occ_cache[q];
+    if (grid > (long long)sm_count * occ_cache[tr][q]) grid = (long long)sm_count * occ_cache[tr][q];
     if (const char *e = getenv("FHMC_CELL_GRID")) { const long long g = atoll(e); if (g > 0) grid = g; }   // (probe)
-    switch (d.n_sel) {
-    case 0: k_sweep_cell<0><<<(unsigned)grid, 256, 0, stream>>>(args); break;
-    case 1: k_sweep_cell<1><<<(unsigned)grid, 256, 0, stream>>>(args); break;
-    default: k_sweep_cell<2><<<(unsigned)grid, 256, 0, stream>>>(args); break;
+    if (tr) {
+        switch (d.n_sel) {
+        case 0: k_sweep_cell_t<0><<<(unsigned)grid, 256, 0, stream>>>(args); break;
+        case 1: k_sweep_cell_t<1><<<(unsigned)grid, 256, 0, stream>>>(args); break;
+        default: k_sweep_cell_t<2><<<(unsigned)grid, 256, 0, stream>>>(args); break;
+        }
+    } else {
+        switch (d.n_sel) {
+        case 0: k_sweep_cell<0><<<(unsigned)grid, 256, 0, stream>>>(args); break;
+        case 1: k_sweep_cell<1><<<(unsigned)grid, 256, 0, stream>>>(args); break;
+        default: k_sweep_cell<2><<<(unsigned)grid, 256, 0, stream>>>(args); break;
+        }
     }
     if (check_cuda(cudaGetLastError(), "k_sweep_cell launch")) return 1;
     const bool s0n = d.n_sel > 0 && d.sel_row[0] == 1;
