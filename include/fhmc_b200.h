@@ -120,7 +120,9 @@ typedef struct fhmc_hist_desc {
      * sums about the centres of small tilt cells, built by fhmc_mu_cells_build() for one range of mu.  Inside an elementary
      * interval the phase bounds are fixed, so every per-phase sum  sum_i exp(lnPI_i + s N_i) X_q(i)  is an entire function of s:
      * a state point then costs one degree-7 polynomial per phase and quantity instead of a walk over the bins (GH:71-78,
-     * 498-554).  State points outside the range, or that fail a rounding-margin test, take the table walk.  NULL: not provided. */
+     * 498-554).  State points outside the range, or that fail a rounding-margin test, take the table walk.  NULL: not provided.
+     * The buffer also holds the counter of the state points a sweep leaves to the table walk: sweeps that share one cells buffer
+     * must be ordered on one stream (or serialised by events); the tables above carry no such restriction.                    */
     const void *mu_cells;
 } fhmc_hist_desc;
 
