@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
                     flags |= FHMC_ST_SAFE;
                 }
                 const double u0 = __dadd_rn(l0, __dmul_rn(s, N_0));
-                const int Mq = shift_for_max(__dadd_rn(w4.x, __dmul_rn(s, w4.y)));
+                const double resc = (double)shift_for_max(__dadd_rn(w4.x, __dmul_rn(s, w4.y))) * 0.6931471805599453 - 644.7236 - u0;
                 const double *b = coef + (size_t)w1.z * BLK;
                 const long long fbase = (4 * cN + 15) & ~15ll, bbase = fbase + (long long)pmax * cN * (1 + NSEL) * 8, rix = a.c.first + sp;
                 // first destination: running pointers over the phase blocks (the other destinations of a fused gather are
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
                     l1 = fma(l1 * eps, eps, eps);
                     const double lnS = (g0.x - u0) + fma(d, g0.y, l1);   // ln S_p - u_0
                     // (diagnostic bit of the walk: this phase's sum underflows next to the global maximum's shift)
-                    if (lnS + u0 - (double)Mq * 0.6931471805599453 < -644.7236) flags |= FHMC_ST_RESCUED;
+                    if (lnS < resc) flags |= FHMC_ST_RESCUED;
                     const double inv = 1.0 / (1.0 + eps);
                     f0[0] = -lnS;
 #pragma unroll
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell_t(const __gr
             flags |= FHMC_ST_SAFE;
         }
         const double u0 = __dadd_rn(l0, __dmul_rn(s, N_0));
-        const int Mq = shift_for_max(__dadd_rn(w4.x, __dmul_rn(s, w4.y)));
+        const double resc = (double)shift_for_max(__dadd_rn(w4.x, __dmul_rn(s, w4.y))) * 0.6931471805599453 - 644.7236 - u0;
         const double *b = coef + (size_t)w1.z * BLK;
         const long long rix = a.c.first + sp, rix0 = rix - lane;
         const int nph_l = act ? nph : 0;
@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell_t(const __gr
                     l1 = fma(l1 * eps, eps, eps);
                     const double lnS = (g0.x - u0) + fma(d, g0.y, l1);   // ln S_p - u_0
                     // (diagnostic bit of the walk: this phase's sum underflows next to the global maximum's shift)
-                    if (lnS + u0 - (double)Mq * 0.6931471805599453 < -644.7236) flags |= FHMC_ST_RESCUED;
+                    if (lnS < resc) flags |= FHMC_ST_RESCUED;
                     const double inv = 1.0 / (1.0 + eps);
                     v[0] = -lnS;
 #pragma unroll
