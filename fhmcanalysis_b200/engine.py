@@ -349,6 +349,7 @@ class DeviceHistogram(object):
             return
         _lib.check(rc, "fhmc_mu_cells_build_for")
         self._cells_key = key
+        self._cells_host_key = None
         self.desc.mu_cells = ptr
 
     # ------------------------------------------------------------------------------------------
@@ -557,6 +558,13 @@ class DeviceHistogram(object):
         if S >= self.FAST_PATH_MIN_STATES and lanes in (0, 1):
             self.ensure_hull()
             self.ensure_mu_tables()
+            # tilt cells for the range of this host array, built once per (buffer, length) from a device copy: the chunks of the
+            # pipeline then take k_sweep_cell (a changed content only costs speed: what the cells miss takes the table walk)
+            if self.use_mu_cells and S >= self.CELLS_MIN_STATES and self.desc.mu_tables:
+                hkey = (mu_h.data_ptr(), S)
+                if getattr(self, "_cells_host_key", None) != hkey:
+                    self.ensure_mu_cells(mu_h.to(dev, non_blocking=True))
+                    self._cells_host_key = hkey
         n_chunks = (S + chunk - 1) // chunk
         if not hasattr(self, "_hpipe") or self._hpipe["key"] != (chunk, pmax):
             ws_bytes = int(L.fhmc_sweep_host_workspace(chunk, pmax, nsel))

@@ -192,3 +192,30 @@ def test_compact_sweep_below_the_fused_threshold_sizes_its_workspace():
         c = dh.sweep_compact(mu, pmax=4)
         g = dh.sweep(mu, pmax=4, lanes=-1).host()
         _check(c, g, 4)
+
+
+def test_cells_in_the_host_pipeline():
+    """fhmc_sweep_host_compact16 with cells built for the range of the host array (once per buffer): every chunk runs k_sweep_cell;
+    a second call with other content in the same buffer is still correct (what the cells miss takes the table walk)."""
+    import torch
+    from fhmcanalysis_b200 import _lib, engine, synth
+    n = 1001
+    lnpi = synth.two_peak_lnpi(n)
+    N = np.arange(n, dtype=np.float64)
+    S = 1 << 18
+    mu_h = torch.from_numpy(np.linspace(-0.03, 0.03, S)).pin_memory()
+    dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=10, sel=["N", N * N])
+    out = None
+    for rnd in range(2):
+        out = dh.sweep_host_compact(mu_h, pmax=4, out=out)
+        assert _lib.last_kernel() == "k_sweep_cell<compact>" and dh.desc.mu_cells
+        g = dh.sweep(mu_h.numpy(), pmax=4, lanes=-1).host()
+        assert np.array_equal(out["status"].numpy().astype(np.int64) & 0xFF, g["code"])
+        assert np.array_equal(out["nphase"].numpy(), g["nphase"])
+        for p in range(3):
+            live = (g["code"] == 0) & (g["nphase"] > p)
+            assert np.array_equal(out["bounds"].numpy()[live, p], g["bounds"][live, p])
+            if live.any():
+                assert np.max(np.abs(out["fe"].numpy()[live, p] - g["fe"][live, p]) / np.maximum(1.0, np.abs(g["fe"][live, p]))) < 1e-10
+                assert np.max(np.abs(out["avg"].numpy()[live, p] - g["avg"][live, p]) / np.maximum(1.0, np.abs(g["avg"][live, p]))) < 1e-10
+        mu_h.mul_(2.5)     # same buffer, twice the range: the cells still cover the middle of it

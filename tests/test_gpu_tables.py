@@ -137,6 +137,7 @@ def test_tables_host_pipeline_and_capacity():
     S = 1 << 18
     mu = np.linspace(-0.03, 0.03, S)
     dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=10, sel=["N", N * N])
+    dh.use_mu_cells = False
     h = dh.sweep_host_compact(mu, pmax=4)
     assert _lib.last_kernel() == "k_sweep_tab2<compact>" and dh.desc.mu_tables
     g = dh.sweep(mu, pmax=4, lanes=-1).host()
