@@ -46,7 +46,8 @@ struct CellHeader {   // 256 bytes at the start of the cells buffer
     double a_lo, a_hi;                    // covered tilt range (device)
     double inv_g;                         // grid cells per unit of tilt (device)
     unsigned long long kmin, kmax;        // order-preserving keys of min / max mu of the sweep (k_cell_range; device)
-    double pad1[14];
+    int sel_row[2], n, smooth;            // what the coefficients were built for
+    double pad1[12];
 };
 static_assert(sizeof(CellHeader) <= 256, "header must fit its slot");
 
@@ -386,8 +387,9 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
     const double dN = th->dN, Na = th->Na, lmax = th->lmax, a_lo = ch->a_lo, a_hi = ch->a_hi, inv_g = ch->inv_g;
     const double *lnpi = a.blob, *Nrow = a.blob + a.d.n_pad;
     const bool usable = th->magic == FHMC_TAB_MAGIC && !th->bad && th->n == n && th->smooth == a.d.smooth && ch->magic == FHMC_CELL_MAGIC &&
-                        ch->n_sel == NSEL && th->n_sel == NSEL && (NSEL < 1 || th->sel_row[0] == a.d.sel_row[0]) &&
-                        (NSEL < 2 || th->sel_row[1] == a.d.sel_row[1]) && n >= 3 && ch->n_pieces > 0;
+                        ch->n_sel == NSEL && th->n_sel == NSEL && (NSEL < 1 || (th->sel_row[0] == a.d.sel_row[0] && ch->sel_row[0] == a.d.sel_row[0])) &&
+                        (NSEL < 2 || (th->sel_row[1] == a.d.sel_row[1] && ch->sel_row[1] == a.d.sel_row[1])) && ch->n == n && ch->smooth == a.d.smooth &&
+                        n >= 3 && ch->n_pieces > 0;
     const double l0 = lnpi[0], N_0 = Nrow[0], l_last = lnpi[last], N_last = Nrow[last];
     const int lane = threadIdx.x & 31;
     const long long S = a.st.n_states;
@@ -569,8 +571,9 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell_t(const __gr
     const double dN = th->dN, Na = th->Na, lmax = th->lmax, a_lo = ch->a_lo, a_hi = ch->a_hi, inv_g = ch->inv_g;
     const double *lnpi = a.blob, *Nrow = a.blob + a.d.n_pad;
     const bool usable = th->magic == FHMC_TAB_MAGIC && !th->bad && th->n == n && th->smooth == a.d.smooth && ch->magic == FHMC_CELL_MAGIC &&
-                        ch->n_sel == NSEL && th->n_sel == NSEL && (NSEL < 1 || th->sel_row[0] == a.d.sel_row[0]) &&
-                        (NSEL < 2 || th->sel_row[1] == a.d.sel_row[1]) && n >= 3 && ch->n_pieces > 0;
+                        ch->n_sel == NSEL && th->n_sel == NSEL && (NSEL < 1 || (th->sel_row[0] == a.d.sel_row[0] && ch->sel_row[0] == a.d.sel_row[0])) &&
+                        (NSEL < 2 || (th->sel_row[1] == a.d.sel_row[1] && ch->sel_row[1] == a.d.sel_row[1])) && ch->n == n && ch->smooth == a.d.smooth &&
+                        n >= 3 && ch->n_pieces > 0;
     const double l0 = lnpi[0], N_0 = Nrow[0], l_last = lnpi[last], N_last = Nrow[last];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     double *slab = s_slab[wib];
@@ -766,6 +769,10 @@ static CellLayout cell_layout(const fhmc_hist_desc &d, int extra_pieces)
     CellHeader &h = L.h;
     h.magic = FHMC_CELL_MAGIC;
     h.n_sel = d.n_sel;
+    h.sel_row[0] = d.n_sel > 0 ? d.sel_row[0] : 0;
+    h.sel_row[1] = d.n_sel > 1 ? d.sel_row[1] : 0;
+    h.n = d.n;
+    h.smooth = d.smooth;
     h.blk = cell_blk(d.n_sel);
     h.iv_cap = (int)upc((size_t)4 * d.n + d.hull_len, 256) + 1;   // (= MuTabHeader::ep_cap + 1)
     h.piece_cap = h.iv_cap + (extra_pieces > 0 ? extra_pieces : 0);

@@ -642,10 +642,12 @@ __device__ __forceinline__ void tab2_warp_tiles(const SweepArgs &a, const W &w, 
         const long long k0 = wt * 64 + lane, k1 = k0 + 32;
         const long long sp0 = (IDX && k0 < S) ? a.c.ix_list[k0] : k0, sp1 = (IDX && k1 < S) ? a.c.ix_list[k1] : k1;
         bool ok0 = true, ok1 = true;
-        if (k0 < S) {
+        // (an index list can only name state points of this sweep; anything else is a stale entry and is skipped)
+        const bool v0 = k0 < S && (!IDX || (sp0 >= 0 && sp0 < a.st.n_states)), v1 = k1 < S && (!IDX || (sp1 >= 0 && sp1 < a.st.n_states));
+        if (v0) {
             typename W::PS p0, p1;
             w.init(p0, sp0, a.st.mu1[(sp0 / a.st.mu1_div) % a.st.n_mu1]);
-            if (k1 < S) {
+            if (v1) {
                 w.init(p1, sp1, a.st.mu1[(sp1 / a.st.mu1_div) % a.st.n_mu1], p0.ivl);
                 TAB_PROF_T(0)
                 if (!((p0.fl | p1.fl) & W::F_BAD)) {
