@@ -219,3 +219,48 @@ def test_cells_in_the_host_pipeline():
                 assert np.max(np.abs(out["fe"].numpy()[live, p] - g["fe"][live, p]) / np.maximum(1.0, np.abs(g["fe"][live, p]))) < 1e-10
                 assert np.max(np.abs(out["avg"].numpy()[live, p] - g["avg"][live, p]) / np.maximum(1.0, np.abs(g["avg"][live, p]))) < 1e-10
         mu_h.mul_(2.5)     # same buffer, twice the range: the cells still cover the middle of it
+
+
+def test_cells_two_destinations_take_the_transposing_kernel():
+    """Two destination buffers (what a sweep fused with its gather hands the kernel: this GPU's buffer and its NVLink peers') run
+    k_sweep_cell_t -- warp-uniform phase loop, fields transposed through shared memory into 16-byte stores.  Both buffers must hold
+    the records of the general kernel; a first-record offset and an odd record count exercise the unaligned per-lane path, a shuffled
+    sweep the warps whose lanes disagree about the phase count."""
+    import torch
+    from fhmcanalysis_b200 import _lib, engine, synth
+    n = 1001
+    lnpi = synth.two_peak_lnpi(n)
+    N = np.arange(n, dtype=np.float64)
+    rng = np.random.default_rng(5)
+    L = _lib.load()
+    for S, first, shuffle, sel in ((S_MIN + 64, 0, False, ["N", N * N]), (S_MIN + 33, 7, True, ["N", N * N]), (S_MIN + 1, 3, True, [N * N]),
+                                   (S_MIN + 2, 0, False, [])):
+        mu = np.linspace(-0.2, 0.2, S)
+        if shuffle:
+            rng.shuffle(mu)
+        dh = engine.DeviceHistogram(lnpi, N, 1.0, 0.0, smooth=10, sel=sel)
+        dh.CELLS_MIN_STATES = 1
+        n_total = S + first + 5
+        nbytes = int(L.fhmc_pack_soa16_bytes(n_total, 4, len(sel)))
+        bufs = [torch.full((nbytes,), 0xFF, dtype=torch.uint8, device="cuda") for _ in range(2)]
+        dh.sweep_compact(mu, pmax=4, dst=[b.data_ptr() for b in bufs], n_total=n_total, first=first, fill_dead=False)
+        assert _lib.last_kernel() == "k_sweep_cell<compact>"
+        g = dh.sweep(mu, pmax=4, lanes=-1).host()
+        for b in bufs:
+            v = engine.soa16_views(b, n_total, 4, len(sel))
+            st = v["status"].cpu().numpy().astype(np.int64)[first:first + S]
+            assert np.array_equal(st & 0xFF, g["code"]) and np.array_equal(v["nphase"].cpu().numpy()[first:first + S], g["nphase"])
+            assert float(v["path"][first:first + S].double().mean()) > 0.95
+            P = g["nphase"]
+            for p in range(4):
+                live = (g["code"] == 0) & (P > p)
+                fe = v["fe"].cpu().numpy()[first:first + S, p]
+                assert np.array_equal(v["bounds"].cpu().numpy()[first:first + S, p][live], g["bounds"][live, p])
+                assert np.all(np.isnan(fe[~live]))          # untouched 0xFF bytes
+                if live.any():
+                    assert np.max(np.abs(fe[live] - g["fe"][live, p]) / np.maximum(1.0, np.abs(g["fe"][live, p]))) < 1e-10
+                    if sel:
+                        a = v["avg"].cpu().numpy()[first:first + S, p][live]
+                        assert np.max(np.abs(a - g["avg"][live, p]) / np.maximum(1.0, np.abs(g["avg"][live, p]))) < 1e-10
+            # records outside [first, first + S) stay untouched
+            assert np.all(v["status"].cpu().numpy()[:first] == -1) and np.all(v["status"].cpu().numpy()[first + S:] == -1)
