@@ -368,177 +368,257 @@ __global__ void __launch_bounds__(256) k_cell_coef(const unsigned char *tables, 
 #ifndef FHMC_CELL_MINB
 #define FHMC_CELL_MINB 4
 #endif
+
+// what every thread of a sweep kernel reads from the two table headers and the descriptor
+struct CellCtx {
+    const CellPiece *cpc;
+    const double *coef, *pstart;
+    const int *gfirst;
+    int last, pmax, grid_n;
+    double dN, Na, lmax, a_lo, a_hi, inv_g, l0, N_0, l_last, N_last;
+    bool usable;   // the cells belong to this descriptor and hold at least one cell
+};
+
 template <int NSEL>
-__global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid_constant__ SweepArgs a)
+__device__ __forceinline__ CellCtx cell_ctx(const SweepArgs &a)
 {
-    constexpr int K = FHMC_CELL_K, BLK = cell_blk(NSEL);
-    // the indexed walk behind this kernel is launched with programmatic stream serialisation: its CTAs may be placed as soon as
-    // SMs drain here (it waits for this grid's completion itself before it reads the leftover list)
-    asm volatile("griddepcontrol.launch_dependents;");
     const unsigned char *tables = static_cast<const unsigned char *>(a.d.mu_tables);
     const unsigned char *cells = static_cast<const unsigned char *>(a.d.mu_cells);
     const MuTabHeader *th = reinterpret_cast<const MuTabHeader *>(tables);
     const CellHeader *ch = reinterpret_cast<const CellHeader *>(cells);
-    const CellPiece *cpc = reinterpret_cast<const CellPiece *>(cells + ch->off_piece);
-    const double *coef = reinterpret_cast<const double *>(cells + ch->off_coef);
-    const double *pstart = reinterpret_cast<const double *>(cells + ch->off_pstart);
-    const int *gfirst = reinterpret_cast<const int *>(cells + ch->off_grid);
-    const int n = a.d.n, last = n - 1, pmax = a.d.pmax, grid_n = ch->grid_n;
-    const double dN = th->dN, Na = th->Na, lmax = th->lmax, a_lo = ch->a_lo, a_hi = ch->a_hi, inv_g = ch->inv_g;
+    const int n = a.d.n;
     const double *lnpi = a.blob, *Nrow = a.blob + a.d.n_pad;
-    const bool usable = th->magic == FHMC_TAB_MAGIC && !th->bad && th->n == n && th->smooth == a.d.smooth && ch->magic == FHMC_CELL_MAGIC &&
-                        ch->n_sel == NSEL && th->n_sel == NSEL && (NSEL < 1 || (th->sel_row[0] == a.d.sel_row[0] && ch->sel_row[0] == a.d.sel_row[0])) &&
-                        (NSEL < 2 || (th->sel_row[1] == a.d.sel_row[1] && ch->sel_row[1] == a.d.sel_row[1])) && ch->n == n && ch->smooth == a.d.smooth &&
-                        n >= 3 && ch->n_pieces > 0;
-    const double l0 = lnpi[0], N_0 = Nrow[0], l_last = lnpi[last], N_last = Nrow[last];
-    const int lane = threadIdx.x & 31;
-    const long long S = a.st.n_states;
+    CellCtx c;
+    c.cpc = reinterpret_cast<const CellPiece *>(cells + ch->off_piece);
+    c.coef = reinterpret_cast<const double *>(cells + ch->off_coef);
+    c.pstart = reinterpret_cast<const double *>(cells + ch->off_pstart);
+    c.gfirst = reinterpret_cast<const int *>(cells + ch->off_grid);
+    c.last = n - 1;
+    c.pmax = a.d.pmax;
+    c.grid_n = ch->grid_n;
+    c.dN = th->dN; c.Na = th->Na; c.lmax = th->lmax;
+    c.a_lo = ch->a_lo; c.a_hi = ch->a_hi; c.inv_g = ch->inv_g;
+    c.usable = th->magic == FHMC_TAB_MAGIC && !th->bad && th->n == n && th->smooth == a.d.smooth && ch->magic == FHMC_CELL_MAGIC &&
+               ch->n_sel == NSEL && th->n_sel == NSEL && (NSEL < 1 || (th->sel_row[0] == a.d.sel_row[0] && ch->sel_row[0] == a.d.sel_row[0])) &&
+               (NSEL < 2 || (th->sel_row[1] == a.d.sel_row[1] && ch->sel_row[1] == a.d.sel_row[1])) && ch->n == n && ch->smooth == a.d.smooth &&
+               n >= 3 && ch->n_pieces > 0;
+    c.l0 = lnpi[0]; c.N_0 = Nrow[0]; c.l_last = lnpi[c.last]; c.N_last = Nrow[c.last];
+    return c;
+}
+
+// one state point after its lookup
+struct CellPoint {
+    double d, u0, resc;   // s - s_c; fl(lnPI_0 + fl(s N_0)); threshold of the RESCUED bit on ln S_p - u_0
+    const double *b;      // coefficient block of phase 0
+    int nph;
+    unsigned flags;
+};
+
+// Lookup and every per-state-point test.  Returns false when the state point is left to the table walk (outside the cells, margin
+// test, capacity rules, is_safe closer to its cutoff than rounding).  Safe to call with act == false (an idle lane of a warp that
+// stays convergent): such a lane reads valid table memory and gets false.  Requires c.usable.
+template <int NSEL>
+__device__ __forceinline__ bool cell_point(const SweepArgs &a, const CellCtx &c, double mu1, bool act, CellPoint &p)
+{
+    const double s = __dmul_rn(__dsub_rn(mu1, a.d.mu1_ref), a.d.beta_ref);   // GH:77, evaluated left to right
+    const double sdn = s * c.dN, av = -sdn;
+    act = act && (fabs(4.0 * sdn) < 200.0) && (av >= c.a_lo && av <= c.a_hi);
+    // the cell of this tilt: lookup grid, then a bisection over the few cells that start inside the grid cell
+    const int g = act ? min((int)((av - c.a_lo) * c.inv_g), c.grid_n - 1) : 0;
+    int lo = __ldg(c.gfirst + g), hi = act ? __ldg(c.gfirst + g + 1) : lo;
+    while (lo < hi) {   // last cell with pstart <= tilt, in [lo, hi]
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(c.pstart + mid) <= av) lo = mid; else hi = mid - 1;
+    }
+    const CellPiece *cp = c.cpc + lo;
+    const double2 w0 = __ldg(reinterpret_cast<const double2 *>(cp));       // {s_c, safe_lo}
+    const int4 w1 = __ldg(reinterpret_cast<const int4 *>(cp) + 1);         // {safe_hi lo, safe_hi hi, block, ivl}
+    const int4 w2 = __ldg(reinterpret_cast<const int4 *>(cp) + 2);         // {nph | lastmax, hidx | cntM, cntm | nmin, -}
+    const double2 w3 = __ldg(reinterpret_cast<const double2 *>(cp) + 3);   // {lnPI, N} at the last maximum
+    const double2 w4 = __ldg(reinterpret_cast<const double2 *>(cp) + 4);   // {lnPI, N} at the hull vertex
+    const double safe_hi = __hiloint2double(w1.y, w1.x);
+    const int nph = w2.x & 0xffff, lastmax = (w2.x >> 16) & 0xffff, pmax = c.pmax;
+    // margin test of the table walk (the tilt is further from both interval ends than rounding can move a comparison), folded into
+    // the cell's safe range; the capacity rules of PointEval::repair() for the caller's pmax (such a state point is a capacity error)
+    act = act && (av >= w0.y && av <= safe_hi) &&
+          !(nph > pmax || ((w2.y >> 16) & 0xffff) > pmax - 1 || (w2.z & 0xffff) > pmax || ((w2.z >> 16) & 0xffff) > pmax + 1);
+    // is_safe (GH:586-591): fl(fl(u_M - c) - fl(u_last - c)) < cutoff, decided without c when it is not a rounding matter
+    const double dl = tab_margin(c.lmax, fabs(s), c.Na);
+    const double u_last = __dadd_rn(c.l_last, __dmul_rn(s, c.N_last));
+    p.flags = FHMC_ST_FAST;
+    if (lastmax != c.last) {
+        const double D = __dadd_rn(w3.x, __dmul_rn(s, w3.y)) - u_last;
+        if (fabs(D - a.d.cutoff) <= 2.0 * dl) act = false;
+        if (!(D < a.d.cutoff)) p.flags |= FHMC_ST_SAFE;
+    } else if (!(0.0 < a.d.cutoff)) {
+        p.flags |= FHMC_ST_SAFE;
+    }
+    p.d = s - w0.x;
+    p.u0 = __dadd_rn(c.l0, __dmul_rn(s, c.N_0));
+    // (diagnostic bit of the walk: a phase whose sum underflows next to the global maximum's shift -- ln S_p - u_0 below this)
+    p.resc = (double)shift_for_max(__dadd_rn(w4.x, __dmul_rn(s, w4.y))) * 0.6931471805599453 - 644.7236 - p.u0;
+    p.b = c.coef + (size_t)w1.z * cell_blk(NSEL);
+    p.nph = nph;
+    return act;
+}
+
+// One phase of one state point from its coefficient block b: v[0] = F.E./kT, v[1 ..] = the averages, bword = {left, right}.
+// Returns false when the state point is outside the range of the expansion (never for a cell found by cell_point(), up to rounding).
+template <int NSEL>
+__device__ __forceinline__ bool cell_phase(const double *b, CellPoint &p, double (&v)[1 + NSEL], int &bword)
+{
+    constexpr int K = FHMC_CELL_K;
+    const double2 g0 = __ldg(reinterpret_cast<const double2 *>(b)), g1 = __ldg(reinterpret_cast<const double2 *>(b) + 1);
+    const double y = p.d * g1.x;
+    bword = __double2loint(g1.y);
+    double P[1 + NSEL];
+#pragma unroll
+    for (int q = 0; q <= NSEL; ++q) {
+        const double2 *cq = reinterpret_cast<const double2 *>(b + 4 + q * K);
+        const double2 k01 = __ldg(cq), k23 = __ldg(cq + 1), k45 = __ldg(cq + 2), k67 = __ldg(cq + 3);
+        double t = fma(k67.y, y, k67.x);
+        t = fma(t, y, k45.y);
+        t = fma(t, y, k45.x);
+        t = fma(t, y, k23.y);
+        t = fma(t, y, k23.x);
+        t = fma(t, y, k01.y);
+        P[q] = q == 0 ? t * y : fma(t, y, k01.x);   // (quantity 0: eps = P_0 / C_0 - 1, its constant term is 1)
+    }
+    const double eps = P[0];
+    if (!(fabs(y) <= FHMC_CELL_YMAX * (1.0 + 1e-6)) || !(fabs(eps) < 0.06)) return false;   // (|eps| <= e^0.05 - 1 by construction)
+    // log1p(eps), |eps| < 0.06: alternating series through eps^13 / 13 (next term < 1e-17 relative)
+    double l1 = fma(eps, 1.0 / 13.0, -1.0 / 12.0);
+    l1 = fma(l1, eps, 1.0 / 11.0);
+    l1 = fma(l1, eps, -1.0 / 10.0);
+    l1 = fma(l1, eps, 1.0 / 9.0);
+    l1 = fma(l1, eps, -1.0 / 8.0);
+    l1 = fma(l1, eps, 1.0 / 7.0);
+    l1 = fma(l1, eps, -1.0 / 6.0);
+    l1 = fma(l1, eps, 1.0 / 5.0);
+    l1 = fma(l1, eps, -1.0 / 4.0);
+    l1 = fma(l1, eps, 1.0 / 3.0);
+    l1 = fma(l1, eps, -0.5);
+    l1 = fma(l1 * eps, eps, eps);
+    const double lnS = (g0.x - p.u0) + fma(p.d, g0.y, l1);   // ln S_p - u_0
+    if (lnS < p.resc) p.flags |= FHMC_ST_RESCUED;
+    const double inv = 1.0 / (1.0 + eps);
+    v[0] = -lnS;
+#pragma unroll
+    for (int q = 0; q < NSEL; ++q) v[1 + q] = P[1 + q] * inv;
+    return true;
+}
+
+// head of a finished record (+ NaN / -1 in the dead phase slots when the caller asked for it) in every destination
+template <int NSEL>
+__device__ __forceinline__ void cell_head(const SweepArgs &a, long long rix, unsigned flags, int nph, long long fbase, long long bbase)
+{
     const long long cN = a.c.n_total;
-    int top = 0;
-    // flat list of mu (the usual case): no 64-bit division per state point; the next round's mu is fetched a round ahead
-    const bool flat = a.st.mu1_div == 1 && a.st.n_mu1 >= S;
-    // Blocked partition: a CTA owns one contiguous run of state points.  Neighbouring state points of a sweep share their cell, so
-    // after the first round the coefficient blocks a warp needs are in this SM's L1 (with a grid-stride loop every round of every
-    // CTA lands in another cell and waits for L2).
+    const uchar4 hd = make_uchar4((unsigned char)(flags & 0xFFu), (unsigned char)((flags >> 8) & 0xFFu), (unsigned char)nph, 1);   // (byte 3: written by the tilt cells -- diagnostic)
+    for (int dd = 0; dd < a.c.n_dst; ++dd) {
+        reinterpret_cast<uchar4 *>(a.c.dst[dd])[rix] = hd;
+        if (a.c.fill_dead)
+            for (int ph = nph; ph < a.d.pmax; ++ph) {
+                double *f = reinterpret_cast<double *>(a.c.dst[dd] + fbase) + ((long long)ph * cN + rix) * (1 + NSEL);
+#pragma unroll
+                for (int q = 0; q <= NSEL; ++q) f[q] = CUDART_NAN;
+                reinterpret_cast<int *>(a.c.dst[dd] + bbase)[(long long)ph * cN + rix] = -1;
+            }
+    }
+}
+
+// leftovers of a warp: appended to the index list of the table walk (one atomic per warp; the list holds n_states + 32 entries)
+__device__ __forceinline__ void cell_leftovers(const SweepArgs &a, bool left, long long sp, int lane)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, left);
+    if (m) {
+        int pos = 0;
+        if (lane == 0) pos = atomicAdd(a.c.ix_count, __popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (left && pos >= 0 && pos <= a.st.n_states) a.c.ix_list[pos + __popc(m & ((1u << lane) - 1u))] = sp;
+    }
+}
+
+// the contiguous run of state points of this CTA, and the mu of one of them (flat lists: no 64-bit division per state point)
+struct CellRun {
+    long long first, end;
+    bool flat;
+};
+__device__ __forceinline__ CellRun cell_run(const SweepArgs &a)
+{
+    // Blocked partition: neighbouring state points of a sweep share their cell, so after the first round the coefficient blocks a
+    // warp needs are in this SM's L1 (with a grid-stride loop every round of every CTA lands in another cell and waits for L2).
+    const long long S = a.st.n_states;
     const long long run = (((S + gridDim.x - 1) / gridDim.x) + 255) & ~255ll;
-    const long long first = (long long)blockIdx.x * run, end = first + run < S ? first + run : S;
-    auto load_mu = [&](long long q) -> double {
-        if (q >= end) return 0.0;
-        return flat ? __ldg(a.st.mu1 + q) : a.st.mu1[(q / a.st.mu1_div) % a.st.n_mu1];
-    };
-    double mu_next = load_mu(first + threadIdx.x);
-    for (long long base = first; base < end; base += 256) {
+    CellRun r;
+    r.first = (long long)blockIdx.x * run;
+    r.end = r.first + run < S ? r.first + run : S;
+    r.flat = a.st.mu1_div == 1 && a.st.n_mu1 >= S;
+    return r;
+}
+__device__ __forceinline__ double cell_mu(const SweepArgs &a, const CellRun &r, long long q)
+{
+    if (q >= r.end) return 0.0;
+    return r.flat ? __ldg(a.st.mu1 + q) : a.st.mu1[(q / a.st.mu1_div) % a.st.n_mu1];
+}
+
+template <int NSEL>
+__global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid_constant__ SweepArgs a)
+{
+    constexpr int BLK = cell_blk(NSEL), NF = 1 + NSEL;
+    // the indexed walk behind this kernel is launched with programmatic stream serialisation: its CTAs may be placed as soon as
+    // SMs drain here (it waits for this grid's completion itself before it reads the leftover list)
+    asm volatile("griddepcontrol.launch_dependents;");
+    const CellCtx c = cell_ctx<NSEL>(a);
+    const int lane = threadIdx.x & 31;
+    const long long cN = a.c.n_total;
+    const long long fbase = (4 * cN + 15) & ~15ll, bbase = fbase + (long long)c.pmax * cN * NF * 8;
+    const CellRun r = cell_run(a);
+    int top = 0;
+    double mu_next = cell_mu(a, r, r.first + threadIdx.x);   // the next round's mu is fetched a round ahead
+    for (long long base = r.first; base < r.end; base += 256) {
         const long long sp = base + threadIdx.x;
-        bool done = true;
         const double mu1 = mu_next;
-        mu_next = load_mu(sp + 256);
-        if (sp < end) {
-            done = false;
-            const double s = __dmul_rn(__dsub_rn(mu1, a.d.mu1_ref), a.d.beta_ref);   // GH:77, evaluated left to right
-            const double sdn = s * dN, av = -sdn;
-            do {
-                if (!usable || !(fabs(4.0 * sdn) < 200.0) || !(av >= a_lo && av <= a_hi)) break;
-                // the cell of this tilt: lookup grid, then a bisection over the few cells that start inside the grid cell
-                const int g = min((int)((av - a_lo) * inv_g), grid_n - 1);
-                int lo = __ldg(gfirst + g), hi = __ldg(gfirst + g + 1);
-                while (lo < hi) {   // last cell with pstart <= tilt, in [lo, hi]
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (__ldg(pstart + mid) <= av) lo = mid; else hi = mid - 1;
-                }
-                const CellPiece *cp = cpc + lo;
-                const double2 w0 = __ldg(reinterpret_cast<const double2 *>(cp));       // {s_c, safe_lo}
-                const int4 w1 = __ldg(reinterpret_cast<const int4 *>(cp) + 1);         // {safe_hi lo, safe_hi hi, block, ivl}
-                const int4 w2 = __ldg(reinterpret_cast<const int4 *>(cp) + 2);         // {nph | lastmax, hidx | cntM, cntm | nmin, -}
-                const double2 w3 = __ldg(reinterpret_cast<const double2 *>(cp) + 3);   // {lnPI, N} at the last maximum
-                const double2 w4 = __ldg(reinterpret_cast<const double2 *>(cp) + 4);   // {lnPI, N} at the hull vertex
-                const double s_c = w0.x, safe_hi = __hiloint2double(w1.y, w1.x);
-                // margin test of the table walk (the tilt is further from both interval ends than rounding can move a comparison)
-                if (!(av >= w0.y && av <= safe_hi)) break;
-                const int nph = w2.x & 0xffff, lastmax = (w2.x >> 16) & 0xffff;
-                // (the capacity rules of PointEval::repair() for the caller's pmax: such a state point is a capacity error)
-                if (nph > pmax || ((w2.y >> 16) & 0xffff) > pmax - 1 || (w2.z & 0xffff) > pmax || ((w2.z >> 16) & 0xffff) > pmax + 1) break;
-                const double d = s - s_c;
-                const double dl = tab_margin(lmax, fabs(s), Na);
-                // is_safe (GH:586-591): fl(fl(u_M - c) - fl(u_last - c)) < cutoff, decided without c when it is not a rounding matter
-                const double u_last = __dadd_rn(l_last, __dmul_rn(s, N_last));
-                unsigned flags = FHMC_ST_FAST;
-                if (lastmax != last) {
-                    const double uM = __dadd_rn(w3.x, __dmul_rn(s, w3.y));
-                    const double D = uM - u_last;
-                    if (fabs(D - a.d.cutoff) <= 2.0 * dl) break;
-                    if (!(D < a.d.cutoff)) flags |= FHMC_ST_SAFE;
-                } else if (!(0.0 < a.d.cutoff)) {
-                    flags |= FHMC_ST_SAFE;
-                }
-                const double u0 = __dadd_rn(l0, __dmul_rn(s, N_0));
-                const double resc = (double)shift_for_max(__dadd_rn(w4.x, __dmul_rn(s, w4.y))) * 0.6931471805599453 - 644.7236 - u0;
-                const double *b = coef + (size_t)w1.z * BLK;
-                const long long fbase = (4 * cN + 15) & ~15ll, bbase = fbase + (long long)pmax * cN * (1 + NSEL) * 8, rix = a.c.first + sp;
+        mu_next = cell_mu(a, r, sp + 256);
+        bool done = sp >= r.end;
+        if (!done && c.usable) {
+            CellPoint p;
+            if (cell_point<NSEL>(a, c, mu1, true, p)) {
+                const long long rix = a.c.first + sp;
                 // first destination: running pointers over the phase blocks (the other destinations of a fused gather are
                 // addressed per phase)
-                double *f0 = reinterpret_cast<double *>(a.c.dst[0] + fbase) + rix * (1 + NSEL);
+                double *f0 = reinterpret_cast<double *>(a.c.dst[0] + fbase) + rix * NF;
                 int *b0 = reinterpret_cast<int *>(a.c.dst[0] + bbase) + rix;
+                const double *b = p.b;
                 bool good = true;
                 // (a state point that gives up after its first phases has left them in the record: the table walk that takes it
                 // over finds the same phases in the same interval record and overwrites every one of them)
 #pragma unroll
                 for (int ph = 0; ph < FHMC_COMPACT_PMAX; ++ph) {
-                    if (ph >= nph) break;
-                    const double2 g0 = __ldg(reinterpret_cast<const double2 *>(b)), g1 = __ldg(reinterpret_cast<const double2 *>(b) + 1);
-                    const double y = d * g1.x;
-                    const int bword = __double2loint(g1.y);   // {left, right} of this phase
-                    if (!(fabs(y) <= FHMC_CELL_YMAX * (1.0 + 1e-6))) { good = false; break; }
-                    double P[1 + NSEL];
+                    if (ph >= p.nph) break;
+                    double v[NF];
+                    int bword;
+                    if (!cell_phase<NSEL>(b, p, v, bword)) { good = false; break; }
 #pragma unroll
-                    for (int q = 0; q <= NSEL; ++q) {
-                        const double2 *cq = reinterpret_cast<const double2 *>(b + 4 + q * K);
-                        const double2 k01 = __ldg(cq), k23 = __ldg(cq + 1), k45 = __ldg(cq + 2), k67 = __ldg(cq + 3);
-                        double v = fma(k67.y, y, k67.x);
-                        v = fma(v, y, k45.y);
-                        v = fma(v, y, k45.x);
-                        v = fma(v, y, k23.y);
-                        v = fma(v, y, k23.x);
-                        v = fma(v, y, k01.y);
-                        P[q] = q == 0 ? v * y : fma(v, y, k01.x);   // (quantity 0: eps = P_0 / C_0 - 1, its constant term is 1)
-                    }
-                    const double eps = P[0];
-                    if (!(fabs(eps) < 0.06)) { good = false; break; }   // (|eps| <= e^0.05 - 1 by construction)
-                    // log1p(eps), |eps| < 0.06: alternating series through eps^13 / 13 (next term < 1e-17 relative)
-                    double l1 = fma(eps, 1.0 / 13.0, -1.0 / 12.0);
-                    l1 = fma(l1, eps, 1.0 / 11.0);
-                    l1 = fma(l1, eps, -1.0 / 10.0);
-                    l1 = fma(l1, eps, 1.0 / 9.0);
-                    l1 = fma(l1, eps, -1.0 / 8.0);
-                    l1 = fma(l1, eps, 1.0 / 7.0);
-                    l1 = fma(l1, eps, -1.0 / 6.0);
-                    l1 = fma(l1, eps, 1.0 / 5.0);
-                    l1 = fma(l1, eps, -1.0 / 4.0);
-                    l1 = fma(l1, eps, 1.0 / 3.0);
-                    l1 = fma(l1, eps, -0.5);
-                    l1 = fma(l1 * eps, eps, eps);
-                    const double lnS = (g0.x - u0) + fma(d, g0.y, l1);   // ln S_p - u_0
-                    // (diagnostic bit of the walk: this phase's sum underflows next to the global maximum's shift)
-                    if (lnS < resc) flags |= FHMC_ST_RESCUED;
-                    const double inv = 1.0 / (1.0 + eps);
-                    f0[0] = -lnS;
-#pragma unroll
-                    for (int q = 0; q < NSEL; ++q) f0[1 + q] = P[1 + q] * inv;
+                    for (int q = 0; q < NF; ++q) f0[q] = v[q];
                     *b0 = bword;
                     for (int dd = 1; dd < a.c.n_dst; ++dd) {
-                        double *f = reinterpret_cast<double *>(a.c.dst[dd] + fbase) + ((long long)ph * cN + rix) * (1 + NSEL);
-                        f[0] = -lnS;
+                        double *f = reinterpret_cast<double *>(a.c.dst[dd] + fbase) + ((long long)ph * cN + rix) * NF;
 #pragma unroll
-                        for (int q = 0; q < NSEL; ++q) f[1 + q] = P[1 + q] * inv;
+                        for (int q = 0; q < NF; ++q) f[q] = v[q];
                         reinterpret_cast<int *>(a.c.dst[dd] + bbase)[(long long)ph * cN + rix] = bword;
                     }
-                    f0 += cN * (1 + NSEL);
+                    f0 += cN * NF;
                     b0 += cN;
                     b += BLK;
                 }
-                if (!good) break;
-                const uchar4 hd = make_uchar4((unsigned char)(flags & 0xFFu), (unsigned char)((flags >> 8) & 0xFFu), (unsigned char)nph, 1);   // (byte 3: written by the tilt cells -- diagnostic)
-                for (int dd = 0; dd < a.c.n_dst; ++dd) {
-                    reinterpret_cast<uchar4 *>(a.c.dst[dd])[rix] = hd;
-                    if (a.c.fill_dead)
-                        for (int ph = nph; ph < pmax; ++ph) {
-                            double *f = reinterpret_cast<double *>(a.c.dst[dd] + fbase) + ((long long)ph * cN + rix) * (1 + NSEL);
-#pragma unroll
-                            for (int q = 0; q <= NSEL; ++q) f[q] = CUDART_NAN;
-                            reinterpret_cast<int *>(a.c.dst[dd] + bbase)[(long long)ph * cN + rix] = -1;
-                        }
+                if (good) {
+                    cell_head<NSEL>(a, rix, p.flags, p.nph, fbase, bbase);
+                    top = max(top, p.nph);
+                    done = true;
                 }
-                top = max(top, nph);
-                done = true;
-            } while (false);
+            }
         }
-        // leftovers: appended to the index list of the table walk (one atomic per warp)
-        const unsigned m = __ballot_sync(0xffffffffu, !done);
-        if (m) {
-            int pos = 0;
-            if (lane == 0) pos = atomicAdd(a.c.ix_count, __popc(m));
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (!done && pos >= 0 && pos + 32 <= S + 32) a.c.ix_list[pos + __popc(m & ((1u << lane) - 1u))] = sp;   // (the list holds S + 32 entries)
-        }
+        cell_leftovers(a, !done, sp, lane);
     }
     if (a.c.max_nphase) {
 #pragma unroll
@@ -556,144 +636,39 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
 template <int NSEL>
 __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell_t(const __grid_constant__ SweepArgs a)
 {
-    constexpr int K = FHMC_CELL_K, BLK = cell_blk(NSEL), NF = 1 + NSEL, CHUNKS = 16 * NF;
+    constexpr int BLK = cell_blk(NSEL), NF = 1 + NSEL, CHUNKS = 16 * NF, ROUNDS = (CHUNKS + 31) / 32;
     asm volatile("griddepcontrol.launch_dependents;");
     __shared__ __align__(16) double s_slab[8][32 * NF];
-    const unsigned char *tables = static_cast<const unsigned char *>(a.d.mu_tables);
-    const unsigned char *cells = static_cast<const unsigned char *>(a.d.mu_cells);
-    const MuTabHeader *th = reinterpret_cast<const MuTabHeader *>(tables);
-    const CellHeader *ch = reinterpret_cast<const CellHeader *>(cells);
-    const CellPiece *cpc = reinterpret_cast<const CellPiece *>(cells + ch->off_piece);
-    const double *coef = reinterpret_cast<const double *>(cells + ch->off_coef);
-    const double *pstart = reinterpret_cast<const double *>(cells + ch->off_pstart);
-    const int *gfirst = reinterpret_cast<const int *>(cells + ch->off_grid);
-    const int n = a.d.n, last = n - 1, pmax = a.d.pmax, grid_n = ch->grid_n;
-    const double dN = th->dN, Na = th->Na, lmax = th->lmax, a_lo = ch->a_lo, a_hi = ch->a_hi, inv_g = ch->inv_g;
-    const double *lnpi = a.blob, *Nrow = a.blob + a.d.n_pad;
-    const bool usable = th->magic == FHMC_TAB_MAGIC && !th->bad && th->n == n && th->smooth == a.d.smooth && ch->magic == FHMC_CELL_MAGIC &&
-                        ch->n_sel == NSEL && th->n_sel == NSEL && (NSEL < 1 || (th->sel_row[0] == a.d.sel_row[0] && ch->sel_row[0] == a.d.sel_row[0])) &&
-                        (NSEL < 2 || (th->sel_row[1] == a.d.sel_row[1] && ch->sel_row[1] == a.d.sel_row[1])) && ch->n == n && ch->smooth == a.d.smooth &&
-                        n >= 3 && ch->n_pieces > 0;
-    const double l0 = lnpi[0], N_0 = Nrow[0], l_last = lnpi[last], N_last = Nrow[last];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double *slab = s_slab[wib];
-    const long long S = a.st.n_states;
+    const CellCtx c = cell_ctx<NSEL>(a);
+    const int lane = threadIdx.x & 31;
+    double *slab = s_slab[threadIdx.x >> 5];
     const long long cN = a.c.n_total;
-    const long long fbase = (4 * cN + 15) & ~15ll, bbase = fbase + (long long)pmax * cN * NF * 8;
+    const long long fbase = (4 * cN + 15) & ~15ll, bbase = fbase + (long long)c.pmax * cN * NF * 8;
+    const CellRun r = cell_run(a);
     int top = 0;
-    const bool flat = a.st.mu1_div == 1 && a.st.n_mu1 >= S;
-    const long long run = (((S + gridDim.x - 1) / gridDim.x) + 255) & ~255ll;
-    const long long first = (long long)blockIdx.x * run, end = first + run < S ? first + run : S;
-    auto load_mu = [&](long long q) -> double {
-        if (q >= end) return 0.0;
-        return flat ? __ldg(a.st.mu1 + q) : a.st.mu1[(q / a.st.mu1_div) % a.st.n_mu1];
-    };
-    if (!usable) {   // cells that do not belong to this descriptor: every state point is left to the table walk
-        for (long long base = first; base < end; base += 256) {
-            const long long sp = base + threadIdx.x;
-            const unsigned m = __ballot_sync(0xffffffffu, sp < end);
-            int pos = 0;
-            if (lane == 0) pos = atomicAdd(a.c.ix_count, __popc(m));
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (sp < end && pos >= 0 && pos + 32 <= S + 32) a.c.ix_list[pos + __popc(m & ((1u << lane) - 1u))] = sp;
-        }
+    if (!c.usable) {   // cells that do not belong to this descriptor: every state point is left to the table walk
+        for (long long base = r.first; base < r.end; base += 256) cell_leftovers(a, base + threadIdx.x < r.end, base + threadIdx.x, lane);
         return;
     }
-    double mu_next = load_mu(first + threadIdx.x);
-    for (long long base = first; base < end; base += 256) {
+    double mu_next = cell_mu(a, r, r.first + threadIdx.x);
+    for (long long base = r.first; base < r.end; base += 256) {
         const long long sp = base + threadIdx.x;
         const double mu1 = mu_next;
-        mu_next = load_mu(sp + 256);
-        const bool mine = sp < end;
-        const double s = __dmul_rn(__dsub_rn(mu1, a.d.mu1_ref), a.d.beta_ref);   // GH:77, evaluated left to right
-        const double sdn = s * dN, av = -sdn;
-        bool act = mine && usable && (fabs(4.0 * sdn) < 200.0) && (av >= a_lo && av <= a_hi);
-        // the cell of this tilt: lookup grid, then a bisection over the few cells that start inside the grid cell
-        const int g = act ? min((int)((av - a_lo) * inv_g), grid_n - 1) : 0;
-        int lo = __ldg(gfirst + g), hi = act ? __ldg(gfirst + g + 1) : lo;
-        while (lo < hi) {   // last cell with pstart <= tilt, in [lo, hi]
-            const int mid = (lo + hi + 1) >> 1;
-            if (__ldg(pstart + mid) <= av) lo = mid; else hi = mid - 1;
-        }
-        const CellPiece *cp = cpc + lo;
-        const double2 w0 = __ldg(reinterpret_cast<const double2 *>(cp));       // {s_c, safe_lo}
-        const int4 w1 = __ldg(reinterpret_cast<const int4 *>(cp) + 1);         // {safe_hi lo, safe_hi hi, block, ivl}
-        const int4 w2 = __ldg(reinterpret_cast<const int4 *>(cp) + 2);         // {nph | lastmax, hidx | cntM, cntm | nmin, -}
-        const double2 w3 = __ldg(reinterpret_cast<const double2 *>(cp) + 3);   // {lnPI, N} at the last maximum
-        const double2 w4 = __ldg(reinterpret_cast<const double2 *>(cp) + 4);   // {lnPI, N} at the hull vertex
-        const double s_c = w0.x, safe_hi = __hiloint2double(w1.y, w1.x);
-        const int nph = w2.x & 0xffff, lastmax = (w2.x >> 16) & 0xffff;
-        // margin test of the table walk; the capacity rules of PointEval::repair() for the caller's pmax
-        act = act && (av >= w0.y && av <= safe_hi) &&
-              !(nph > pmax || ((w2.y >> 16) & 0xffff) > pmax - 1 || (w2.z & 0xffff) > pmax || ((w2.z >> 16) & 0xffff) > pmax + 1);
-        const double d = s - s_c;
-        const double dl = tab_margin(lmax, fabs(s), Na);
-        // is_safe (GH:586-591): fl(fl(u_M - c) - fl(u_last - c)) < cutoff, decided without c when it is not a rounding matter
-        const double u_last = __dadd_rn(l_last, __dmul_rn(s, N_last));
-        unsigned flags = FHMC_ST_FAST;
-        if (lastmax != last) {
-            const double D = __dadd_rn(w3.x, __dmul_rn(s, w3.y)) - u_last;
-            if (fabs(D - a.d.cutoff) <= 2.0 * dl) act = false;
-            if (!(D < a.d.cutoff)) flags |= FHMC_ST_SAFE;
-        } else if (!(0.0 < a.d.cutoff)) {
-            flags |= FHMC_ST_SAFE;
-        }
-        const double u0 = __dadd_rn(l0, __dmul_rn(s, N_0));
-        const double resc = (double)shift_for_max(__dadd_rn(w4.x, __dmul_rn(s, w4.y))) * 0.6931471805599453 - 644.7236 - u0;
-        const double *b = coef + (size_t)w1.z * BLK;
+        mu_next = cell_mu(a, r, sp + 256);
+        const bool mine = sp < r.end;
+        CellPoint p;
+        bool act = cell_point<NSEL>(a, c, mu1, mine, p);
         const long long rix = a.c.first + sp, rix0 = rix - lane;
-        const int nph_l = act ? nph : 0;
+        const int nph_l = act ? p.nph : 0;
         const int nmax = __reduce_max_sync(0xffffffffu, nph_l);
+        const double *b = p.b;
         for (int ph = 0; ph < nmax; ++ph, b += BLK) {   // (uniform across the warp)
             bool on = act && ph < nph_l;
             double v[NF];
 #pragma unroll
             for (int q = 0; q < NF; ++q) v[q] = 0.0;
             int bword = 0;
-            if (on) {
-                const double2 g0 = __ldg(reinterpret_cast<const double2 *>(b)), g1 = __ldg(reinterpret_cast<const double2 *>(b) + 1);
-                const double y = d * g1.x;
-                bword = __double2loint(g1.y);   // {left, right} of this phase
-                double P[NF];
-#pragma unroll
-                for (int q = 0; q < NF; ++q) {
-                    const double2 *cq = reinterpret_cast<const double2 *>(b + 4 + q * K);
-                    const double2 k01 = __ldg(cq), k23 = __ldg(cq + 1), k45 = __ldg(cq + 2), k67 = __ldg(cq + 3);
-                    double t = fma(k67.y, y, k67.x);
-                    t = fma(t, y, k45.y);
-                    t = fma(t, y, k45.x);
-                    t = fma(t, y, k23.y);
-                    t = fma(t, y, k23.x);
-                    t = fma(t, y, k01.y);
-                    P[q] = q == 0 ? t * y : fma(t, y, k01.x);   // (quantity 0: eps = P_0 / C_0 - 1, its constant term is 1)
-                }
-                const double eps = P[0];
-                if (!(fabs(y) <= FHMC_CELL_YMAX * (1.0 + 1e-6)) || !(fabs(eps) < 0.06)) {   // (|eps| <= e^0.05 - 1 by construction)
-                    act = false;
-                    on = false;
-                } else {
-                    // log1p(eps), |eps| < 0.06: alternating series through eps^13 / 13 (next term < 1e-17 relative)
-                    double l1 = fma(eps, 1.0 / 13.0, -1.0 / 12.0);
-                    l1 = fma(l1, eps, 1.0 / 11.0);
-                    l1 = fma(l1, eps, -1.0 / 10.0);
-                    l1 = fma(l1, eps, 1.0 / 9.0);
-                    l1 = fma(l1, eps, -1.0 / 8.0);
-                    l1 = fma(l1, eps, 1.0 / 7.0);
-                    l1 = fma(l1, eps, -1.0 / 6.0);
-                    l1 = fma(l1, eps, 1.0 / 5.0);
-                    l1 = fma(l1, eps, -1.0 / 4.0);
-                    l1 = fma(l1, eps, 1.0 / 3.0);
-                    l1 = fma(l1, eps, -0.5);
-                    l1 = fma(l1 * eps, eps, eps);
-                    const double lnS = (g0.x - u0) + fma(d, g0.y, l1);   // ln S_p - u_0
-                    // (diagnostic bit of the walk: this phase's sum underflows next to the global maximum's shift)
-                    if (lnS < resc) flags |= FHMC_ST_RESCUED;
-                    const double inv = 1.0 / (1.0 + eps);
-                    v[0] = -lnS;
-#pragma unroll
-                    for (int q = 0; q < NSEL; ++q) v[1 + q] = P[1 + q] * inv;
-                }
-            }
+            if (on && !cell_phase<NSEL>(b, p, v, bword)) act = on = false;
             const long long prow = (long long)ph * cN;
             // all 32 state points of the warp have this phase and the warp's slice of the block starts on a 16-byte boundary:
             // transpose through shared memory and write full 16-byte chunks; else every lane writes its own fields
@@ -702,16 +677,16 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell_t(const __gr
 #pragma unroll
                 for (int q = 0; q < NF; ++q) slab[NF * lane + q] = v[q];
                 __syncwarp();
-                double2 c[(CHUNKS + 31) / 32];
+                double2 ch[ROUNDS];
 #pragma unroll
-                for (int r = 0; r < (CHUNKS + 31) / 32; ++r)
-                    c[r] = (lane + 32 * r < CHUNKS) ? reinterpret_cast<const double2 *>(slab)[lane + 32 * r] : make_double2(0.0, 0.0);
+                for (int k = 0; k < ROUNDS; ++k)
+                    ch[k] = (lane + 32 * k < CHUNKS) ? reinterpret_cast<const double2 *>(slab)[lane + 32 * k] : make_double2(0.0, 0.0);
                 __syncwarp();
                 for (int dd = 0; dd < a.c.n_dst; ++dd) {
                     double2 *o = reinterpret_cast<double2 *>(reinterpret_cast<double *>(a.c.dst[dd] + fbase) + (prow + rix0) * NF);
 #pragma unroll
-                    for (int r = 0; r < (CHUNKS + 31) / 32; ++r)
-                        if (lane + 32 * r < CHUNKS) o[lane + 32 * r] = c[r];
+                    for (int k = 0; k < ROUNDS; ++k)
+                        if (lane + 32 * k < CHUNKS) o[lane + 32 * k] = ch[k];
                 }
             } else if (on) {
                 for (int dd = 0; dd < a.c.n_dst; ++dd) {
@@ -726,27 +701,10 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell_t(const __gr
         // (a state point that gave up after its first phases has left them in the record: the table walk that takes it over finds
         // the same phases in the same interval record and overwrites every one of them)
         if (act) {
-            const uchar4 hd = make_uchar4((unsigned char)(flags & 0xFFu), (unsigned char)((flags >> 8) & 0xFFu), (unsigned char)nph, 1);   // (byte 3: written by the tilt cells -- diagnostic)
-            for (int dd = 0; dd < a.c.n_dst; ++dd) {
-                reinterpret_cast<uchar4 *>(a.c.dst[dd])[rix] = hd;
-                if (a.c.fill_dead)
-                    for (int ph = nph; ph < pmax; ++ph) {
-                        double *f = reinterpret_cast<double *>(a.c.dst[dd] + fbase) + ((long long)ph * cN + rix) * NF;
-#pragma unroll
-                        for (int q = 0; q < NF; ++q) f[q] = CUDART_NAN;
-                        reinterpret_cast<int *>(a.c.dst[dd] + bbase)[(long long)ph * cN + rix] = -1;
-                    }
-            }
-            top = max(top, nph);
+            cell_head<NSEL>(a, rix, p.flags, p.nph, fbase, bbase);
+            top = max(top, p.nph);
         }
-        // leftovers: appended to the index list of the table walk (one atomic per warp)
-        const unsigned m = __ballot_sync(0xffffffffu, mine && !act);
-        if (m) {
-            int pos = 0;
-            if (lane == 0) pos = atomicAdd(a.c.ix_count, __popc(m));
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (mine && !act && pos >= 0 && pos + 32 <= S + 32) a.c.ix_list[pos + __popc(m & ((1u << lane) - 1u))] = sp;
-        }
+        cell_leftovers(a, mine && !act, sp, lane);
     }
     if (a.c.max_nphase) {
 #pragma unroll
