@@ -406,6 +406,10 @@ __device__ __forceinline__ CellCtx cell_ctx(const SweepArgs &a)
     return c;
 }
 
+// log1p(x) = x + x^2 (c[0] + c[1] x + ... + c[11] x^11),  c[k] = (-1)^(k+1) / (k + 2)
+__constant__ double c_log1p[12] = {-1.0 / 2.0, 1.0 / 3.0, -1.0 / 4.0, 1.0 / 5.0, -1.0 / 6.0, 1.0 / 7.0, -1.0 / 8.0, 1.0 / 9.0, -1.0 / 10.0, 1.0 / 11.0,
+                                   -1.0 / 12.0, 1.0 / 13.0};
+
 // one state point after its lookup
 struct CellPoint {
     double d, u0, resc;   // s - s_c; fl(lnPI_0 + fl(s N_0)); threshold of the RESCUED bit on ln S_p - u_0
@@ -486,18 +490,11 @@ __device__ __forceinline__ bool cell_phase(const double *b, CellPoint &p, double
     }
     const double eps = P[0];
     if (!(fabs(y) <= FHMC_CELL_YMAX * (1.0 + 1e-6)) || !(fabs(eps) < 0.06)) return false;   // (|eps| <= e^0.05 - 1 by construction)
-    // log1p(eps), |eps| < 0.06: alternating series through eps^13 / 13 (next term < 1e-17 relative)
-    double l1 = fma(eps, 1.0 / 13.0, -1.0 / 12.0);
-    l1 = fma(l1, eps, 1.0 / 11.0);
-    l1 = fma(l1, eps, -1.0 / 10.0);
-    l1 = fma(l1, eps, 1.0 / 9.0);
-    l1 = fma(l1, eps, -1.0 / 8.0);
-    l1 = fma(l1, eps, 1.0 / 7.0);
-    l1 = fma(l1, eps, -1.0 / 6.0);
-    l1 = fma(l1, eps, 1.0 / 5.0);
-    l1 = fma(l1, eps, -1.0 / 4.0);
-    l1 = fma(l1, eps, 1.0 / 3.0);
-    l1 = fma(l1, eps, -0.5);
+    // log1p(eps), |eps| < 0.06: alternating series through eps^13 / 13 (next term < 1e-17 relative); the coefficients are
+    // constant-bank operands of the DFMAs (as literals each costs two UMOV per use)
+    double l1 = fma(eps, c_log1p[11], c_log1p[10]);
+#pragma unroll
+    for (int k = 9; k >= 0; --k) l1 = fma(l1, eps, c_log1p[k]);
     l1 = fma(l1 * eps, eps, eps);
     const double lnS = (g0.x - p.u0) + fma(p.d, g0.y, l1);   // ln S_p - u_0
     if (lnS < p.resc) p.flags |= FHMC_ST_RESCUED;
