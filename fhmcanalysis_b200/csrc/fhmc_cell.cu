@@ -418,52 +418,84 @@ struct CellPoint {
     unsigned flags;
 };
 
-// Lookup and every per-state-point test.  Returns false when the state point is left to the table walk (outside the cells, margin
-// test, capacity rules, is_safe closer to its cutoff than rounding).  Safe to call with act == false (an idle lane of a warp that
-// stays convergent): such a lane reads valid table memory and gets false.  Requires c.usable.
-template <int NSEL>
-__device__ __forceinline__ bool cell_point(const SweepArgs &a, const CellCtx &c, double mu1, bool act, CellPoint &p)
+// The cell of the state point this thread evaluated last: consecutive rounds of a thread are 256 state points apart and mostly fall
+// into the same cell, whose safe range is then checked from registers -- no lookup chain (grid -> cell starts -> cell), and the
+// coefficient loads do not wait for the cell's record.  lo > hi: no hint.
+struct CellHint {
+    const CellPiece *cp;
+    const double *b;
+    double lo, hi, s_c;
+    int nph;
+};
+__device__ __forceinline__ CellHint cell_no_hint(const CellCtx &c)
 {
+    CellHint h;
+    h.cp = c.cpc;
+    h.b = c.coef;
+    h.lo = CUDART_INF;
+    h.hi = -CUDART_INF;
+    h.s_c = 0.0;
+    h.nph = 0;
+    return h;
+}
+
+// Lookup and the per-state-point tests.  Returns false when the state point is left to the table walk (outside the cells, margin test,
+// capacity rules); `border`: is_safe is closer to its cutoff than rounding -- the caller leaves such a state point to the walk as well,
+// but may evaluate its phases first (the walk overwrites them), so that nothing waits for the words is_safe needs.  act == false (an
+// idle lane of a warp that stays convergent) returns false at once.  Requires c.usable.
+// HINT = false: the hint is only scratch (every state point is looked up): the per-lane-store kernel measured slower with the five
+// extra live values (64-register budget), the transposing one faster.
+template <int NSEL, bool HINT>
+__device__ __forceinline__ bool cell_point(const SweepArgs &a, const CellCtx &c, double mu1, bool act, CellPoint &p, CellHint &h, bool &border)
+{
+    border = false;
+    if (!act) return false;
     const double s = __dmul_rn(__dsub_rn(mu1, a.d.mu1_ref), a.d.beta_ref);   // GH:77, evaluated left to right
     const double sdn = s * c.dN, av = -sdn;
-    act = act && (fabs(4.0 * sdn) < 200.0) && (av >= c.a_lo && av <= c.a_hi);
-    // the cell of this tilt: lookup grid, then a bisection over the few cells that start inside the grid cell
-    const int g = act ? min((int)((av - c.a_lo) * c.inv_g), c.grid_n - 1) : 0;
-    int lo = __ldg(c.gfirst + g), hi = act ? __ldg(c.gfirst + g + 1) : lo;
-    while (lo < hi) {   // last cell with pstart <= tilt, in [lo, hi]
-        const int mid = (lo + hi + 1) >> 1;
-        if (__ldg(c.pstart + mid) <= av) lo = mid; else hi = mid - 1;
+    if (!(fabs(4.0 * sdn) < 200.0)) return false;
+    if (!HINT || !(av >= h.lo && av <= h.hi)) {
+        if (!(av >= c.a_lo && av <= c.a_hi)) return false;
+        // the cell of this tilt: lookup grid, then a bisection over the few cells that start inside the grid cell
+        const int g = min((int)((av - c.a_lo) * c.inv_g), c.grid_n - 1);
+        int lo = __ldg(c.gfirst + g), hi = __ldg(c.gfirst + g + 1);
+        while (lo < hi) {   // last cell with pstart <= tilt, in [lo, hi]
+            const int mid = (lo + hi + 1) >> 1;
+            if (__ldg(c.pstart + mid) <= av) lo = mid; else hi = mid - 1;
+        }
+        const CellPiece *cp = c.cpc + lo;
+        const double2 w0 = __ldg(reinterpret_cast<const double2 *>(cp));   // {s_c, safe_lo}
+        const int4 w1 = __ldg(reinterpret_cast<const int4 *>(cp) + 1);     // {safe_hi lo, safe_hi hi, block, ivl}
+        const int4 w2 = __ldg(reinterpret_cast<const int4 *>(cp) + 2);     // {nph | lastmax, hidx | cntM, cntm | nmin, -}
+        const double safe_hi = __hiloint2double(w1.y, w1.x);
+        const int nph = w2.x & 0xffff, pmax = c.pmax;
+        // margin test of the table walk (the tilt is further from both interval ends than rounding can move a comparison), folded
+        // into the cell's safe range; the capacity rules of PointEval::repair() for the caller's pmax (a capacity error otherwise)
+        if (!(av >= w0.y && av <= safe_hi) ||
+            nph > pmax || ((w2.y >> 16) & 0xffff) > pmax - 1 || (w2.z & 0xffff) > pmax || ((w2.z >> 16) & 0xffff) > pmax + 1)
+            return false;
+        h.cp = cp;
+        h.b = c.coef + (size_t)w1.z * cell_blk(NSEL);
+        h.lo = w0.y;
+        h.hi = safe_hi;
+        h.s_c = w0.x;
+        h.nph = nph;
     }
-    const CellPiece *cp = c.cpc + lo;
-    const double2 w0 = __ldg(reinterpret_cast<const double2 *>(cp));       // {s_c, safe_lo}
-    const int4 w1 = __ldg(reinterpret_cast<const int4 *>(cp) + 1);         // {safe_hi lo, safe_hi hi, block, ivl}
-    const int4 w2 = __ldg(reinterpret_cast<const int4 *>(cp) + 2);         // {nph | lastmax, hidx | cntM, cntm | nmin, -}
-    const double2 w3 = __ldg(reinterpret_cast<const double2 *>(cp) + 3);   // {lnPI, N} at the last maximum
-    const double2 w4 = __ldg(reinterpret_cast<const double2 *>(cp) + 4);   // {lnPI, N} at the hull vertex
-    const double safe_hi = __hiloint2double(w1.y, w1.x);
-    const int nph = w2.x & 0xffff, lastmax = (w2.x >> 16) & 0xffff, pmax = c.pmax;
-    // margin test of the table walk (the tilt is further from both interval ends than rounding can move a comparison), folded into
-    // the cell's safe range; the capacity rules of PointEval::repair() for the caller's pmax (such a state point is a capacity error)
-    act = act && (av >= w0.y && av <= safe_hi) &&
-          !(nph > pmax || ((w2.y >> 16) & 0xffff) > pmax - 1 || (w2.z & 0xffff) > pmax || ((w2.z >> 16) & 0xffff) > pmax + 1);
-    // is_safe (GH:586-591): fl(fl(u_M - c) - fl(u_last - c)) < cutoff, decided without c when it is not a rounding matter
+    const double2 w3 = __ldg(reinterpret_cast<const double2 *>(h.cp) + 3);   // {lnPI, N} at the last maximum
+    const double2 w4 = __ldg(reinterpret_cast<const double2 *>(h.cp) + 4);   // {lnPI, N} at the hull vertex
+    // is_safe (GH:586-591): fl(fl(u_M - c) - fl(u_last - c)) < cutoff, decided without c when it is not a rounding matter (a last
+    // maximum AT the last bin gives u_M == u_last bit for bit, D = 0, as in the reference)
     const double dl = tab_margin(c.lmax, fabs(s), c.Na);
-    const double u_last = __dadd_rn(c.l_last, __dmul_rn(s, c.N_last));
-    p.flags = FHMC_ST_FAST;
-    if (lastmax != c.last) {
-        const double D = __dadd_rn(w3.x, __dmul_rn(s, w3.y)) - u_last;
-        if (fabs(D - a.d.cutoff) <= 2.0 * dl) act = false;
-        if (!(D < a.d.cutoff)) p.flags |= FHMC_ST_SAFE;
-    } else if (!(0.0 < a.d.cutoff)) {
-        p.flags |= FHMC_ST_SAFE;
-    }
-    p.d = s - w0.x;
+    const double D = __dadd_rn(w3.x, __dmul_rn(s, w3.y)) - __dadd_rn(c.l_last, __dmul_rn(s, c.N_last));
+    border = fabs(D - a.d.cutoff) <= 2.0 * dl;
+    if (!HINT && border) return false;
+    p.flags = FHMC_ST_FAST | (!(D < a.d.cutoff) ? FHMC_ST_SAFE : 0u);
+    p.d = s - h.s_c;
     p.u0 = __dadd_rn(c.l0, __dmul_rn(s, c.N_0));
     // (diagnostic bit of the walk: a phase whose sum underflows next to the global maximum's shift -- ln S_p - u_0 below this)
     p.resc = (double)shift_for_max(__dadd_rn(w4.x, __dmul_rn(s, w4.y))) * 0.6931471805599453 - 644.7236 - p.u0;
-    p.b = c.coef + (size_t)w1.z * cell_blk(NSEL);
-    p.nph = nph;
-    return act;
+    p.b = h.b;
+    p.nph = h.nph;
+    return true;
 }
 
 // One phase of one state point from its coefficient block b: v[0] = F.E./kT, v[1 ..] = the averages, bword = {left, right}.
@@ -572,6 +604,7 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
     const CellRun r = cell_run(a);
     int top = 0;
     double mu_next = cell_mu(a, r, r.first + threadIdx.x);   // the next round's mu is fetched a round ahead
+    CellHint hint = cell_no_hint(c);
     for (long long base = r.first; base < r.end; base += 256) {
         const long long sp = base + threadIdx.x;
         const double mu1 = mu_next;
@@ -579,7 +612,8 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
         bool done = sp >= r.end;
         if (!done && c.usable) {
             CellPoint p;
-            if (cell_point<NSEL>(a, c, mu1, true, p)) {
+            bool border;
+            if (cell_point<NSEL, false>(a, c, mu1, true, p, hint, border)) {
                 const long long rix = a.c.first + sp;
                 // first destination: running pointers over the phase blocks (the other destinations of a fused gather are
                 // addressed per phase)
@@ -608,7 +642,7 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
                     b0 += cN;
                     b += BLK;
                 }
-                if (good) {
+                if (good && !border) {
                     cell_head<NSEL>(a, rix, p.flags, p.nph, fbase, bbase);
                     top = max(top, p.nph);
                     done = true;
@@ -648,17 +682,19 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell_t(const __gr
         return;
     }
     double mu_next = cell_mu(a, r, r.first + threadIdx.x);
+    CellHint hint = cell_no_hint(c);
     for (long long base = r.first; base < r.end; base += 256) {
         const long long sp = base + threadIdx.x;
         const double mu1 = mu_next;
         mu_next = cell_mu(a, r, sp + 256);
         const bool mine = sp < r.end;
         CellPoint p;
-        bool act = cell_point<NSEL>(a, c, mu1, mine, p);
+        bool border;
+        bool act = cell_point<NSEL, true>(a, c, mu1, mine, p, hint, border);
         const long long rix = a.c.first + sp, rix0 = rix - lane;
         const int nph_l = act ? p.nph : 0;
         const int nmax = __reduce_max_sync(0xffffffffu, nph_l);
-        const double *b = p.b;
+        const double *b = act ? p.b : c.coef;
         for (int ph = 0; ph < nmax; ++ph, b += BLK) {   // (uniform across the warp)
             bool on = act && ph < nph_l;
             double v[NF];
@@ -697,6 +733,7 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell_t(const __gr
         }
         // (a state point that gave up after its first phases has left them in the record: the table walk that takes it over finds
         // the same phases in the same interval record and overwrites every one of them)
+        act = act && !border;
         if (act) {
             cell_head<NSEL>(a, rix, p.flags, p.nph, fbase, bbase);
             top = max(top, p.nph);
