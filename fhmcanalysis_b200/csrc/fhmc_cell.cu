@@ -365,8 +365,13 @@ __global__ void __launch_bounds__(256) k_cell_coef(const unsigned char *tables, 
 // ---------------------------------------------------------------------------------------------------------------------
 // sweep: a thread per state point
 // ---------------------------------------------------------------------------------------------------------------------
+// resident CTAs per SM: the per-lane-store kernel at 80 registers (3 CTAs, no spills on its hot path, room for the hint), the
+// transposing one at 64 (4 CTAs) -- measured: 100 vs 111 us per 4x10^6 state points for the former, 115 vs 118 us for the latter
 #ifndef FHMC_CELL_MINB
-#define FHMC_CELL_MINB 4
+#define FHMC_CELL_MINB 3
+#endif
+#ifndef FHMC_CELL_T_MINB
+#define FHMC_CELL_T_MINB 4
 #endif
 
 // what every thread of a sweep kernel reads from the two table headers and the descriptor
@@ -443,8 +448,7 @@ __device__ __forceinline__ CellHint cell_no_hint(const CellCtx &c)
 // capacity rules); `border`: is_safe is closer to its cutoff than rounding -- the caller leaves such a state point to the walk as well,
 // but may evaluate its phases first (the walk overwrites them), so that nothing waits for the words is_safe needs.  act == false (an
 // idle lane of a warp that stays convergent) returns false at once.  Requires c.usable.
-// HINT = false: the hint is only scratch (every state point is looked up): the per-lane-store kernel measured slower with the five
-// extra live values (64-register budget), the transposing one faster.
+// HINT = false: the hint is only scratch (every state point is looked up).
 template <int NSEL, bool HINT>
 __device__ __forceinline__ bool cell_point(const SweepArgs &a, const CellCtx &c, double mu1, bool act, CellPoint &p, CellHint &h, bool &border)
 {
@@ -613,7 +617,10 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
         if (!done && c.usable) {
             CellPoint p;
             bool border;
-            if (cell_point<NSEL, false>(a, c, mu1, true, p, hint, border)) {
+            #ifndef FHMC_CELL_PLAIN_HINT
+#define FHMC_CELL_PLAIN_HINT true
+#endif
+            if (cell_point<NSEL, FHMC_CELL_PLAIN_HINT>(a, c, mu1, true, p, hint, border)) {
                 const long long rix = a.c.first + sp;
                 // first destination: running pointers over the phase blocks (the other destinations of a fused gather are
                 // addressed per phase)
@@ -665,7 +672,7 @@ __global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell(const __grid
 // store sectors at NSEL = 2, which is what bounds a gather fused into the sweep (every record crosses NVLink to every peer).
 // ---------------------------------------------------------------------------------------------------------------------
 template <int NSEL>
-__global__ void __launch_bounds__(256, FHMC_CELL_MINB) k_sweep_cell_t(const __grid_constant__ SweepArgs a)
+__global__ void __launch_bounds__(256, FHMC_CELL_T_MINB) k_sweep_cell_t(const __grid_constant__ SweepArgs a)
 {
     constexpr int BLK = cell_blk(NSEL), NF = 1 + NSEL, CHUNKS = 16 * NF, ROUNDS = (CHUNKS + 31) / 32;
     asm volatile("griddepcontrol.launch_dependents;");
