@@ -10,15 +10,16 @@
 // and the same with w_i X_q(i) for the averages.  All w_i >= 0, so the series is dominated term by term by exp(|y|) sum_i w_i:
 // cut after K = 8 terms with |y| <= 0.05 the relative truncation error is below 0.05^8 / 8! * e^0.1 = 1.1e-15.  A cell is
 // therefore at most 0.1 / R wide in tilt units (2e-4 for a 1001-bin one-phase histogram): a few hundred cells over the mu
-// range of a dense sweep, each costing one pass over the bins to build (k_cell_coef: a warp per cell) -- against one pass
-// PER STATE POINT for the walk.  A state point then costs, per phase, (1 + n_sel) degree-7 polynomials, one log and one
-// reciprocal, whatever the histogram length: the sweep is bound by its record traffic (8 bytes of mu in, 60 bytes out per
-// two-phase state point), not by the fp64 pipe.
+// range of a dense sweep, each costing one pass over the bins to build (k_cell_coef: a CTA per cell) -- against one pass
+// PER STATE POINT for the walk.  The coefficients are stored divided by C_0, so the sum is C_0 (1 + eps) with |eps| <= e^0.05 - 1
+// and its logarithm ln C_0 + log1p(eps) by a 12-term series: a state point costs, per phase, (1 + n_sel) degree-7 polynomials,
+// that series and one reciprocal, whatever the histogram length -- what is left is its record traffic (8 bytes of mu in, 60 bytes
+// out per two-phase state point).
 //
-// What stays exactly as in the table walk: the interval lookup and its rounding-margin test (integers -- phase count and
-// bounds -- come from the interval record, i.e. from the general evaluator at the interval's representative), the capacity
-// rules for the caller's pmax, is_safe() (decided from u_lastmax - u_last against the cutoff, with a margin; GH:586-591), the
-// RESCUED diagnostic bit.  Whatever the cells do not cover (state points outside the range they were built for, intervals
+// What stays exactly as in the table walk: integers (phase count, bounds) come from the interval record, i.e. from the general
+// evaluator at the interval's representative; the rounding-margin test of the interval lookup is folded into a safe range per cell
+// (k_cell_pieces); the capacity rules for the caller's pmax; is_safe() (decided from u_lastmax - u_last against the cutoff, with a
+// margin; GH:586-591); the RESCUED diagnostic bit.  Whatever the cells do not cover (state points outside the range they were built for, intervals
 // without a valid record, failed margin tests, is_safe closer to its cutoff than rounding) is appended to an index list and
 // walked by k_sweep_tab2_idx -- the parity-pinned table walk with its own fallback to the general evaluator -- in the same
 // call.
