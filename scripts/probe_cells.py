@@ -72,3 +72,23 @@ for reps in (20, 200):
     t1 = time.perf_counter()
     torch.cuda.synchronize()
     print("back to back x%d: host %.1f us per call, device %.1f us per call" % (reps, 1e6 * (t1 - t0) / reps, 1e3 * a.elapsed_time(b) / reps))
+
+# the product's sharded call (what bench.py times), host cost per call
+from fhmcanalysis_b200 import parallel
+mu_all = torch.linspace(-0.03, 0.03, S, dtype=torch.float64, device="cuda")
+hold = {"state": None}
+def step():
+    _, hold["state"] = parallel.sweep_sharded_compact(dh, mu_all, pmax=4, state=hold["state"], gather=False)
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+for reps in (200,):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(reps):
+        step()
+    b.record()
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    print("sweep_sharded_compact back to back x%d: host %.1f us per call, device %.1f us per call" % (reps, 1e6 * (t1 - t0) / reps, 1e3 * a.elapsed_time(b) / reps))
