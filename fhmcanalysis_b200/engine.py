@@ -355,6 +355,11 @@ class DeviceHistogram(object):
     # ------------------------------------------------------------------------------------------
     def _desc(self, pmax, complete=False, compare_raw=False, cutoff=None, smooth=None):
         d = _lib.HistDesc.from_buffer_copy(self.desc)
+        if not self.use_mu_cells:
+            d.mu_cells = None
+        if not self.use_mu_tables:
+            d.mu_tables = None
+            d.mu_cells = None
         d.pmax = int(pmax)
         d.complete = 1 if complete else 0
         d.compare_raw = 1 if compare_raw else 0
@@ -439,7 +444,8 @@ class DeviceHistogram(object):
         if (states is None and isinstance(mu1, t.Tensor) and mu1.is_cuda and isinstance(dst, t.Tensor)):
             mkey = (mu1.data_ptr(), mu1.numel(), mu1._version)
             plan_key = (mkey, int(pmax), dst.data_ptr(), dst.numel(), n_total, int(first), bool(fill_dead),
-                        max_nphase.data_ptr() if max_nphase is not None else 0, self.desc.mu_tables, self.desc.mu_cells)
+                        max_nphase.data_ptr() if max_nphase is not None else 0, self.desc.mu_tables,
+                        self.desc.mu_cells if self.use_mu_cells and self.use_mu_tables else None)
             plan = getattr(self, "_compact_plan", None)
             if plan is not None and plan[0] == plan_key and getattr(self, "_cells_key", None) == mkey and plan[7] is self._cws:
                 _, d, st, co, ws_ptr, ws_bytes, out, _ = plan
@@ -494,7 +500,7 @@ class DeviceHistogram(object):
         if plan_key is not None:
             # (keyed on what the descriptor points at NOW: the call above may have built tables / cells)
             mkey = plan_key[0]
-            plan_key = plan_key[:8] + (self.desc.mu_tables, self.desc.mu_cells)
+            plan_key = plan_key[:8] + (self.desc.mu_tables, self.desc.mu_cells if self.use_mu_cells and self.use_mu_tables else None)
             if getattr(self, "_cells_key", None) == mkey and plan_key[4] == n_total:
                 self._compact_plan = (plan_key, d, st, co, ws_ptr, ws_bytes, out, self._cws)
         return out

@@ -28,9 +28,10 @@ def test_cells_headline_config_against_general_kernel_table_walk_oracle_and_refe
     assert _check(c, g, 4) > 0.999
     assert _cell_fraction(c) > 0.995, _cell_fraction(c)
     # the table walk on the same state points: same integers, values to the joint rounding
-    dh.use_mu_cells = False
-    dh.desc.mu_cells = None
+    dh.use_mu_cells = False          # (the descriptor keeps the cells; the switch alone must take them out of the call)
     w = dh.sweep_compact(mu, pmax=4)
+    from fhmcanalysis_b200 import _lib
+    assert _lib.last_kernel() == "k_sweep_tab2<compact>" and float(w["path"].double().mean()) == 0.0
     assert np.array_equal(w["nphase"].cpu().numpy(), c["nphase"].cpu().numpy())
     assert np.array_equal(w["bounds"].cpu().numpy(), c["bounds"].cpu().numpy())
     assert np.array_equal(w["status"].cpu().numpy() & 0x1FF, c["status"].cpu().numpy() & 0x1FF)
